@@ -1,0 +1,163 @@
+/*
+ * dtb200.h -- C ABI of libdtb200.so: descriptools' per-cell terrain-descriptor path
+ * (slope, D8, flow accumulation, flow distance / river index / HAND, downslope, GFI,
+ * ln(hl/H), TI / MTI) as hand-written sm_100a CUDA kernels.
+ *
+ * The reference (JVBSouza/descriptools) has no FFI: its boundary is a set of Python
+ * module functions that move NumPy arrays to the device, launch one Numba @cuda.jit
+ * kernel and copy the result back.  Each entry point below replaces one of those
+ * host-wrapper + kernel pairs; the reference interface it replaces is cited as
+ * file:line (paths under descriptools/ in the reference checkout).  The Python modules
+ * in descriptools_b200/ keep the reference's function names and NumPy signatures and
+ * call these symbols through ctypes (see INTEGRATION.md for the binding a maintainer
+ * of the reference would add).
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer unless its name ends in _host; buffers are
+ *     caller-owned, row-major, dense (leading dimension == cols); nothing is allocated
+ *     or freed by the library except through dtb_ws_* ;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls
+ *     are asynchronous with respect to the host unless stated;
+ *   - return value: 0 = DTB_OK, negative = error (dtb_error_string()); no exceptions,
+ *     no CPU fallback: without a usable CUDA device every compute call fails;
+ *   - nodata sentinel is -100 everywhere (slope.py:231, flowhand.py:601, gfi.py:289);
+ *   - D8 codes: 1=E 2=SE 4=S 8=SW 16=W 32=NW 64=N 128=NE, 0 = nodata
+ *     (flowhand.py:801-824, downslope.py:490-513);
+ *   - linear cell index idx = row * cols + col over the FULL raster (flowhand.py:845).
+ *
+ * Row bands (multi-GPU): the *_band entry points operate on rows [row0, row0+rows) of a
+ * raster with grows x cols cells; see each function.
+ */
+#ifndef DTB200_H
+#define DTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTB_ABI_VERSION 1
+
+enum {
+    DTB_OK = 0,
+    DTB_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, bad dtype)  */
+    DTB_ERR_CUDA = -2,      /* a CUDA runtime/driver call failed; see dtb_last_cuda_error */
+    DTB_ERR_WORKSPACE = -3, /* workspace too small                                   */
+    DTB_ERR_UNSUPPORTED = -4
+};
+
+enum { DTB_F32 = 0, DTB_I16 = 1 };  /* DEM / HAND element type            */
+enum { DTB_I32 = 0, DTB_I64 = 1 };  /* index / accumulation element type  */
+
+int dtb_abi_version(void);
+const char *dtb_error_string(int code);
+/* text of the last CUDA error seen by this thread's library calls ("" if none) */
+const char *dtb_last_cuda_error(void);
+/* number of kernels launched by the library since load / last reset (all threads) */
+int64_t dtb_launch_count(void);
+void dtb_reset_launch_count(void);
+
+/* ---- slope + D8 (fused 3x3 stencil) -----------------------------------------------
+ * Replaces slope_cpu + slope_gpu (slope.py:152-206, 209-259) and adds the D8 direction
+ * the reference only consumes (flowhand.py:801-824).  `dem` holds buf_rows x cols
+ * elements; rows [row_begin,row_end) are computed and written to slope/d8 starting at
+ * their element 0 (i.e. out[(r-row_begin)*cols + c]).  Rows outside [0,buf_rows) are
+ * off-raster.  For a band, the caller passes a buffer with one halo row above and below
+ * (NaN-filled where the band touches the raster edge) and row_begin = 1.
+ * slope (f32, percent) and d8 may each be NULL. */
+int dtb_slope_d8(const void *dem, int dem_dtype, int64_t buf_rows, int64_t cols,
+                 int64_t row_begin, int64_t row_end, double px, float *slope, uint8_t *d8,
+                 void *stream);
+
+/* ---- D8 flow accumulation ------------------------------------------------------------
+ * New stage (no reference code; convention pinned by 12_fdr.tif -> 12_fac.tif and the
+ * consumers gfi.py:432, topoindexes.py:252-255): acc[p] = number of cells strictly
+ * upstream of p.  code-0 cells receive nodata_fill.  acc is int32 or int64 (acc_dtype).
+ * seeds (may be NULL): int64 per-cell external inflow added to the cell before the sweep
+ * (used by the band driver's second pass).  Returns in *unfinalised_host (may be NULL,
+ * forces a stream sync) the number of valid cells on D8 cycles. */
+size_t dtb_flowacc_workspace_bytes(int64_t rows, int64_t cols);
+int dtb_flowacc(const uint8_t *d8, int64_t rows, int64_t cols, void *acc, int acc_dtype,
+                int64_t nodata_fill, const int64_t *seeds, void *ws, size_t ws_bytes,
+                int64_t *unfinalised_host, void *stream);
+
+/* ---- flow distance + river-cell index + HAND (+ optional fused GFI) -------------------
+ * Replaces flow_distance_index_cpu + flow_distance_index_gpu (flowhand.py:476-562,
+ * 565-846, unpartitioned: out = 0) and hand_calculator (flowhand.py:414-442); with
+ * gfi != NULL also river_accumulation + geomorphic_flood_index_gpu (gfi.py:118-147,
+ * 267-294) in the same epilogue.
+ *   fdr u8, river i8 (0/1) or NULL with (acc, river_threshold): river = acc > threshold
+ *   (example.py:52); dem f32 or i16.
+ * Outputs (each may be NULL): fdist f32; idx int32/int64 (idx_dtype; -100 = unresolved);
+ * hand in the DEM's dtype; gfi f32 (needs acc).  max_moves <= 0 selects the reference's
+ * 20000 (flowhand.py:835). */
+typedef struct dtb_hand_args {
+    const uint8_t *fdr;
+    const int8_t *river;      /* or NULL */
+    const void *acc;          /* int32/int64 per acc_dtype; needed if river==NULL or gfi */
+    int acc_dtype;
+    int64_t river_threshold;
+    const void *dem;          /* f32 / i16 per dem_dtype; needed for hand / gfi */
+    int dem_dtype;
+    int64_t rows, cols;
+    double px;
+    int64_t max_moves;
+    float *fdist;
+    void *idx;
+    int idx_dtype;
+    void *hand;
+    float *gfi;
+    double gfi_n, gfi_b, gfi_size;
+} dtb_hand_args;
+
+size_t dtb_hand_workspace_bytes(int64_t rows, int64_t cols);
+int dtb_hand(const dtb_hand_args *args, void *ws, size_t ws_bytes, void *stream);
+
+/* hand_calculator alone (flowhand.py:414-442) on a caller-supplied index raster */
+int dtb_hand_from_index(const void *dem, int dem_dtype, const void *idx, int idx_dtype,
+                        int64_t n, void *hand, void *stream);
+
+/* ---- downslope index -------------------------------------------------------------------
+ * Replaces downslope_cpu + downslope_gpu (downslope.py:379-431, 434-532) AND the CPU
+ * fix-up pass over the -50 flags (downslope_sequential_jit, downslope.py:160-314,
+ * 373-374): one kernel produces the composite result.  max_moves <= 0 selects 5000. */
+int dtb_downslope(const void *dem, int dem_dtype, const uint8_t *fdr, int64_t rows,
+                  int64_t cols, double px, double delta, int64_t max_moves, float *out,
+                  void *stream);
+
+/* ---- pointwise indices -----------------------------------------------------------------
+ * dtb_river_accumulation: gfi.py:118-147.  out has acc's dtype.
+ * dtb_gfi: geomorphic_flood_index_cpu/_gpu (gfi.py:210-264, 267-294); racc is the
+ *          pre-gathered river accumulation.
+ * dtb_lnhlh: ln_hl_H_cpu/_gpu (gfi.py:349-400, 403-440).
+ * dtb_ti_mti: topographic_index_cpu + both kernels (topoindexes.py:170-230, 233-295)
+ *          in one pass; ti / mti may each be NULL. */
+int dtb_river_accumulation(const void *acc, int acc_dtype, const void *idx, int idx_dtype,
+                           int64_t n, void *out, void *stream);
+int dtb_gfi(const void *hand, int hand_dtype, const void *racc, int acc_dtype, int64_t n,
+            double expo, double scale, double size, float *out, void *stream);
+int dtb_lnhlh(const void *hand, int hand_dtype, const void *acc, int acc_dtype, int64_t n,
+              double expo, double scale, double size, float *out, void *stream);
+int dtb_ti_mti(const void *acc, int acc_dtype, const float *slope_rad, int64_t n, double px,
+               double expo, float *ti, float *mti, void *stream);
+/* example.py:63-64 glue: slope in percent -> radians with nodata patched back to -100 */
+int dtb_slope_to_radians(const float *slope_pct, int64_t n, float *slope_rad, void *stream);
+
+/* ---- benchmark support: synthetic DEM "dtb-synth-v1" + depression filling ---------------
+ * No reference counterpart (its fixtures were conditioned by an external GIS,
+ * Example/example.py:33-39).  Bit-identical to oracle/dt_condition.cpp. */
+int dtb_synth_dem_f32(int64_t rows, int64_t cols, int64_t row0, uint32_t seed,
+                      const float *amp10_host, float z0, float sr, float sc, float depth,
+                      float *out, void *stream);
+/* in-place priority-flood+epsilon fixed point; ws = rows*cols floats + 256 bytes.
+ * Synchronous.  *iterations_host (may be NULL) receives the number of sweeps. */
+size_t dtb_fill_workspace_bytes(int64_t rows, int64_t cols);
+int dtb_fill_depressions_f32(float *dem, int64_t rows, int64_t cols, void *ws, size_t ws_bytes,
+                             int *iterations_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTB200_H */
