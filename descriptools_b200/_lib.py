@@ -1,0 +1,105 @@
+"""ctypes binding of libdtb200.so (C ABI: include/dtb200.h).
+
+There is no fallback: if the shared library is missing or a call fails, an exception is
+raised.  PyTorch is used only to own device buffers and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint32, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdtb200.so")
+
+DTB_F32, DTB_I16 = 0, 1
+DTB_I32, DTB_I64 = 0, 1
+
+
+class DtbError(RuntimeError):
+    pass
+
+
+class HandArgs(Structure):
+    _fields_ = [
+        ("fdr", c_void_p),
+        ("river", c_void_p),
+        ("acc", c_void_p),
+        ("acc_dtype", c_int),
+        ("river_threshold", c_int64),
+        ("dem", c_void_p),
+        ("dem_dtype", c_int),
+        ("rows", c_int64),
+        ("cols", c_int64),
+        ("px", c_double),
+        ("max_moves", c_int64),
+        ("fdist", c_void_p),
+        ("idx", c_void_p),
+        ("idx_dtype", c_int),
+        ("hand", c_void_p),
+        ("gfi", c_void_p),
+        ("gfi_n", c_double),
+        ("gfi_b", c_double),
+        ("gfi_size", c_double),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/dtb200.h one to one
+SIGNATURES = {
+    "dtb_abi_version": (c_int, []),
+    "dtb_error_string": (c_char_p, [c_int]),
+    "dtb_last_cuda_error": (c_char_p, []),
+    "dtb_launch_count": (c_int64, []),
+    "dtb_reset_launch_count": (None, []),
+    "dtb_slope_d8": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
+    "dtb_flowacc_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "dtb_flowacc": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_size_t,
+                            POINTER(c_int64), c_void_p]),
+    "dtb_hand_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "dtb_hand": (c_int, [POINTER(HandArgs), c_void_p, c_size_t, c_void_p]),
+    "dtb_hand_from_index": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "dtb_downslope": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_double, c_double, c_int64, c_void_p, c_void_p]),
+    "dtb_river_accumulation": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "dtb_gfi": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_double, c_double, c_double, c_void_p, c_void_p]),
+    "dtb_lnhlh": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_double, c_double, c_double, c_void_p, c_void_p]),
+    "dtb_ti_mti": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p]),
+    "dtb_slope_to_radians": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "dtb_synth_dem_f32": (c_int, [c_int64, c_int64, c_int64, c_uint32, POINTER(c_float), c_float, c_float, c_float,
+                                  c_float, c_void_p, c_void_p]),
+    "dtb_fill_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "dtb_fill_depressions_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_size_t, POINTER(c_int), c_void_p]),
+}
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise DtbError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C descriptools_b200/csrc).  descriptools_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dtb_abi_version() != 1:
+        raise DtbError("libdtb200.so ABI version mismatch")
+    return lib
+
+
+lib = _load()
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib.dtb_error_string(code).decode()
+        detail = lib.dtb_last_cuda_error().decode()
+        raise DtbError(f"{what or 'libdtb200'} failed: {msg}" + (f" [{detail}]" if detail and code == -2 else ""))
+
+
+def launch_count() -> int:
+    return int(lib.dtb_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib.dtb_reset_launch_count()

@@ -1,0 +1,86 @@
+// downslope.cu -- downslope index: walk the D8 path from each cell until the drop reaches
+// `delta`; index = drop / path length (not in percent).
+//
+// Semantics: the COMPOSITE the reference's public downsloper() produces -- downslope_gpu
+// (downslope.py:458-532) followed by the whole-raster CPU pass over the cells it flagged -50
+// (downslope_sequential_jit, downslope.py:194-312, 373-374): walks that leave the raster or
+// would step onto nodata return the partial slope to the last valid cell (0 if no move was
+// made), walks that reach max_moves (5000, downslope.py:303) return the partial slope.  The
+// reference's GPU kernel punts ~10 % of the cells of its own example to that single-threaded
+// CPU pass; here one kernel finishes every cell.  The stop condition depends on the start
+// cell's elevation (downslope.py:468), so the walk cannot be pointer-jumped; the distance is
+// summed move by move in f64 exactly as the reference does (downslope.py:490-513), which
+// makes the result bit-identical to oracle/dt_oracle.c.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace dtb {
+namespace {
+
+constexpr int DS_THREADS = 256;
+
+template <typename T> struct Diff;
+template <> struct Diff<float> {
+    static __device__ __forceinline__ double sub(float a, float b) { return (double)(a - b); }  // f32 - f32 -> f32
+};
+template <> struct Diff<int16_t> {
+    static __device__ __forceinline__ double sub(int16_t a, int16_t b) { return (double)((int)a - (int)b); }  // i64 in Numba
+};
+
+template <typename T>
+__global__ void __launch_bounds__(DS_THREADS)
+downslope_kernel(const T *__restrict__ dem, const uint8_t *__restrict__ fdr, int64_t rows, int64_t cols, double px,
+                 double pd, double delta, int64_t max_moves, float *__restrict__ out)
+{
+    const int64_t n = rows * cols;
+    const int64_t i = (int64_t)blockIdx.x * DS_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const T z0 = dem[i];
+    if (z0 <= (T)ND_I) {  // downslope.py:459
+        out[i] = ND_F;
+        return;
+    }
+    int64_t y = i / cols, x = i - y * cols, pos = i, loop = 0;
+    double dist = 0.0;
+    T zc = z0;
+    while (Diff<T>::sub(z0, zc) < delta) {  // downslope.py:211 / :468
+        const unsigned f = fdr[pos];
+        int dr, dc;
+        if (d8_offset(f, dr, dc)) {
+            const int64_t yy = y + dr, xx = x + dc;
+            if (yy < 0 || yy >= rows || xx < 0 || xx >= cols) break;  // downslope.py:212-231
+            const int64_t q = yy * cols + xx;
+            const T zq = dem[q];
+            if (zq == (T)ND_I) break;  // downslope.py:234-276: do not step onto nodata
+            y = yy; x = xx; pos = q; zc = zq;
+            dist += d8_is_diag(f) ? pd : px;
+        }
+        if (++loop == max_moves) break;  // downslope.py:300-304
+    }
+    // downslope.py:306-312 (dist == 0 also covers the reference's 0/0 ZeroDivisionError case)
+    out[i] = (dist == 0.0) ? 0.0f : (float)(Diff<T>::sub(z0, zc) / dist);
+}
+
+}  // namespace
+}  // namespace dtb
+
+extern "C" int dtb_downslope(const void *dem, int dem_dtype, const uint8_t *fdr, int64_t rows, int64_t cols, double px,
+                             double delta, int64_t max_moves, float *out, void *stream)
+{
+    using namespace dtb;
+    if (!dem || !fdr || !out || rows <= 0 || cols <= 0 || !(px > 0.0)) return DTB_ERR_INVALID;
+    if (max_moves <= 0) max_moves = 5000;
+    const int64_t n = rows * cols;
+    const unsigned blocks = (unsigned)((n + DS_THREADS - 1) / DS_THREADS);
+    cudaStream_t st = as_stream(stream);
+    const double pd = px * sqrt(2.0);
+    if (dem_dtype == DTB_F32)
+        downslope_kernel<float><<<blocks, DS_THREADS, 0, st>>>((const float *)dem, fdr, rows, cols, px, pd, delta, max_moves, out);
+    else if (dem_dtype == DTB_I16)
+        downslope_kernel<int16_t><<<blocks, DS_THREADS, 0, st>>>((const int16_t *)dem, fdr, rows, cols, px, pd, delta, max_moves, out);
+    else
+        return DTB_ERR_INVALID;
+    DTB_LAUNCH_CHECK("downslope_kernel");
+    return DTB_OK;
+}

@@ -1,0 +1,265 @@
+"""Device-resident entry points: torch CUDA tensors in, torch CUDA tensors out.
+
+These are thin argument marshallers around the C ABI (include/dtb200.h); the arithmetic is in
+descriptools_b200/csrc/*.cu.  The NumPy drop-in modules (slope.py, flowhand.py, ...) and the
+benchmark both go through here.  All calls are enqueued on torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DTB_F32, DTB_I16, DTB_I32, DTB_I64, HandArgs, check, lib
+
+_DEM_DT = {torch.float32: DTB_F32, torch.int16: DTB_I16}
+_INT_DT = {torch.int32: DTB_I32, torch.int64: DTB_I64}
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.DtbError("descriptools_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk2d(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor")
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D")
+    return t.contiguous()
+
+
+def _dem_dtype(t: torch.Tensor) -> int:
+    try:
+        return _DEM_DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"DEM/HAND tensors must be float32 or int16, got {t.dtype}") from None
+
+
+def _int_dtype(t: torch.Tensor) -> int:
+    try:
+        return _INT_DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"index/accumulation tensors must be int32 or int64, got {t.dtype}") from None
+
+
+class _Workspace:
+    """One cached scratch buffer per device, grown on demand (caller-owned from the ABI's view)."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def get(self, nbytes: int) -> torch.Tensor:
+        dev = torch.cuda.current_device()
+        b = self.buf.get(dev)
+        if b is None or b.numel() < nbytes:
+            self.buf[dev] = None
+            b = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{dev}")
+            self.buf[dev] = b
+        return b
+
+    def release(self):
+        self.buf.clear()
+
+
+workspace = _Workspace()
+
+
+def slope_d8(dem: torch.Tensor, px: float, want_slope: bool = True, want_d8: bool = True,
+             row_begin: int = 0, row_end: int | None = None):
+    """Fused slope (%) + D8 over rows [row_begin,row_end) of `dem` (slope.py:152-259 + SURVEY A2)."""
+    dem = _chk2d(dem, "dem")
+    rows, cols = dem.shape
+    row_end = rows if row_end is None else row_end
+    nr = row_end - row_begin
+    slope = torch.empty((nr, cols), dtype=torch.float32, device=dem.device) if want_slope else None
+    d8 = torch.empty((nr, cols), dtype=torch.uint8, device=dem.device) if want_d8 else None
+    check(lib.dtb_slope_d8(_ptr(dem), _dem_dtype(dem), rows, cols, row_begin, row_end, float(px), _ptr(slope), _ptr(d8),
+                           _stream()), "dtb_slope_d8")
+    return slope, d8
+
+
+def flow_accumulation(d8: torch.Tensor, dtype: torch.dtype = torch.int32, nodata_fill: int = -100,
+                      seeds: torch.Tensor | None = None, check_cycles: bool = False):
+    """D8 flow accumulation.  Returns acc, or (acc, n_cycle_cells) if check_cycles."""
+    d8 = _chk2d(d8, "d8")
+    if d8.dtype != torch.uint8:
+        raise TypeError("d8 must be uint8")
+    rows, cols = d8.shape
+    acc = torch.empty((rows, cols), dtype=dtype, device=d8.device)
+    nbytes = lib.dtb_flowacc_workspace_bytes(rows, cols)
+    ws = workspace.get(nbytes)
+    left = ctypes.c_int64(0)
+    if seeds is not None:
+        seeds = _chk2d(seeds, "seeds")
+        if seeds.dtype != torch.int64:
+            raise TypeError("seeds must be int64")
+    check(lib.dtb_flowacc(_ptr(d8), rows, cols, _ptr(acc), _int_dtype(acc), int(nodata_fill), _ptr(seeds), _ptr(ws), nbytes,
+                          ctypes.byref(left) if check_cycles else None, _stream()), "dtb_flowacc")
+    return (acc, int(left.value)) if check_cycles else acc
+
+
+def hand(fdr: torch.Tensor, dem: torch.Tensor | None, px: float, river: torch.Tensor | None = None,
+         acc: torch.Tensor | None = None, river_threshold: int = 0, max_moves: int = 0,
+         want_fdist: bool = True, want_idx: bool = True, want_hand: bool = True,
+         gfi_params: tuple[float, float, float] | None = None, idx_dtype: torch.dtype | None = None):
+    """Flow distance, river index, HAND and (optionally) fused GFI.
+
+    flowhand.py:476-846 + 414-442 (+ gfi.py:118-147, 267-294 when gfi_params=(n, b, size)).
+    Returns a dict with the requested tensors: fdist f32, idx int32/int64, hand (DEM dtype), gfi f32.
+    """
+    fdr = _chk2d(fdr, "fdr")
+    if fdr.dtype != torch.uint8:
+        raise TypeError("fdr must be uint8")
+    rows, cols = fdr.shape
+    dev = fdr.device
+    a = HandArgs()
+    a.fdr = _ptr(fdr)
+    if river is not None:
+        river = _chk2d(river, "river")
+        if river.dtype != torch.int8:
+            raise TypeError("river must be int8")
+    a.river = _ptr(river)
+    if acc is not None:
+        acc = _chk2d(acc, "acc")
+        a.acc_dtype = _int_dtype(acc)
+    a.acc = _ptr(acc)
+    a.river_threshold = int(river_threshold)
+    if dem is not None:
+        dem = _chk2d(dem, "dem")
+        a.dem_dtype = _dem_dtype(dem)
+    a.dem = _ptr(dem)
+    a.rows, a.cols, a.px, a.max_moves = rows, cols, float(px), int(max_moves)
+    out = {}
+    if want_fdist:
+        out["fdist"] = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+    if want_idx:
+        if idx_dtype is None:
+            idx_dtype = torch.int32 if rows * cols < 2**31 else torch.int64
+        out["idx"] = torch.empty((rows, cols), dtype=idx_dtype, device=dev)
+        a.idx_dtype = _int_dtype(out["idx"])
+    if want_hand:
+        if dem is None:
+            raise ValueError("hand needs dem")
+        out["hand"] = torch.empty((rows, cols), dtype=dem.dtype, device=dev)
+    if gfi_params is not None:
+        if dem is None or acc is None:
+            raise ValueError("fused gfi needs dem and acc")
+        out["gfi"] = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+        a.gfi_n, a.gfi_b, a.gfi_size = (float(v) for v in gfi_params)
+    a.fdist, a.idx, a.hand, a.gfi = _ptr(out.get("fdist")), _ptr(out.get("idx")), _ptr(out.get("hand")), _ptr(out.get("gfi"))
+    nbytes = lib.dtb_hand_workspace_bytes(rows, cols)
+    ws = workspace.get(nbytes)
+    check(lib.dtb_hand(ctypes.byref(a), _ptr(ws), nbytes, _stream()), "dtb_hand")
+    return out
+
+
+def hand_from_index(dem: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    dem, idx = _chk2d(dem, "dem"), _chk2d(idx, "idx")
+    out = torch.empty_like(dem)
+    check(lib.dtb_hand_from_index(_ptr(dem), _dem_dtype(dem), _ptr(idx), _int_dtype(idx), dem.numel(), _ptr(out), _stream()),
+          "dtb_hand_from_index")
+    return out
+
+
+def downslope(dem: torch.Tensor, fdr: torch.Tensor, px: float, delta: float, max_moves: int = 0) -> torch.Tensor:
+    dem, fdr = _chk2d(dem, "dem"), _chk2d(fdr, "fdr")
+    rows, cols = dem.shape
+    out = torch.empty((rows, cols), dtype=torch.float32, device=dem.device)
+    check(lib.dtb_downslope(_ptr(dem), _dem_dtype(dem), _ptr(fdr), rows, cols, float(px), float(delta), int(max_moves),
+                            _ptr(out), _stream()), "dtb_downslope")
+    return out
+
+
+def river_accumulation(acc: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    acc, idx = _chk2d(acc, "acc"), _chk2d(idx, "idx")
+    out = torch.empty_like(acc)
+    check(lib.dtb_river_accumulation(_ptr(acc), _int_dtype(acc), _ptr(idx), _int_dtype(idx), acc.numel(), _ptr(out), _stream()),
+          "dtb_river_accumulation")
+    return out
+
+
+def gfi(hand_t: torch.Tensor, racc: torch.Tensor, n: float, b: float, size: float) -> torch.Tensor:
+    hand_t, racc = _chk2d(hand_t, "hand"), _chk2d(racc, "racc")
+    out = torch.empty(hand_t.shape, dtype=torch.float32, device=hand_t.device)
+    check(lib.dtb_gfi(_ptr(hand_t), _dem_dtype(hand_t), _ptr(racc), _int_dtype(racc), hand_t.numel(), float(n), float(b),
+                      float(size), _ptr(out), _stream()), "dtb_gfi")
+    return out
+
+
+def ln_hl_H(hand_t: torch.Tensor, acc: torch.Tensor, n: float, b: float, size: float) -> torch.Tensor:
+    hand_t, acc = _chk2d(hand_t, "hand"), _chk2d(acc, "acc")
+    out = torch.empty(hand_t.shape, dtype=torch.float32, device=hand_t.device)
+    check(lib.dtb_lnhlh(_ptr(hand_t), _dem_dtype(hand_t), _ptr(acc), _int_dtype(acc), hand_t.numel(), float(n), float(b),
+                        float(size), _ptr(out), _stream()), "dtb_lnhlh")
+    return out
+
+
+def ti_mti(acc: torch.Tensor, slope_rad: torch.Tensor, px: float, n: float, want_ti: bool = True, want_mti: bool = True):
+    acc, slope_rad = _chk2d(acc, "acc"), _chk2d(slope_rad, "slope")
+    if slope_rad.dtype != torch.float32:
+        raise TypeError("slope must be float32 (radians)")
+    ti = torch.empty(acc.shape, dtype=torch.float32, device=acc.device) if want_ti else None
+    mti = torch.empty(acc.shape, dtype=torch.float32, device=acc.device) if want_mti else None
+    check(lib.dtb_ti_mti(_ptr(acc), _int_dtype(acc), _ptr(slope_rad), acc.numel(), float(px), float(n), _ptr(ti), _ptr(mti),
+                         _stream()), "dtb_ti_mti")
+    return ti, mti
+
+
+def slope_to_radians(slope_pct: torch.Tensor) -> torch.Tensor:
+    slope_pct = _chk2d(slope_pct, "slope")
+    out = torch.empty_like(slope_pct)
+    check(lib.dtb_slope_to_radians(_ptr(slope_pct), slope_pct.numel(), _ptr(out), _stream()), "dtb_slope_to_radians")
+    return out
+
+
+# ---- benchmark support -----------------------------------------------------------------
+SYNTH_SEED = 20260101
+SYNTH_Z0, SYNTH_SR, SYNTH_SC, SYNTH_DEPTH = 100.0, 0.02, 0.005, 6.0
+SYNTH_AMP0, SYNTH_HURST = 15.0, 0.6
+
+
+def synth_amplitudes() -> np.ndarray:
+    k = np.arange(10, dtype=np.float64)
+    return (SYNTH_AMP0 * (0.5 ** k) ** SYNTH_HURST).astype(np.float32)
+
+
+def synth_dem(rows: int, cols: int, row0: int = 0, seed: int = SYNTH_SEED) -> torch.Tensor:
+    """Synthetic DEM recipe 'dtb-synth-v1'  generated on the device."""
+    dev = require_cuda()
+    out = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+    amp = synth_amplitudes()
+    check(lib.dtb_synth_dem_f32(rows, cols, row0, seed, amp.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                SYNTH_Z0, SYNTH_SR, SYNTH_SC, SYNTH_DEPTH, _ptr(out), _stream()), "dtb_synth_dem_f32")
+    return out
+
+
+def fill_depressions(dem: torch.Tensor) -> int:
+    """In-place priority-flood+epsilon fixed point; returns the number of relaxation passes."""
+    dem_c = _chk2d(dem, "dem")
+    if dem_c.data_ptr() != dem.data_ptr() or dem.dtype != torch.float32:
+        raise ValueError("dem must be a contiguous float32 CUDA tensor")
+    rows, cols = dem.shape
+    nbytes = lib.dtb_fill_workspace_bytes(rows, cols)
+    ws = workspace.get(nbytes)
+    it = ctypes.c_int(0)
+    check(lib.dtb_fill_depressions_f32(_ptr(dem), rows, cols, _ptr(ws), nbytes, ctypes.byref(it), _stream()),
+          "dtb_fill_depressions_f32")
+    return int(it.value)
+
+
+def conditioned_dem(rows: int, cols: int, seed: int = SYNTH_SEED) -> torch.Tensor:
+    dem = synth_dem(rows, cols, 0, seed)
+    fill_depressions(dem)
+    return dem

@@ -57,8 +57,8 @@ static inline int code_offset(uint8_t code, int *dr, int *dc)
  * slope.py:175-182 expressed as bounds checks.  D8 is new:
  * the neighbour that last updated the running maximum (strict '<' keeps the
  * first maximum in scan order); nodata -> 0; a valid cell with no strictly
- * lower valid neighbour points at its first skipped (off-raster, == -100 or NaN)
- * neighbour in scan order, else 0.
+ * lower valid neighbour points at its first neighbour in scan order whose gradient
+ * is undefined (off-raster, == -100, or a NaN difference), else 0.
  * Rows [row_begin,row_end) of a raster with `rows` rows are computed; outputs are
  * indexed from row_begin (used by the band tests). */
 #define SLOPE_D8_BODY(T, DIFF_T)                                                         \
@@ -94,7 +94,8 @@ static inline int code_offset(uint8_t code, int *dr, int *dc)
                         int skipped = (rr < 0 || rr >= rows || cc < 0 || cc >= cols);    \
                         if (!skipped) {                                                  \
                             const T zq = dem[rr * cols + cc];                            \
-                            skipped = (zq == (T)ND) || (zq != zq);                       \
+                            const DIFF_T df = (DIFF_T)zc - (DIFF_T)zq;                   \
+                            skipped = (zq == (T)ND) || (df != df);                       \
                         }                                                                \
                         if (skipped) { code = SCAN_CODE[k]; break; }                     \
                     }                                                                    \
