@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- DEM Mcells/s for slope -> D8 -> flow accumulation -> HAND -> GFI (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--rows R --cols C]
+
+A "step" is one pass of the whole chain over one synthetic hydrologically conditioned DEM
+(recipe dtb-synth-v1, generated and depression-filled on the device before timing).  At N=1 the
+workload is BASELINE.json configs[2]: 40 000 x 40 000 f32, full chain, one B200.  At N>1 the same
+DEM is sharded into N contiguous row bands (configs[3]; "scaling": "strong").
+
+  value  : cells / time with the DEM already resident in HBM (CUDA events, max over ranks)
+  e2e    : same metric through the host API (pinned NumPy DEM in, all seven rasters out),
+           host<->device copies inside the timed region
+  roofline : dominant stage, algorithmic bytes / CUDA-event time vs measured HBM peak
+  cpu_baseline : the oracle port (oracle/dt_oracle.c, OpenMP) on a bounded sample, rank 0, N=1
+
+--impl reference times the reference's CPU path on the host cores: the reference is Python/Numba
+and is not on the GPU box, so this arm runs the oracle port (kind "port").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+PX, RIVER_THR, N_GFI, B_GFI = 12.5, 128000, 0.4, 0.1
+BYTES_PER_CELL = {"slope_d8": 9, "flowacc": 5, "hand_gfi": 41}  # SURVEY.md 8(d), int32 indices
+CHAIN_BYTES = 55
+SAMPLE_ROWS = SAMPLE_COLS = 3072  # bounded CPU sample
+
+
+def measured_hbm_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) >= 6)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_chain(dem, threads_note=True):
+    """the oracle port over one DEM: slope+D8, accumulation, flow distance/index, HAND, GFI"""
+    import numpy as np
+    import oracle
+
+    t0 = time.perf_counter()
+    slope, d8 = oracle.slope_d8(dem, PX)
+    acc, _ = oracle.flow_accumulation(d8)
+    river = (acc > RIVER_THR).astype(np.int8)
+    fdist, idx, hand = oracle.flow_hand_index(dem, d8, river, PX)
+    gfi = oracle.gfi(hand, acc, idx, N_GFI, B_GFI, PX)
+    return time.perf_counter() - t0
+
+
+def sample_dem():
+    """bounded CPU sample: a SAMPLE_ROWS x SAMPLE_COLS DEM of the same recipe, conditioned on the device"""
+    from descriptools_b200 import device
+
+    return device.conditioned_dem(SAMPLE_ROWS, SAMPLE_COLS).cpu().numpy()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+
+    oracle.build()
+    dem = sample_dem()
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_chain(dem)
+    t = [cpu_chain(dem) for _ in range(args.steps)]
+    dt = sum(t)
+    val = dem.size * args.steps / dt / 1e6
+    sample = f"{SAMPLE_ROWS}x{SAMPLE_COLS} f32 dtb-synth-v1 DEM per step, river = acc > {RIVER_THR}"
+    print(json.dumps({
+        "impl": "reference", "metric": "DEM Mcells/s slope->D8->flowacc->HAND->GFI", "value": val, "unit": "Mcells/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_name(args):
+    return f"synthetic {args.rows}x{args.cols} f32 DEM (dtb-synth-v1, depression-filled), full slope->D8->flowacc->HAND->GFI chain"
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from descriptools_b200 import _lib, device, pipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rows, cols = args.rows, args.cols
+    n_cells = rows * cols
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    stage_ms = {k: 0.0 for k in BYTES_PER_CELL}
+
+    if world == 1:
+        dem = device.conditioned_dem(rows, cols)
+        torch.cuda.synchronize()
+        int_dt = torch.int32 if n_cells < 2**31 else torch.int64
+
+        def step(timed):
+            e = [ev() for _ in range(4)]
+            e[0].record()
+            slope, d8 = device.slope_d8(dem, PX)
+            e[1].record()
+            acc = device.flow_accumulation(d8, dtype=int_dt)
+            e[2].record()
+            out = device.hand(d8, dem, PX, acc=acc, river_threshold=RIVER_THR, gfi_params=(N_GFI, B_GFI, PX), idx_dtype=int_dt)
+            e[3].record()
+            return e, (slope, d8, acc, out)
+
+        runner = None
+    else:
+        from descriptools_b200 import bands
+
+        runner = bands.BandRunner(rows, cols, PX, RIVER_THR, N_GFI, B_GFI)
+        runner.load_synthetic()  # rank 0 conditions the DEM, bands are scattered over NCCL (untimed)
+
+        def step(timed):
+            return runner.step_events(), None
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    launches0 = _lib.launch_count()
+    t_start, t_end = ev(), ev()
+    with ClockSampler(local) as clk:
+        t_start.record()
+        events = []
+        for _ in range(args.steps):
+            e, keep = step(True)
+            events.append(e)
+        t_end.record()
+        barrier()
+    launches = _lib.launch_count() - launches0
+    ms = t_start.elapsed_time(t_end)
+    for e in events:
+        for i, k in enumerate(stage_ms):
+            stage_ms[k] += e[i].elapsed_time(e[i + 1])
+    if world > 1:
+        t = torch.tensor([ms] + [stage_ms[k] for k in stage_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        for i, k in enumerate(stage_ms):
+            stage_ms[k] = float(t[1 + i])
+    ms_step = ms / args.steps
+    value = n_cells / (ms_step * 1e-3) / 1e6
+    keep = None
+
+    # ---- end-to-end through the host API: pinned DEM in, seven rasters out ----------------------
+    e2e = None
+    if world == 1:
+        try:
+            dts = pipeline.output_dtypes(np.float32, n_cells)
+            dem_host = torch.empty((rows, cols), dtype=torch.float32, pin_memory=True)
+            dem_host.copy_(dem)
+            pinned = {k: torch.empty((rows, cols), dtype=getattr(torch, np.dtype(v).name), pin_memory=True) for k, v in dts.items()}
+            del dem
+            device.workspace.release()
+            torch.cuda.empty_cache()
+            pipeline.pipeline(dem_host, PX, RIVER_THR, N_GFI, B_GFI, pinned_out=pinned)  # warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            k_e2e = max(1, min(args.steps, 2))
+            for _ in range(k_e2e):
+                pipeline.pipeline(dem_host, PX, RIVER_THR, N_GFI, B_GFI, pinned_out=pinned)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / k_e2e
+            e2e = {"value": n_cells / dt / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": n_cells * 4,
+                   "d2h_bytes_per_step": int(sum(np.dtype(v).itemsize for v in dts.values())) * n_cells, "steps": k_e2e,
+                   "ms_per_step": dt * 1e3}
+            del pinned, dem_host
+        except Exception as ex:  # host RAM too small for the pinned staging buffers
+            e2e = {"value": None, "unit": "Mcells/s", "error": repr(ex)[:200]}
+    elif runner is not None:
+        e2e = runner.e2e(max(1, min(args.steps, 2)))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_kind = measured_hbm_peak()
+    peak_total = peak * world
+    stages = {}
+    for k, b in BYTES_PER_CELL.items():
+        t_ms = stage_ms[k] / args.steps
+        gbs = b * n_cells / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
+        stages[k] = {"ms": t_ms, "bytes_per_cell": b, "achieved_gbs": gbs, "frac": gbs / peak_total}
+    dom = max(stages, key=lambda k: stages[k]["ms"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_gbs"], "peak": peak_total, "unit": "GB/s",
+                "frac": stages[dom]["frac"], "traffic": None, "peak_kind": peak_kind + " (burst copy)",
+                "chain_frac": CHAIN_BYTES * n_cells / (ms_step * 1e-3) / 1e9 / peak_total, "stages": stages}
+
+    line = {
+        "metric": "DEM Mcells/s slope->D8->flowacc->HAND->GFI", "value": value, "unit": "Mcells/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "rows": rows, "cols": cols, "px": PX, "river_threshold": RIVER_THR,
+                   "parallelism": "1 GPU" if world == 1 else f"{world} row bands", "l2": "inputs larger than L2 (no flush needed)"},
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu:
+        import oracle
+
+        oracle.build()
+        sdem = sample_dem()
+        cpu_chain(sdem)
+        dt = cpu_chain(sdem)
+        line["cpu_baseline"] = {"value": sdem.size / dt / 1e6, "unit": "Mcells/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": f"{SAMPLE_ROWS}x{SAMPLE_COLS} f32 dtb-synth-v1 DEM, same chain, oracle/dt_oracle.c with OpenMP"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=40000)
+    ap.add_argument("--cols", type=int, default=40000)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -6,7 +6,9 @@
 // outlets point at their first undefined neighbour).  Bit-exact against oracle/dt_oracle.c.
 //
 // B200 design: persistent CTAs (2 per SM) walk 128x64-cell tiles in row-major order; each
-// tile plus its 1-cell halo (a 132x66 f32 box) is staged in shared memory by TMA
+// tile plus its halo (a 136x66 f32 box starting 4 columns left of the tile: the TMA unit
+// faults unless the box's innermost start coordinate is 16-byte aligned -- measured on B200,
+// scripts/tma_probe.cu) is staged in shared memory by TMA
 // (cp.async.bulk.tensor.2d, out-of-bounds elements filled with NaN, which stands in for
 // the reference's -100 padding ring) through a 3-stage mbarrier ring, so the next two
 // tiles are in flight while one is computed.  A thread owns 4 columns x 8 rows and slides
@@ -23,6 +25,7 @@
 //   * slope = f32(f64(diff)/d*100) is computed as f64(diff)*(100/d) and falls back to the
 //     exact expression when the product sits within 16 ulp of an f32 rounding boundary.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -31,14 +34,15 @@ namespace {
 
 constexpr int TW = 128;           // tile width  (cells)
 constexpr int TH = 64;            // tile height (cells)
-constexpr int BOXW = TW + 4;      // staged columns c0-1 .. c0+TW+2 (16-byte multiple)
+constexpr int HALO_L = 4;         // staged columns start at c0-4 (TMA: 16-byte aligned box start)
+constexpr int BOXW = TW + 8;      // staged columns c0-4 .. c0+TW+3
 constexpr int BOXH = TH + 2;      // staged rows    r0-1 .. r0+TH
 constexpr int NTHREADS = 256;     // 32 column groups x 8 row groups
 constexpr int RPT = TH / 8;       // rows per thread
 constexpr int STAGES = 3;
 constexpr int STAGE_BYTES = ((BOXW * BOXH * 4 + 127) / 128) * 128;
 constexpr int TMA_BYTES = BOXW * BOXH * 4;
-constexpr size_t SMEM_TMA = (size_t)STAGES * STAGE_BYTES + 128;
+constexpr size_t SMEM_TMA = (size_t)STAGES * STAGE_BYTES + 256;
 
 struct SlopeConsts {
     double px;   // cardinal step            (slope.py:250)
@@ -131,9 +135,9 @@ __device__ __forceinline__ void finish_cell(float ac, int cc, float ad, int cd, 
 // load one staged row (6 values around the thread's 4 cells), NaN-ify -100, report centre nodata
 __device__ __forceinline__ void load_row(const float *p, float (&w)[6], unsigned &ndmask)
 {
+    // p -> staged column of the thread's first cell (16-byte aligned); halos at p[-1], p[4]
     const float4 a = *reinterpret_cast<const float4 *>(p);
-    const float2 b = *reinterpret_cast<const float2 *>(p + 4);
-    float raw[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+    float raw[6] = {p[-1], a.x, a.y, a.z, a.w, p[4]};
     ndmask = 0;
 #pragma unroll
     for (int j = 1; j <= 4; ++j) ndmask |= (raw[j] <= ND_F) ? (1u << (j - 1)) : 0u;  // slope.py:231
@@ -143,7 +147,7 @@ __device__ __forceinline__ void load_row(const float *p, float (&w)[6], unsigned
 }
 
 // The stencil over one thread strip: 4 columns x nrows rows of the staged tile.
-//   tile: smem, row pitch BOXW; smem (row j, col k) <-> raster (r0-1+j, c0-1+k)
+//   tile: smem, row pitch BOXW; smem (row j, col k) <-> raster (r0-1+j, c0-HALO_L+k)
 //   gx: column group (cells c0+4gx..+3), ry0: first tile row of the strip
 template <bool VEC>
 __device__ __forceinline__ void stencil_strip(const float *tile, int gx, int ry0, const SlopeConsts &k,
@@ -151,7 +155,7 @@ __device__ __forceinline__ void stencil_strip(const float *tile, int gx, int ry0
                                               int64_t c_first /* raster col of the first cell */, int64_t cols,
                                               float *__restrict__ slope, uint8_t *__restrict__ d8)
 {
-    const float *base = tile + 4 * gx;
+    const float *base = tile + 4 * gx + HALO_L;
     float up[6], mid[6], dn[6];
     unsigned nd_mid, nd_dn, nd_unused;
     load_row(base + (ry0)*BOXW, up, nd_unused);
@@ -247,15 +251,15 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 slope_d8_tma_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_begin, int64_t row_end, int64_t cols,
                     int tiles_x, int ntiles, SlopeConsts k, float *__restrict__ slope, uint8_t *__restrict__ d8)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 127u) != 0u) __trap();  // TMA destination alignment
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES);
     const int tid = threadIdx.x;
 
     auto issue = [&](int tile, int stage) {
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         mbar_expect_tx(&full[stage], TMA_BYTES);
-        tma_load_2d(smem + (size_t)stage * STAGE_BYTES, &dem_map, tx * TW - 1, (int)(row_begin + (int64_t)ty * TH - 1),
+        tma_load_2d(smem + (size_t)stage * STAGE_BYTES, &dem_map, tx * TW - HALO_L, (int)(row_begin + (int64_t)ty * TH - 1),
                     &full[stage]);
     };
 
@@ -297,7 +301,7 @@ slope_d8_generic_kernel(const T *__restrict__ dem, int64_t buf_rows, int64_t row
     __shared__ __align__(16) float tile[BOXH * BOXW];
     const int tid = threadIdx.x;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-    const int64_t r0 = row_begin + (int64_t)ty * TH - 1, c0 = (int64_t)tx * TW - 1;
+    const int64_t r0 = row_begin + (int64_t)ty * TH - 1, c0 = (int64_t)tx * TW - HALO_L;
     const float qnan = __int_as_float(0x7fc00000);
     for (int idx = tid; idx < BOXH * BOXW; idx += NTHREADS) {
         const int j = idx / BOXW, kk = idx - j * BOXW;
@@ -358,7 +362,8 @@ extern "C" int dtb_slope_d8(const void *dem, int dem_dtype, int64_t buf_rows, in
     if (ntiles64 > 0x7fffffff) return DTB_ERR_UNSUPPORTED;
     const int ntiles = (int)ntiles64;
 
-    const bool aligned = dem_dtype == DTB_F32 && (cols % 4 == 0) && (((uintptr_t)dem) % 16 == 0) &&
+    static const bool tma_disabled = getenv("DTB_DISABLE_TMA") != nullptr;  // debugging aid only
+    const bool aligned = !tma_disabled && dem_dtype == DTB_F32 && (cols % 4 == 0) && (((uintptr_t)dem) % 16 == 0) &&
                          (!slope || ((uintptr_t)slope) % 16 == 0) && (!d8 || ((uintptr_t)d8) % 4 == 0);
     if (aligned) {
         EncodeTiledFn enc = get_encode_fn();
