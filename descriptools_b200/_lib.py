@@ -44,6 +44,27 @@ class HandArgs(Structure):
     ]
 
 
+class FlowaccArgs(Structure):
+    _fields_ = [
+        ("d8", c_void_p),
+        ("rows", c_int64),
+        ("cols", c_int64),
+        ("halo_above", c_void_p),
+        ("halo_below", c_void_p),
+        ("inflow_above", c_void_p),
+        ("inflow_below", c_void_p),
+        ("acc", c_void_p),
+        ("acc_dtype", c_int),
+        ("nodata_fill", c_int64),
+        ("exit_above", c_void_p),
+        ("exit_below", c_void_p),
+        ("term_above", c_void_p),
+        ("term_below", c_void_p),
+        ("reuse_summary", c_int),
+        ("unfinalised_host", POINTER(c_int64)),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/dtb200.h one to one
 SIGNATURES = {
     "dtb_abi_version": (c_int, []),
@@ -53,8 +74,9 @@ SIGNATURES = {
     "dtb_reset_launch_count": (None, []),
     "dtb_slope_d8": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
     "dtb_flowacc_workspace_bytes": (c_size_t, [c_int64, c_int64]),
-    "dtb_flowacc": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_size_t,
+    "dtb_flowacc": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int64, c_void_p, c_size_t,
                             POINTER(c_int64), c_void_p]),
+    "dtb_flowacc_band": (c_int, [POINTER(FlowaccArgs), c_void_p, c_size_t, c_void_p]),
     "dtb_hand_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "dtb_hand": (c_int, [POINTER(HandArgs), c_void_p, c_size_t, c_void_p]),
     "dtb_hand_from_index": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p]),

@@ -4,116 +4,546 @@
 // topoindexes.py:252-255, example.py:52); semantics per SURVEY.md App. A3, restated in
 // oracle/dt_oracle.c:orc_flowacc and pinned by the bundled 12_fdr.tif -> 12_fac.tif pair.
 //
-// Algorithm (single sweep, no level synchronisation, every cell visited once):
-//   1. init:  per cell, pending = number of valid neighbours whose D8 code points at it
-//             (a gather over the 3x3 neighbourhood, no atomics); one packed 64-bit word per
-//             cell: [63 source flag | 47..44 pending | 43..0 running count (+ seed)].
-//   2. sweep: one thread per source cell walks downstream.  Each step is ONE 64-bit
-//             atomicAdd on the next cell's word that adds (count+1) to the low field and
-//             subtracts 1 from `pending`; the returned old value tells the walker whether it
-//             was the last tributary to arrive -- only then it owns the cell's final count,
-//             stores it and continues.  All other walkers retire.  No thread ever waits.
-//   3. fix:   only if the grid has D8 cycles (count of finalised cells != valid cells):
-//             cycle cells keep their partial count, like the oracle's Kahn sweep.
+// B200 design: a two-level sweep over the D8 forest (DESIGN.md "flow accumulation").
+//   T1  one CTA per 64x64 tile, the tile's codes (+1-cell halo) and one packed word per cell in
+//       shared memory.  Every source cell (no in-tile tributary) walks downstream; a step is one
+//       shared-memory atomicAdd that adds (count+1) and decrements the `pending` field of the next
+//       cell, and only the LAST tributary to arrive continues -- every cell is visited once, no
+//       thread waits, no barrier per level.  The tile emits a summary for its 252 perimeter
+//       cells only: weight leaving the tile (exitw), where the in-tile path of every cell that
+//       receives flow from outside ends (term/link), how many such paths end in each exit (nterm).
+//   N   the perimeter cells that receive outside flow ("entry nodes", ~3 % of the cells) form a
+//       forest of their own: node q -> the entry node its in-tile path drains into.  fa_node_init
+//       gathers each node's base inflow and in-degree from the neighbouring tiles' summaries,
+//       fa_node_sweep runs the same last-arriver walk on that forest with 64-bit global atomics.
+//   T2  the tile kernel again, now seeded with the resolved inflow of its entry nodes, writes acc.
+// d8 is read twice, acc written once; the node arrays are ~1 byte per cell.
+// Row bands (multi-GPU): the band's neighbours are represented by one halo row of codes above and
+// below plus the inflow carried by those rows (dtb_flowacc_args); the band-level summary
+// (exit_* / term_*) is the same construction one level up and is solved by the band driver.
+//
+// D8 cycles (possible only in caller-supplied grids, never in dtb_slope_d8 output) are detected
+// on the device (a tile or node that cannot be finalised) and handled by the single-level sweep
+// fa_flat_* over the whole raster, which reproduces the oracle's Kahn-order partial counts.
 #include "common.cuh"
 
 namespace dtb {
 namespace {
 
-constexpr int FA_THREADS = 256;
-constexpr uint64_t CNT_MASK = (1ull << 44) - 1ull;
-constexpr uint64_t PEND_ONE = 1ull << 44;
-constexpr uint64_t SRC_FLAG = 1ull << 63;
+constexpr int T = 64;                 // tile edge (cells)
+constexpr int TCELLS = T * T;
+constexpr int SLOTS = 256;            // perimeter slots per tile (252 used)
+constexpr int FT_THREADS = 256;
+constexpr int CPT = TCELLS / FT_THREADS;  // cells per thread (16 consecutive columns of one row)
+constexpr int CP = 80;                // shared-memory pitch of a code row: col -1 at 15, col 0 at 16
+constexpr uint32_t NXT_EXIT = 0xFFFEu, NXT_TERM = 0xFFFFu;
+constexpr uint32_t LINK_NONE = 0xFFFFFFFFu;   // in-tile path ends inside the tile
+constexpr uint32_t LINK_OUT = 0x80000000u;    // leaves the band: | (below ? 0x40000000 : 0) | column
+constexpr uint32_t LINK_BELOW = 0x40000000u;
+constexpr uint32_t TERM_NONE = 255u;
 
-// counters: [0] valid cells, [1] finalised cells
-__global__ void __launch_bounds__(FA_THREADS)
-fa_init_kernel(const uint8_t *__restrict__ d8, int64_t rows, int64_t cols, const int64_t *__restrict__ seeds,
-               unsigned long long *__restrict__ state, unsigned long long *__restrict__ counters)
+// node state: [63 source | 62 active | 61..48 pending | 47..0 inflow count]
+constexpr uint64_t N_SRC = 1ull << 63, N_ACTIVE = 1ull << 62, N_PEND_ONE = 1ull << 48;
+constexpr uint64_t N_CNT = N_PEND_ONE - 1ull, N_PEND = 0x3FFFull;
+constexpr int N_PEND_SHIFT = 48;
+
+__host__ __device__ __forceinline__ int slot_of(int lr, int lc)
 {
-    const int64_t n = rows * cols;
-    const int64_t p = (int64_t)blockIdx.x * FA_THREADS + threadIdx.x;
-    int valid = 0;
-    if (p < n) {
-        const unsigned code = d8[p];
-        if (code != 0) {
-            valid = 1;
-            const int64_t r = p / cols, c = p - r * cols;
-            int pending = 0;
-            // neighbour at (r+dr, c+dc) points at p iff its code is the opposite direction
-            // E(1)<->W(16), SE(2)<->NW(32), S(4)<->N(64), SW(8)<->NE(128)
-            const bool up = r > 0, dn = r + 1 < rows, lf = c > 0, rt = c + 1 < cols;
-            if (up && lf) pending += d8[p - cols - 1] == 2;
-            if (up) pending += d8[p - cols] == 4;
-            if (up && rt) pending += d8[p - cols + 1] == 8;
-            if (lf) pending += d8[p - 1] == 1;
-            if (rt) pending += d8[p + 1] == 16;
-            if (dn && lf) pending += d8[p + cols - 1] == 128;
-            if (dn) pending += d8[p + cols] == 64;
-            if (dn && rt) pending += d8[p + cols + 1] == 32;
-            uint64_t w = seeds ? (uint64_t)seeds[p] & CNT_MASK : 0ull;
-            w |= (uint64_t)pending << 44;
-            if (pending == 0) w |= SRC_FLAG;
-            state[p] = w;
-        } else {
-            state[p] = 0ull;
-        }
-    }
-    const unsigned ballot = __ballot_sync(0xffffffffu, valid);
-    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&counters[0], (unsigned long long)__popc(ballot));
+    if (lr == 0) return lc;
+    if (lr == T - 1) return T + lc;
+    if (lc == 0) return 2 * T + lr - 1;
+    return 2 * T + (T - 2) + lr - 1;  // lc == T-1
+}
+__host__ __device__ __forceinline__ void slot_cell(int s, int &lr, int &lc)
+{
+    if (s < T) { lr = 0; lc = s; }
+    else if (s < 2 * T) { lr = T - 1; lc = s - T; }
+    else if (s < 2 * T + (T - 2)) { lr = s - 2 * T + 1; lc = 0; }
+    else { lr = s - (2 * T + (T - 2)) + 1; lc = T - 1; }
+}
+constexpr int USED_SLOTS = 4 * T - 4;
+
+// neighbour positions in scan order NW,N,NE,W,E,SW,S,SE (bit k of the in-masks)
+__device__ __forceinline__ void nbr_offset(int k, int &dr, int &dc)
+{
+    const int kk = k < 4 ? k : k + 1;  // skip the centre of the 3x3
+    dr = kk / 3 - 1;
+    dc = kk % 3 - 1;
 }
 
-template <typename ACC>
-__global__ void __launch_bounds__(FA_THREADS)
-fa_sweep_kernel(const uint8_t *__restrict__ d8, int64_t rows, int64_t cols, ACC *__restrict__ acc, ACC nodata_fill,
-                unsigned long long *__restrict__ state, unsigned long long *__restrict__ counters)
+struct TileView {
+    const uint8_t *d8, *halo_above, *halo_below;
+    int64_t rows, cols;
+    int tiles_x;
+};
+
+__device__ __forceinline__ unsigned fetch_code(const TileView &v, int64_t gr, int64_t gc)
 {
-    const int64_t n = rows * cols;
-    int64_t p = (int64_t)blockIdx.x * FA_THREADS + threadIdx.x;
-    unsigned finalised = 0;
-    if (p < n) {
-        unsigned code = d8[p];
-        if (code == 0) {
-            acc[p] = nodata_fill;
+    if (gc < 0 || gc >= v.cols) return 0;
+    if (gr >= 0 && gr < v.rows) return v.d8[gr * v.cols + gc];
+    if (gr == -1 && v.halo_above) return v.halo_above[gc];
+    if (gr == v.rows && v.halo_below) return v.halo_below[gc];
+    return 0;
+}
+
+// ---- T1 / T2: the tile kernel -------------------------------------------------------------
+// SEEDED = false: local counts only, writes the perimeter summary (exitw, link, meta).
+// SEEDED = true : entry cells start from their resolved inflow (nstate), writes acc.
+// Shared-memory cell word, !SEEDED: [31..28 pending | 27..0 count].
+//                          SEEDED: lo = count bits 31..0; hi = [31..28 pending | 27..0 count bits 59..32].
+template <bool SEEDED, typename ACC>
+__global__ void __launch_bounds__(FT_THREADS)
+fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ link, uint32_t *__restrict__ meta,
+               const unsigned long long *__restrict__ nstate, ACC *__restrict__ acc, ACC nodata_fill,
+               unsigned long long *__restrict__ counters)
+{
+    __shared__ __align__(16) uint8_t codes[(T + 2) * CP + 16];  // col T of the last row sits at (T+2)*CP
+    __shared__ uint16_t nxt[TCELLS];
+    __shared__ uint32_t lo[TCELLS];
+    __shared__ uint32_t hi[SEEDED ? TCELLS : 1];
+    __shared__ uint32_t nterm_s[SLOTS];
+    __shared__ uint8_t inmask_s[SLOTS];
+    __shared__ unsigned cyc_s;
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
+    const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
+    auto C = [&](int lr, int lc) -> unsigned { return codes[(lr + 1) * CP + 16 + lc]; };
+
+    // ---- stage the codes: 64 rows x 64 B as one 16-byte load per thread, halo ring by bytes ----
+    const bool fast = (v.cols % 16 == 0) && ((reinterpret_cast<uintptr_t>(v.d8) & 15u) == 0) && (c0 + T <= v.cols);
+    if (fast) {
+        const int lr = tid >> 2, ch = tid & 3;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (r0 + lr < v.rows) w = __ldg(reinterpret_cast<const uint4 *>(v.d8 + (r0 + lr) * v.cols + c0 + ch * 16));
+        *reinterpret_cast<uint4 *>(&codes[(lr + 1) * CP + 16 + ch * 16]) = w;
+        for (int h = tid; h < 4 * T + 4; h += FT_THREADS) {
+            int lr2, lc2;
+            if (h < T + 2) { lr2 = -1; lc2 = h - 1; }
+            else if (h < 2 * T + 4) { lr2 = T; lc2 = h - (T + 2) - 1; }
+            else if (h < 3 * T + 4) { lr2 = h - (2 * T + 4); lc2 = -1; }
+            else { lr2 = h - (3 * T + 4); lc2 = T; }
+            codes[(lr2 + 1) * CP + 16 + lc2] = (uint8_t)fetch_code(v, r0 + lr2, c0 + lc2);
+        }
+    } else {
+        for (int h = tid; h < (T + 2) * (T + 2); h += FT_THREADS) {
+            const int lr2 = h / (T + 2) - 1, lc2 = h % (T + 2) - 1;
+            codes[(lr2 + 1) * CP + 16 + lc2] = (uint8_t)fetch_code(v, r0 + lr2, c0 + lc2);
+        }
+    }
+    if (tid < SLOTS) { nterm_s[tid] = 0; inmask_s[tid] = 0; }
+    if (tid == 0) cyc_s = 0;
+    __syncthreads();
+
+    // ---- per-cell set-up: successor, in-tile in-degree, outside tributaries ----
+    const int lr = tid >> 2, lcb = (tid & 3) * CPT;
+    unsigned srcmask = 0, validmask = 0;
+    unsigned unresolved = 0;  // SEEDED: entry nodes whose inflow was never finalised (node-level cycle)
+#pragma unroll 4
+    for (int i = 0; i < CPT; ++i) {
+        const int lc = lcb + i, p = lr * T + lc;
+        const unsigned code = C(lr, lc);
+        unsigned inm = 0;
+        if (code != 0) {
+            inm |= (C(lr - 1, lc - 1) == 2u) << 0;
+            inm |= (C(lr - 1, lc) == 4u) << 1;
+            inm |= (C(lr - 1, lc + 1) == 8u) << 2;
+            inm |= (C(lr, lc - 1) == 1u) << 3;
+            inm |= (C(lr, lc + 1) == 16u) << 4;
+            inm |= (C(lr + 1, lc - 1) == 128u) << 5;
+            inm |= (C(lr + 1, lc) == 64u) << 6;
+            inm |= (C(lr + 1, lc + 1) == 32u) << 7;
+        }
+        const unsigned outm = (lr == 0 ? 0x07u : 0u) | (lr == T - 1 ? 0xE0u : 0u) | (lc == 0 ? 0x29u : 0u) |
+                              (lc == T - 1 ? 0x94u : 0u);
+        const unsigned pending = __popc(inm & ~outm), extm = inm & outm;
+        uint32_t nx = NXT_TERM;
+        int dr, dc;
+        if (d8_offset(code, dr, dc)) {
+            const int tr = lr + dr, tc = lc + dc;
+            if (C(tr, tc) != 0) nx = ((unsigned)tr < (unsigned)T && (unsigned)tc < (unsigned)T) ? (uint32_t)(tr * T + tc) : NXT_EXIT;
+        }
+        nxt[p] = (uint16_t)nx;
+        uint64_t seed = 0;
+        if (outm) {
+            const int s = slot_of(lr, lc);
+            inmask_s[s] = (uint8_t)extm;
+            if (SEEDED && extm) {
+                const uint64_t ns = nstate[(size_t)tile * SLOTS + s];
+                seed = ns & N_CNT;
+                if ((ns >> N_PEND_SHIFT) & N_PEND) ++unresolved;
+            }
+        }
+        if (SEEDED) {
+            lo[p] = (uint32_t)seed;
+            hi[p] = (pending << 28) | (uint32_t)(seed >> 32);
         } else {
-            const uint64_t w = state[p];
-            if (w & SRC_FLAG) {
-                uint64_t carry = w & CNT_MASK;
-                acc[p] = (ACC)carry;
+            lo[p] = pending << 28;
+        }
+        if (code != 0) {
+            validmask |= 1u << i;
+            if (pending == 0) srcmask |= 1u << i;
+        }
+    }
+    __syncthreads();
+
+    // ---- sweep: every source walks until it is not the last tributary to arrive ----
+    unsigned finalised = 0;
+    while (srcmask) {
+        const int i = __ffs((int)srcmask) - 1;
+        srcmask &= srcmask - 1;
+        uint32_t p = (uint32_t)(lr * T + lcb + i);
+        ++finalised;
+        if (SEEDED) {
+            uint64_t carry = ((uint64_t)(hi[p] & 0x0FFFFFFFu) << 32) | lo[p];
+            for (;;) {
+                const uint32_t n = nxt[p];
+                if (n >= NXT_EXIT) break;
+                const uint64_t add = carry + 1ull;
+                const uint32_t lo_old = atomicAdd(&lo[n], (uint32_t)add);
+                const uint32_t c = (uint32_t)(((uint64_t)lo_old + (uint32_t)add) >> 32);  // carry out of the low word
+                const uint32_t hi_add = (uint32_t)(add >> 32) + c;
+                const uint32_t hi_old = atomicAdd(&hi[n], hi_add - (1u << 28));  // issued after lo's add returned
+                if ((hi_old >> 28) != 1u) break;                                     // other tributaries pending
+                const uint32_t lo_now = *reinterpret_cast<volatile uint32_t *>(&lo[n]);
+                carry = ((uint64_t)((hi_old + hi_add) & 0x0FFFFFFFu) << 32) | lo_now;
+                p = n;
                 ++finalised;
-                int64_t r = p / cols, c = p - r * cols;
-                for (;;) {
-                    int dr, dc;
-                    if (!d8_offset(code, dr, dc)) break;
-                    r += dr;
-                    c += dc;
-                    if (r < 0 || r >= rows || c < 0 || c >= cols) break;
-                    p = r * cols + c;
-                    code = d8[p];
-                    if (code == 0) break;
-                    const uint64_t old = atomicAdd(&state[p], (unsigned long long)((carry + 1ull) - PEND_ONE));
-                    if (((old >> 44) & 0xFull) != 1ull) break;  // other tributaries still pending
-                    carry = (old & CNT_MASK) + carry + 1ull;
-                    acc[p] = (ACC)carry;
-                    ++finalised;
-                }
+            }
+        } else {
+            uint32_t carry = 0;
+            for (;;) {
+                const uint32_t n = nxt[p];
+                if (n >= NXT_EXIT) break;
+                const uint32_t old = atomicAdd(&lo[n], carry + 1u - (1u << 28));
+                if ((old >> 28) != 1u) break;
+                carry += (old & 0x0FFFFFFFu) + 1u;
+                p = n;
+                ++finalised;
             }
         }
     }
+    // a tile (or, SEEDED, an entry node) that cannot be finalised means the grid has a D8 cycle
+    // (per-thread differences wrap, their sum over the CTA is exact)
+    if (SEEDED) {
+        const unsigned bad = __reduce_add_sync(0xffffffffu, (unsigned)__popc(validmask) - finalised + unresolved);
+        if ((tid & 31) == 0 && bad) atomicAdd(&cyc_s, bad);
+    }
+    __syncthreads();
+
+    if (SEEDED) {
+        if (tid == 0 && cyc_s) atomicAdd(&counters[0], (unsigned long long)cyc_s);
+        // ---- write acc: 16 consecutive cells per thread ----
+        const int64_t gr = r0 + lr;
+        if (gr < v.rows) {
+            ACC out[CPT];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) finalised += __shfl_xor_sync(0xffffffffu, finalised, o);
-    if ((threadIdx.x & 31) == 0 && finalised) atomicAdd(&counters[1], (unsigned long long)finalised);
+            for (int i = 0; i < CPT; ++i) {
+                const int p = lr * T + lcb + i;
+                const uint64_t cnt = ((uint64_t)(hi[p] & 0x0FFFFFFFu) << 32) | lo[p];
+                out[i] = ((validmask >> i) & 1u) ? (ACC)cnt : nodata_fill;
+            }
+            ACC *dst = acc + gr * v.cols + c0 + lcb;
+            if (fast && ((reinterpret_cast<uintptr_t>(acc) & 15u) == 0)) {
+                constexpr int V = 16 / sizeof(ACC);
+#pragma unroll
+                for (int i = 0; i < CPT; i += V) *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(&out[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < CPT; ++i)
+                    if (c0 + lcb + i < v.cols) dst[i] = out[i];
+            }
+        }
+        return;
+    }
+
+    // ---- T1 summary of the perimeter ----
+    uint32_t my_link = LINK_NONE, my_term = TERM_NONE, my_exitw = 0, my_inmask = 0;
+    if (tid < USED_SLOTS) {
+        int plr, plc;
+        slot_cell(tid, plr, plc);
+        const uint32_t p0 = (uint32_t)(plr * T + plc);
+        if (nxt[p0] == NXT_EXIT) my_exitw = (lo[p0] & 0x0FFFFFFFu) + 1u;
+        my_inmask = inmask_s[tid];
+        if (my_inmask) {
+            uint32_t q = p0;
+            int steps = 0;
+            while (nxt[q] < NXT_EXIT && steps < TCELLS) { q = nxt[q]; ++steps; }
+            if (nxt[q] == NXT_EXIT) {
+                const int qr = (int)(q / T), qc = (int)(q % T);
+                my_term = (uint32_t)slot_of(qr, qc);
+                atomicAdd(&nterm_s[my_term], 1u);
+                int dr, dc;
+                d8_offset(C(qr, qc), dr, dc);
+                const int64_t gr = r0 + qr + dr, gc = c0 + qc + dc;
+                if (gr < 0) my_link = LINK_OUT | (uint32_t)gc;
+                else if (gr >= v.rows) my_link = LINK_OUT | LINK_BELOW | (uint32_t)gc;
+                else
+                    my_link = (uint32_t)(((gr / T) * v.tiles_x + gc / T) * SLOTS + slot_of((int)(gr % T), (int)(gc % T)));
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < SLOTS) {
+        const size_t node = (size_t)tile * SLOTS + tid;
+        exitw[node] = my_exitw;
+        link[node] = my_link;
+        meta[node] = my_term | (nterm_s[tid] << 8) | (my_inmask << 16);
+    }
+}
+
+// ---- N: entry-node forest ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fa_node_init_kernel(int64_t nnodes, int64_t rows, int64_t cols, int tiles_x, const uint32_t *__restrict__ exitw,
+                    const uint32_t *__restrict__ meta, const int64_t *__restrict__ inflow_above,
+                    const int64_t *__restrict__ inflow_below, unsigned long long *__restrict__ nstate)
+{
+    const int64_t node = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (node >= nnodes) return;
+    const uint32_t m = meta[node];
+    const unsigned inmask = (m >> 16) & 0xFFu;
+    if (!inmask) { nstate[node] = 0ull; return; }
+    const int64_t tile = node / SLOTS;
+    const int s = (int)(node % SLOTS);
+    int lr, lc;
+    slot_cell(s, lr, lc);
+    const int64_t gr = (tile / tiles_x) * T + lr, gc = (tile % tiles_x) * T + lc;
+    uint64_t base = 0, pend = 0;
+    for (int k = 0; k < 8; ++k) {
+        if (!((inmask >> k) & 1u)) continue;
+        int dr, dc;
+        nbr_offset(k, dr, dc);
+        const int64_t ur = gr + dr, uc = gc + dc;
+        if (ur < 0) base += inflow_above ? (uint64_t)inflow_above[uc] : 0ull;
+        else if (ur >= rows) base += inflow_below ? (uint64_t)inflow_below[uc] : 0ull;
+        else {
+            const int64_t un = ((ur / T) * tiles_x + uc / T) * SLOTS + slot_of((int)(ur % T), (int)(uc % T));
+            base += exitw[un];
+            pend += (meta[un] >> 8) & 0xFFu;
+        }
+    }
+    nstate[node] = N_ACTIVE | (pend == 0 ? N_SRC : 0ull) | (pend << N_PEND_SHIFT) | (base & N_CNT);
+}
+
+__global__ void __launch_bounds__(256)
+fa_node_sweep_kernel(int64_t nnodes, const uint32_t *__restrict__ link, unsigned long long *nstate)
+{
+    const int64_t node = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (node >= nnodes) return;
+    const uint64_t s = nstate[node];
+    if (!(s & N_SRC)) return;
+    uint64_t w = s & N_CNT;
+    uint32_t q = (uint32_t)node;
+    for (;;) {
+        const uint32_t l = __ldg(&link[q]);
+        if (l & LINK_OUT) break;  // LINK_NONE or out of the band
+        const uint64_t old = atomicAdd(&nstate[l], (unsigned long long)(w - N_PEND_ONE));
+        if (((old >> N_PEND_SHIFT) & N_PEND) != 1ull) break;
+        w += old & N_CNT;
+        q = l;
+    }
+}
+
+// ---- cyclic grids: single-level sweep over the whole raster (gated on counters[0] != 0) -----------
+constexpr uint64_t F_CNT = (1ull << 44) - 1ull, F_PEND_ONE = 1ull << 44, F_SRC = 1ull << 63;
+constexpr int FLAT_BLOCKS = kNumSMs * 8;
+
+// counters: [0] cyclic evidence, [1] valid cells, [2] finalised cells
+__global__ void __launch_bounds__(256)
+fa_flat_init_kernel(TileView v, const int64_t *__restrict__ inflow_above, const int64_t *__restrict__ inflow_below,
+                    unsigned long long *__restrict__ state, unsigned long long *__restrict__ counters)
+{
+    if (counters[0] == 0) return;
+    const int64_t n = v.rows * v.cols;
+    unsigned long long valid = 0;
+    for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < n; p += (int64_t)gridDim.x * 256) {
+        const unsigned code = v.d8[p];
+        if (code == 0) { state[p] = 0ull; continue; }
+        ++valid;
+        const int64_t r = p / v.cols, c = p - r * v.cols;
+        uint64_t pending = 0, seed = 0;
+        const unsigned want[8] = {2, 4, 8, 1, 16, 128, 64, 32};
+        for (int k = 0; k < 8; ++k) {
+            int dr, dc;
+            nbr_offset(k, dr, dc);
+            if (fetch_code(v, r + dr, c + dc) != want[k]) continue;
+            if (r + dr < 0) seed += inflow_above ? (uint64_t)inflow_above[c + dc] : 0ull;
+            else if (r + dr >= v.rows) seed += inflow_below ? (uint64_t)inflow_below[c + dc] : 0ull;
+            else ++pending;
+        }
+        state[p] = (pending == 0 ? F_SRC : 0ull) | (pending << 44) | (seed & F_CNT);
+    }
+    valid = __reduce_add_sync(0xffffffffu, (unsigned)valid);
+    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&counters[1], valid);
 }
 
 template <typename ACC>
-__global__ void __launch_bounds__(FA_THREADS)
-fa_fix_kernel(const uint8_t *__restrict__ d8, int64_t n, ACC *__restrict__ acc, const unsigned long long *__restrict__ state,
-              const unsigned long long *__restrict__ counters)
+__global__ void __launch_bounds__(256)
+fa_flat_sweep_kernel(TileView v, ACC *__restrict__ acc, unsigned long long *state, unsigned long long *__restrict__ counters)
 {
-    if (counters[0] == counters[1]) return;  // no cycles: nothing to do
-    const int64_t p = (int64_t)blockIdx.x * FA_THREADS + threadIdx.x;
-    if (p >= n || d8[p] == 0) return;
-    const uint64_t w = state[p];
-    if ((w >> 44) & 0xFull) acc[p] = (ACC)(w & CNT_MASK);  // never finalised: partial count
+    if (counters[0] == 0) return;
+    const int64_t n = v.rows * v.cols;
+    unsigned finalised = 0;
+    for (int64_t p0 = (int64_t)blockIdx.x * 256 + threadIdx.x; p0 < n; p0 += (int64_t)gridDim.x * 256) {
+        const uint64_t w = state[p0];
+        if (!(w & F_SRC)) continue;
+        uint64_t carry = w & F_CNT;
+        int64_t p = p0;
+        unsigned code = v.d8[p];
+        acc[p] = (ACC)carry;
+        ++finalised;
+        int64_t r = p / v.cols, c = p - r * v.cols;
+        for (;;) {
+            int dr, dc;
+            if (!d8_offset(code, dr, dc)) break;
+            r += dr;
+            c += dc;
+            if (r < 0 || r >= v.rows || c < 0 || c >= v.cols) break;
+            p = r * v.cols + c;
+            code = v.d8[p];
+            if (code == 0) break;
+            const uint64_t old = atomicAdd(&state[p], (unsigned long long)((carry + 1ull) - F_PEND_ONE));
+            if (((old >> 44) & 0xFull) != 1ull) break;
+            carry = (old & F_CNT) + carry + 1ull;
+            acc[p] = (ACC)carry;
+            ++finalised;
+        }
+    }
+    finalised = __reduce_add_sync(0xffffffffu, finalised);
+    if ((threadIdx.x & 31) == 0 && finalised) atomicAdd(&counters[2], (unsigned long long)finalised);
+}
+
+template <typename ACC>
+__global__ void __launch_bounds__(256)
+fa_flat_fix_kernel(TileView v, ACC *__restrict__ acc, const unsigned long long *__restrict__ state,
+                   const unsigned long long *__restrict__ counters)
+{
+    if (counters[0] == 0) return;
+    const int64_t n = v.rows * v.cols;
+    for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < n; p += (int64_t)gridDim.x * 256) {
+        if (v.d8[p] == 0) continue;
+        const uint64_t w = state[p];
+        if ((w >> 44) & 0xFull) acc[p] = (ACC)(w & F_CNT);  // never finalised: partial count (oracle: Kahn leftovers)
+    }
+}
+
+// ---- band summary (multi-GPU): the same construction one level up ------------------------------
+// For the band's first (side 0) or last (side 1) row: exit_out[c] = acc+1 of a cell that drains into the
+// halo row (else 0); term_out[c] for a cell that receives flow from the halo row = where its in-band
+// path leaves the band, encoded (side << 30) | column, or -1 if it ends inside the band.
+template <typename ACC>
+__global__ void __launch_bounds__(256)
+fa_band_summary_kernel(TileView v, int side, const ACC *__restrict__ acc, const uint32_t *__restrict__ link,
+                       const uint32_t *__restrict__ meta, int64_t *__restrict__ exit_out, int32_t *__restrict__ term_out)
+{
+    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c >= v.cols) return;
+    const int64_t r = side ? v.rows - 1 : 0;
+    const unsigned code = v.d8[r * v.cols + c];
+    int dr, dc;
+    int64_t ex = 0;
+    if (d8_offset(code, dr, dc) && (side ? dr > 0 : dr < 0) && fetch_code(v, r + dr, c + dc) != 0) ex = (int64_t)acc[r * v.cols + c] + 1;
+    exit_out[c] = ex;
+    // entry?  (a cell of a 1-row band is on both sides; the node's in-mask tells which halo feeds it)
+    const int64_t node = ((r / T) * v.tiles_x + c / T) * SLOTS + slot_of((int)(r % T), (int)(c % T));
+    const unsigned inmask = (meta[node] >> 16) & 0xFFu;
+    const unsigned from_side = side ? 0xE0u : 0x07u;
+    int32_t t = -1;
+    bool fed = false;
+    if (inmask & from_side) {
+        // only tributaries that really sit in the halo row count (tile-edge rows inside the band do not)
+        fed = side ? (r + 1 == v.rows) : (r == 0);
+    }
+    if (fed) {
+        uint32_t q = (uint32_t)node;
+        for (int64_t hops = 0; hops < (int64_t)1 << 40; ++hops) {
+            const uint32_t l = link[q];
+            if (l == LINK_NONE) break;
+            if (l & LINK_OUT) { t = (int32_t)(((l & LINK_BELOW) ? 1u << 30 : 0u) | (l & 0x3FFFFFFFu)); break; }
+            q = l;
+        }
+    }
+    term_out[c] = fed ? t : -2;  // -2: not an entry from this side
+}
+
+struct NodeLayout {
+    int64_t tiles, nnodes;
+    size_t off_counters, off_exitw, off_link, off_meta, off_nstate, off_flat, total;
+};
+
+NodeLayout layout(int64_t rows, int64_t cols)
+{
+    NodeLayout L;
+    const int64_t tx = (cols + T - 1) / T, ty = (rows + T - 1) / T;
+    L.tiles = tx * ty;
+    L.nnodes = L.tiles * SLOTS;
+    size_t o = 0;
+    L.off_counters = o; o += 256;
+    L.off_exitw = o; o += (size_t)L.nnodes * 4;
+    L.off_link = o; o += (size_t)L.nnodes * 4;
+    L.off_meta = o; o += (size_t)L.nnodes * 4;
+    L.off_nstate = o; o += (size_t)L.nnodes * 8;
+    o = (o + 255) & ~(size_t)255;
+    L.off_flat = o; o += (size_t)rows * (size_t)cols * 8;  // only touched for cyclic grids
+    L.total = o;
+    return L;
+}
+
+template <typename ACC>
+int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
+{
+    const NodeLayout L = layout(a->rows, a->cols);
+    char *base = reinterpret_cast<char *>(ws);
+    unsigned long long *counters = reinterpret_cast<unsigned long long *>(base + L.off_counters);
+    uint32_t *exitw = reinterpret_cast<uint32_t *>(base + L.off_exitw);
+    uint32_t *link = reinterpret_cast<uint32_t *>(base + L.off_link);
+    uint32_t *meta = reinterpret_cast<uint32_t *>(base + L.off_meta);
+    unsigned long long *nstate = reinterpret_cast<unsigned long long *>(base + L.off_nstate);
+    unsigned long long *flat = reinterpret_cast<unsigned long long *>(base + L.off_flat);
+    TileView v{a->d8, a->halo_above, a->halo_below, a->rows, a->cols, (int)((a->cols + T - 1) / T)};
+    ACC *acc = reinterpret_cast<ACC *>(a->acc);
+    const unsigned nb_nodes = (unsigned)((L.nnodes + 255) / 256);
+
+    if (!a->reuse_summary) {
+        DTB_CUDA(cudaMemsetAsync(counters, 0, 256, st));
+        fa_tile_kernel<false, ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, exitw, link, meta, nullptr, nullptr, (ACC)0, counters);
+        DTB_LAUNCH_CHECK("fa_tile_kernel<summary>");
+    }
+    fa_node_init_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, a->rows, a->cols, v.tiles_x, exitw, meta, a->inflow_above,
+                                                 a->inflow_below, nstate);
+    DTB_LAUNCH_CHECK("fa_node_init_kernel");
+    fa_node_sweep_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, link, nstate);
+    DTB_LAUNCH_CHECK("fa_node_sweep_kernel");
+    fa_tile_kernel<true, ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, nullptr, nullptr, nullptr, nstate, acc,
+                                                                        (ACC)a->nodata_fill, counters);
+    DTB_LAUNCH_CHECK("fa_tile_kernel<final>");
+    // cyclic grids only (each kernel returns at once when counters[0] == 0)
+    fa_flat_init_kernel<<<FLAT_BLOCKS, 256, 0, st>>>(v, a->inflow_above, a->inflow_below, flat, counters);
+    DTB_LAUNCH_CHECK("fa_flat_init_kernel");
+    fa_flat_sweep_kernel<ACC><<<FLAT_BLOCKS, 256, 0, st>>>(v, acc, flat, counters);
+    DTB_LAUNCH_CHECK("fa_flat_sweep_kernel");
+    fa_flat_fix_kernel<ACC><<<FLAT_BLOCKS, 256, 0, st>>>(v, acc, flat, counters);
+    DTB_LAUNCH_CHECK("fa_flat_fix_kernel");
+
+    if (a->exit_above || a->exit_below) {
+        const unsigned nbc = (unsigned)((a->cols + 255) / 256);
+        if (a->exit_above && a->term_above) {
+            fa_band_summary_kernel<ACC><<<nbc, 256, 0, st>>>(v, 0, acc, link, meta, a->exit_above, a->term_above);
+            DTB_LAUNCH_CHECK("fa_band_summary_kernel<above>");
+        }
+        if (a->exit_below && a->term_below) {
+            fa_band_summary_kernel<ACC><<<nbc, 256, 0, st>>>(v, 1, acc, link, meta, a->exit_below, a->term_below);
+            DTB_LAUNCH_CHECK("fa_band_summary_kernel<below>");
+        }
+    }
+    if (a->unfinalised_host) {
+        unsigned long long h[3];
+        DTB_CUDA(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, st));
+        DTB_CUDA(cudaStreamSynchronize(st));
+        *a->unfinalised_host = h[0] ? (int64_t)(h[1] - h[2]) : 0;
+    }
+    return DTB_OK;
 }
 
 }  // namespace
@@ -122,42 +552,35 @@ fa_fix_kernel(const uint8_t *__restrict__ d8, int64_t n, ACC *__restrict__ acc, 
 extern "C" size_t dtb_flowacc_workspace_bytes(int64_t rows, int64_t cols)
 {
     if (rows <= 0 || cols <= 0) return 0;
-    return (size_t)rows * (size_t)cols * 8 + 256;
+    return dtb::layout(rows, cols).total;
+}
+
+extern "C" int dtb_flowacc_band(const dtb_flowacc_args *a, void *ws, size_t ws_bytes, void *stream)
+{
+    using namespace dtb;
+    if (!a || !a->d8 || !a->acc || !ws || a->rows <= 0 || a->cols <= 0) return DTB_ERR_INVALID;
+    if (a->acc_dtype != DTB_I32 && a->acc_dtype != DTB_I64) return DTB_ERR_INVALID;
+    if (ws_bytes < dtb_flowacc_workspace_bytes(a->rows, a->cols)) return DTB_ERR_WORKSPACE;
+    if (a->cols >= (int64_t)1 << 30) return DTB_ERR_UNSUPPORTED;
+    if (a->halo_below && a->rows % T != 0) return DTB_ERR_INVALID;  // band seams sit on tile seams
+    const NodeLayout L = layout(a->rows, a->cols);
+    if (L.nnodes >= (int64_t)1 << 30) return DTB_ERR_UNSUPPORTED;  // node ids share a word with the LINK_OUT flags
+    if (a->rows * a->cols >= (int64_t)1 << 43) return DTB_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    return a->acc_dtype == DTB_I32 ? run<int32_t>(a, ws, st) : run<int64_t>(a, ws, st);
 }
 
 extern "C" int dtb_flowacc(const uint8_t *d8, int64_t rows, int64_t cols, void *acc, int acc_dtype, int64_t nodata_fill,
-                           const int64_t *seeds, void *ws, size_t ws_bytes, int64_t *unfinalised_host, void *stream)
+                           void *ws, size_t ws_bytes, int64_t *unfinalised_host, void *stream)
 {
-    using namespace dtb;
-    if (!d8 || !acc || !ws || rows <= 0 || cols <= 0) return DTB_ERR_INVALID;
-    if (acc_dtype != DTB_I32 && acc_dtype != DTB_I64) return DTB_ERR_INVALID;
-    if (ws_bytes < dtb_flowacc_workspace_bytes(rows, cols)) return DTB_ERR_WORKSPACE;
-    const int64_t n = rows * cols;
-    if (acc_dtype == DTB_I32 && n > 0x7fffffffLL) return DTB_ERR_UNSUPPORTED;
-    if (n >= (int64_t)1 << 43) return DTB_ERR_UNSUPPORTED;
-    cudaStream_t st = as_stream(stream);
-    unsigned long long *counters = reinterpret_cast<unsigned long long *>(ws);
-    unsigned long long *state = reinterpret_cast<unsigned long long *>((char *)ws + 256);
-    const unsigned blocks = (unsigned)((n + FA_THREADS - 1) / FA_THREADS);
-    DTB_CUDA(cudaMemsetAsync(counters, 0, 256, st));
-    fa_init_kernel<<<blocks, FA_THREADS, 0, st>>>(d8, rows, cols, seeds, state, counters);
-    DTB_LAUNCH_CHECK("fa_init_kernel");
-    if (acc_dtype == DTB_I32) {
-        fa_sweep_kernel<int32_t><<<blocks, FA_THREADS, 0, st>>>(d8, rows, cols, (int32_t *)acc, (int32_t)nodata_fill, state, counters);
-        DTB_LAUNCH_CHECK("fa_sweep_kernel<i32>");
-        fa_fix_kernel<int32_t><<<blocks, FA_THREADS, 0, st>>>(d8, n, (int32_t *)acc, state, counters);
-        DTB_LAUNCH_CHECK("fa_fix_kernel<i32>");
-    } else {
-        fa_sweep_kernel<int64_t><<<blocks, FA_THREADS, 0, st>>>(d8, rows, cols, (int64_t *)acc, (int64_t)nodata_fill, state, counters);
-        DTB_LAUNCH_CHECK("fa_sweep_kernel<i64>");
-        fa_fix_kernel<int64_t><<<blocks, FA_THREADS, 0, st>>>(d8, n, (int64_t *)acc, state, counters);
-        DTB_LAUNCH_CHECK("fa_fix_kernel<i64>");
-    }
-    if (unfinalised_host) {
-        unsigned long long h[2];
-        DTB_CUDA(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, st));
-        DTB_CUDA(cudaStreamSynchronize(st));
-        *unfinalised_host = (int64_t)(h[0] - h[1]);
-    }
-    return DTB_OK;
+    dtb_flowacc_args a = {};
+    a.d8 = d8;
+    a.rows = rows;
+    a.cols = cols;
+    a.acc = acc;
+    a.acc_dtype = acc_dtype;
+    a.nodata_fill = nodata_fill;
+    a.unfinalised_host = unfinalised_host;
+    if (acc_dtype == DTB_I32 && rows * cols > 0x7fffffffLL) return DTB_ERR_UNSUPPORTED;
+    return dtb_flowacc_band(&a, ws, ws_bytes, stream);
 }

@@ -91,7 +91,7 @@ def slope_d8(dem: torch.Tensor, px: float, want_slope: bool = True, want_d8: boo
 
 
 def flow_accumulation(d8: torch.Tensor, dtype: torch.dtype = torch.int32, nodata_fill: int = -100,
-                      seeds: torch.Tensor | None = None, check_cycles: bool = False):
+                      check_cycles: bool = False):
     """D8 flow accumulation.  Returns acc, or (acc, n_cycle_cells) if check_cycles."""
     d8 = _chk2d(d8, "d8")
     if d8.dtype != torch.uint8:
@@ -101,11 +101,7 @@ def flow_accumulation(d8: torch.Tensor, dtype: torch.dtype = torch.int32, nodata
     nbytes = lib.dtb_flowacc_workspace_bytes(rows, cols)
     ws = workspace.get(nbytes)
     left = ctypes.c_int64(0)
-    if seeds is not None:
-        seeds = _chk2d(seeds, "seeds")
-        if seeds.dtype != torch.int64:
-            raise TypeError("seeds must be int64")
-    check(lib.dtb_flowacc(_ptr(d8), rows, cols, _ptr(acc), _int_dtype(acc), int(nodata_fill), _ptr(seeds), _ptr(ws), nbytes,
+    check(lib.dtb_flowacc(_ptr(d8), rows, cols, _ptr(acc), _int_dtype(acc), int(nodata_fill), _ptr(ws), nbytes,
                           ctypes.byref(left) if check_cycles else None, _stream()), "dtb_flowacc")
     return (acc, int(left.value)) if check_cycles else acc
 

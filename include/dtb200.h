@@ -75,13 +75,40 @@ int dtb_slope_d8(const void *dem, int dem_dtype, int64_t buf_rows, int64_t cols,
  * New stage (no reference code; convention pinned by 12_fdr.tif -> 12_fac.tif and the
  * consumers gfi.py:432, topoindexes.py:252-255): acc[p] = number of cells strictly
  * upstream of p.  code-0 cells receive nodata_fill.  acc is int32 or int64 (acc_dtype).
- * seeds (may be NULL): int64 per-cell external inflow added to the cell before the sweep
- * (used by the band driver's second pass).  Returns in *unfinalised_host (may be NULL,
- * forces a stream sync) the number of valid cells on D8 cycles. */
+ * Returns in *unfinalised_host (may be NULL, forces a stream sync) the number of valid
+ * cells on or below D8 cycles (they keep their partial count). */
 size_t dtb_flowacc_workspace_bytes(int64_t rows, int64_t cols);
 int dtb_flowacc(const uint8_t *d8, int64_t rows, int64_t cols, void *acc, int acc_dtype,
-                int64_t nodata_fill, const int64_t *seeds, void *ws, size_t ws_bytes,
-                int64_t *unfinalised_host, void *stream);
+                int64_t nodata_fill, void *ws, size_t ws_bytes, int64_t *unfinalised_host,
+                void *stream);
+
+/* Row-band form (multi-GPU): `d8` holds the band's rows x cols codes;
+ * halo_above / halo_below are the code rows adjacent to the band (NULL at the raster
+ * edge); inflow_above / inflow_below give, per column of those halo rows, acc+1 of the
+ * halo cell (NULL = 0; only cells that point into the band are read).  A band that has
+ * a halo_below must have rows % 64 == 0.  If exit_X and term_X are given they receive the
+ * band's boundary summary for its first (above) / last (below) row:
+ *   exit_X[c] = acc[c]+1 if the cell drains into the halo row, else 0;
+ *   term_X[c] = -2 if the cell takes no flow from that halo row, else where the in-band
+ *               path that starts there leaves the band: (side << 30) | column of the halo
+ *               cell it lands on (side 0 = above, 1 = below), or -1 if it ends in the band.
+ * The band driver (descriptools_b200/bands.py) calls this once with zero inflow, solves
+ * the boundary graph, and calls it again with reuse_summary = 1 and the resolved inflow
+ * (same workspace, untouched in between). */
+typedef struct dtb_flowacc_args {
+    const uint8_t *d8;
+    int64_t rows, cols;
+    const uint8_t *halo_above, *halo_below;
+    const int64_t *inflow_above, *inflow_below;
+    void *acc;
+    int acc_dtype;
+    int64_t nodata_fill;
+    int64_t *exit_above, *exit_below;
+    int32_t *term_above, *term_below;
+    int reuse_summary;
+    int64_t *unfinalised_host;
+} dtb_flowacc_args;
+int dtb_flowacc_band(const dtb_flowacc_args *args, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- flow distance + river-cell index + HAND (+ optional fused GFI) -------------------
  * Replaces flow_distance_index_cpu + flow_distance_index_gpu (flowhand.py:476-562,
