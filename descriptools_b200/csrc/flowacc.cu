@@ -25,66 +25,15 @@
 // D8 cycles (possible only in caller-supplied grids, never in dtb_slope_d8 output) are detected
 // on the device (a tile or node that cannot be finalised) and handled by the single-level sweep
 // fa_flat_* over the whole raster, which reproduces the oracle's Kahn-order partial counts.
-#include "common.cuh"
+#include "tiles.cuh"
 
 namespace dtb {
 namespace {
-
-constexpr int T = 64;                 // tile edge (cells)
-constexpr int TCELLS = T * T;
-constexpr int SLOTS = 256;            // perimeter slots per tile (252 used)
-constexpr int FT_THREADS = 256;
-constexpr int CPT = TCELLS / FT_THREADS;  // cells per thread (16 consecutive columns of one row)
-constexpr int CP = 80;                // shared-memory pitch of a code row: col -1 at 15, col 0 at 16
-constexpr uint32_t NXT_EXIT = 0xFFFEu, NXT_TERM = 0xFFFFu;
-constexpr uint32_t LINK_NONE = 0xFFFFFFFFu;   // in-tile path ends inside the tile
-constexpr uint32_t LINK_OUT = 0x80000000u;    // leaves the band: | (below ? 0x40000000 : 0) | column
-constexpr uint32_t LINK_BELOW = 0x40000000u;
-constexpr uint32_t TERM_NONE = 255u;
 
 // node state: [63 source | 62 active | 61..48 pending | 47..0 inflow count]
 constexpr uint64_t N_SRC = 1ull << 63, N_ACTIVE = 1ull << 62, N_PEND_ONE = 1ull << 48;
 constexpr uint64_t N_CNT = N_PEND_ONE - 1ull, N_PEND = 0x3FFFull;
 constexpr int N_PEND_SHIFT = 48;
-
-__host__ __device__ __forceinline__ int slot_of(int lr, int lc)
-{
-    if (lr == 0) return lc;
-    if (lr == T - 1) return T + lc;
-    if (lc == 0) return 2 * T + lr - 1;
-    return 2 * T + (T - 2) + lr - 1;  // lc == T-1
-}
-__host__ __device__ __forceinline__ void slot_cell(int s, int &lr, int &lc)
-{
-    if (s < T) { lr = 0; lc = s; }
-    else if (s < 2 * T) { lr = T - 1; lc = s - T; }
-    else if (s < 2 * T + (T - 2)) { lr = s - 2 * T + 1; lc = 0; }
-    else { lr = s - (2 * T + (T - 2)) + 1; lc = T - 1; }
-}
-constexpr int USED_SLOTS = 4 * T - 4;
-
-// neighbour positions in scan order NW,N,NE,W,E,SW,S,SE (bit k of the in-masks)
-__device__ __forceinline__ void nbr_offset(int k, int &dr, int &dc)
-{
-    const int kk = k < 4 ? k : k + 1;  // skip the centre of the 3x3
-    dr = kk / 3 - 1;
-    dc = kk % 3 - 1;
-}
-
-struct TileView {
-    const uint8_t *d8, *halo_above, *halo_below;
-    int64_t rows, cols;
-    int tiles_x;
-};
-
-__device__ __forceinline__ unsigned fetch_code(const TileView &v, int64_t gr, int64_t gc)
-{
-    if (gc < 0 || gc >= v.cols) return 0;
-    if (gr >= 0 && gr < v.rows) return v.d8[gr * v.cols + gc];
-    if (gr == -1 && v.halo_above) return v.halo_above[gc];
-    if (gr == v.rows && v.halo_below) return v.halo_below[gc];
-    return 0;
-}
 
 // ---- T1 / T2: the tile kernel -------------------------------------------------------------
 // SEEDED = false: local counts only, writes the perimeter summary (exitw, link, meta).
@@ -112,26 +61,7 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
     auto C = [&](int lr, int lc) -> unsigned { return codes[(lr + 1) * CP + 16 + lc]; };
 
     // ---- stage the codes: 64 rows x 64 B as one 16-byte load per thread, halo ring by bytes ----
-    const bool fast = (v.cols % 16 == 0) && ((reinterpret_cast<uintptr_t>(v.d8) & 15u) == 0) && (c0 + T <= v.cols);
-    if (fast) {
-        const int lr = tid >> 2, ch = tid & 3;
-        uint4 w = make_uint4(0, 0, 0, 0);
-        if (r0 + lr < v.rows) w = __ldg(reinterpret_cast<const uint4 *>(v.d8 + (r0 + lr) * v.cols + c0 + ch * 16));
-        *reinterpret_cast<uint4 *>(&codes[(lr + 1) * CP + 16 + ch * 16]) = w;
-        for (int h = tid; h < 4 * T + 4; h += FT_THREADS) {
-            int lr2, lc2;
-            if (h < T + 2) { lr2 = -1; lc2 = h - 1; }
-            else if (h < 2 * T + 4) { lr2 = T; lc2 = h - (T + 2) - 1; }
-            else if (h < 3 * T + 4) { lr2 = h - (2 * T + 4); lc2 = -1; }
-            else { lr2 = h - (3 * T + 4); lc2 = T; }
-            codes[(lr2 + 1) * CP + 16 + lc2] = (uint8_t)fetch_code(v, r0 + lr2, c0 + lc2);
-        }
-    } else {
-        for (int h = tid; h < (T + 2) * (T + 2); h += FT_THREADS) {
-            const int lr2 = h / (T + 2) - 1, lc2 = h % (T + 2) - 1;
-            codes[(lr2 + 1) * CP + 16 + lc2] = (uint8_t)fetch_code(v, r0 + lr2, c0 + lc2);
-        }
-    }
+    const bool fast = stage_codes(v, r0, c0, codes, tid, FT_THREADS);
     if (tid < SLOTS) { nterm_s[tid] = 0; inmask_s[tid] = 0; }
     if (tid == 0) cyc_s = 0;
     __syncthreads();

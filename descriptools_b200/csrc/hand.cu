@@ -6,28 +6,39 @@
 //
 // The reference walks every cell down the D8 pointers (O(path length) dependent loads per
 // cell, mean 214 on its example).  Here the D8 forest is resolved by pointer jumping over a
-// packed 64-bit state per cell:
-//     [63..62 kind | 61..47 diagonal moves | 46..32 cardinal moves | 31..0 target cell]
-// kind: ACTIVE (target = cell reached so far), RIVER (target = river cell), FAIL.
-// One round = every ACTIVE cell adopts its target's state and adds the move counts.  Rounds
-// update in place (asynchronously): any state read is a valid description of that cell's
-// path, and every launch at least doubles the moves covered by each ACTIVE cell, so
-// ceil(log2(max_moves+1)) launches decide every cell: whatever is still ACTIVE needs more
-// than max_moves moves or sits on / drains into a cycle -> FAIL, exactly the reference's
-// outcomes (flowhand.py:826 code-0 landing, :830 cycle detector, :835 move cap, border
-// exits :623-764).  A launch whose predecessor left nothing ACTIVE exits immediately.
+// packed 64-bit state per cell
+//     [63..62 kind | 61..47 diagonal moves | 46..32 cardinal moves | 31..0 target]
+// in two levels that share the 64x64 tiling of flowacc.cu (tiles.cuh):
+//   H1  hand_entry_kernel: per tile, only the perimeter cells that receive flow from outside
+//       (entry nodes) walk their in-tile path: it ends on a river cell, fails, or leaves the tile
+//       into another entry node.  One 64-bit state per node.
+//   H2  hand_node_jump_kernel: pointer jumping over the entry nodes in global memory.  In-place and
+//       asynchronous: any state read is a valid description of that node's path, every launch at
+//       least doubles the hops covered, so ceil(log2(max_moves+1)) launches decide every node;
+//       what is still ACTIVE then needs more than max_moves moves or sits on / drains into a
+//       cycle -> FAIL, the reference's outcomes (flowhand.py:826 code-0 landing, :830 cycle
+//       detector, :835 move cap, border exits :623-764).  A launch whose predecessor left
+//       nothing ACTIVE returns at once.
+//   H3  hand_tile_kernel: per tile, pointer jumping over all 4096 cells in shared memory (targets:
+//       river cell, failure, or the tile's exit cell), composition with the resolved state of the
+//       entry node behind each exit, then the epilogue: idx, flow distance, HAND = z - z[idx]
+//       and GFI from the gathered accumulation of the river cell, written once.
 // Distance = n_card*px + n_diag*(px*sqrt(2)) in f64 (the reference adds the same terms one
 // move at a time, flowhand.py:803-824; the two agree far below f32 resolution).
+// GFI = ln(b) + n*ln(A_r*size^2) - ln(H + 0.01) in f64: the reference's
+// log(b*pow(A_r*size^2, n)/(H+0.01)) (gfi.py:292-294) rearranged to drop the pow; both are
+// correctly rounded far below the f32 the result is stored in.
 #include <math.h>
 
-#include "common.cuh"
+#include "tiles.cuh"
 
 namespace dtb {
 namespace {
 
 constexpr int H_THREADS = 256;
-constexpr uint64_t KIND_ACTIVE = 0, KIND_RIVER = 1, KIND_FAIL = 2;
+constexpr uint64_t KIND_ACTIVE = 0, KIND_RIVER = 1, KIND_FAIL = 2, KIND_EXIT = 3;
 constexpr uint32_t CNT_SAT = 32767;
+constexpr int JUMP_BLOCKS = kNumSMs * 8;
 
 __device__ __forceinline__ uint64_t pack(uint64_t kind, uint32_t nd, uint32_t nc, uint32_t ptr)
 {
@@ -38,78 +49,130 @@ __device__ __forceinline__ uint32_t nd_of(uint64_t s) { return (uint32_t)(s >> 4
 __device__ __forceinline__ uint32_t nc_of(uint64_t s) { return (uint32_t)(s >> 32) & 0x7FFFu; }
 __device__ __forceinline__ uint32_t ptr_of(uint64_t s) { return (uint32_t)s; }
 __device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b) { return min(a + b, CNT_SAT); }
-
-template <typename ACC>
-__device__ __forceinline__ bool is_river(const int8_t *river, const ACC *acc, int64_t thr, int64_t p)
+// state of a path that continues with `t` after the moves recorded in `s`
+__device__ __forceinline__ uint64_t compose(uint64_t s, uint64_t t)
 {
-    return river ? (river[p] == 1) : ((int64_t)acc[p] > thr);  // flowhand.py:609 / example.py:52
+    const uint64_t kt = kind_of(t);
+    if (kt == KIND_FAIL) return pack(KIND_FAIL, 0, 0, 0);
+    return pack(kt, sat_add(nd_of(s), nd_of(t)), sat_add(nc_of(s), nc_of(t)), ptr_of(t));
 }
 
+struct RiverSrc {
+    const int8_t *river;  // 0/1 mask (flowhand.py:609) or NULL
+    const void *acc;      // river = acc > thr (example.py:52)
+    int64_t thr;
+};
+
+// 16-bit river mask of the 16 cells (row lr, columns lcb..lcb+15) of the tile at (r0, c0)
+template <typename ACC>
+__device__ __forceinline__ unsigned river_bits(const RiverSrc &rs, const TileView &v, int64_t r0, int64_t c0, int lr, int lcb,
+                                               bool fast)
+{
+    const int64_t gr = r0 + lr;
+    unsigned m = 0;
+    if (gr >= v.rows) return 0;
+    const int64_t o = gr * v.cols + c0 + lcb;
+    if (rs.river) {
+        if (fast && ((reinterpret_cast<uintptr_t>(rs.river) & 15u) == 0)) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4 *>(rs.river + o));
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m |= (((ww[i >> 2] >> (8 * (i & 3))) & 0xFFu) == 1u) << i;
+        } else {
+            for (int i = 0; i < 16; ++i)
+                if (c0 + lcb + i < v.cols) m |= (unsigned)(rs.river[o + i] == 1) << i;
+        }
+    } else {
+        const ACC *a = reinterpret_cast<const ACC *>(rs.acc);
+        if (fast && ((reinterpret_cast<uintptr_t>(a) & 15u) == 0)) {
+            constexpr int V = 16 / sizeof(ACC);
+#pragma unroll
+            for (int i = 0; i < 16; i += V) {
+                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(a + o + i));
+                const ACC *e = reinterpret_cast<const ACC *>(&w);
+#pragma unroll
+                for (int j = 0; j < V; ++j) m |= (unsigned)((int64_t)e[j] > rs.thr) << (i + j);
+            }
+        } else {
+            for (int i = 0; i < 16; ++i)
+                if (c0 + lcb + i < v.cols) m |= (unsigned)((int64_t)a[o + i] > rs.thr) << i;
+        }
+    }
+    return m;
+}
+
+// ---- H1: entry nodes walk their in-tile path -------------------------------------------------------
 template <typename ACC>
 __global__ void __launch_bounds__(H_THREADS)
-hand_init_kernel(const uint8_t *__restrict__ fdr, const int8_t *__restrict__ river, const ACC *__restrict__ acc,
-                 int64_t thr, int64_t rows, int64_t cols, unsigned long long *__restrict__ state,
-                 unsigned *__restrict__ active)
+hand_entry_kernel(TileView v, RiverSrc rs, unsigned long long *__restrict__ nstate, unsigned *__restrict__ active)
 {
-    const int64_t n = rows * cols;
-    const int64_t p = (int64_t)blockIdx.x * H_THREADS + threadIdx.x;
+    __shared__ __align__(16) uint8_t codes[(T + 2) * CP + 16];
+    __shared__ uint16_t rivm[H_THREADS];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
+    const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
+    const bool fast = stage_codes(v, r0, c0, codes, tid, H_THREADS);
+    rivm[tid] = (uint16_t)river_bits<ACC>(rs, v, r0, c0, tid >> 2, (tid & 3) * CPT, fast);
+    __syncthreads();
+    auto C = [&](int lr, int lc) -> unsigned { return codes[(lr + 1) * CP + 16 + lc]; };
+
+    uint64_t s = 0ull;  // inactive slot (never referenced)
     int is_active = 0;
-    if (p < n) {
-        const unsigned code = fdr[p];
-        uint64_t s;
-        if (code == 0) {
-            s = pack(KIND_FAIL, 0, 0, 0);  // flowhand.py:601
-        } else if (is_river<ACC>(river, acc, thr, p)) {
-            s = pack(KIND_RIVER, 0, 0, (uint32_t)p);  // flowhand.py:609-612
-        } else {
-            int dr, dc;
-            const int64_t r = p / cols, c = p - r * cols;
-            if (!d8_offset(code, dr, dc)) {
-                s = pack(KIND_FAIL, 0, 0, 0);  // unknown code: "did not move", flowhand.py:830
-            } else {
-                const int64_t rr = r + dr, cc = c + dc;
-                if (rr < 0 || rr >= rows || cc < 0 || cc >= cols) {
-                    s = pack(KIND_FAIL, 0, 0, 0);  // leaves the raster, flowhand.py:623-764
-                } else {
-                    const int64_t q = rr * cols + cc;
-                    if (fdr[q] == 0) s = pack(KIND_FAIL, 0, 0, 0);  // flowhand.py:826
-                    else {
-                        const bool diag = d8_is_diag(code);
-                        s = pack(KIND_ACTIVE, diag ? 1u : 0u, diag ? 0u : 1u, (uint32_t)q);
-                        is_active = 1;
-                    }
+    if (tid < USED_SLOTS) {
+        int lr, lc;
+        slot_cell(tid, lr, lc);
+        if (C(lr, lc) != 0 && (in_mask(codes, lr, lc) & out_mask(lr, lc))) {
+            uint32_t nc = 0, nd = 0;
+            s = pack(KIND_FAIL, 0, 0, 0);  // in-tile cycle if the loop runs out
+            for (int steps = 0; steps <= TCELLS; ++steps) {
+                const int p = lr * T + lc;
+                if ((rivm[p >> 4] >> (p & 15)) & 1u) {  // flowhand.py:622
+                    s = pack(KIND_RIVER, nd, nc, (uint32_t)((r0 + lr) * v.cols + c0 + lc));
+                    break;
                 }
+                const unsigned code = C(lr, lc);
+                int dr, dc;
+                if (!d8_offset(code, dr, dc)) break;             // unknown code: "did not move", flowhand.py:830
+                const int tr = lr + dr, tc = lc + dc;
+                if (C(tr, tc) == 0) break;                        // off-raster or code 0, flowhand.py:623-764, 826
+                if (d8_is_diag(code)) ++nd; else ++nc;
+                if ((unsigned)tr >= (unsigned)T || (unsigned)tc >= (unsigned)T) {
+                    const int64_t gr = r0 + tr, gc = c0 + tc;
+                    if (gr < 0) s = pack(KIND_EXIT, nd, nc, LINK_OUT | (uint32_t)gc);
+                    else if (gr >= v.rows) s = pack(KIND_EXIT, nd, nc, LINK_OUT | LINK_BELOW | (uint32_t)gc);
+                    else { s = pack(KIND_ACTIVE, nd, nc, (uint32_t)node_of_cell(gr, gc, v.tiles_x)); is_active = 1; }
+                    break;
+                }
+                lr = tr;
+                lc = tc;
             }
         }
-        state[p] = s;
     }
+    nstate[(size_t)tile * SLOTS + tid] = s;
     const unsigned ballot = __ballot_sync(0xffffffffu, is_active);
-    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&active[0], (unsigned)__popc(ballot));
+    if ((tid & 31) == 0 && ballot) atomicAdd(&active[0], (unsigned)__popc(ballot));
 }
 
-// round `rnd` (1-based): reads active[rnd-1], writes the number of cells still ACTIVE to active[rnd]
+// ---- H2: pointer jumping over the entry nodes ------------------------------------------------------
+// round `rnd` (1-based): reads active[rnd-1], adds the number of nodes still ACTIVE to active[rnd]
 __global__ void __launch_bounds__(H_THREADS)
-hand_jump_kernel(int64_t n, unsigned long long *state, unsigned *__restrict__ active, int rnd, int jumps)
+hand_node_jump_kernel(int64_t nnodes, unsigned long long *nstate, unsigned *__restrict__ active, int rnd, int jumps)
 {
     if (active[rnd - 1] == 0) return;
-    const int64_t p = (int64_t)blockIdx.x * H_THREADS + threadIdx.x;
-    int still = 0;
-    if (p < n) {
-        uint64_t s = __ldcg(&state[p]);
-        if (kind_of(s) == KIND_ACTIVE) {
-            for (int j = 0; j < jumps; ++j) {
-                const uint64_t t = __ldcg(&state[ptr_of(s)]);
-                const uint64_t kt = kind_of(t);
-                if (kt == KIND_FAIL) { s = pack(KIND_FAIL, 0, 0, 0); break; }
-                s = pack(kt, sat_add(nd_of(s), nd_of(t)), sat_add(nc_of(s), nc_of(t)), ptr_of(t));
-                if (kt != KIND_ACTIVE) break;
-            }
-            __stcg(&state[p], s);
-            still = kind_of(s) == KIND_ACTIVE;
+    unsigned still = 0;
+    for (int64_t q = (int64_t)blockIdx.x * H_THREADS + threadIdx.x; q < nnodes; q += (int64_t)gridDim.x * H_THREADS) {
+        uint64_t s = __ldcg(&nstate[q]);
+        if (kind_of(s) != KIND_ACTIVE || s == 0ull) continue;  // 0 = inactive slot
+        for (int j = 0; j < jumps; ++j) {
+            s = compose(s, __ldcg(&nstate[ptr_of(s)]));
+            if (kind_of(s) != KIND_ACTIVE) break;
         }
+        __stcg(&nstate[q], s);
+        still += kind_of(s) == KIND_ACTIVE;
     }
-    const unsigned ballot = __ballot_sync(0xffffffffu, still);
-    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&active[rnd], (unsigned)__popc(ballot));
+    still = __reduce_add_sync(0xffffffffu, still);
+    if ((threadIdx.x & 31) == 0 && still) atomicAdd(&active[rnd], still);
 }
 
 template <typename T> struct HandOps;
@@ -142,28 +205,178 @@ __device__ __forceinline__ float gfi_value(T h, double racc, double n, double b,
     return (float)log(b * pow(racc * s2, n) / ((double)h + 0.01));
 }
 
-template <typename T, typename IDX, typename ACC>
-__global__ void __launch_bounds__(H_THREADS)
-hand_final_kernel(int64_t n, const unsigned long long *__restrict__ state, const T *__restrict__ dem,
-                  const ACC *__restrict__ acc, double px, double pd, uint32_t max_moves, float *__restrict__ fdist,
-                  IDX *__restrict__ idx_out, T *__restrict__ hand, float *__restrict__ gfi, double gn, double gb, double gs2)
+
+// ---- H3: per-tile resolution + epilogue ---------------------------------------------------------
+struct HandOut {
+    float *fdist;
+    void *idx;
+    void *hand;
+    float *gfi;
+    double px, pd;
+    uint32_t max_moves;
+    double gfi_logb, gfi_n, gfi_s2;
+};
+
+// four consecutive cells of one row, as one vector store when the row is 16-byte tileable
+template <typename V>
+__device__ __forceinline__ void store4(V *dst, const V (&val)[4], bool vec, int64_t c_first, int64_t cols)
 {
-    const int64_t p = (int64_t)blockIdx.x * H_THREADS + threadIdx.x;
-    if (p >= n) return;
-    const uint64_t s = state[p];
-    const uint32_t nc = nc_of(s), nd = nd_of(s);
-    const bool ok = kind_of(s) == KIND_RIVER && nc + nd <= max_moves;  // flowhand.py:835
-    const int64_t idx = ok ? (int64_t)ptr_of(s) : (int64_t)ND_I;
-    if (fdist) fdist[p] = ok ? (float)((double)nc * px + (double)nd * pd) : ND_F;  // flowhand.py:840-843
-    if (idx_out) idx_out[p] = (IDX)idx;
-    if (hand || gfi) {
-        const T h = hand_value<T>(dem[p], ok, dem, idx);
-        if (hand) hand[p] = h;
-        if (gfi) {
-            // river_accumulation: idx == -100 -> fac.flat[0] (gfi.py:141-143); irrelevant: H is -100 then
-            const double racc = (double)acc[ok ? idx : 0];
-            gfi[p] = gfi_value<T>(h, racc, gn, gb, gs2);
+    if (vec) {
+        if (sizeof(V) == 2) *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(&val[0]);
+        else if (sizeof(V) == 4) *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(&val[0]);
+        else {
+            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(&val[0]);
+            *reinterpret_cast<uint4 *>(dst + 2) = *reinterpret_cast<const uint4 *>(&val[2]);
         }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (c_first + i < cols) dst[i] = val[i];
+    }
+}
+template <typename V>
+__device__ __forceinline__ void load4(const V *src, V (&val)[4], bool vec, int64_t c_first, int64_t cols, V fill)
+{
+    if (vec) {
+        if (sizeof(V) == 2) *reinterpret_cast<uint2 *>(&val[0]) = __ldg(reinterpret_cast<const uint2 *>(src));
+        else *reinterpret_cast<uint4 *>(&val[0]) = __ldg(reinterpret_cast<const uint4 *>(src));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) val[i] = (c_first + i < cols) ? src[i] : fill;
+    }
+}
+
+template <typename TD, typename IDX, typename ACC>
+__global__ void __launch_bounds__(H_THREADS)
+hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC *__restrict__ acc,
+                 const unsigned long long *__restrict__ nstate, HandOut o)
+{
+    __shared__ __align__(16) uint8_t codes[(T + 2) * CP + 16];
+    __shared__ uint16_t rivm[H_THREADS];
+    __shared__ unsigned long long st[TCELLS];
+    __shared__ unsigned long long exit_state[SLOTS];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
+    const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
+    const bool fast = stage_codes(v, r0, c0, codes, tid, H_THREADS);
+    const int lr = tid >> 2, lcb = (tid & 3) * CPT;
+    const unsigned myriv = river_bits<ACC>(rs, v, r0, c0, lr, lcb, fast);
+    rivm[tid] = (uint16_t)myriv;
+    __syncthreads();
+    auto C = [&](int r, int c) -> unsigned { return codes[(r + 1) * CP + 16 + c]; };
+
+    // ---- initial state of my 16 cells ----
+    unsigned activemask = 0;
+#pragma unroll 4
+    for (int i = 0; i < CPT; ++i) {
+        const int lc = lcb + i, p = lr * T + lc;
+        const unsigned code = C(lr, lc);
+        uint64_t s = pack(KIND_FAIL, 0, 0, 0);  // code 0 (flowhand.py:601), unknown code, bad landing
+        int dr, dc;
+        if (code != 0) {
+            if ((myriv >> i) & 1u) s = pack(KIND_RIVER, 0, 0, (uint32_t)((r0 + lr) * v.cols + c0 + lc));  // flowhand.py:609-612
+            else if (d8_offset(code, dr, dc)) {
+                const int tr = lr + dr, tc = lc + dc;
+                if (C(tr, tc) != 0) {
+                    if ((unsigned)tr < (unsigned)T && (unsigned)tc < (unsigned)T) {
+                        const bool diag = d8_is_diag(code);
+                        s = pack(KIND_ACTIVE, diag ? 1u : 0u, diag ? 0u : 1u, (uint32_t)(tr * T + tc));
+                        activemask |= 1u << i;
+                    } else {
+                        s = pack(KIND_EXIT, 0, 0, (uint32_t)p);  // the exit move is added with the node state
+                    }
+                }
+            }
+        }
+        st[p] = s;
+    }
+    __syncthreads();
+
+    // ---- in-tile pointer jumping (in place, asynchronous) ----
+    for (int round = 0; round < 13; ++round) {
+        unsigned m = activemask;
+        while (m) {
+            const int i = __ffs((int)m) - 1;
+            m &= m - 1;
+            const int p = lr * T + lcb + i;
+            uint64_t s = st[p];
+            s = compose(s, st[ptr_of(s)]);
+            if (kind_of(s) == KIND_ACTIVE) s = compose(s, st[ptr_of(s)]);
+            st[p] = s;
+            if (kind_of(s) != KIND_ACTIVE) activemask &= ~(1u << i);
+        }
+        if (!__syncthreads_or(activemask != 0)) break;
+    }
+    // still ACTIVE after 13 double rounds: in-tile cycle -> FAIL (flowhand.py:830/835)
+
+    // ---- resolved state behind every exit cell of the perimeter ----
+    if (tid < USED_SLOTS) {
+        int plr, plc;
+        slot_cell(tid, plr, plc);
+        const unsigned code = C(plr, plc);
+        uint64_t e = pack(KIND_FAIL, 0, 0, 0);
+        int dr, dc;
+        if (d8_offset(code, dr, dc)) {
+            const int tr = plr + dr, tc = plc + dc;
+            if (((unsigned)tr >= (unsigned)T || (unsigned)tc >= (unsigned)T) && C(tr, tc) != 0) {
+                const int64_t gr = r0 + tr, gc = c0 + tc;
+                const bool diag = d8_is_diag(code);
+                const uint64_t mv = pack(KIND_ACTIVE, diag ? 1u : 0u, diag ? 0u : 1u, 0);
+                if (gr >= 0 && gr < v.rows) {
+                    const uint64_t ns = nstate[node_of_cell(gr, gc, v.tiles_x)];
+                    e = compose(mv, ns);
+                    if (kind_of(e) != KIND_RIVER) e = pack(KIND_FAIL, 0, 0, 0);  // ACTIVE left over: cycle or > cap
+                }
+            }
+        }
+        exit_state[tid] = e;
+    }
+    __syncthreads();
+
+    // ---- epilogue: idx, flow distance, HAND, GFI for my 16 cells ----
+    const int64_t gr = r0 + lr;
+    if (gr >= v.rows) return;
+    const bool vec = fast && (((reinterpret_cast<uintptr_t>(dem) | reinterpret_cast<uintptr_t>(o.fdist) |
+                                reinterpret_cast<uintptr_t>(o.idx) | reinterpret_cast<uintptr_t>(o.hand) |
+                                reinterpret_cast<uintptr_t>(o.gfi)) & 15u) == 0);
+#pragma unroll 1
+    for (int g4 = 0; g4 < CPT; g4 += 4) {
+        const int64_t c_first = c0 + lcb + g4, obase = gr * v.cols + c_first;
+        alignas(16) TD z[4];
+        alignas(16) float fd[4], gf[4];
+        alignas(16) IDX ix[4];
+        alignas(16) TD hd[4];
+        if (o.hand || o.gfi) load4<TD>(dem + obase, z, vec, c_first, v.cols, HandOps<TD>::nd());
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint64_t s = st[lr * T + lcb + g4 + i];
+            if (kind_of(s) == KIND_EXIT) {
+                const uint32_t x = ptr_of(s);
+                s = compose(s, exit_state[slot_of((int)(x / T), (int)(x % T))]);
+            }
+            const uint32_t nc = nc_of(s), nd = nd_of(s);
+            const bool ok = kind_of(s) == KIND_RIVER && nc + nd <= o.max_moves;  // flowhand.py:835
+            const int64_t idx = ok ? (int64_t)ptr_of(s) : (int64_t)ND_I;
+            fd[i] = ok ? (float)((double)nc * o.px + (double)nd * o.pd) : ND_F;  // flowhand.py:840-843
+            ix[i] = (IDX)idx;
+            TD h = HandOps<TD>::nd();
+            float g = ND_F;
+            if (o.hand || o.gfi) {
+                h = hand_value<TD>(z[i], ok, dem, idx);
+                if (o.gfi && !(h <= HandOps<TD>::nd())) {
+                    // river_accumulation: idx == -100 -> fac.flat[0] (gfi.py:141-143); H is -100 then anyway
+                    const double racc = (double)acc[ok ? idx : 0];
+                    g = (float)(o.gfi_logb + o.gfi_n * log(racc * o.gfi_s2) - log((double)h + 0.01));  // gfi.py:292-294
+                }
+            }
+            hd[i] = h;
+            gf[i] = g;
+        }
+        if (o.fdist) store4<float>(o.fdist + obase, fd, vec, c_first, v.cols);
+        if (o.idx) store4<IDX>(reinterpret_cast<IDX *>(o.idx) + obase, ix, vec, c_first, v.cols);
+        if (o.hand) store4<TD>(reinterpret_cast<TD *>(o.hand) + obase, hd, vec, c_first, v.cols);
+        if (o.gfi) store4<float>(o.gfi + obase, gf, vec, c_first, v.cols);
     }
 }
 
@@ -185,28 +398,40 @@ inline int rounds_for(int64_t max_moves)
     return r;
 }
 
-template <typename T, typename IDX, typename ACC>
-int run_final(const dtb_hand_args *a, const unsigned long long *state, uint32_t max_moves, cudaStream_t st)
+template <typename TD, typename IDX, typename ACC>
+int run_tiles(const dtb_hand_args *a, const TileView &v, const RiverSrc &rs, const unsigned long long *nstate, int64_t tiles,
+              uint32_t max_moves, cudaStream_t st)
 {
-    const int64_t n = a->rows * a->cols;
-    const unsigned blocks = (unsigned)((n + H_THREADS - 1) / H_THREADS);
-    hand_final_kernel<T, IDX, ACC><<<blocks, H_THREADS, 0, st>>>(
-        n, state, (const T *)a->dem, (const ACC *)a->acc, a->px, a->px * sqrt(2.0), max_moves, a->fdist, (IDX *)a->idx,
-        (T *)a->hand, a->gfi, a->gfi_n, a->gfi_b, a->gfi_size * a->gfi_size);
-    DTB_LAUNCH_CHECK("hand_final_kernel");
+    HandOut o;
+    o.fdist = a->fdist;
+    o.idx = a->idx;
+    o.hand = a->hand;
+    o.gfi = a->gfi;
+    o.px = a->px;
+    o.pd = a->px * sqrt(2.0);
+    o.max_moves = max_moves;
+    o.gfi_logb = log(a->gfi_b);
+    o.gfi_n = a->gfi_n;
+    o.gfi_s2 = a->gfi_size * a->gfi_size;
+    hand_tile_kernel<TD, IDX, ACC><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, (const TD *)a->dem, (const ACC *)a->acc, nstate, o);
+    DTB_LAUNCH_CHECK("hand_tile_kernel");
     return DTB_OK;
 }
 
-template <typename T, typename IDX>
-int run_final_acc(const dtb_hand_args *a, const unsigned long long *state, uint32_t mm, cudaStream_t st)
+template <typename TD, typename IDX>
+int run_tiles_acc(const dtb_hand_args *a, const TileView &v, const RiverSrc &rs, const unsigned long long *ns, int64_t tiles,
+                  uint32_t mm, cudaStream_t st)
 {
-    return a->acc_dtype == DTB_I64 ? run_final<T, IDX, int64_t>(a, state, mm, st) : run_final<T, IDX, int32_t>(a, state, mm, st);
+    return a->acc_dtype == DTB_I64 ? run_tiles<TD, IDX, int64_t>(a, v, rs, ns, tiles, mm, st)
+                                   : run_tiles<TD, IDX, int32_t>(a, v, rs, ns, tiles, mm, st);
 }
 
-template <typename T>
-int run_final_idx(const dtb_hand_args *a, const unsigned long long *state, uint32_t mm, cudaStream_t st)
+template <typename TD>
+int run_tiles_idx(const dtb_hand_args *a, const TileView &v, const RiverSrc &rs, const unsigned long long *ns, int64_t tiles,
+                  uint32_t mm, cudaStream_t st)
 {
-    return a->idx_dtype == DTB_I64 ? run_final_acc<T, int64_t>(a, state, mm, st) : run_final_acc<T, int32_t>(a, state, mm, st);
+    return a->idx_dtype == DTB_I64 ? run_tiles_acc<TD, int64_t>(a, v, rs, ns, tiles, mm, st)
+                                   : run_tiles_acc<TD, int32_t>(a, v, rs, ns, tiles, mm, st);
 }
 
 }  // namespace
@@ -215,7 +440,8 @@ int run_final_idx(const dtb_hand_args *a, const unsigned long long *state, uint3
 extern "C" size_t dtb_hand_workspace_bytes(int64_t rows, int64_t cols)
 {
     if (rows <= 0 || cols <= 0) return 0;
-    return (size_t)rows * (size_t)cols * 8 + 256;
+    const int64_t tiles = ((rows + dtb::T - 1) / dtb::T) * ((cols + dtb::T - 1) / dtb::T);
+    return (size_t)tiles * dtb::SLOTS * 8 + 256;
 }
 
 extern "C" int dtb_hand(const dtb_hand_args *a, void *ws, size_t ws_bytes, void *stream)
@@ -234,25 +460,25 @@ extern "C" int dtb_hand(const dtb_hand_args *a, void *ws, size_t ws_bytes, void 
     if (max_moves > 32000) return DTB_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
     unsigned *active = reinterpret_cast<unsigned *>(ws);
-    unsigned long long *state = reinterpret_cast<unsigned long long *>((char *)ws + 256);
-    const unsigned blocks = (unsigned)((n + H_THREADS - 1) / H_THREADS);
+    unsigned long long *nstate = reinterpret_cast<unsigned long long *>((char *)ws + 256);
+    TileView v{a->fdr, nullptr, nullptr, a->rows, a->cols, (int)((a->cols + T - 1) / T)};
+    const int64_t tiles = (int64_t)v.tiles_x * ((a->rows + T - 1) / T);
+    const int64_t nnodes = tiles * SLOTS;
+    if (nnodes >= (int64_t)1 << 30) return DTB_ERR_UNSUPPORTED;
+    RiverSrc rs{a->river, a->acc, a->river_threshold};
 
     DTB_CUDA(cudaMemsetAsync(active, 0, 256, st));
-    if (a->acc_dtype == DTB_I64)
-        hand_init_kernel<int64_t><<<blocks, H_THREADS, 0, st>>>(a->fdr, a->river, (const int64_t *)a->acc, a->river_threshold,
-                                                                a->rows, a->cols, state, active);
-    else
-        hand_init_kernel<int32_t><<<blocks, H_THREADS, 0, st>>>(a->fdr, a->river, (const int32_t *)a->acc, a->river_threshold,
-                                                                a->rows, a->cols, state, active);
-    DTB_LAUNCH_CHECK("hand_init_kernel");
+    if (a->acc_dtype == DTB_I64) hand_entry_kernel<int64_t><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, nstate, active);
+    else hand_entry_kernel<int32_t><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, nstate, active);
+    DTB_LAUNCH_CHECK("hand_entry_kernel");
     const int rounds = rounds_for(max_moves);
     for (int r = 1; r <= rounds; ++r) {
-        hand_jump_kernel<<<blocks, H_THREADS, 0, st>>>(n, state, active, r, 2);
-        DTB_LAUNCH_CHECK("hand_jump_kernel");
+        hand_node_jump_kernel<<<JUMP_BLOCKS, H_THREADS, 0, st>>>(nnodes, nstate, active, r, 2);
+        DTB_LAUNCH_CHECK("hand_node_jump_kernel");
     }
     if (!a->fdist && !a->idx && !a->hand && !a->gfi) return DTB_OK;
-    return a->dem_dtype == DTB_I16 ? run_final_idx<int16_t>(a, state, (uint32_t)max_moves, st)
-                                   : run_final_idx<float>(a, state, (uint32_t)max_moves, st);
+    return a->dem_dtype == DTB_I16 ? run_tiles_idx<int16_t>(a, v, rs, nstate, tiles, (uint32_t)max_moves, st)
+                                   : run_tiles_idx<float>(a, v, rs, nstate, tiles, (uint32_t)max_moves, st);
 }
 
 extern "C" int dtb_hand_from_index(const void *dem, int dem_dtype, const void *idx, int idx_dtype, int64_t n, void *hand,

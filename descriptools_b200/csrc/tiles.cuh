@@ -1,0 +1,118 @@
+// tiles.cuh -- 64x64 tile geometry shared by the tiled D8-forest kernels (flowacc.cu, hand.cu).
+//
+// A raster (or row band) is cut into 64x64 tiles; the 252 perimeter cells of a tile own a "slot"
+// and the pair (tile, slot) is a node id.  Cells that receive flow from outside their tile are the
+// entry nodes of the second-level forest both stages resolve.
+#pragma once
+#include "common.cuh"
+
+namespace dtb {
+
+constexpr int T = 64;                 // tile edge (cells)
+constexpr int TCELLS = T * T;
+constexpr int SLOTS = 256;            // perimeter slots per tile (252 used)
+constexpr int FT_THREADS = 256;
+constexpr int CPT = TCELLS / FT_THREADS;  // cells per thread (16 consecutive columns of one row)
+constexpr int CP = 80;                // shared-memory pitch of a code row: col -1 at 15, col 0 at 16
+constexpr uint32_t NXT_EXIT = 0xFFFEu, NXT_TERM = 0xFFFFu;
+constexpr uint32_t LINK_NONE = 0xFFFFFFFFu;   // in-tile path ends inside the tile
+constexpr uint32_t LINK_OUT = 0x80000000u;    // leaves the band: | (below ? 0x40000000 : 0) | column
+constexpr uint32_t LINK_BELOW = 0x40000000u;
+constexpr uint32_t TERM_NONE = 255u;
+
+__host__ __device__ __forceinline__ int slot_of(int lr, int lc)
+{
+    if (lr == 0) return lc;
+    if (lr == T - 1) return T + lc;
+    if (lc == 0) return 2 * T + lr - 1;
+    return 2 * T + (T - 2) + lr - 1;  // lc == T-1
+}
+__host__ __device__ __forceinline__ void slot_cell(int s, int &lr, int &lc)
+{
+    if (s < T) { lr = 0; lc = s; }
+    else if (s < 2 * T) { lr = T - 1; lc = s - T; }
+    else if (s < 2 * T + (T - 2)) { lr = s - 2 * T + 1; lc = 0; }
+    else { lr = s - (2 * T + (T - 2)) + 1; lc = T - 1; }
+}
+constexpr int USED_SLOTS = 4 * T - 4;
+
+// neighbour positions in scan order NW,N,NE,W,E,SW,S,SE (bit k of the in-masks)
+__device__ __forceinline__ void nbr_offset(int k, int &dr, int &dc)
+{
+    const int kk = k < 4 ? k : k + 1;  // skip the centre of the 3x3
+    dr = kk / 3 - 1;
+    dc = kk % 3 - 1;
+}
+
+struct TileView {
+    const uint8_t *d8, *halo_above, *halo_below;
+    int64_t rows, cols;
+    int tiles_x;
+};
+
+__device__ __forceinline__ unsigned fetch_code(const TileView &v, int64_t gr, int64_t gc)
+{
+    if (gc < 0 || gc >= v.cols) return 0;
+    if (gr >= 0 && gr < v.rows) return v.d8[gr * v.cols + gc];
+    if (gr == -1 && v.halo_above) return v.halo_above[gc];
+    if (gr == v.rows && v.halo_below) return v.halo_below[gc];
+    return 0;
+}
+
+
+// Stage the tile's codes plus a 1-cell halo ring into shared memory.  Layout: row j (-1..T) at
+// (j+1)*CP, column k (-1..T) at 16+k; `codes` must hold (T+2)*CP+16 bytes, 16-byte aligned.
+// Returns true if the vector path was used (16-byte aligned full-width rows).
+__device__ __forceinline__ bool stage_codes(const TileView &v, int64_t r0, int64_t c0, uint8_t *codes, int tid, int nthreads)
+{
+    const bool fast = (v.cols % 16 == 0) && ((reinterpret_cast<uintptr_t>(v.d8) & 15u) == 0) && (c0 + T <= v.cols);
+    if (fast) {
+        for (int t = tid; t < T * 4; t += nthreads) {
+            const int lr = t >> 2, ch = t & 3;
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (r0 + lr < v.rows) w = __ldg(reinterpret_cast<const uint4 *>(v.d8 + (r0 + lr) * v.cols + c0 + ch * 16));
+            *reinterpret_cast<uint4 *>(&codes[(lr + 1) * CP + 16 + ch * 16]) = w;
+        }
+        for (int h = tid; h < 4 * T + 4; h += nthreads) {
+            int lr2, lc2;
+            if (h < T + 2) { lr2 = -1; lc2 = h - 1; }
+            else if (h < 2 * T + 4) { lr2 = T; lc2 = h - (T + 2) - 1; }
+            else if (h < 3 * T + 4) { lr2 = h - (2 * T + 4); lc2 = -1; }
+            else { lr2 = h - (3 * T + 4); lc2 = T; }
+            codes[(lr2 + 1) * CP + 16 + lc2] = (uint8_t)fetch_code(v, r0 + lr2, c0 + lc2);
+        }
+    } else {
+        for (int h = tid; h < (T + 2) * (T + 2); h += nthreads) {
+            const int lr2 = h / (T + 2) - 1, lc2 = h % (T + 2) - 1;
+            codes[(lr2 + 1) * CP + 16 + lc2] = (uint8_t)fetch_code(v, r0 + lr2, c0 + lc2);
+        }
+    }
+    return fast;
+}
+
+// in-mask of a cell: bit k set iff the neighbour at scan position k (NW,N,NE,W,E,SW,S,SE) points at it
+__device__ __forceinline__ unsigned in_mask(const uint8_t *codes, int lr, int lc)
+{
+    const uint8_t *c = codes + (lr + 1) * CP + 16 + lc;
+    unsigned inm = 0;
+    inm |= (c[-CP - 1] == 2u) << 0;
+    inm |= (c[-CP] == 4u) << 1;
+    inm |= (c[-CP + 1] == 8u) << 2;
+    inm |= (c[-1] == 1u) << 3;
+    inm |= (c[1] == 16u) << 4;
+    inm |= (c[CP - 1] == 128u) << 5;
+    inm |= (c[CP] == 64u) << 6;
+    inm |= (c[CP + 1] == 32u) << 7;
+    return inm;
+}
+// neighbour positions that lie outside the tile
+__device__ __forceinline__ unsigned out_mask(int lr, int lc)
+{
+    return (lr == 0 ? 0x07u : 0u) | (lr == T - 1 ? 0xE0u : 0u) | (lc == 0 ? 0x29u : 0u) | (lc == T - 1 ? 0x94u : 0u);
+}
+__device__ __forceinline__ int64_t node_of_cell(int64_t gr, int64_t gc, int tiles_x)
+{
+    return ((gr / T) * tiles_x + gc / T) * SLOTS + slot_of((int)(gr % T), (int)(gc % T));
+}
+
+}  // namespace dtb
