@@ -14,10 +14,30 @@ LIB_PATH = os.path.join(_HERE, "libdtb200.so")
 
 DTB_F32, DTB_I16 = 0, 1
 DTB_I32, DTB_I64 = 0, 1
+DTB_FA_FULL, DTB_FA_SUMMARY, DTB_FA_FINISH = 0, 1, 2
+DTB_HAND_FULL, DTB_HAND_SUMMARY, DTB_HAND_FINISH = 0, 1, 2
 
 
 class DtbError(RuntimeError):
     pass
+
+
+class HandSeam(Structure):
+    _fields_ = [
+        ("halo", c_void_p),
+        ("sum_state", c_void_p),
+        ("sum_idx", c_void_p),
+        ("sum_z", c_void_p),
+        ("sum_acc", c_void_p),
+        ("res_state", c_void_p),
+        ("res_idx", c_void_p),
+        ("res_z", c_void_p),
+        ("res_acc", c_void_p),
+    ]
+
+
+class HandBand(Structure):
+    _fields_ = [("mode", c_int), ("row_offset", c_int64), ("above", HandSeam), ("below", HandSeam)]
 
 
 class HandArgs(Structure):
@@ -41,6 +61,7 @@ class HandArgs(Structure):
         ("gfi_n", c_double),
         ("gfi_b", c_double),
         ("gfi_size", c_double),
+        ("band", POINTER(HandBand)),
     ]
 
 
@@ -60,7 +81,7 @@ class FlowaccArgs(Structure):
         ("exit_below", c_void_p),
         ("term_above", c_void_p),
         ("term_below", c_void_p),
-        ("reuse_summary", c_int),
+        ("mode", c_int),
         ("unfinalised_host", POINTER(c_int64)),
     ]
 

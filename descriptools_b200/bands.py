@@ -1,0 +1,389 @@
+"""bands.py -- the chain sharded into row bands, one band per GPU.
+
+The reference scales a raster by a *serial* loop over tiles on one GPU (slope.py:126-147 ships a 1-cell halo
+with each tile; flowhand.py:282-402 pre-resolves separator lines and hands them to the tiles as look-up rows).
+Here the same decomposition runs in parallel, one process per GPU (torch.distributed / NCCL):
+
+  * slope + D8      : 1 DEM row exchanged with each neighbour (send/recv), then 1 row of D8 codes;
+  * flow accumulation: every band runs its tile pass and node sweep with zero inflow and emits a boundary
+                      summary (dtb_flowacc_band, DTB_FA_SUMMARY); the summaries are gathered on rank 0, which
+                      solves the boundary graph (`solve_flowacc_boundary`) and scatters the inflow carried by
+                      each halo row; a second node sweep + the final tile pass finish the band;
+  * HAND / GFI      : same pattern (dtb_hand band modes + `solve_hand_boundary`); paths may cross seams many
+                      times, so rank 0 does real pointer jumping over the boundary nodes.
+
+Band seams sit on multiples of 64 rows (the tile edge of the device kernels).  Results are bit-identical to the
+single-GPU run.  The boundary solvers are pure torch (device-agnostic) so the whole driver can be exercised on
+CPU with gloo, with the per-band kernels replaced by a stand-in (tests/test_bands_cpu.py); `LocalBands` runs
+k logical bands on ONE GPU through the very same kernels and solvers (tests/test_gpu_parity.py).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+TILE = 64
+KIND_RIVER, KIND_FAIL, KIND_EXIT = 1, 2, 3
+CNT_SAT = 32767
+FAIL_STATE = -(1 << 63)  # kind 2 in bits 63..62 of an int64
+
+
+def band_edges(rows: int, nbands: int) -> list[int]:
+    """Row ranges [e[i], e[i+1]) of the bands; interior seams on multiples of 64 rows."""
+    if nbands < 1:
+        raise ValueError("nbands must be >= 1")
+    edges = [0]
+    for i in range(1, nbands):
+        e = int(round(i * rows / nbands / TILE)) * TILE
+        edges.append(min(max(e, edges[-1]), rows))
+    edges.append(rows)
+    if any(b <= a for a, b in zip(edges, edges[1:])):
+        raise ValueError(f"{rows} rows cannot be cut into {nbands} bands with seams on multiples of {TILE}")
+    return edges
+
+
+# ---- boundary solvers (rank 0; pure torch, any device) -------------------------------------------
+def forest_accumulate(nxt: torch.Tensor, base: torch.Tensor) -> torch.Tensor:
+    """out[i] = base[i] + sum of out[j] over j with nxt[j] == i  (nxt < 0: none), by pointer doubling."""
+    s, a = base.clone(), nxt.clone()
+    for _ in range(64):
+        live = a >= 0
+        if not bool(live.any()):
+            return s
+        tgt = a[live]
+        add = torch.zeros_like(s)
+        add.index_add_(0, tgt, s[live])
+        a2 = a.clone()
+        a2[live] = a[tgt]
+        s, a = s + add, a2
+    raise RuntimeError("flow accumulation boundary graph has a cycle")
+
+
+def solve_flowacc_boundary(summ: torch.Tensor) -> torch.Tensor:
+    """summ int64 [N, 6, cols]: exit_above, exit_below, term_above, term_below, d8 first row, d8 last row.
+    Returns inflow int64 [N, 2, cols]: (acc+1) carried by the halo row above / below each band."""
+    n, _, cols = summ.shape
+    dev = summ.device
+    base = summ[:, 0:2, :].reshape(-1).clone()                  # node (b, side, c) -> (b*2+side)*cols + c
+    term = summ[:, 2:4, :]
+    code = summ[:, 4:6, :]
+    b = torch.arange(n, device=dev).view(n, 1, 1).expand(n, 2, cols)
+    side = torch.arange(2, device=dev).view(1, 2, 1).expand(n, 2, cols)
+    c = torch.arange(cols, device=dev).view(1, 1, cols).expand(n, 2, cols)
+    # column shift of the move across the seam: NW/SW -1, N/S 0, NE/SE +1 (flowhand.py:801-824)
+    dc = torch.zeros_like(code)
+    dc[(code == 32) | (code == 8)] = -1
+    dc[(code == 128) | (code == 2)] = 1
+    b2 = torch.where(side == 0, b - 1, b + 1)                   # band the exit lands in
+    s2 = 1 - side                                               # ... on its opposite boundary row
+    c2 = c + dc
+    is_exit = (summ[:, 0:2, :] > 0) & (b2 >= 0) & (b2 < n) & (c2 >= 0) & (c2 < cols)
+    b2c, c2c = b2.clamp(0, n - 1), c2.clamp(0, cols - 1)
+    t = term[b2c, s2, c2c]                                      # where the landing cell's in-band path leaves
+    t_side, t_col = (t >> 30) & 1, t & 0x3FFFFFFF
+    nxt = torch.where(is_exit & (t >= 0), (b2c * 2 + t_side) * cols + t_col, torch.full_like(t, -1)).reshape(-1)
+    f = forest_accumulate(nxt, base).view(n, 2, cols)
+    inflow = torch.zeros((n, 2, cols), dtype=torch.int64, device=dev)
+    inflow[1:, 0, :] = f[:-1, 1, :]                             # above band b = last row of band b-1
+    inflow[:-1, 1, :] = f[1:, 0, :]                             # below band b = first row of band b+1
+    return inflow
+
+
+def solve_hand_boundary(summ: torch.Tensor) -> torch.Tensor:
+    """summ int64 [N, 8, cols]: (state, idx, z-bits, acc) of the first row, then of the last row.
+    Returns int64 [N, 8, cols]: resolved (state, idx, z-bits, acc) of the halo row above, then below."""
+    n, _, cols = summ.shape
+    dev = summ.device
+    st = torch.stack([summ[:, 0, :], summ[:, 4, :]], 1).reshape(-1)          # node (b, side, c)
+    pay = torch.stack([summ[:, 1:4, :], summ[:, 5:8, :]], 1)                 # [N, 2, 3, cols]
+    pay = pay.permute(0, 1, 3, 2).reshape(-1, 3)
+    kind = (st >> 62) & 3
+    nd = (st >> 47) & 0x7FFF
+    nc = (st >> 32) & 0x7FFF
+    ptr = st & 0xFFFFFFFF
+    kind = torch.where(st == 0, torch.full_like(kind, KIND_FAIL), kind)      # not an entry: never referenced
+    node = torch.arange(2 * n * cols, device=dev)
+    b, side = node // (2 * cols), (node // cols) % 2
+    t_side, t_col = (ptr >> 30) & 1, ptr & 0x3FFFFFFF
+    b2 = torch.where(t_side == 0, b - 1, b + 1)
+    ok = (kind == KIND_EXIT) & (b2 >= 0) & (b2 < n) & (t_col < cols)
+    tgt = torch.where(ok, (b2.clamp(0, n - 1) * 2 + (1 - t_side)) * cols + t_col.clamp(max=cols - 1), torch.full_like(node, -1))
+    kind = torch.where((kind == KIND_EXIT) & ~ok, torch.full_like(kind, KIND_FAIL), kind)
+    src = node.clone()                                                       # whose payload the node ends up with
+    for _ in range(64):
+        live = kind == KIND_EXIT
+        if not bool(live.any()):
+            break
+        t = tgt[live]
+        nd2, nc2 = nd.clone(), nc.clone()
+        nd2[live] = (nd[live] + nd[t]).clamp(max=CNT_SAT)
+        nc2[live] = (nc[live] + nc[t]).clamp(max=CNT_SAT)
+        kind2, tgt2, src2 = kind.clone(), tgt.clone(), src.clone()
+        kind2[live], tgt2[live], src2[live] = kind[t], tgt[t], src[t]
+        kind, nd, nc, tgt, src = kind2, nd2, nc2, tgt2, src2
+    kind = torch.where(kind == KIND_EXIT, torch.full_like(kind, KIND_FAIL), kind)   # cycle across seams
+    state = ((kind << 62) | (nd << 47) | (nc << 32)).view(n, 2, cols)
+    pay = pay[src].view(n, 2, cols, 3)
+    res = torch.zeros((n, 8, cols), dtype=torch.int64, device=dev)
+    res[:, 0, :] = FAIL_STATE
+    res[:, 4, :] = FAIL_STATE
+    res[1:, 0, :] = state[:-1, 1, :]                                         # above band b = last row of band b-1
+    res[1:, 1:4, :] = pay[:-1, 1].permute(0, 2, 1)
+    res[:-1, 4, :] = state[1:, 0, :]                                         # below band b = first row of band b+1
+    res[:-1, 5:8, :] = pay[1:, 0].permute(0, 2, 1)
+    return res
+
+
+# ---- one band on one device ------------------------------------------------------------------------
+class Band:
+    """Device buffers and kernel calls of one row band (rows [r0, r1) of a `grows` x `cols` raster)."""
+
+    def __init__(self, index: int, nbands: int, r0: int, r1: int, grows: int, cols: int, px: float, thr: int, n_gfi: float,
+                 b_gfi: float, device):
+        from ._lib import lib
+
+        self.lib = lib
+        self.index, self.nbands, self.r0, self.r1, self.grows, self.cols = index, nbands, r0, r1, grows, cols
+        self.rows = r1 - r0
+        self.px, self.thr, self.n_gfi, self.b_gfi = float(px), int(thr), float(n_gfi), float(b_gfi)
+        self.dev = device
+        self.first, self.last = index == 0, index == nbands - 1
+        self.int_dt = torch.int32 if grows * cols < 2**31 else torch.int64
+        rows = self.rows
+        f32, u8, i64 = torch.float32, torch.uint8, torch.int64
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)
+        self.dem_buf = torch.full((rows + 2, cols), float("nan"), dtype=f32, device=device)   # halo rows 0 and rows+1
+        self.d8_buf = torch.zeros((rows + 2, cols), dtype=u8, device=device)
+        self.slope = mk((rows, cols), f32)
+        self.acc = mk((rows, cols), self.int_dt)
+        self.fdist, self.hand, self.gfi = mk((rows, cols), f32), mk((rows, cols), f32), mk((rows, cols), f32)
+        self.idx = mk((rows, cols), self.int_dt)
+        self.ws_fa = mk((lib.dtb_flowacc_workspace_bytes(rows, cols),), u8)
+        self.ws_hand = mk((lib.dtb_hand_workspace_bytes(rows, cols),), u8)
+        self.fa_exit = torch.zeros((2, cols), dtype=i64, device=device)
+        self.fa_term = torch.full((2, cols), -2, dtype=torch.int32, device=device)
+        self.fa_inflow = torch.zeros((2, cols), dtype=i64, device=device)
+        self.hand_sum = torch.zeros((8, cols), dtype=i64, device=device)
+        self.hand_res = torch.zeros((8, cols), dtype=i64, device=device)
+
+    # views
+    @property
+    def dem(self):
+        return self.dem_buf[1:self.rows + 1]
+
+    @property
+    def d8(self):
+        return self.d8_buf[1:self.rows + 1]
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _check(self, code, what):
+        from ._lib import check
+
+        check(code, what)
+
+    # stages
+    def slope_d8(self):
+        self._check(self.lib.dtb_slope_d8(self.dem_buf.data_ptr(), 0, self.rows + 2, self.cols, 1, self.rows + 1, self.px,
+                                          self.slope.data_ptr(), self.d8.data_ptr(), self._stream()), "dtb_slope_d8")
+
+    def _fa_args(self, mode):
+        from ._lib import DTB_I32, DTB_I64, FlowaccArgs
+
+        a = FlowaccArgs()
+        a.d8, a.rows, a.cols = self.d8.data_ptr(), self.rows, self.cols
+        a.halo_above = 0 if self.first else self.d8_buf[0].data_ptr()
+        a.halo_below = 0 if self.last else self.d8_buf[self.rows + 1].data_ptr()
+        a.acc, a.acc_dtype, a.nodata_fill = self.acc.data_ptr(), DTB_I64 if self.int_dt == torch.int64 else DTB_I32, -100
+        a.mode = mode
+        return a
+
+    def flowacc_summary(self) -> torch.Tensor:
+        """int64 [6, cols]: exit_above, exit_below, term_above, term_below, d8 first row, d8 last row."""
+        from ._lib import DTB_FA_SUMMARY
+
+        a = self._fa_args(DTB_FA_SUMMARY)
+        if not self.first:
+            a.exit_above, a.term_above = self.fa_exit[0].data_ptr(), self.fa_term[0].data_ptr()
+        if not self.last:
+            a.exit_below, a.term_below = self.fa_exit[1].data_ptr(), self.fa_term[1].data_ptr()
+        self._check(self.lib.dtb_flowacc_band(ctypes.byref(a), self.ws_fa.data_ptr(), self.ws_fa.numel(), self._stream()),
+                    "dtb_flowacc_band(summary)")
+        return torch.cat([self.fa_exit, self.fa_term.to(torch.int64), self.d8[0:1].to(torch.int64),
+                          self.d8[self.rows - 1:self.rows].to(torch.int64)], 0)
+
+    def flowacc_finish(self, inflow: torch.Tensor | None):
+        """inflow int64 [2, cols] from the boundary solve; None = the band is the whole raster (one call)."""
+        from ._lib import DTB_FA_FINISH, DTB_FA_FULL
+
+        if inflow is not None:
+            self.fa_inflow.copy_(inflow)
+        a = self._fa_args(DTB_FA_FINISH if inflow is not None else DTB_FA_FULL)
+        a.inflow_above = 0 if self.first else self.fa_inflow[0].data_ptr()
+        a.inflow_below = 0 if self.last else self.fa_inflow[1].data_ptr()
+        self._check(self.lib.dtb_flowacc_band(ctypes.byref(a), self.ws_fa.data_ptr(), self.ws_fa.numel(), self._stream()),
+                    "dtb_flowacc_band(finish)")
+
+    def _hand_args(self, mode):
+        from ._lib import DTB_F32, DTB_I32, DTB_I64, HandArgs, HandBand
+
+        a, b = HandArgs(), HandBand()
+        idt = DTB_I64 if self.int_dt == torch.int64 else DTB_I32
+        a.fdr, a.acc, a.acc_dtype, a.river_threshold = self.d8.data_ptr(), self.acc.data_ptr(), idt, self.thr
+        a.dem, a.dem_dtype, a.rows, a.cols, a.px = self.dem.data_ptr(), DTB_F32, self.rows, self.cols, self.px
+        a.idx_dtype = idt
+        a.gfi_n, a.gfi_b, a.gfi_size = self.n_gfi, self.b_gfi, self.px
+        b.mode, b.row_offset = mode, self.r0
+        b.above.halo = 0 if self.first else self.d8_buf[0].data_ptr()
+        b.below.halo = 0 if self.last else self.d8_buf[self.rows + 1].data_ptr()
+        a.band = ctypes.pointer(b)
+        return a, b
+
+    def hand_summary(self) -> torch.Tensor:
+        """int64 [8, cols]: (state, idx, z-bits, acc) of the first row, then of the last row."""
+        from ._lib import DTB_HAND_SUMMARY
+
+        a, b = self._hand_args(DTB_HAND_SUMMARY)
+        s = self.hand_sum
+        if not self.first:
+            b.above.sum_state, b.above.sum_idx, b.above.sum_z, b.above.sum_acc = (s[k].data_ptr() for k in range(4))
+        if not self.last:
+            b.below.sum_state, b.below.sum_idx, b.below.sum_z, b.below.sum_acc = (s[k].data_ptr() for k in range(4, 8))
+        self._check(self.lib.dtb_hand(ctypes.byref(a), self.ws_hand.data_ptr(), self.ws_hand.numel(), self._stream()),
+                    "dtb_hand(summary)")
+        return s
+
+    def hand_finish(self, res: torch.Tensor | None):
+        """res int64 [8, cols] from the boundary solve; None = the band is the whole raster (one call)."""
+        from ._lib import DTB_HAND_FINISH, DTB_HAND_FULL
+
+        if res is not None:
+            self.hand_res.copy_(res)
+        a, b = self._hand_args(DTB_HAND_FINISH if res is not None else DTB_HAND_FULL)
+        r = self.hand_res
+        if not self.first:
+            b.above.res_state, b.above.res_idx, b.above.res_z, b.above.res_acc = (r[k].data_ptr() for k in range(4))
+        if not self.last:
+            b.below.res_state, b.below.res_idx, b.below.res_z, b.below.res_acc = (r[k].data_ptr() for k in range(4, 8))
+        a.fdist, a.idx, a.hand, a.gfi = self.fdist.data_ptr(), self.idx.data_ptr(), self.hand.data_ptr(), self.gfi.data_ptr()
+        self._check(self.lib.dtb_hand(ctypes.byref(a), self.ws_hand.data_ptr(), self.ws_hand.numel(), self._stream()),
+                    "dtb_hand(finish)")
+
+    def outputs(self) -> dict:
+        return dict(slope=self.slope, d8=self.d8, acc=self.acc, fdist=self.fdist, idx=self.idx, hand=self.hand, gfi=self.gfi)
+
+
+# ---- exchange back-ends ----------------------------------------------------------------------------
+class LocalExchange:
+    """All bands live in this process (tests; k logical bands on one GPU)."""
+
+    def __init__(self, nbands):
+        self.nbands = nbands
+
+    def halo(self, items):
+        """items[i] = (first_row, last_row, halo_above_dst, halo_below_dst) of band i"""
+        for i, (_, _, above, below) in enumerate(items):
+            if i > 0:
+                above.copy_(items[i - 1][1])
+            if i + 1 < len(items):
+                below.copy_(items[i + 1][0])
+
+    def solve(self, per_band, solver):
+        out = solver(torch.stack(per_band, 0))
+        return [out[i] for i in range(len(per_band))]
+
+
+class DistExchange:
+    """One band per rank over torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.nbands = self.world
+
+    def halo(self, items):
+        (first_row, last_row, above, below), = items
+        d, ops = self.dist, []
+        if self.rank > 0:
+            ops += [d.P2POp(d.isend, first_row, self.rank - 1, self.group), d.P2POp(d.irecv, above, self.rank - 1, self.group)]
+        if self.rank + 1 < self.world:
+            ops += [d.P2POp(d.isend, last_row, self.rank + 1, self.group), d.P2POp(d.irecv, below, self.rank + 1, self.group)]
+        if ops:
+            for w in d.batch_isend_irecv(ops):
+                w.wait()
+
+    def solve(self, per_band, solver):
+        """gather the summaries on rank 0, solve the boundary graph there, scatter the answers"""
+        (mine,), d = per_band, self.dist
+        mine = mine.contiguous()
+        gathered = [torch.empty_like(mine) for _ in range(self.world)] if self.rank == 0 else None
+        d.gather(mine, gathered, dst=0, group=self.group)
+        out = torch.empty_like(mine)
+        parts = None
+        if self.rank == 0:
+            res = solver(torch.stack(gathered, 0))
+            parts = [res[i].contiguous() for i in range(self.world)]
+            out = torch.empty_like(parts[0])
+        else:
+            out = torch.empty(self._out_shape(mine, solver), dtype=mine.dtype, device=mine.device)
+        d.scatter(out, parts, src=0, group=self.group)
+        return [out]
+
+    @staticmethod
+    def _out_shape(mine, solver):
+        return (2, mine.shape[1]) if solver is solve_flowacc_boundary else tuple(mine.shape)
+
+
+# ---- the driver --------------------------------------------------------------------------------------
+class BandRunner:
+    """Runs the chain over row bands.  `exchange=None` picks torch.distributed (one band per rank)."""
+
+    def __init__(self, rows, cols, px, river_threshold, n_gfi=0.4, b_gfi=0.1, nbands=None, exchange=None, device=None):
+        if exchange is None:
+            exchange = DistExchange() if nbands is None else LocalExchange(nbands)
+        self.x = exchange
+        self.nbands = exchange.nbands
+        self.rows, self.cols = rows, cols
+        self.edges = band_edges(rows, self.nbands)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        mine = range(self.nbands) if isinstance(exchange, LocalExchange) else [exchange.rank]
+        self.bands = [Band(i, self.nbands, self.edges[i], self.edges[i + 1], rows, cols, px, river_threshold, n_gfi, b_gfi, device)
+                      for i in mine]
+
+    def load(self, dem_rows: list[torch.Tensor]):
+        """dem_rows[k]: the DEM rows of local band k (device or host tensor)"""
+        for b, d in zip(self.bands, dem_rows):
+            b.dem.copy_(d, non_blocking=True)
+
+    def step(self, events=None):
+        """One pass of the chain; `events` (4 CUDA events) are recorded at the stage boundaries."""
+        rec = (lambda i: events[i].record()) if events is not None else (lambda i: None)
+        B = self.bands
+        rec(0)
+        self.x.halo([(b.dem_buf[1], b.dem_buf[b.rows], b.dem_buf[0], b.dem_buf[b.rows + 1]) for b in B])
+        for b in B:
+            b.slope_d8()
+        self.x.halo([(b.d8_buf[1], b.d8_buf[b.rows], b.d8_buf[0], b.d8_buf[b.rows + 1]) for b in B])
+        rec(1)
+        if self.nbands == 1:
+            B[0].flowacc_finish(None)
+        else:
+            inflow = self.x.solve([b.flowacc_summary() for b in B], solve_flowacc_boundary)
+            for b, f in zip(B, inflow):
+                b.flowacc_finish(f)
+        rec(2)
+        if self.nbands == 1:
+            B[0].hand_finish(None)
+        else:
+            res = self.x.solve([b.hand_summary() for b in B], solve_hand_boundary)
+            for b, r in zip(B, res):
+                b.hand_finish(r)
+        rec(3)
+
+    def outputs(self) -> list[dict]:
+        return [b.outputs() for b in self.bands]

@@ -207,8 +207,9 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
                 int dr, dc;
                 d8_offset(C(qr, qc), dr, dc);
                 const int64_t gr = r0 + qr + dr, gc = c0 + qc + dc;
-                if (gr < 0) my_link = LINK_OUT | (uint32_t)gc;
-                else if (gr >= v.rows) my_link = LINK_OUT | LINK_BELOW | (uint32_t)gc;
+                // leaving the band: remember the column of the band cell the path leaves through
+                if (gr < 0) my_link = LINK_OUT | (uint32_t)(c0 + qc);
+                else if (gr >= v.rows) my_link = LINK_OUT | LINK_BELOW | (uint32_t)(c0 + qc);
                 else
                     my_link = (uint32_t)(((gr / T) * v.tiles_x + gc / T) * SLOTS + slot_of((int)(gr % T), (int)(gc % T)));
             }
@@ -359,42 +360,63 @@ fa_flat_fix_kernel(TileView v, ACC *__restrict__ acc, const unsigned long long *
 }
 
 // ---- band summary (multi-GPU): the same construction one level up ------------------------------
-// For the band's first (side 0) or last (side 1) row: exit_out[c] = acc+1 of a cell that drains into the
-// halo row (else 0); term_out[c] for a cell that receives flow from the halo row = where its in-band
-// path leaves the band, encoded (side << 30) | column, or -1 if it ends inside the band.
-template <typename ACC>
+// For the band's first (side 0) or last (side 1) row:
+//   exit_out[c] = (band-local acc)+1 of a cell that drains into the halo row, else 0.  The band-local
+//                 count of such a perimeter cell is its tile count (exitw-1) plus the resolved inflow of
+//                 every entry node of its tile that ends there (scattered by fa_band_exit_scatter_kernel);
+//   term_out[c] = -2 if the cell takes no flow from that halo row, else where the in-band path that
+//                 starts there leaves the band: (side << 30) | column of the band cell it leaves through, or -1.
+__device__ __forceinline__ bool drains_across(const TileView &v, int side, int64_t r, int64_t c)
+{
+    int dr, dc;
+    if (!d8_offset(v.d8[r * v.cols + c], dr, dc)) return false;
+    if (side ? !(dr > 0 && r + 1 == v.rows) : !(dr < 0 && r == 0)) return false;
+    return fetch_code(v, r + dr, c + dc) != 0;
+}
+
 __global__ void __launch_bounds__(256)
-fa_band_summary_kernel(TileView v, int side, const ACC *__restrict__ acc, const uint32_t *__restrict__ link,
-                       const uint32_t *__restrict__ meta, int64_t *__restrict__ exit_out, int32_t *__restrict__ term_out)
+fa_band_summary_kernel(TileView v, int side, const uint32_t *__restrict__ exitw, const uint32_t *__restrict__ link,
+                       const uint32_t *__restrict__ meta, long long *__restrict__ exit_out, int32_t *__restrict__ term_out)
 {
     const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (c >= v.cols) return;
     const int64_t r = side ? v.rows - 1 : 0;
-    const unsigned code = v.d8[r * v.cols + c];
-    int dr, dc;
-    int64_t ex = 0;
-    if (d8_offset(code, dr, dc) && (side ? dr > 0 : dr < 0) && fetch_code(v, r + dr, c + dc) != 0) ex = (int64_t)acc[r * v.cols + c] + 1;
-    exit_out[c] = ex;
-    // entry?  (a cell of a 1-row band is on both sides; the node's in-mask tells which halo feeds it)
-    const int64_t node = ((r / T) * v.tiles_x + c / T) * SLOTS + slot_of((int)(r % T), (int)(c % T));
+    const int64_t node = node_of_cell(r, c, v.tiles_x);
+    exit_out[c] = drains_across(v, side, r, c) ? (long long)exitw[node] : 0ll;
     const unsigned inmask = (meta[node] >> 16) & 0xFFu;
-    const unsigned from_side = side ? 0xE0u : 0x07u;
-    int32_t t = -1;
-    bool fed = false;
-    if (inmask & from_side) {
-        // only tributaries that really sit in the halo row count (tile-edge rows inside the band do not)
-        fed = side ? (r + 1 == v.rows) : (r == 0);
-    }
+    const bool fed = (inmask & (side ? 0xE0u : 0x07u)) != 0;  // tributaries in the halo row (band seams are tile seams)
+    int32_t t = -2;
     if (fed) {
+        t = -1;
         uint32_t q = (uint32_t)node;
-        for (int64_t hops = 0; hops < (int64_t)1 << 40; ++hops) {
+        for (;;) {
             const uint32_t l = link[q];
             if (l == LINK_NONE) break;
             if (l & LINK_OUT) { t = (int32_t)(((l & LINK_BELOW) ? 1u << 30 : 0u) | (l & 0x3FFFFFFFu)); break; }
             q = l;
         }
     }
-    term_out[c] = fed ? t : -2;  // -2: not an entry from this side
+    term_out[c] = t;
+}
+
+// one thread per node of the band's first / last tile row
+__global__ void __launch_bounds__(256)
+fa_band_exit_scatter_kernel(TileView v, int side, int64_t tile0, const uint32_t *__restrict__ meta,
+                            const unsigned long long *__restrict__ nstate, long long *__restrict__ exit_out)
+{
+    const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k >= (int64_t)v.tiles_x * SLOTS) return;
+    const int64_t node = tile0 * SLOTS + k;
+    const uint32_t m = meta[node];
+    if (!((m >> 16) & 0xFFu)) return;           // not an entry node
+    const unsigned ts = m & 0xFFu;
+    if (ts == TERM_NONE) return;
+    int lr, lc;
+    slot_cell((int)ts, lr, lc);
+    const int64_t tile = node / SLOTS;
+    const int64_t r = (tile / v.tiles_x) * T + lr, c = (tile % v.tiles_x) * T + lc;
+    if (r != (side ? v.rows - 1 : 0) || !drains_across(v, side, r, c)) return;
+    atomicAdd(reinterpret_cast<unsigned long long *>(&exit_out[c]), (unsigned long long)(nstate[node] & N_CNT));
 }
 
 struct NodeLayout {
@@ -435,7 +457,7 @@ int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
     ACC *acc = reinterpret_cast<ACC *>(a->acc);
     const unsigned nb_nodes = (unsigned)((L.nnodes + 255) / 256);
 
-    if (!a->reuse_summary) {
+    if (a->mode != DTB_FA_FINISH) {
         DTB_CUDA(cudaMemsetAsync(counters, 0, 256, st));
         fa_tile_kernel<false, ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, exitw, link, meta, nullptr, nullptr, (ACC)0, counters);
         DTB_LAUNCH_CHECK("fa_tile_kernel<summary>");
@@ -445,6 +467,23 @@ int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
     DTB_LAUNCH_CHECK("fa_node_init_kernel");
     fa_node_sweep_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, link, nstate);
     DTB_LAUNCH_CHECK("fa_node_sweep_kernel");
+
+    if (a->mode == DTB_FA_SUMMARY) {
+        const unsigned nbc = (unsigned)((a->cols + 255) / 256);
+        const unsigned nbs = (unsigned)(((int64_t)v.tiles_x * SLOTS + 255) / 256);
+        const int64_t tiles_y = (a->rows + T - 1) / T;
+        for (int side = 0; side < 2; ++side) {
+            long long *ex = reinterpret_cast<long long *>(side ? a->exit_below : a->exit_above);
+            int32_t *tm = side ? a->term_below : a->term_above;
+            if (!ex || !tm) continue;
+            fa_band_summary_kernel<<<nbc, 256, 0, st>>>(v, side, exitw, link, meta, ex, tm);
+            DTB_LAUNCH_CHECK("fa_band_summary_kernel");
+            fa_band_exit_scatter_kernel<<<nbs, 256, 0, st>>>(v, side, side ? (tiles_y - 1) * v.tiles_x : 0, meta, nstate, ex);
+            DTB_LAUNCH_CHECK("fa_band_exit_scatter_kernel");
+        }
+        return DTB_OK;
+    }
+
     fa_tile_kernel<true, ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, nullptr, nullptr, nullptr, nstate, acc,
                                                                         (ACC)a->nodata_fill, counters);
     DTB_LAUNCH_CHECK("fa_tile_kernel<final>");
@@ -455,18 +494,6 @@ int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
     DTB_LAUNCH_CHECK("fa_flat_sweep_kernel");
     fa_flat_fix_kernel<ACC><<<FLAT_BLOCKS, 256, 0, st>>>(v, acc, flat, counters);
     DTB_LAUNCH_CHECK("fa_flat_fix_kernel");
-
-    if (a->exit_above || a->exit_below) {
-        const unsigned nbc = (unsigned)((a->cols + 255) / 256);
-        if (a->exit_above && a->term_above) {
-            fa_band_summary_kernel<ACC><<<nbc, 256, 0, st>>>(v, 0, acc, link, meta, a->exit_above, a->term_above);
-            DTB_LAUNCH_CHECK("fa_band_summary_kernel<above>");
-        }
-        if (a->exit_below && a->term_below) {
-            fa_band_summary_kernel<ACC><<<nbc, 256, 0, st>>>(v, 1, acc, link, meta, a->exit_below, a->term_below);
-            DTB_LAUNCH_CHECK("fa_band_summary_kernel<below>");
-        }
-    }
     if (a->unfinalised_host) {
         unsigned long long h[3];
         DTB_CUDA(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -488,7 +515,9 @@ extern "C" size_t dtb_flowacc_workspace_bytes(int64_t rows, int64_t cols)
 extern "C" int dtb_flowacc_band(const dtb_flowacc_args *a, void *ws, size_t ws_bytes, void *stream)
 {
     using namespace dtb;
-    if (!a || !a->d8 || !a->acc || !ws || a->rows <= 0 || a->cols <= 0) return DTB_ERR_INVALID;
+    if (!a || !a->d8 || !ws || a->rows <= 0 || a->cols <= 0) return DTB_ERR_INVALID;
+    if (a->mode < DTB_FA_FULL || a->mode > DTB_FA_FINISH) return DTB_ERR_INVALID;
+    if (a->mode != DTB_FA_SUMMARY && !a->acc) return DTB_ERR_INVALID;
     if (a->acc_dtype != DTB_I32 && a->acc_dtype != DTB_I64) return DTB_ERR_INVALID;
     if (ws_bytes < dtb_flowacc_workspace_bytes(a->rows, a->cols)) return DTB_ERR_WORKSPACE;
     if (a->cols >= (int64_t)1 << 30) return DTB_ERR_UNSUPPORTED;

@@ -215,6 +215,12 @@ struct HandOut {
     double px, pd;
     uint32_t max_moves;
     double gfi_logb, gfi_n, gfi_s2;
+    // row bands: global index offset and the resolved paths behind the halo rows (side 0 above, 1 below)
+    int64_t idx_offset;
+    const unsigned long long *res_state[2];
+    const int64_t *res_idx[2];
+    const double *res_z[2];
+    const int64_t *res_acc[2];
 };
 
 // four consecutive cells of one row, as one vector store when the row is 16-byte tileable
@@ -255,6 +261,7 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
     __shared__ uint16_t rivm[H_THREADS];
     __shared__ unsigned long long st[TCELLS];
     __shared__ unsigned long long exit_state[SLOTS];
+    __shared__ uint8_t exit_remote[SLOTS];  // 0: resolved inside the band, 1/2: by the band above/below
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
     const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
@@ -316,6 +323,7 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
         slot_cell(tid, plr, plc);
         const unsigned code = C(plr, plc);
         uint64_t e = pack(KIND_FAIL, 0, 0, 0);
+        unsigned remote = 0;
         int dr, dc;
         if (d8_offset(code, dr, dc)) {
             const int tr = plr + dr, tc = plc + dc;
@@ -323,14 +331,28 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
                 const int64_t gr = r0 + tr, gc = c0 + tc;
                 const bool diag = d8_is_diag(code);
                 const uint64_t mv = pack(KIND_ACTIVE, diag ? 1u : 0u, diag ? 0u : 1u, 0);
-                if (gr >= 0 && gr < v.rows) {
-                    const uint64_t ns = nstate[node_of_cell(gr, gc, v.tiles_x)];
+                uint64_t ns = pack(KIND_FAIL, 0, 0, 0);
+                if (gr >= 0 && gr < v.rows) ns = nstate[node_of_cell(gr, gc, v.tiles_x)];
+                if (kind_of(ns) == KIND_EXIT || gr < 0 || gr >= v.rows) {
+                    // the path leaves the band (now, or further down inside the band): continue with the
+                    // resolved path of the halo cell it lands on
+                    int side;
+                    int64_t col;
+                    uint64_t pre = mv;
+                    if (gr < 0 || gr >= v.rows) { side = gr < 0 ? 0 : 1; col = gc; }
+                    else { side = (ptr_of(ns) & LINK_BELOW) ? 1 : 0; col = ptr_of(ns) & 0x3FFFFFFFu; pre = compose(mv, ns); }
+                    ns = o.res_state[side] ? o.res_state[side][col] : pack(KIND_FAIL, 0, 0, 0);
+                    ns = (ns & ~0xFFFFFFFFull) | (uint64_t)(uint32_t)col;
+                    e = compose(pack(KIND_ACTIVE, nd_of(pre), nc_of(pre), 0), ns);
+                    remote = 1u + (unsigned)side;
+                } else {
                     e = compose(mv, ns);
-                    if (kind_of(e) != KIND_RIVER) e = pack(KIND_FAIL, 0, 0, 0);  // ACTIVE left over: cycle or > cap
                 }
+                if (kind_of(e) != KIND_RIVER) { e = pack(KIND_FAIL, 0, 0, 0); remote = 0; }  // ACTIVE left over: cycle or > cap
             }
         }
         exit_state[tid] = e;
+        exit_remote[tid] = (uint8_t)remote;
     }
     __syncthreads();
 
@@ -351,22 +373,35 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             uint64_t s = st[lr * T + lcb + g4 + i];
+            unsigned remote = 0;
             if (kind_of(s) == KIND_EXIT) {
                 const uint32_t x = ptr_of(s);
-                s = compose(s, exit_state[slot_of((int)(x / T), (int)(x % T))]);
+                const int slot = slot_of((int)(x / T), (int)(x % T));
+                s = compose(s, exit_state[slot]);
+                remote = exit_remote[slot];
             }
             const uint32_t nc = nc_of(s), nd = nd_of(s);
             const bool ok = kind_of(s) == KIND_RIVER && nc + nd <= o.max_moves;  // flowhand.py:835
-            const int64_t idx = ok ? (int64_t)ptr_of(s) : (int64_t)ND_I;
+            // river cell: a local index into this band, or (remote) a column of the halo row's tables
+            const int64_t loc = (int64_t)ptr_of(s);
+            int64_t idx = (int64_t)ND_I;
+            if (ok) idx = remote ? o.res_idx[remote - 1][loc] : loc + o.idx_offset;
             fd[i] = ok ? (float)((double)nc * o.px + (double)nd * o.pd) : ND_F;  // flowhand.py:840-843
             ix[i] = (IDX)idx;
             TD h = HandOps<TD>::nd();
             float g = ND_F;
             if (o.hand || o.gfi) {
-                h = hand_value<TD>(z[i], ok, dem, idx);
+                // flowhand.py:436-438
+                if (!HandOps<TD>::is_nd(z[i]) && ok) {
+                    const TD zr = remote ? (TD)o.res_z[remote - 1][loc] : dem[loc];
+                    h = HandOps<TD>::sub(z[i], zr);
+                }
+                if (h < (TD)0 && h != HandOps<TD>::nd()) h = (TD)0;
                 if (o.gfi && !(h <= HandOps<TD>::nd())) {
                     // river_accumulation: idx == -100 -> fac.flat[0] (gfi.py:141-143); H is -100 then anyway
-                    const double racc = (double)acc[ok ? idx : 0];
+                    double racc;
+                    if (!ok) racc = o.idx_offset == 0 ? (double)acc[0] : 1.0;
+                    else racc = remote ? (double)o.res_acc[remote - 1][loc] : (double)acc[loc];
                     g = (float)(o.gfi_logb + o.gfi_n * log(racc * o.gfi_s2) - log((double)h + 0.01));  // gfi.py:292-294
                 }
             }
@@ -378,6 +413,39 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
         if (o.hand) store4<TD>(reinterpret_cast<TD *>(o.hand) + obase, hd, vec, c_first, v.cols);
         if (o.gfi) store4<float>(o.gfi + obase, gf, vec, c_first, v.cols);
     }
+}
+
+// ---- band summary: the path that starts at each boundary-row cell fed by the halo row ----
+template <typename TD, typename ACC>
+__global__ void __launch_bounds__(H_THREADS)
+hand_band_summary_kernel(TileView v, int side, const unsigned long long *__restrict__ nstate, const TD *__restrict__ dem,
+                         const ACC *__restrict__ acc, int64_t idx_offset, unsigned long long *__restrict__ sum_state,
+                         int64_t *__restrict__ sum_idx, double *__restrict__ sum_z, int64_t *__restrict__ sum_acc)
+{
+    const int64_t c = (int64_t)blockIdx.x * H_THREADS + threadIdx.x;
+    if (c >= v.cols) return;
+    const int64_t r = side ? v.rows - 1 : 0, hr = side ? v.rows : -1;
+    uint64_t s = 0ull;
+    int64_t gi = ND_I, ga = 0;
+    double gz = 0.0;
+    if (v.d8[r * v.cols + c] != 0) {
+        const bool fed = side ? (fetch_code(v, hr, c - 1) == 128u || fetch_code(v, hr, c) == 64u || fetch_code(v, hr, c + 1) == 32u)
+                              : (fetch_code(v, hr, c - 1) == 2u || fetch_code(v, hr, c) == 4u || fetch_code(v, hr, c + 1) == 8u);
+        if (fed) {
+            s = nstate[node_of_cell(r, c, v.tiles_x)];
+            if (kind_of(s) == KIND_ACTIVE) s = pack(KIND_FAIL, 0, 0, 0);  // unresolved inside the band: cycle / cap
+            if (kind_of(s) == KIND_RIVER) {
+                const int64_t p = (int64_t)ptr_of(s);
+                gi = p + idx_offset;
+                if (dem) gz = (double)dem[p];
+                if (acc) ga = (int64_t)acc[p];
+            }
+        }
+    }
+    sum_state[c] = s;
+    sum_idx[c] = gi;
+    sum_z[c] = gz;
+    sum_acc[c] = ga;
 }
 
 template <typename T, typename IDX>
@@ -413,6 +481,18 @@ int run_tiles(const dtb_hand_args *a, const TileView &v, const RiverSrc &rs, con
     o.gfi_logb = log(a->gfi_b);
     o.gfi_n = a->gfi_n;
     o.gfi_s2 = a->gfi_size * a->gfi_size;
+    o.idx_offset = 0;
+    for (int k = 0; k < 2; ++k) { o.res_state[k] = nullptr; o.res_idx[k] = nullptr; o.res_z[k] = nullptr; o.res_acc[k] = nullptr; }
+    if (a->band) {
+        o.idx_offset = a->band->row_offset * a->cols;
+        const dtb_hand_seam *sm[2] = {&a->band->above, &a->band->below};
+        for (int k = 0; k < 2; ++k) {
+            o.res_state[k] = reinterpret_cast<const unsigned long long *>(sm[k]->res_state);
+            o.res_idx[k] = sm[k]->res_idx;
+            o.res_z[k] = sm[k]->res_z;
+            o.res_acc[k] = sm[k]->res_acc;
+        }
+    }
     hand_tile_kernel<TD, IDX, ACC><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, (const TD *)a->dem, (const ACC *)a->acc, nstate, o);
     DTB_LAUNCH_CHECK("hand_tile_kernel");
     return DTB_OK;
@@ -461,20 +541,46 @@ extern "C" int dtb_hand(const dtb_hand_args *a, void *ws, size_t ws_bytes, void 
     cudaStream_t st = as_stream(stream);
     unsigned *active = reinterpret_cast<unsigned *>(ws);
     unsigned long long *nstate = reinterpret_cast<unsigned long long *>((char *)ws + 256);
-    TileView v{a->fdr, nullptr, nullptr, a->rows, a->cols, (int)((a->cols + T - 1) / T)};
+    const dtb_hand_band *band = a->band;
+    const int mode = band ? band->mode : DTB_HAND_FULL;
+    if (mode < DTB_HAND_FULL || mode > DTB_HAND_FINISH) return DTB_ERR_INVALID;
+    if (band && band->below.halo && a->rows % T != 0) return DTB_ERR_INVALID;  // band seams sit on tile seams
+    TileView v{a->fdr, band ? band->above.halo : nullptr, band ? band->below.halo : nullptr, a->rows, a->cols,
+               (int)((a->cols + T - 1) / T)};
     const int64_t tiles = (int64_t)v.tiles_x * ((a->rows + T - 1) / T);
     const int64_t nnodes = tiles * SLOTS;
     if (nnodes >= (int64_t)1 << 30) return DTB_ERR_UNSUPPORTED;
     RiverSrc rs{a->river, a->acc, a->river_threshold};
 
-    DTB_CUDA(cudaMemsetAsync(active, 0, 256, st));
-    if (a->acc_dtype == DTB_I64) hand_entry_kernel<int64_t><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, nstate, active);
-    else hand_entry_kernel<int32_t><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, nstate, active);
-    DTB_LAUNCH_CHECK("hand_entry_kernel");
-    const int rounds = rounds_for(max_moves);
-    for (int r = 1; r <= rounds; ++r) {
-        hand_node_jump_kernel<<<JUMP_BLOCKS, H_THREADS, 0, st>>>(nnodes, nstate, active, r, 2);
-        DTB_LAUNCH_CHECK("hand_node_jump_kernel");
+    if (mode != DTB_HAND_FINISH) {
+        DTB_CUDA(cudaMemsetAsync(active, 0, 256, st));
+        if (a->acc_dtype == DTB_I64) hand_entry_kernel<int64_t><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, nstate, active);
+        else hand_entry_kernel<int32_t><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, nstate, active);
+        DTB_LAUNCH_CHECK("hand_entry_kernel");
+        const int rounds = rounds_for(max_moves);
+        for (int r = 1; r <= rounds; ++r) {
+            hand_node_jump_kernel<<<JUMP_BLOCKS, H_THREADS, 0, st>>>(nnodes, nstate, active, r, 2);
+            DTB_LAUNCH_CHECK("hand_node_jump_kernel");
+        }
+    }
+    if (mode == DTB_HAND_SUMMARY) {
+        const unsigned nbc = (unsigned)((a->cols + H_THREADS - 1) / H_THREADS);
+        const int64_t off = band->row_offset * a->cols;
+        const dtb_hand_seam *sm[2] = {&band->above, &band->below};
+        for (int side = 0; side < 2; ++side) {
+            const dtb_hand_seam *q = sm[side];
+            if (!q->sum_state) continue;
+            if (!q->sum_idx || !q->sum_z || !q->sum_acc) return DTB_ERR_INVALID;
+            unsigned long long *ss = reinterpret_cast<unsigned long long *>(q->sum_state);
+#define DTB_SUMMARY(TD, ACC)                                                                                            \
+    hand_band_summary_kernel<TD, ACC><<<nbc, H_THREADS, 0, st>>>(v, side, nstate, (const TD *)a->dem, (const ACC *)a->acc, off, \
+                                                                 ss, q->sum_idx, q->sum_z, q->sum_acc)
+            if (a->dem_dtype == DTB_I16) { if (a->acc_dtype == DTB_I64) DTB_SUMMARY(int16_t, int64_t); else DTB_SUMMARY(int16_t, int32_t); }
+            else { if (a->acc_dtype == DTB_I64) DTB_SUMMARY(float, int64_t); else DTB_SUMMARY(float, int32_t); }
+#undef DTB_SUMMARY
+            DTB_LAUNCH_CHECK("hand_band_summary_kernel");
+        }
+        return DTB_OK;
     }
     if (!a->fdist && !a->idx && !a->hand && !a->gfi) return DTB_OK;
     return a->dem_dtype == DTB_I16 ? run_tiles_idx<int16_t>(a, v, rs, nstate, tiles, (uint32_t)max_moves, st)

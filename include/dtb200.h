@@ -86,15 +86,21 @@ int dtb_flowacc(const uint8_t *d8, int64_t rows, int64_t cols, void *acc, int ac
  * halo_above / halo_below are the code rows adjacent to the band (NULL at the raster
  * edge); inflow_above / inflow_below give, per column of those halo rows, acc+1 of the
  * halo cell (NULL = 0; only cells that point into the band are read).  A band that has
- * a halo_below must have rows % 64 == 0.  If exit_X and term_X are given they receive the
- * band's boundary summary for its first (above) / last (below) row:
- *   exit_X[c] = acc[c]+1 if the cell drains into the halo row, else 0;
- *   term_X[c] = -2 if the cell takes no flow from that halo row, else where the in-band
- *               path that starts there leaves the band: (side << 30) | column of the halo
- *               cell it lands on (side 0 = above, 1 = below), or -1 if it ends in the band.
- * The band driver (descriptools_b200/bands.py) calls this once with zero inflow, solves
- * the boundary graph, and calls it again with reuse_summary = 1 and the resolved inflow
- * (same workspace, untouched in between). */
+ * a halo_below must have rows % 64 == 0 (band seams sit on tile seams).
+ *   mode DTB_FA_FULL    : whole computation in one call (what dtb_flowacc does).
+ *   mode DTB_FA_SUMMARY : tile pass + node sweep with zero inflow, then the band's boundary
+ *       summary for its first (above) / last (below) row:
+ *         exit_X[c] = band-local acc[c]+1 if the cell drains into the halo row, else 0;
+ *         term_X[c] = -2 if the cell takes no flow from that halo row, else where the in-band
+ *                     path that starts there leaves the band: (side << 30) | column of the band's
+ *                     own first/last-row cell it leaves through (side 0 = above, 1 = below), or -1
+ *                     if it ends in the band.
+ *       acc is not written.
+ *   mode DTB_FA_FINISH  : node sweep with the resolved inflow + final tile pass writing acc;
+ *       reuses the tile summaries the SUMMARY call left in the same, untouched workspace.
+ * The band driver (descriptools_b200/bands.py) solves the boundary graph between the two calls.
+ * Cross-band D8 cycles are not detected (dtb_slope_d8 never produces cycles). */
+enum { DTB_FA_FULL = 0, DTB_FA_SUMMARY = 1, DTB_FA_FINISH = 2 };
 typedef struct dtb_flowacc_args {
     const uint8_t *d8;
     int64_t rows, cols;
@@ -105,7 +111,7 @@ typedef struct dtb_flowacc_args {
     int64_t nodata_fill;
     int64_t *exit_above, *exit_below;
     int32_t *term_above, *term_below;
-    int reuse_summary;
+    int mode;
     int64_t *unfinalised_host;
 } dtb_flowacc_args;
 int dtb_flowacc_band(const dtb_flowacc_args *args, void *ws, size_t ws_bytes, void *stream);
@@ -137,7 +143,38 @@ typedef struct dtb_hand_args {
     void *hand;
     float *gfi;
     double gfi_n, gfi_b, gfi_size;
+    const struct dtb_hand_band *band; /* NULL: the buffers hold the whole raster */
 } dtb_hand_args;
+
+/* Row-band form (multi-GPU).  One dtb_hand_seam per side of the band.
+ *   mode DTB_HAND_SUMMARY: entry walks + node jumping inside the band, then per column of the band's
+ *     first / last row the state of the path that starts there, for cells that take flow from the
+ *     halo row (sum_state = 0 otherwise): packed [63..62 kind | 61..47 n_diag | 46..32 n_card | 31..0 ptr]
+ *     with kind 1 = reaches a river cell in the band (sum_idx = its GLOBAL cell index, sum_z its
+ *     elevation, sum_acc its accumulation), 2 = fails, 3 = leaves the band again
+ *     (ptr = (side << 30) | column of the halo cell it lands on).  No rasters are written.
+ *   mode DTB_HAND_FINISH: the tile pass + epilogue; a path that leaves the band continues with
+ *     res_*[column]: the resolved path that starts AT that halo cell (kind 1 or 2, move counts,
+ *     global river index, river elevation and accumulation), as solved by the band driver.
+ *     Reuses the node states the SUMMARY call left in the same, untouched workspace.
+ * idx outputs are global: row_offset * cols + local index.  rows % 64 == 0 if below.halo != NULL. */
+enum { DTB_HAND_FULL = 0, DTB_HAND_SUMMARY = 1, DTB_HAND_FINISH = 2 };
+typedef struct dtb_hand_seam {
+    const uint8_t *halo;
+    uint64_t *sum_state;
+    int64_t *sum_idx;
+    double *sum_z;
+    int64_t *sum_acc;
+    const uint64_t *res_state;
+    const int64_t *res_idx;
+    const double *res_z;
+    const int64_t *res_acc;
+} dtb_hand_seam;
+typedef struct dtb_hand_band {
+    int mode;
+    int64_t row_offset;
+    dtb_hand_seam above, below;
+} dtb_hand_band;
 
 size_t dtb_hand_workspace_bytes(int64_t rows, int64_t cols);
 int dtb_hand(const dtb_hand_args *args, void *ws, size_t ws_bytes, void *stream);

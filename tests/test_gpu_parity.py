@@ -356,3 +356,59 @@ def test_pipeline_properties_large():
     s_ref, d_ref = oracle.slope_d8(dem[:300].cpu().numpy(), PX, 0, 299)
     np.testing.assert_array_equal(res["slope"][:299].cpu().numpy(), s_ref)
     np.testing.assert_array_equal(d8[:299].cpu().numpy(), d_ref)
+
+
+# ---- row bands (multi-GPU decomposition, k logical bands on one GPU) ------------------------------
+def weaving_dem(rows, cols, seam, amp=20.0, period=90.0):
+    """a valley that weaves across row `seam` many times: every HAND / accumulation path re-enters bands"""
+    r = np.arange(rows, dtype=np.float64)[:, None]
+    c = np.arange(cols, dtype=np.float64)[None, :]
+    centre = seam + amp * np.sin(2 * np.pi * c / period)
+    z = 50.0 + 0.35 * np.abs(r - centre) + 0.05 * (cols - c) + 0.001 * ((r * 7 + c * 13) % 11)
+    return oracle.priority_flood_eps(z.astype(np.float32))
+
+
+def _run_bands(dem, k, thr):
+    from descriptools_b200 import bands
+
+    rows, cols = dem.shape
+    runner = bands.BandRunner(rows, cols, PX, thr, 0.4, 0.1, nbands=k)
+    runner.load([torch.from_numpy(dem[a:b]) for a, b in zip(runner.edges, runner.edges[1:])])
+    runner.step()
+    torch.cuda.synchronize()
+    outs = runner.outputs()
+    return {name: torch.cat([o[name] for o in outs], 0).cpu().numpy() for name in outs[0]}
+
+
+@pytest.mark.parametrize("shape,k,thr", [((512, 320), 2, 200), ((768, 400), 3, 300), ((1024, 272), 4, 150), ((200, 130), 1, 50)])
+def test_bands_equal_single_gpu(shape, k, thr):
+    """k row bands + boundary-graph solve == the single-raster run, bit for bit (all seven rasters)."""
+    from descriptools_b200 import pipeline
+
+    dem = synth(*shape, seed=shape[1])
+    ref = pipeline.run_device(torch.from_numpy(dem).cuda(), PX, thr)
+    got = _run_bands(dem, k, thr)
+    for name in ("slope", "d8", "acc", "idx", "fdist", "hand", "gfi"):
+        np.testing.assert_array_equal(got[name], ref[name].cpu().numpy(), err_msg=name)
+
+
+def test_bands_weaving_valley_vs_oracle():
+    """paths that cross the seam many times (river running along a band edge): bands == oracle."""
+    rows, cols, thr = 256, 720, 400
+    dem = weaving_dem(rows, cols, seam=128)
+    got = _run_bands(dem, 2, thr)
+    slope, d8 = oracle.slope_d8(dem, PX)
+    acc, left = oracle.flow_accumulation(d8)
+    assert left == 0
+    river = (acc > thr).astype(np.int8)
+    assert river.sum() > 100
+    fdist, idx, hand = oracle.flow_hand_index(dem, d8, river, PX)
+    # the valley (and with it many paths) really crosses the seam repeatedly
+    on_seam = river[127:129].sum(axis=0)
+    assert (np.diff((river[:128].sum(axis=0) > 0).astype(int)) != 0).sum() >= 6 and on_seam.sum() > 0
+    np.testing.assert_array_equal(got["d8"], d8)
+    np.testing.assert_array_equal(got["acc"], acc)
+    np.testing.assert_array_equal(got["idx"], idx)
+    np.testing.assert_array_equal(got["hand"], hand)
+    np.testing.assert_allclose(got["fdist"], fdist, rtol=RTOL, atol=0)
+    np.testing.assert_allclose(got["gfi"], oracle.gfi(hand, acc, idx, 0.4, 0.1, PX), rtol=RTOL, atol=ATOL)
