@@ -177,10 +177,27 @@ def run_ours(args):
         from descriptools_b200 import bands
 
         runner = bands.BandRunner(rows, cols, PX, RIVER_THR, N_GFI, B_GFI)
-        runner.load_synthetic()  # rank 0 conditions the DEM, bands are scattered over NCCL (untimed)
+        band = runner.bands[0]
+        # rank 0 generates and depression-fills the whole DEM (untimed), bands travel over NCCL
+        if rank == 0:
+            full = device.conditioned_dem(rows, cols)
+            for i in range(1, world):
+                dist.send(full[runner.edges[i]:runner.edges[i + 1]].contiguous(), dst=i)
+            band.dem.copy_(full[runner.edges[0]:runner.edges[1]])
+            del full
+            device.workspace.release()
+            torch.cuda.empty_cache()
+        else:
+            tmp = torch.empty((band.rows, cols), dtype=torch.float32, device="cuda")
+            dist.recv(tmp, src=0)
+            band.dem.copy_(tmp)
+            del tmp
+        torch.cuda.synchronize()
 
         def step(timed):
-            return runner.step_events(), None
+            e = [ev() for _ in range(4)]
+            runner.step(e)
+            return e, None
 
     for _ in range(args.warmup):
         step(False)
@@ -236,7 +253,39 @@ def run_ours(args):
         except Exception as ex:  # host RAM too small for the pinned staging buffers
             e2e = {"value": None, "unit": "Mcells/s", "error": repr(ex)[:200]}
     elif runner is not None:
-        e2e = runner.e2e(max(1, min(args.steps, 2)))
+        # every rank: pinned band DEM in, its seven band rasters out; wall clock between barriers, max over ranks
+        try:
+            band = runner.bands[0]
+            outs = band.outputs()
+            dem_host = torch.empty((band.rows, cols), dtype=torch.float32, pin_memory=True)
+            dem_host.copy_(band.dem)
+            pinned = {k: torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True) for k, t in outs.items()}
+
+            def host_step():
+                band.dem.copy_(dem_host, non_blocking=True)
+                runner.step()
+                for k, t in band.outputs().items():
+                    pinned[k].copy_(t, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+            host_step()
+            barrier()
+            k_e2e = max(1, min(args.steps, 2))
+            t0 = time.perf_counter()
+            for _ in range(k_e2e):
+                host_step()
+            barrier()
+            dt = torch.tensor([(time.perf_counter() - t0) / k_e2e], device="cuda", dtype=torch.float64)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dt = float(dt[0])
+            d2h = sum(t.numel() * t.element_size() for t in outs.values())
+            tot = torch.tensor([band.rows * cols * 4, d2h], device="cuda", dtype=torch.int64)
+            dist.all_reduce(tot)
+            e2e = {"value": n_cells / dt / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": int(tot[0]),
+                   "d2h_bytes_per_step": int(tot[1]), "steps": k_e2e, "ms_per_step": dt * 1e3}
+            del pinned, dem_host
+        except Exception as ex:
+            e2e = {"value": None, "unit": "Mcells/s", "error": repr(ex)[:200]}
 
     if rank != 0:
         if world > 1:
