@@ -53,4 +53,35 @@ __host__ __device__ __forceinline__ bool d8_offset(unsigned code, int &dr, int &
 
 __host__ __device__ __forceinline__ bool d8_is_diag(unsigned code) { return (code & 0xAAu) != 0u; }
 
+#ifdef __CUDACC__
+// Natural logarithm in f64 with |error| < 1e-12 (absolute, on results up to ~700) in ~25 instructions:
+// x = 2^e * m, m in [sqrt(1/2), sqrt(2)); s = (m-1)/(m+1); ln m = 2 atanh(s) = 2s + s z P(z), z = s^2
+// (series through s^13, |s| <= 0.1716 -> truncation 4e-13); the quotient uses rcp.approx + two Newton steps.
+// Used where the result is rounded to f32 afterwards (GFI: gfi.py:292-294).  Non-positive, subnormal,
+// infinite and NaN arguments take libdevice's log().
+__device__ __forceinline__ double fast_log(double x)
+{
+    const int hi = __double2hiint(x);
+    if (hi < 0x00100000 || hi >= 0x7FF00000) return log(x);
+    int e = (hi >> 20) - 1023;
+    int mhi = (hi & 0x000FFFFF) | 0x3FF00000;  // mantissa in [1, 2)
+    if (mhi >= 0x3FF6A09F) { mhi -= 0x00100000; ++e; }  // >= sqrt(2): halve
+    const double m = __hiloint2double(mhi, __double2loint(x));
+    const double f = m - 1.0, d = m + 1.0;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = r * (2.0 - d * r);
+    r = r * (2.0 - d * r);
+    const double s = f * r, z = s * s;
+    double p = 2.0 / 13.0;
+    p = fma(p, z, 2.0 / 11.0);
+    p = fma(p, z, 2.0 / 9.0);
+    p = fma(p, z, 2.0 / 7.0);
+    p = fma(p, z, 2.0 / 5.0);
+    p = fma(p, z, 2.0 / 3.0);
+    const double lm = fma(s * z, p, 2.0 * s);
+    return fma((double)e, 0.693147180559945309417232, lm);
+}
+#endif
+
 }  // namespace dtb

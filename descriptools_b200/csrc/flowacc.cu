@@ -25,6 +25,8 @@
 // D8 cycles (possible only in caller-supplied grids, never in dtb_slope_d8 output) are detected
 // on the device (a tile or node that cannot be finalised) and handled by the single-level sweep
 // fa_flat_* over the whole raster, which reproduces the oracle's Kahn-order partial counts.
+#include <type_traits>
+
 #include "tiles.cuh"
 
 namespace dtb {
@@ -35,21 +37,19 @@ constexpr uint64_t N_SRC = 1ull << 63, N_ACTIVE = 1ull << 62, N_PEND_ONE = 1ull 
 constexpr uint64_t N_CNT = N_PEND_ONE - 1ull, N_PEND = 0x3FFFull;
 constexpr int N_PEND_SHIFT = 48;
 
-// ---- T1 / T2: the tile kernel -------------------------------------------------------------
-// SEEDED = false: local counts only, writes the perimeter summary (exitw, link, meta).
-// SEEDED = true : entry cells start from their resolved inflow (nstate), writes acc.
-// Shared-memory cell word, !SEEDED: [31..28 pending | 27..0 count].
-//                          SEEDED: lo = count bits 31..0; hi = [31..28 pending | 27..0 count bits 59..32].
-template <bool SEEDED, typename ACC>
+// ---- T1: tile-local accumulation + perimeter summary ---------------------------------------------
+// Shared word per cell: [31..28 pending | 27..14 local count | 13..0 successor slot] -- one atomicAdd per
+// step both accumulates and returns the successor of the cell just finalised.
+constexpr uint32_t W_EXIT = 0x3FFEu, W_TERM = 0x3FFFu, W_NXT = 0x3FFFu, W_PEND_ONE = 1u << 28;
+constexpr int W_CNT_SHIFT = 14;
+
+template <typename ACC>
 __global__ void __launch_bounds__(FT_THREADS)
 fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ link, uint32_t *__restrict__ meta,
-               const unsigned long long *__restrict__ nstate, ACC *__restrict__ acc, ACC nodata_fill,
-               unsigned long long *__restrict__ counters)
+               ACC *__restrict__ acc, ACC nodata_fill, unsigned long long *__restrict__ counters)
 {
     __shared__ __align__(16) uint8_t codes[(T + 2) * CP + 16];  // col T of the last row sits at (T+2)*CP
-    __shared__ uint16_t nxt[TCELLS];
-    __shared__ uint32_t lo[TCELLS];
-    __shared__ uint32_t hi[SEEDED ? TCELLS : 1];
+    __shared__ uint32_t word[TCELLS];
     __shared__ uint32_t nterm_s[SLOTS];
     __shared__ uint8_t inmask_s[SLOTS];
     __shared__ unsigned cyc_s;
@@ -58,9 +58,6 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
     const int tile = blockIdx.x;
     const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
     const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
-    auto C = [&](int lr, int lc) -> unsigned { return codes[(lr + 1) * CP + 16 + lc]; };
-
-    // ---- stage the codes: 64 rows x 64 B as one 16-byte load per thread, halo ring by bytes ----
     const bool fast = stage_codes(v, r0, c0, codes, tid, FT_THREADS);
     if (tid < SLOTS) { nterm_s[tid] = 0; inmask_s[tid] = 0; }
     if (tid == 0) cyc_s = 0;
@@ -69,51 +66,31 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
     // ---- per-cell set-up: successor, in-tile in-degree, outside tributaries ----
     const int lr = tid >> 2, lcb = (tid & 3) * CPT;
     unsigned srcmask = 0, validmask = 0;
-    unsigned unresolved = 0;  // SEEDED: entry nodes whose inflow was never finalised (node-level cycle)
-#pragma unroll 4
-    for (int i = 0; i < CPT; ++i) {
-        const int lc = lcb + i, p = lr * T + lc;
-        const unsigned code = C(lr, lc);
-        unsigned inm = 0;
-        if (code != 0) {
-            inm |= (C(lr - 1, lc - 1) == 2u) << 0;
-            inm |= (C(lr - 1, lc) == 4u) << 1;
-            inm |= (C(lr - 1, lc + 1) == 8u) << 2;
-            inm |= (C(lr, lc - 1) == 1u) << 3;
-            inm |= (C(lr, lc + 1) == 16u) << 4;
-            inm |= (C(lr + 1, lc - 1) == 128u) << 5;
-            inm |= (C(lr + 1, lc) == 64u) << 6;
-            inm |= (C(lr + 1, lc + 1) == 32u) << 7;
-        }
-        const unsigned outm = (lr == 0 ? 0x07u : 0u) | (lr == T - 1 ? 0xE0u : 0u) | (lc == 0 ? 0x29u : 0u) |
-                              (lc == T - 1 ? 0x94u : 0u);
-        const unsigned pending = __popc(inm & ~outm), extm = inm & outm;
-        uint32_t nx = NXT_TERM;
-        int dr, dc;
-        if (d8_offset(code, dr, dc)) {
-            const int tr = lr + dr, tc = lc + dc;
-            if (C(tr, tc) != 0) nx = ((unsigned)tr < (unsigned)T && (unsigned)tc < (unsigned)T) ? (uint32_t)(tr * T + tc) : NXT_EXIT;
-        }
-        nxt[p] = (uint16_t)nx;
-        uint64_t seed = 0;
-        if (outm) {
-            const int s = slot_of(lr, lc);
-            inmask_s[s] = (uint8_t)extm;
-            if (SEEDED && extm) {
-                const uint64_t ns = nstate[(size_t)tile * SLOTS + s];
-                seed = ns & N_CNT;
-                if ((ns >> N_PEND_SHIFT) & N_PEND) ++unresolved;
+    {
+        const uint8_t *crow = codes + (lr + 1) * CP + 16 + lcb;
+        const uint4 cw = *reinterpret_cast<const uint4 *>(crow);
+        const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            const int lc = lcb + i, p = lr * T + lc;
+            const unsigned code = (cws[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            const unsigned inm = code != 0 ? in_mask(codes, lr, lc) : 0u;
+            unsigned pending = __popc(inm);
+            if (lr == 0 || lr == T - 1 || i == 0 || i == CPT - 1) {
+                const unsigned outm = out_mask(lr, lc);
+                if (outm) {
+                    pending = __popc(inm & ~outm);
+                    inmask_s[slot_of(lr, lc)] = (uint8_t)(inm & outm);
+                }
             }
-        }
-        if (SEEDED) {
-            lo[p] = (uint32_t)seed;
-            hi[p] = (pending << 28) | (uint32_t)(seed >> 32);
-        } else {
-            lo[p] = pending << 28;
-        }
-        if (code != 0) {
-            validmask |= 1u << i;
-            if (pending == 0) srcmask |= 1u << i;
+            uint32_t nx = W_TERM;
+            int dloc, dcode;
+            if (d8_delta(code, dloc, dcode) && crow[i + dcode] != 0) nx = (code & exit_codes(lr, lc)) ? W_EXIT : phys_of((uint32_t)(p + dloc));
+            word[i * FT_THREADS + tid] = (pending << 28) | nx;
+            if (code != 0) {
+                validmask |= 1u << i;
+                if (pending == 0) srcmask |= 1u << i;
+            }
         }
     }
     __syncthreads();
@@ -123,95 +100,67 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
     while (srcmask) {
         const int i = __ffs((int)srcmask) - 1;
         srcmask &= srcmask - 1;
-        uint32_t p = (uint32_t)(lr * T + lcb + i);
         ++finalised;
-        if (SEEDED) {
-            uint64_t carry = ((uint64_t)(hi[p] & 0x0FFFFFFFu) << 32) | lo[p];
-            for (;;) {
-                const uint32_t n = nxt[p];
-                if (n >= NXT_EXIT) break;
-                const uint64_t add = carry + 1ull;
-                const uint32_t lo_old = atomicAdd(&lo[n], (uint32_t)add);
-                const uint32_t c = (uint32_t)(((uint64_t)lo_old + (uint32_t)add) >> 32);  // carry out of the low word
-                const uint32_t hi_add = (uint32_t)(add >> 32) + c;
-                const uint32_t hi_old = atomicAdd(&hi[n], hi_add - (1u << 28));  // issued after lo's add returned
-                if ((hi_old >> 28) != 1u) break;                                     // other tributaries pending
-                const uint32_t lo_now = *reinterpret_cast<volatile uint32_t *>(&lo[n]);
-                carry = ((uint64_t)((hi_old + hi_add) & 0x0FFFFFFFu) << 32) | lo_now;
-                p = n;
-                ++finalised;
-            }
-        } else {
-            uint32_t carry = 0;
-            for (;;) {
-                const uint32_t n = nxt[p];
-                if (n >= NXT_EXIT) break;
-                const uint32_t old = atomicAdd(&lo[n], carry + 1u - (1u << 28));
-                if ((old >> 28) != 1u) break;
-                carry += (old & 0x0FFFFFFFu) + 1u;
-                p = n;
-                ++finalised;
-            }
+        uint32_t n = word[i * FT_THREADS + tid] & W_NXT, carry = 0;
+        while (n < W_EXIT) {
+            const uint32_t old = atomicAdd(&word[n], ((carry + 1u) << W_CNT_SHIFT) - W_PEND_ONE);
+            if ((old >> 28) != 1u) break;  // other tributaries still pending
+            carry += ((old >> W_CNT_SHIFT) & 0x3FFFu) + 1u;
+            n = old & W_NXT;
+            ++finalised;
         }
     }
-    // a tile (or, SEEDED, an entry node) that cannot be finalised means the grid has a D8 cycle
-    // (per-thread differences wrap, their sum over the CTA is exact)
-    if (SEEDED) {
-        const unsigned bad = __reduce_add_sync(0xffffffffu, (unsigned)__popc(validmask) - finalised + unresolved);
+    // a tile that cannot be finalised means the grid has a D8 cycle (per-thread differences wrap, the sum is exact)
+    {
+        const unsigned bad = __reduce_add_sync(0xffffffffu, (unsigned)__popc(validmask) - finalised);
         if ((tid & 31) == 0 && bad) atomicAdd(&cyc_s, bad);
     }
     __syncthreads();
+    if (tid == 0 && cyc_s) atomicAdd(&counters[0], (unsigned long long)cyc_s);
 
-    if (SEEDED) {
-        if (tid == 0 && cyc_s) atomicAdd(&counters[0], (unsigned long long)cyc_s);
-        // ---- write acc: 16 consecutive cells per thread ----
-        const int64_t gr = r0 + lr;
-        if (gr < v.rows) {
-            ACC out[CPT];
+    // ---- tile-local counts -> acc (the finish pass adds the inflow along the entry paths) ----
+    const int64_t gr = r0 + lr;
+    if (acc && gr < v.rows) {
+        alignas(16) ACC out[CPT];
 #pragma unroll
-            for (int i = 0; i < CPT; ++i) {
-                const int p = lr * T + lcb + i;
-                const uint64_t cnt = ((uint64_t)(hi[p] & 0x0FFFFFFFu) << 32) | lo[p];
-                out[i] = ((validmask >> i) & 1u) ? (ACC)cnt : nodata_fill;
-            }
-            ACC *dst = acc + gr * v.cols + c0 + lcb;
-            if (fast && ((reinterpret_cast<uintptr_t>(acc) & 15u) == 0)) {
-                constexpr int V = 16 / sizeof(ACC);
+        for (int i = 0; i < CPT; ++i)
+            out[i] = ((validmask >> i) & 1u) ? (ACC)((word[i * FT_THREADS + tid] >> W_CNT_SHIFT) & 0x3FFFu) : nodata_fill;
+        ACC *dst = acc + gr * v.cols + c0 + lcb;
+        if (fast && ((reinterpret_cast<uintptr_t>(acc) & 15u) == 0)) {
+            constexpr int V = 16 / sizeof(ACC);
 #pragma unroll
-                for (int i = 0; i < CPT; i += V) *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(&out[i]);
-            } else {
+            for (int i = 0; i < CPT; i += V) *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(&out[i]);
+        } else {
 #pragma unroll
-                for (int i = 0; i < CPT; ++i)
-                    if (c0 + lcb + i < v.cols) dst[i] = out[i];
-            }
+            for (int i = 0; i < CPT; ++i)
+                if (c0 + lcb + i < v.cols) dst[i] = out[i];
         }
-        return;
     }
 
-    // ---- T1 summary of the perimeter ----
+    // ---- summary of the perimeter ----
     uint32_t my_link = LINK_NONE, my_term = TERM_NONE, my_exitw = 0, my_inmask = 0;
     if (tid < USED_SLOTS) {
         int plr, plc;
         slot_cell(tid, plr, plc);
-        const uint32_t p0 = (uint32_t)(plr * T + plc);
-        if (nxt[p0] == NXT_EXIT) my_exitw = (lo[p0] & 0x0FFFFFFFu) + 1u;
+        uint32_t q = phys_of((uint32_t)(plr * T + plc));
+        uint32_t w = word[q];
+        if ((w & W_NXT) == W_EXIT) my_exitw = ((w >> W_CNT_SHIFT) & 0x3FFFu) + 1u;
         my_inmask = inmask_s[tid];
         if (my_inmask) {
-            uint32_t q = p0;
             int steps = 0;
-            while (nxt[q] < NXT_EXIT && steps < TCELLS) { q = nxt[q]; ++steps; }
-            if (nxt[q] == NXT_EXIT) {
-                const int qr = (int)(q / T), qc = (int)(q % T);
+            while ((w & W_NXT) < W_EXIT && steps < TCELLS) { q = w & W_NXT; w = word[q]; ++steps; }
+            if ((w & W_NXT) == W_EXIT) {
+                const uint32_t ql = logical_of(q);
+                const int qr = (int)(ql / T), qc = (int)(ql % T);
                 my_term = (uint32_t)slot_of(qr, qc);
                 atomicAdd(&nterm_s[my_term], 1u);
                 int dr, dc;
-                d8_offset(C(qr, qc), dr, dc);
-                const int64_t gr = r0 + qr + dr, gc = c0 + qc + dc;
+                d8_offset(codes[(qr + 1) * CP + 16 + qc], dr, dc);
+                const int64_t tr = r0 + qr + dr, tc = c0 + qc + dc;
                 // leaving the band: remember the column of the band cell the path leaves through
-                if (gr < 0) my_link = LINK_OUT | (uint32_t)(c0 + qc);
-                else if (gr >= v.rows) my_link = LINK_OUT | LINK_BELOW | (uint32_t)(c0 + qc);
-                else
-                    my_link = (uint32_t)(((gr / T) * v.tiles_x + gc / T) * SLOTS + slot_of((int)(gr % T), (int)(gc % T)));
+                if (tr < 0) my_link = LINK_OUT | (uint32_t)(c0 + qc);
+                else if (tr >= v.rows) my_link = LINK_OUT | LINK_BELOW | (uint32_t)(c0 + qc);
+                else my_link = (uint32_t)node_of_cell(tr, tc, v.tiles_x);
             }
         }
     }
@@ -221,6 +170,75 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
         exitw[node] = my_exitw;
         link[node] = my_link;
         meta[node] = my_term | (nterm_s[tid] << 8) | (my_inmask << 16);
+    }
+}
+
+// ---- T2: add the resolved inflow of the entry nodes along their in-tile paths --------------------------
+// acc already holds the tile-local counts; only the 64-byte runs that an entry path touches are rewritten.
+template <typename ACC>
+__global__ void __launch_bounds__(FT_THREADS)
+fa_tile_finish_kernel(TileView v, const unsigned long long *__restrict__ nstate, ACC *__restrict__ acc,
+                      unsigned long long *__restrict__ counters)
+{
+    typedef typename std::conditional<sizeof(ACC) == 8, unsigned long long, uint32_t>::type EXT;
+    __shared__ __align__(16) uint8_t codes[(T + 2) * CP + 16];
+    __shared__ EXT ext[TCELLS];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
+    const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
+    const bool fast = stage_codes(v, r0, c0, codes, tid, FT_THREADS);
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) ext[i * FT_THREADS + tid] = 0;
+    __syncthreads();
+
+    unsigned unresolved = 0;
+    if (tid < USED_SLOTS) {
+        int lr, lc;
+        slot_cell(tid, lr, lc);
+        const uint8_t *cp = codes + (lr + 1) * CP + 16 + lc;
+        if (*cp != 0 && (in_mask(codes, lr, lc) & out_mask(lr, lc))) {
+            const uint64_t ns = nstate[(size_t)tile * SLOTS + tid];
+            if ((ns >> N_PEND_SHIFT) & N_PEND) ++unresolved;  // never finalised: node-level cycle
+            const EXT w = (EXT)(ns & N_CNT);
+            int p = lr * T + lc;
+            for (int steps = 0; w != 0 && steps < TCELLS; ++steps) {
+                atomicAdd(&ext[phys_of((uint32_t)p)], w);
+                const unsigned code = *cp;
+                int dloc, dcode;
+                if (!d8_delta(code, dloc, dcode) || cp[dcode] == 0 || (code & exit_codes(p >> 6, p & (T - 1)))) break;
+                p += dloc;
+                cp += dcode;
+            }
+        }
+    }
+    unresolved = __reduce_add_sync(0xffffffffu, unresolved);
+    if ((tid & 31) == 0 && unresolved) atomicAdd(&counters[0], (unsigned long long)unresolved);
+    __syncthreads();
+
+    const int lr = tid >> 2, lcb = (tid & 3) * CPT;
+    const int64_t gr = r0 + lr;
+    if (gr >= v.rows) return;
+    EXT e[CPT];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) { e[i] = ext[i * FT_THREADS + tid]; any |= e[i] != 0; }
+    if (!any) return;
+    ACC *dst = acc + gr * v.cols + c0 + lcb;
+    if (fast && ((reinterpret_cast<uintptr_t>(acc) & 15u) == 0)) {
+        constexpr int V = 16 / sizeof(ACC);
+#pragma unroll
+        for (int i = 0; i < CPT; i += V) {
+            uint4 w = *reinterpret_cast<const uint4 *>(dst + i);
+            ACC *a = reinterpret_cast<ACC *>(&w);
+#pragma unroll
+            for (int j = 0; j < V; ++j) a[j] += (ACC)e[i + j];
+            *reinterpret_cast<uint4 *>(dst + i) = w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CPT; ++i)
+            if (e[i] != 0 && c0 + lcb + i < v.cols) dst[i] += (ACC)e[i];
     }
 }
 
@@ -459,8 +477,8 @@ int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
 
     if (a->mode != DTB_FA_FINISH) {
         DTB_CUDA(cudaMemsetAsync(counters, 0, 256, st));
-        fa_tile_kernel<false, ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, exitw, link, meta, nullptr, nullptr, (ACC)0, counters);
-        DTB_LAUNCH_CHECK("fa_tile_kernel<summary>");
+        fa_tile_kernel<ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, exitw, link, meta, acc, (ACC)a->nodata_fill, counters);
+        DTB_LAUNCH_CHECK("fa_tile_kernel");
     }
     fa_node_init_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, a->rows, a->cols, v.tiles_x, exitw, meta, a->inflow_above,
                                                  a->inflow_below, nstate);
@@ -484,9 +502,8 @@ int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
         return DTB_OK;
     }
 
-    fa_tile_kernel<true, ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, nullptr, nullptr, nullptr, nstate, acc,
-                                                                        (ACC)a->nodata_fill, counters);
-    DTB_LAUNCH_CHECK("fa_tile_kernel<final>");
+    fa_tile_finish_kernel<ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, nstate, acc, counters);
+    DTB_LAUNCH_CHECK("fa_tile_finish_kernel");
     // cyclic grids only (each kernel returns at once when counters[0] == 0)
     fa_flat_init_kernel<<<FLAT_BLOCKS, 256, 0, st>>>(v, a->inflow_above, a->inflow_below, flat, counters);
     DTB_LAUNCH_CHECK("fa_flat_init_kernel");
@@ -517,7 +534,7 @@ extern "C" int dtb_flowacc_band(const dtb_flowacc_args *a, void *ws, size_t ws_b
     using namespace dtb;
     if (!a || !a->d8 || !ws || a->rows <= 0 || a->cols <= 0) return DTB_ERR_INVALID;
     if (a->mode < DTB_FA_FULL || a->mode > DTB_FA_FINISH) return DTB_ERR_INVALID;
-    if (a->mode != DTB_FA_SUMMARY && !a->acc) return DTB_ERR_INVALID;
+    if (!a->acc) return DTB_ERR_INVALID;  // the tile pass leaves its local counts in acc
     if (a->acc_dtype != DTB_I32 && a->acc_dtype != DTB_I64) return DTB_ERR_INVALID;
     if (ws_bytes < dtb_flowacc_workspace_bytes(a->rows, a->cols)) return DTB_ERR_WORKSPACE;
     if (a->cols >= (int64_t)1 << 30) return DTB_ERR_UNSUPPORTED;

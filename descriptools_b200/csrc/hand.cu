@@ -259,7 +259,9 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
 {
     __shared__ __align__(16) uint8_t codes[(T + 2) * CP + 16];
     __shared__ uint16_t rivm[H_THREADS];
-    __shared__ unsigned long long st[TCELLS];
+    // in-tile state, slot layout of tiles.cuh: x = target (slot of the next cell while ACTIVE, global index of the
+    // river cell, local index of the exit cell), y = [31..30 kind | 29..15 n_diag | 14..0 n_card]
+    __shared__ uint2 st[TCELLS];
     __shared__ unsigned long long exit_state[SLOTS];
     __shared__ uint8_t exit_remote[SLOTS];  // 0: resolved inside the band, 1/2: by the band above/below
     const int tid = threadIdx.x;
@@ -274,29 +276,33 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
     auto C = [&](int r, int c) -> unsigned { return codes[(r + 1) * CP + 16 + c]; };
 
     // ---- initial state of my 16 cells ----
+    // Inside the tile a path is at most 4095 moves, so the two 15-bit counters never carry and composing
+    // "s then t" is one 32-bit add (s is ACTIVE = kind 0) plus taking t's target.
     unsigned activemask = 0;
-#pragma unroll 4
-    for (int i = 0; i < CPT; ++i) {
-        const int lc = lcb + i, p = lr * T + lc;
-        const unsigned code = C(lr, lc);
-        uint64_t s = pack(KIND_FAIL, 0, 0, 0);  // code 0 (flowhand.py:601), unknown code, bad landing
-        int dr, dc;
-        if (code != 0) {
-            if ((myriv >> i) & 1u) s = pack(KIND_RIVER, 0, 0, (uint32_t)((r0 + lr) * v.cols + c0 + lc));  // flowhand.py:609-612
-            else if (d8_offset(code, dr, dc)) {
-                const int tr = lr + dr, tc = lc + dc;
-                if (C(tr, tc) != 0) {
-                    if ((unsigned)tr < (unsigned)T && (unsigned)tc < (unsigned)T) {
-                        const bool diag = d8_is_diag(code);
-                        s = pack(KIND_ACTIVE, diag ? 1u : 0u, diag ? 0u : 1u, (uint32_t)(tr * T + tc));
-                        activemask |= 1u << i;
+    {
+        const uint8_t *crow = codes + (lr + 1) * CP + 16 + lcb;
+        const uint4 cw = *reinterpret_cast<const uint4 *>(crow);
+        const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            const int lc = lcb + i, p = lr * T + lc;
+            const unsigned code = (cws[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            uint2 s = make_uint2(0u, (uint32_t)KIND_FAIL << 30);  // code 0 (flowhand.py:601), unknown code, bad landing
+            int dloc, dcode;
+            if ((myriv >> i) & 1u) {
+                if (code != 0) s = make_uint2((uint32_t)((r0 + lr) * v.cols + c0 + lc), (uint32_t)KIND_RIVER << 30);  // flowhand.py:609-612
+            } else if (d8_delta(code, dloc, dcode)) {
+                if (crow[i + dcode] != 0) {  // landing cell valid (flowhand.py:623-764, 826)
+                    if (code & exit_codes(lr, lc)) {
+                        s = make_uint2((uint32_t)p, (uint32_t)KIND_EXIT << 30);  // the exit move is added with the node state
                     } else {
-                        s = pack(KIND_EXIT, 0, 0, (uint32_t)p);  // the exit move is added with the node state
+                        s = make_uint2(phys_of((uint32_t)(p + dloc)), (code & 0xAAu) ? (1u << 15) : 1u);
+                        activemask |= 1u << i;
                     }
                 }
             }
+            st[i * H_THREADS + tid] = s;
         }
-        st[p] = s;
     }
     __syncthreads();
 
@@ -306,16 +312,24 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
         while (m) {
             const int i = __ffs((int)m) - 1;
             m &= m - 1;
-            const int p = lr * T + lcb + i;
-            uint64_t s = st[p];
-            s = compose(s, st[ptr_of(s)]);
-            if (kind_of(s) == KIND_ACTIVE) s = compose(s, st[ptr_of(s)]);
+            const int p = i * H_THREADS + tid;
+            uint2 s = st[p];
+            uint2 t = st[s.x];
+            s.x = t.x;
+            s.y += t.y;
+            if ((s.y >> 30) == 0u) {
+                t = st[s.x];
+                s.x = t.x;
+                s.y += t.y;
+            }
+            // a simple path inside the tile has < 4096 moves: more means the cell sits on / drains into an
+            // in-tile cycle (FAIL, flowhand.py:830/835); this also keeps the 15-bit counters from carrying
+            if ((s.y >> 30) == 0u && (s.y & 0x7FFFu) + ((s.y >> 15) & 0x7FFFu) >= (unsigned)TCELLS) s.y = (uint32_t)KIND_FAIL << 30;
             st[p] = s;
-            if (kind_of(s) != KIND_ACTIVE) activemask &= ~(1u << i);
+            if (s.y >> 30) activemask &= ~(1u << i);
         }
         if (!__syncthreads_or(activemask != 0)) break;
     }
-    // still ACTIVE after 13 double rounds: in-tile cycle -> FAIL (flowhand.py:830/835)
 
     // ---- resolved state behind every exit cell of the perimeter ----
     if (tid < USED_SLOTS) {
@@ -372,10 +386,11 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
         if (o.hand || o.gfi) load4<TD>(dem + obase, z, vec, c_first, v.cols, HandOps<TD>::nd());
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            uint64_t s = st[lr * T + lcb + g4 + i];
+            const uint2 s2 = st[(g4 + i) * H_THREADS + tid];
+            uint64_t s = pack(s2.y >> 30, (s2.y >> 15) & 0x7FFFu, s2.y & 0x7FFFu, s2.x);
             unsigned remote = 0;
             if (kind_of(s) == KIND_EXIT) {
-                const uint32_t x = ptr_of(s);
+                const uint32_t x = s2.x;
                 const int slot = slot_of((int)(x / T), (int)(x % T));
                 s = compose(s, exit_state[slot]);
                 remote = exit_remote[slot];
@@ -402,7 +417,7 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
                     double racc;
                     if (!ok) racc = o.idx_offset == 0 ? (double)acc[0] : 1.0;
                     else racc = remote ? (double)o.res_acc[remote - 1][loc] : (double)acc[loc];
-                    g = (float)(o.gfi_logb + o.gfi_n * log(racc * o.gfi_s2) - log((double)h + 0.01));  // gfi.py:292-294
+                    g = (float)(o.gfi_logb + o.gfi_n * fast_log(racc * o.gfi_s2) - fast_log((double)h + 0.01));  // gfi.py:292-294
                 }
             }
             hd[i] = h;

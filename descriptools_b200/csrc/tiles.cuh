@@ -90,6 +90,37 @@ __device__ __forceinline__ bool stage_codes(const TileView &v, int64_t r0, int64
     return fast;
 }
 
+// D8 code -> displacement of the move inside the staged tile.  `code` must be one of the eight one-hot
+// direction codes (bit b: 0=E 1=SE 2=S 3=SW 4=W 5=NW 6=N 7=NE); returns false for 0 / unknown codes.
+//   dloc  = dr*T  + dc  (local cell index)      dcode = dr*CP + dc  (byte offset in the staged codes)
+__device__ __forceinline__ bool d8_delta(unsigned code, int &dloc, int &dcode)
+{
+    if (code == 0u || (code & (code - 1u)) != 0u || code > 128u) { dloc = 0; dcode = 0; return false; }
+    const unsigned b = (unsigned)__ffs((int)code) - 1u;
+    // signed bytes, LSB first: E, SE, S, SW | W, NW, N, NE
+    constexpr unsigned L0 = (1u & 0xFF) | ((unsigned)(T + 1) << 8) | ((unsigned)T << 16) | ((unsigned)(T - 1) << 24);
+    constexpr unsigned L1 = ((unsigned)(-1) & 0xFF) | (((unsigned)(-T - 1) & 0xFF) << 8) | (((unsigned)(-T) & 0xFF) << 16) |
+                            (((unsigned)(-T + 1) & 0xFF) << 24);
+    constexpr unsigned C0 = (1u & 0xFF) | ((unsigned)(CP + 1) << 8) | ((unsigned)CP << 16) | ((unsigned)(CP - 1) << 24);
+    constexpr unsigned C1 = ((unsigned)(-1) & 0xFF) | (((unsigned)(-CP - 1) & 0xFF) << 8) | (((unsigned)(-CP) & 0xFF) << 16) |
+                            (((unsigned)(-CP + 1) & 0xFF) << 24);
+    dloc = (int)(int8_t)__byte_perm(L0, L1, b);
+    dcode = (int)(int8_t)__byte_perm(C0, C1, b);
+    return true;
+}
+// Shared-memory layout of per-cell arrays.  Thread t owns the 16 cells 16t..16t+15 (row t/4, columns
+// 16(t%4)..+15), so a row-major array would put every lane of a warp in the same one or two banks.
+// Cell p therefore lives at slot (p % 16) * 256 + p / 16: for a fixed cell number i the 256 threads touch
+// consecutive words.  Pointers between cells are stored as slots.
+__host__ __device__ __forceinline__ uint32_t phys_of(uint32_t p) { return ((p & 15u) << 8) | (p >> 4); }
+__host__ __device__ __forceinline__ uint32_t logical_of(uint32_t q) { return ((q & 255u) << 4) | (q >> 8); }
+
+// one-hot codes whose move leaves the tile from local cell (lr, lc)
+__device__ __forceinline__ unsigned exit_codes(int lr, int lc)
+{
+    return (lr == 0 ? 0xE0u : 0u) | (lr == T - 1 ? 0x0Eu : 0u) | (lc == 0 ? 0x38u : 0u) | (lc == T - 1 ? 0x83u : 0u);
+}
+
 // in-mask of a cell: bit k set iff the neighbour at scan position k (NW,N,NE,W,E,SW,S,SE) points at it
 __device__ __forceinline__ unsigned in_mask(const uint8_t *codes, int lr, int lc)
 {

@@ -95,7 +95,7 @@ int dtb_flowacc(const uint8_t *d8, int64_t rows, int64_t cols, void *acc, int ac
  *                     path that starts there leaves the band: (side << 30) | column of the band's
  *                     own first/last-row cell it leaves through (side 0 = above, 1 = below), or -1
  *                     if it ends in the band.
- *       acc is not written.
+ *       acc receives the tile-local counts (an intermediate the FINISH call completes in place).
  *   mode DTB_FA_FINISH  : node sweep with the resolved inflow + final tile pass writing acc;
  *       reuses the tile summaries the SUMMARY call left in the same, untouched workspace.
  * The band driver (descriptools_b200/bands.py) solves the boundary graph between the two calls.
