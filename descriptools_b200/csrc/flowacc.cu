@@ -42,6 +42,7 @@ constexpr int N_PEND_SHIFT = 48;
 // step both accumulates and returns the successor of the cell just finalised.
 constexpr uint32_t W_EXIT = 0x3FFEu, W_TERM = 0x3FFFu, W_NXT = 0x3FFFu, W_PEND_ONE = 1u << 28;
 constexpr int W_CNT_SHIFT = 14;
+constexpr int WALK_CAP = 8;
 
 template <typename ACC>
 __global__ void __launch_bounds__(FT_THREADS)
@@ -51,21 +52,22 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
     __shared__ __align__(16) uint8_t codes[(T + 2) * CP + 16];  // col T of the last row sits at (T+2)*CP
     __shared__ uint32_t word[TCELLS];
     __shared__ uint32_t nterm_s[SLOTS];
-    __shared__ uint8_t inmask_s[SLOTS];
-    __shared__ unsigned cyc_s;
+    __shared__ uint32_t queue[TCELLS / 4];  // a parked walk has finalised >= WALK_CAP cells: at most TCELLS / WALK_CAP of them
+    __shared__ uint32_t qn;
 
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
     const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
     const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
     const bool fast = stage_codes(v, r0, c0, codes, tid, FT_THREADS);
-    if (tid < SLOTS) { nterm_s[tid] = 0; inmask_s[tid] = 0; }
-    if (tid == 0) cyc_s = 0;
+    if (tid < SLOTS) nterm_s[tid] = 0;
+    if (tid == 0) qn = 0;
     __syncthreads();
 
-    // ---- per-cell set-up: successor, in-tile in-degree, outside tributaries ----
+    // ---- per-cell set-up: successor slot; in-tile in-degree by scatter (one shared RED per cell) ----
     const int lr = tid >> 2, lcb = (tid & 3) * CPT;
-    unsigned srcmask = 0, validmask = 0;
+    unsigned validmask = 0;
+    uint32_t mynx[CPT];
     {
         const uint8_t *crow = codes + (lr + 1) * CP + 16 + lcb;
         const uint4 cw = *reinterpret_cast<const uint4 *>(crow);
@@ -74,49 +76,63 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
         for (int i = 0; i < CPT; ++i) {
             const int lc = lcb + i, p = lr * T + lc;
             const unsigned code = (cws[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-            const unsigned inm = code != 0 ? in_mask(codes, lr, lc) : 0u;
-            unsigned pending = __popc(inm);
-            if (lr == 0 || lr == T - 1 || i == 0 || i == CPT - 1) {
-                const unsigned outm = out_mask(lr, lc);
-                if (outm) {
-                    pending = __popc(inm & ~outm);
-                    inmask_s[slot_of(lr, lc)] = (uint8_t)(inm & outm);
-                }
-            }
             uint32_t nx = W_TERM;
             int dloc, dcode;
             if (d8_delta(code, dloc, dcode) && crow[i + dcode] != 0) nx = (code & exit_codes(lr, lc)) ? W_EXIT : phys_of((uint32_t)(p + dloc));
-            word[i * FT_THREADS + tid] = (pending << 28) | nx;
-            if (code != 0) {
-                validmask |= 1u << i;
-                if (pending == 0) srcmask |= 1u << i;
-            }
+            mynx[i] = nx;
+            word[i * FT_THREADS + tid] = nx;
+            validmask |= (code != 0 ? 1u : 0u) << i;
         }
     }
     __syncthreads();
+#pragma unroll
+    for (int i = 0; i < CPT; ++i)
+        if (mynx[i] < W_EXIT) atomicAdd(&word[mynx[i]], W_PEND_ONE);
+    __syncthreads();
+    unsigned srcmask = 0;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) srcmask |= ((word[i * FT_THREADS + tid] >> 28) == 0u ? 1u : 0u) << i;
+    srcmask &= validmask;
+    __syncthreads();  // every thread has read its pending fields before the sweep starts changing them
 
-    // ---- sweep: every source walks until it is not the last tributary to arrive ----
-    unsigned finalised = 0;
+    // ---- sweep: every source walks until it is not the last tributary to arrive.  A walk that is still
+    // going after WALK_CAP steps (a main stem) is parked in a queue; the parked walks are then spread over
+    // the lanes of as few warps as possible, so the long serial chains do not idle 31 lanes each ----
     while (srcmask) {
         const int i = __ffs((int)srcmask) - 1;
         srcmask &= srcmask - 1;
-        ++finalised;
         uint32_t n = word[i * FT_THREADS + tid] & W_NXT, carry = 0;
+        int left = WALK_CAP;
         while (n < W_EXIT) {
+            if (left-- == 0) {
+                queue[atomicAdd(&qn, 1u)] = (carry << 14) | n;  // carry < 4096 < 2^18
+                break;
+            }
             const uint32_t old = atomicAdd(&word[n], ((carry + 1u) << W_CNT_SHIFT) - W_PEND_ONE);
             if ((old >> 28) != 1u) break;  // other tributaries still pending
             carry += ((old >> W_CNT_SHIFT) & 0x3FFFu) + 1u;
             n = old & W_NXT;
-            ++finalised;
         }
     }
-    // a tile that cannot be finalised means the grid has a D8 cycle (per-thread differences wrap, the sum is exact)
-    {
-        const unsigned bad = __reduce_add_sync(0xffffffffu, (unsigned)__popc(validmask) - finalised);
-        if ((tid & 31) == 0 && bad) atomicAdd(&cyc_s, bad);
+    __syncthreads();
+    for (uint32_t k = tid; k < qn; k += FT_THREADS) {
+        uint32_t n = queue[k] & W_NXT, carry = queue[k] >> 14;
+        while (n < W_EXIT) {
+            const uint32_t old = atomicAdd(&word[n], ((carry + 1u) << W_CNT_SHIFT) - W_PEND_ONE);
+            if ((old >> 28) != 1u) break;
+            carry += ((old >> W_CNT_SHIFT) & 0x3FFFu) + 1u;
+            n = old & W_NXT;
+        }
     }
     __syncthreads();
-    if (tid == 0 && cyc_s) atomicAdd(&counters[0], (unsigned long long)cyc_s);
+    // a cell that was never finalised (pending left) means the grid has a D8 cycle
+    {
+        unsigned bad = 0;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) bad += ((validmask >> i) & 1u) && (word[i * FT_THREADS + tid] >> 28) != 0u;
+        bad = __reduce_add_sync(0xffffffffu, bad);
+        if ((tid & 31) == 0 && bad) atomicAdd(&counters[0], (unsigned long long)bad);
+    }
 
     // ---- tile-local counts -> acc (the finish pass adds the inflow along the entry paths) ----
     const int64_t gr = r0 + lr;
@@ -145,7 +161,7 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
         uint32_t q = phys_of((uint32_t)(plr * T + plc));
         uint32_t w = word[q];
         if ((w & W_NXT) == W_EXIT) my_exitw = ((w >> W_CNT_SHIFT) & 0x3FFFu) + 1u;
-        my_inmask = inmask_s[tid];
+        my_inmask = codes[(plr + 1) * CP + 16 + plc] != 0 ? (in_mask(codes, plr, plc) & out_mask(plr, plc)) : 0u;
         if (my_inmask) {
             int steps = 0;
             while ((w & W_NXT) < W_EXIT && steps < TCELLS) { q = w & W_NXT; w = word[q]; ++steps; }
