@@ -38,29 +38,84 @@ def run_device(dem: torch.Tensor, px: float, river_threshold: int, n_gfi: float 
 
 
 def pipeline(dem, px: float, river_threshold: int, n_gfi: float = 0.4, scale_factor: float = 0.1,
-             size: float | None = None, outputs=STAGE_OUTPUTS, pinned_out: dict | None = None) -> dict:
+             size: float | None = None, outputs=STAGE_OUTPUTS, pinned_out: dict | None = None, chunks: int = 8) -> dict:
     """Host-side chain: NumPy DEM in, NumPy rasters out (dtypes as the reference returns them on the
     device side: slope/fdist/gfi float32, d8 uint8, acc/idx int32 or int64, hand in the DEM's dtype).
+
+    The reference moves every descriptor host->device->host separately (slope.py:195-200,
+    flowhand.py:543-557, gfi.py:252-261).  Here the DEM goes up once, in `chunks` row blocks on a copy
+    stream, the slope/D8 stencil starts on a block as soon as the block below it has landed, and every
+    finished raster streams back on a second copy stream while the next stage computes.
 
     `pinned_out` may hold pre-allocated pinned torch CPU tensors keyed by output name (the benchmark
     reuses them across steps); otherwise pageable arrays are returned.
     """
     dev = device.require_cuda()
-    if isinstance(dem, torch.Tensor):
-        dem_t = dem.to(dev, non_blocking=True)
-    else:
-        dem_t = torch.from_numpy(dem_to_native(dem)).to(dev, non_blocking=True)
-    res = run_device(dem_t, px, river_threshold, n_gfi, scale_factor, size)
-    host = {}
-    for name in outputs:
-        t = res[name]
-        if pinned_out is not None and name in pinned_out:
-            pinned_out[name].copy_(t, non_blocking=True)
-            host[name] = pinned_out[name].numpy()
-        else:
-            host[name] = t.cpu().numpy()
-    torch.cuda.current_stream().synchronize()
-    return host
+    size = px if size is None else size
+    dem_h = dem if isinstance(dem, torch.Tensor) else torch.from_numpy(dem_to_native(dem))
+    if dem_h.is_cuda:
+        res = run_device(dem_h, px, river_threshold, n_gfi, scale_factor, size)
+        host = {name: res[name].cpu().numpy() for name in outputs}
+        return host
+    rows, cols = dem_h.shape
+    int_dt = torch.int32 if rows * cols < 2**31 else torch.int64
+    main = torch.cuda.current_stream()
+    up, down = torch.cuda.Stream(), torch.cuda.Stream()
+    host, keep = {}, []
+
+    def send_back(name, t, r0=None, r1=None):
+        """queue the device->host copy of raster `name` (rows [r0, r1) of it) behind the work recorded so far"""
+        if name not in outputs:
+            return
+        if name not in host:
+            if pinned_out is not None and name in pinned_out:
+                host[name] = pinned_out[name]
+            else:
+                host[name] = torch.empty(t.shape, dtype=t.dtype)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        down.wait_event(ev)
+        with torch.cuda.stream(down):
+            if r0 is None:
+                host[name].copy_(t, non_blocking=True)
+            else:
+                host[name][r0:r1].copy_(t[r0:r1], non_blocking=True)
+
+    # DEM up in row blocks; slope + D8 of a block runs once the block below it (its halo row) is resident
+    dem_d = torch.empty((rows, cols), dtype=dem_h.dtype, device=dev)
+    slope = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+    d8 = torch.empty((rows, cols), dtype=torch.uint8, device=dev)
+    keep += [dem_d, slope, d8]
+    k = max(1, min(chunks, rows // 256 or 1))
+    edges = [rows * i // k for i in range(k + 1)]
+    arrived = []
+    up.wait_stream(main)
+    for i in range(k):
+        with torch.cuda.stream(up):
+            dem_d[edges[i]:edges[i + 1]].copy_(dem_h[edges[i]:edges[i + 1]], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(up)
+        arrived.append(ev)
+    from ._lib import check, lib
+
+    for i in range(k):
+        main.wait_event(arrived[min(i + 1, k - 1)])
+        r0, r1 = edges[i], edges[i + 1]
+        check(lib.dtb_slope_d8(dem_d.data_ptr(), device._dem_dtype(dem_d), rows, cols, r0, r1, float(px),
+                               slope[r0:r1].data_ptr(), d8[r0:r1].data_ptr(), main.cuda_stream), "dtb_slope_d8")
+        send_back("slope", slope, r0, r1)
+        send_back("d8", d8, r0, r1)
+    acc = device.flow_accumulation(d8, dtype=int_dt, nodata_fill=-100)
+    keep.append(acc)
+    send_back("acc", acc)
+    out = device.hand(d8, dem_d, px, acc=acc, river_threshold=river_threshold, gfi_params=(n_gfi, scale_factor, size),
+                      idx_dtype=int_dt)
+    for name in ("idx", "fdist", "hand", "gfi"):
+        keep.append(out[name])
+        send_back(name, out[name])
+    down.synchronize()
+    main.synchronize()
+    return {name: host[name].numpy() for name in outputs}
 
 
 def output_dtypes(dem_dtype: np.dtype, n_cells: int) -> dict:
