@@ -246,6 +246,138 @@ __device__ __forceinline__ void stencil_strip(const float *tile, int gx, int ry0
     }
 }
 
+// ---- fast strip for the TMA kernel ------------------------------------------------------------
+// Same arithmetic as stencil_strip, organised for the B200 issue ports: the compare/select chains
+// (ALU port, half rate) are replaced by 3-input max reductions, a sign-bit mask of (difference - class
+// maximum) built with funnel shifts, and one priority encode.  Everything that is rare is delegated, one
+// row of four cells at a time, to slow_row(): the literal per-neighbour loop of slope.py:244-258 over the
+// staged raw values.  Rare = the 3x6 window holds an undefined value (off-raster NaN or anything <= -100:
+// nodata centres slope.py:231, skipped neighbours slope.py:247), no positive gradient (outlet rule),
+// cardinal/diagonal near-tie, a product next to an f32 rounding boundary, sub-/super-normal range.
+__device__ __noinline__ void slow_row(const float *tile, int trow, int tcol0, double px, double pd, float4 &slope4, uint32_t &codes)
+{
+    // trow/tcol0: position of the first of the four cells inside the staged box
+    const int DR[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, DC[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+    const int CODE[8] = {32, 64, 128, 16, 1, 8, 4, 2};
+    float out[4];
+    codes = 0;
+    for (int c = 0; c < 4; ++c) {
+        const int tcol = tcol0 + c;
+        const float zc = tile[trow * BOXW + tcol];
+        if (zc <= ND_F) { out[c] = ND_F; continue; }  // slope.py:231 (a NaN centre is off-raster: never stored)
+        double m = 0.0;
+        int code = 0, first_undef = 0;
+        for (int k = 0; k < 8; ++k) {
+            const float zq = tile[(trow + DR[k]) * BOXW + tcol + DC[k]];
+            const float diff = zc - zq;
+            if (zq == ND_F || diff != diff) {  // skipped neighbour (slope.py:247) / off-raster
+                if (!first_undef) first_undef = CODE[k];
+                continue;
+            }
+            const double g = (double)diff / ((DR[k] == 0 || DC[k] == 0) ? px : pd);
+            if (m < g) { m = g; code = CODE[k]; }  // slope.py:250,255
+        }
+        out[c] = (float)(m * 100.0);  // slope.py:259
+        if (code == 0) code = first_undef;  // outlet rule, SURVEY.md App. A2
+        codes |= (uint32_t)code << (8 * c);
+    }
+    slope4 = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+// one staged row: 6 values around the thread's 4 cells; `bad` = some value is NaN or <= -100
+__device__ __forceinline__ void load_row_fast(const float *p, float (&w)[6], bool &bad)
+{
+    const float4 a = *reinterpret_cast<const float4 *>(p);
+    w[0] = p[-1]; w[1] = a.x; w[2] = a.y; w[3] = a.z; w[4] = a.w; w[5] = p[4];
+    bad = false;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) bad |= !(w[j] > ND_F);
+}
+
+__device__ __forceinline__ void stencil_strip_fast(const float *tile, int gx, int ry0, const SlopeConsts &k, int64_t out_row0,
+                                                   int64_t out_rows, int64_t c_first, int64_t cols, float *__restrict__ slope,
+                                                   uint8_t *__restrict__ d8)
+{
+    const float *base = tile + 4 * gx + HALO_L;
+    float up[6], mid[6], dn[6];
+    bool bad_up, bad_mid, bad_dn;
+    load_row_fast(base + (ry0)*BOXW, up, bad_up);
+    load_row_fast(base + (ry0 + 1) * BOXW, mid, bad_mid);
+    float vSp[6], sEp[6], sWp[6];
+#pragma unroll
+    for (int j = 1; j <= 4; ++j) vSp[j] = up[j] - mid[j];
+#pragma unroll
+    for (int j = 0; j <= 3; ++j) sEp[j] = up[j] - mid[j + 1];
+#pragma unroll
+    for (int j = 2; j <= 5; ++j) sWp[j] = up[j] - mid[j - 1];
+
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        load_row_fast(base + (ry0 + 2 + i) * BOXW, dn, bad_dn);
+        float hE[5], vS[6], sE[5], sW[6];
+#pragma unroll
+        for (int j = 0; j <= 4; ++j) hE[j] = mid[j] - mid[j + 1];
+#pragma unroll
+        for (int j = 1; j <= 4; ++j) vS[j] = mid[j] - dn[j];
+#pragma unroll
+        for (int j = 0; j <= 4; ++j) sE[j] = mid[j] - dn[j + 1];
+#pragma unroll
+        for (int j = 1; j <= 5; ++j) sW[j] = mid[j] - dn[j - 1];
+
+        float s_out[4];
+        uint32_t codes = 0;
+        bool slow = bad_up | bad_mid | bad_dn;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = c + 1;
+            const float dN = -vSp[j], dW = -hE[j - 1], dE = hE[j], dS = vS[j];
+            const float dNW = -sEp[j - 1], dNE = -sWp[j + 1], dSW = sW[j], dSE = sE[j];
+            const float ac = fmaxf(fmaxf(fmaxf(fmaxf(dN, dW), dE), dS), 0.0f);
+            const float ad = fmaxf(fmaxf(fmaxf(fmaxf(dNW, dNE), dSW), dSE), 0.0f);
+            const float t = ad * k.r32;
+            const bool use_c = ac >= t;
+            const float a = use_c ? ac : ad;
+            // neighbours below their class maximum: sign bit of (d - max); bit order NW,N,NE,W,E,SW,S,SE from bit 0
+            unsigned lose = 0;
+            lose = __funnelshift_l(__float_as_uint(dSE - ad), lose, 1);
+            lose = __funnelshift_l(__float_as_uint(dS - ac), lose, 1);
+            lose = __funnelshift_l(__float_as_uint(dSW - ad), lose, 1);
+            lose = __funnelshift_l(__float_as_uint(dE - ac), lose, 1);
+            lose = __funnelshift_l(__float_as_uint(dW - ac), lose, 1);
+            lose = __funnelshift_l(__float_as_uint(dNE - ad), lose, 1);
+            lose = __funnelshift_l(__float_as_uint(dN - ac), lose, 1);
+            lose = __funnelshift_l(__float_as_uint(dNW - ad), lose, 1);
+            const unsigned win = ~lose & (use_c ? 0x5Au : 0xA5u);
+            const unsigned b = (unsigned)__ffs((int)win) - 1u;  // first maximum in scan order (strict '<', slope.py:250,255)
+            codes |= (__byte_perm(0x10804020u, 0x02040801u, b) & 0xFFu) << (8 * c);
+            const double y = (double)a * (use_c ? k.kc : k.kd);
+            s_out[c] = (float)y;
+            // range (no positive gradient, subnormal / huge), cardinal-diagonal near-tie, product within 16 ulp(f64)
+            // of an f32 rounding boundary
+            slow |= (__float_as_uint(a) - 0x0D800000u >= 0x7E000000u - 0x0D800000u) | (fabsf(ac - t) <= 1e-6f * t) |
+                    ((((uint32_t)__double2loint(y) + 0x10u - 0x10000000u) & 0x1FFFFFE0u) == 0u);
+        }
+        float4 s4 = make_float4(s_out[0], s_out[1], s_out[2], s_out[3]);
+        if (slow) slow_row(tile, ry0 + 1 + i, 4 * gx + HALO_L, k.px, k.pd, s4, codes);
+        const int64_t orow = out_row0 + ry0 + i;
+        if (orow >= 0 && orow < out_rows && c_first < cols) {
+            const int64_t o = orow * cols + c_first;
+            if (slope) *reinterpret_cast<float4 *>(slope + o) = s4;
+            if (d8) *reinterpret_cast<uint32_t *>(d8 + o) = codes;
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { up[j] = mid[j]; mid[j] = dn[j]; }
+#pragma unroll
+        for (int j = 1; j <= 4; ++j) vSp[j] = vS[j];
+#pragma unroll
+        for (int j = 0; j <= 3; ++j) sEp[j] = sE[j];
+#pragma unroll
+        for (int j = 2; j <= 5; ++j) sWp[j] = sW[j];
+        bad_up = bad_mid;
+        bad_mid = bad_dn;
+    }
+}
+
 // ---- TMA persistent kernel (f32, cols % 4 == 0, 16-byte aligned bases) ----------------------
 __global__ void __launch_bounds__(NTHREADS, 2)
 slope_d8_tma_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_begin, int64_t row_end, int64_t cols,
@@ -282,8 +414,8 @@ slope_d8_tma_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_beg
         mbar_wait(&full[stage], parity);
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         const float *tbuf = reinterpret_cast<const float *>(smem + (size_t)stage * STAGE_BYTES);
-        stencil_strip<true>(tbuf, gx, gy * RPT, k, (int64_t)ty * TH, row_end - row_begin, (int64_t)tx * TW + 4 * gx,
-                            cols, slope, d8);
+        stencil_strip_fast(tbuf, gx, gy * RPT, k, (int64_t)ty * TH, row_end - row_begin, (int64_t)tx * TW + 4 * gx, cols,
+                           slope, d8);
         __syncthreads();  // every thread is done reading this stage
         if (tid == 0) {
             const int next = tile + STAGES * gridDim.x;
