@@ -31,6 +31,14 @@ sys.path.insert(0, REPO)
 PX, RIVER_THR, N_GFI, B_GFI = 12.5, 128000, 0.4, 0.1
 BYTES_PER_CELL = {"slope_d8": 9, "flowacc": 5, "hand_gfi": 41}  # SURVEY.md 8(d), int32 indices
 CHAIN_BYTES = 55
+# algorithmic bytes per cell of the individual kernels: what one launch must move
+KERNEL_BYTES = {
+    "slope_d8_tma_kernel": 9,      # dem 4 R, slope 4 W, d8 1 W
+    "fa_tile_kernel": 5,           # d8 1 R, acc 4 W
+    "fa_tile_finish_kernel": 1,    # d8 1 R (+ the acc runs an entry path touches)
+    "hand_entry_kernel": 5,        # d8 1 R, acc 4 R (river mask)
+    "hand_tile_kernel": 33,        # d8 1, acc 4, dem 4 R; gathers dem[idx] 4 + acc[idx] 4; idx, fdist, hand, gfi 16 W
+}
 SAMPLE_ROWS = SAMPLE_COLS = 3072  # bounded CPU sample
 
 
@@ -126,6 +134,36 @@ def run_reference(args):
     }))
 
 
+def stencil_config1(peak):
+    """BASELINE.json configs[1]: synthetic 10k x 10k f32 DEM, fused slope + D8 only, 1 GPU (inputs + outputs 0.9 GB > L2)."""
+    import torch
+
+    from descriptools_b200 import device
+
+    n = 10000
+    dem = device.conditioned_dem(n, n)
+    slope = torch.empty((n, n), dtype=torch.float32, device="cuda")
+    d8 = torch.empty((n, n), dtype=torch.uint8, device="cuda")
+
+    def run():
+        device.check(device.lib.dtb_slope_d8(dem.data_ptr(), 0, n, n, 0, n, PX, slope.data_ptr(), d8.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "dtb_slope_d8")
+
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    gbs = 9 * n * n / (ms * 1e-3) / 1e9
+    return {"workload": "synthetic 10000x10000 f32 DEM, fused slope + D8 stencil", "ms": ms, "mcells_s": n * n / ms / 1e3,
+            "bytes_per_cell": 9, "achieved_gbs": gbs, "frac": gbs / peak}
+
+
 def workload_name(args):
     return f"synthetic {args.rows}x{args.cols} f32 DEM (dtb-synth-v1, depression-filled), full slope->D8->flowacc->HAND->GFI chain"
 
@@ -203,6 +241,7 @@ def run_ours(args):
         step(False)
     barrier()
     launches0 = _lib.launch_count()
+    _lib.profile_enable(True)  # CUDA events around every kernel launch of the timed region (roofline of the top kernel)
     t_start, t_end = ev(), ev()
     with ClockSampler(local) as clk:
         t_start.record()
@@ -213,6 +252,8 @@ def run_ours(args):
         t_end.record()
         barrier()
     launches = _lib.launch_count() - launches0
+    kernel_ms = _lib.profile_collect()
+    _lib.profile_enable(False)
     ms = t_start.elapsed_time(t_end)
     for e in events:
         for i, k in enumerate(stage_ms):
@@ -299,10 +340,29 @@ def run_ours(args):
         t_ms = stage_ms[k] / args.steps
         gbs = b * n_cells / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
         stages[k] = {"ms": t_ms, "bytes_per_cell": b, "achieved_gbs": gbs, "frac": gbs / peak_total}
-    dom = max(stages, key=lambda k: stages[k]["ms"])
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_gbs"], "peak": peak_total, "unit": "GB/s",
-                "frac": stages[dom]["frac"], "traffic": None, "peak_kind": peak_kind + " (burst copy)",
-                "chain_frac": CHAIN_BYTES * n_cells / (ms_step * 1e-3) / 1e9 / peak_total, "stages": stages}
+    # dominant kernel: algorithmic bytes of one launch / its average launch duration (events on its stream)
+    cells_launch = n_cells // world  # rank 0's band
+    kernels = {}
+    for name, (tot_ms, n) in kernel_ms.items():
+        avg = tot_ms / max(n, 1)
+        b = KERNEL_BYTES.get(name)
+        kernels[name] = {"ms_per_step": tot_ms / args.steps, "launches_per_step": n / args.steps, "avg_launch_ms": avg}
+        if b is not None and avg > 0:
+            kernels[name].update(bytes_per_cell=b, achieved_gbs=b * cells_launch / (avg * 1e-3) / 1e9)
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+    traffic = None
+    try:  # ncu --set full capture of the same kernel (profiles/): dram bytes read + written per cell
+        tr = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
+        traffic = tr[dom]["dram_bytes_per_cell"] * cells_launch
+    except Exception:
+        pass
+    dk = kernels.get(dom, {})
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": dk.get("achieved_gbs"), "peak": peak, "unit": "GB/s",
+                "frac": (dk.get("achieved_gbs") or 0.0) / peak, "traffic": traffic, "peak_kind": peak_kind + " (burst copy)",
+                "bytes_per_launch": (dk.get("bytes_per_cell") or 0) * cells_launch, "avg_launch_ms": dk.get("avg_launch_ms"),
+                "chain_frac": CHAIN_BYTES * n_cells / (ms_step * 1e-3) / 1e9 / peak_total, "stages": stages, "kernels": kernels}
+    if world == 1 and not args.no_cpu:
+        roofline["stencil_10k"] = stencil_config1(peak)
 
     line = {
         "metric": "DEM Mcells/s slope->D8->flowacc->HAND->GFI", "value": value, "unit": "Mcells/s", "n_gpus": world,

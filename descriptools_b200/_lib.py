@@ -93,6 +93,8 @@ SIGNATURES = {
     "dtb_last_cuda_error": (c_char_p, []),
     "dtb_launch_count": (c_int64, []),
     "dtb_reset_launch_count": (None, []),
+    "dtb_profile_enable": (None, [c_int]),
+    "dtb_profile_collect": (c_int64, [c_char_p, c_int64]),
     "dtb_slope_d8": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
     "dtb_flowacc_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "dtb_flowacc": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int64, c_void_p, c_size_t,
@@ -146,3 +148,18 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     lib.dtb_reset_launch_count()
+
+
+def profile_enable(on: bool = True) -> None:
+    lib.dtb_profile_enable(1 if on else 0)
+
+
+def profile_collect() -> dict:
+    """{kernel name: (total ms, launches)} since profile_enable / the last collect"""
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.dtb_profile_collect(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, n = line.rsplit(" ", 2)
+        out[name] = (float(ms), int(n))
+    return out

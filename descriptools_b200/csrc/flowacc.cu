@@ -493,14 +493,11 @@ int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
 
     if (a->mode != DTB_FA_FINISH) {
         DTB_CUDA(cudaMemsetAsync(counters, 0, 256, st));
-        fa_tile_kernel<ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, exitw, link, meta, acc, (ACC)a->nodata_fill, counters);
-        DTB_LAUNCH_CHECK("fa_tile_kernel");
+        DTB_KERNEL("fa_tile_kernel", st, fa_tile_kernel<ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, exitw, link, meta, acc, (ACC)a->nodata_fill, counters));
     }
-    fa_node_init_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, a->rows, a->cols, v.tiles_x, exitw, meta, a->inflow_above,
-                                                 a->inflow_below, nstate);
-    DTB_LAUNCH_CHECK("fa_node_init_kernel");
-    fa_node_sweep_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, link, nstate);
-    DTB_LAUNCH_CHECK("fa_node_sweep_kernel");
+    DTB_KERNEL("fa_node_init_kernel", st, fa_node_init_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, a->rows, a->cols, v.tiles_x, exitw, meta, a->inflow_above,
+                                                 a->inflow_below, nstate));
+    DTB_KERNEL("fa_node_sweep_kernel", st, fa_node_sweep_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, link, nstate));
 
     if (a->mode == DTB_FA_SUMMARY) {
         const unsigned nbc = (unsigned)((a->cols + 255) / 256);
@@ -510,23 +507,17 @@ int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
             long long *ex = reinterpret_cast<long long *>(side ? a->exit_below : a->exit_above);
             int32_t *tm = side ? a->term_below : a->term_above;
             if (!ex || !tm) continue;
-            fa_band_summary_kernel<<<nbc, 256, 0, st>>>(v, side, exitw, link, meta, ex, tm);
-            DTB_LAUNCH_CHECK("fa_band_summary_kernel");
-            fa_band_exit_scatter_kernel<<<nbs, 256, 0, st>>>(v, side, side ? (tiles_y - 1) * v.tiles_x : 0, meta, nstate, ex);
-            DTB_LAUNCH_CHECK("fa_band_exit_scatter_kernel");
+            DTB_KERNEL("fa_band_summary_kernel", st, fa_band_summary_kernel<<<nbc, 256, 0, st>>>(v, side, exitw, link, meta, ex, tm));
+            DTB_KERNEL("fa_band_exit_scatter_kernel", st, fa_band_exit_scatter_kernel<<<nbs, 256, 0, st>>>(v, side, side ? (tiles_y - 1) * v.tiles_x : 0, meta, nstate, ex));
         }
         return DTB_OK;
     }
 
-    fa_tile_finish_kernel<ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, nstate, acc, counters);
-    DTB_LAUNCH_CHECK("fa_tile_finish_kernel");
+    DTB_KERNEL("fa_tile_finish_kernel", st, fa_tile_finish_kernel<ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, nstate, acc, counters));
     // cyclic grids only (each kernel returns at once when counters[0] == 0)
-    fa_flat_init_kernel<<<FLAT_BLOCKS, 256, 0, st>>>(v, a->inflow_above, a->inflow_below, flat, counters);
-    DTB_LAUNCH_CHECK("fa_flat_init_kernel");
-    fa_flat_sweep_kernel<ACC><<<FLAT_BLOCKS, 256, 0, st>>>(v, acc, flat, counters);
-    DTB_LAUNCH_CHECK("fa_flat_sweep_kernel");
-    fa_flat_fix_kernel<ACC><<<FLAT_BLOCKS, 256, 0, st>>>(v, acc, flat, counters);
-    DTB_LAUNCH_CHECK("fa_flat_fix_kernel");
+    DTB_KERNEL("fa_flat_init_kernel", st, fa_flat_init_kernel<<<FLAT_BLOCKS, 256, 0, st>>>(v, a->inflow_above, a->inflow_below, flat, counters));
+    DTB_KERNEL("fa_flat_sweep_kernel", st, fa_flat_sweep_kernel<ACC><<<FLAT_BLOCKS, 256, 0, st>>>(v, acc, flat, counters));
+    DTB_KERNEL("fa_flat_fix_kernel", st, fa_flat_fix_kernel<ACC><<<FLAT_BLOCKS, 256, 0, st>>>(v, acc, flat, counters));
     if (a->unfinalised_host) {
         unsigned long long h[3];
         DTB_CUDA(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, st));

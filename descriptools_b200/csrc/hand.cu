@@ -260,7 +260,7 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
     __shared__ __align__(16) uint8_t codes[(T + 2) * CP + 16];
     __shared__ uint16_t rivm[H_THREADS];
     // in-tile state, slot layout of tiles.cuh: x = target (slot of the next cell while ACTIVE, global index of the
-    // river cell, local index of the exit cell), y = [31..30 kind | 29..15 n_diag | 14..0 n_card]
+    // river cell, perimeter slot of the exit cell), y = [31..30 kind | 29..15 n_diag | 14..0 n_card]
     __shared__ uint2 st[TCELLS];
     __shared__ unsigned long long exit_state[SLOTS];
     __shared__ uint8_t exit_remote[SLOTS];  // 0: resolved inside the band, 1/2: by the band above/below
@@ -294,7 +294,7 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
             } else if (d8_delta(code, dloc, dcode)) {
                 if (crow[i + dcode] != 0) {  // landing cell valid (flowhand.py:623-764, 826)
                     if (code & exit_codes(lr, lc)) {
-                        s = make_uint2((uint32_t)p, (uint32_t)KIND_EXIT << 30);  // the exit move is added with the node state
+                        s = make_uint2((uint32_t)slot_of(lr, lc), (uint32_t)KIND_EXIT << 30);  // x = perimeter slot; the exit move is added with the node state
                     } else {
                         s = make_uint2(phys_of((uint32_t)(p + dloc)), (code & 0xAAu) ? (1u << 15) : 1u);
                         activemask |= 1u << i;
@@ -387,37 +387,45 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint2 s2 = st[(g4 + i) * H_THREADS + tid];
-            uint64_t s = pack(s2.y >> 30, (s2.y >> 15) & 0x7FFFu, s2.y & 0x7FFFu, s2.x);
+            uint32_t kind = s2.y >> 30, nd = (s2.y >> 15) & 0x7FFFu, nc = s2.y & 0x7FFFu, tgt = s2.x;
             unsigned remote = 0;
-            if (kind_of(s) == KIND_EXIT) {
-                const uint32_t x = s2.x;
-                const int slot = slot_of((int)(x / T), (int)(x % T));
-                s = compose(s, exit_state[slot]);
-                remote = exit_remote[slot];
+            if (kind == KIND_EXIT) {  // continue with the resolved path behind the tile's exit cell
+                const uint64_t e = exit_state[tgt];
+                remote = exit_remote[tgt];
+                kind = (uint32_t)kind_of(e);
+                nd += nd_of(e);
+                nc += nc_of(e);
+                tgt = ptr_of(e);
             }
-            const uint32_t nc = nc_of(s), nd = nd_of(s);
-            const bool ok = kind_of(s) == KIND_RIVER && nc + nd <= o.max_moves;  // flowhand.py:835
-            // river cell: a local index into this band, or (remote) a column of the halo row's tables
-            const int64_t loc = (int64_t)ptr_of(s);
-            int64_t idx = (int64_t)ND_I;
-            if (ok) idx = remote ? o.res_idx[remote - 1][loc] : loc + o.idx_offset;
+            const bool ok = kind == KIND_RIVER && nc + nd <= o.max_moves;  // flowhand.py:835
             fd[i] = ok ? (float)((double)nc * o.px + (double)nd * o.pd) : ND_F;  // flowhand.py:840-843
-            ix[i] = (IDX)idx;
             TD h = HandOps<TD>::nd();
             float g = ND_F;
-            if (o.hand || o.gfi) {
-                // flowhand.py:436-438
-                if (!HandOps<TD>::is_nd(z[i]) && ok) {
-                    const TD zr = remote ? (TD)o.res_z[remote - 1][loc] : dem[loc];
-                    h = HandOps<TD>::sub(z[i], zr);
+            if (!remote) {
+                // river cell = local index `tgt` of this band
+                ix[i] = ok ? (IDX)((int64_t)tgt + o.idx_offset) : (IDX)ND_I;
+                if (o.hand || o.gfi) {
+                    if (ok && !HandOps<TD>::is_nd(z[i])) {  // flowhand.py:436-438
+                        h = HandOps<TD>::sub(z[i], dem[tgt]);
+                        if (h < (TD)0 && h != HandOps<TD>::nd()) h = (TD)0;
+                        if (o.gfi && !(h <= HandOps<TD>::nd())) {  // gfi.py:289
+                            const double ra = (double)acc[tgt] * o.gfi_s2;  // river_accumulation, gfi.py:141-143
+                            g = (float)(o.gfi_logb + o.gfi_n * fast_log(ra) - fast_log_pos((double)h + 0.01));  // gfi.py:292-294
+                        }
+                    }
                 }
-                if (h < (TD)0 && h != HandOps<TD>::nd()) h = (TD)0;
-                if (o.gfi && !(h <= HandOps<TD>::nd())) {
-                    // river_accumulation: idx == -100 -> fac.flat[0] (gfi.py:141-143); H is -100 then anyway
-                    double racc;
-                    if (!ok) racc = o.idx_offset == 0 ? (double)acc[0] : 1.0;
-                    else racc = remote ? (double)o.res_acc[remote - 1][loc] : (double)acc[loc];
-                    g = (float)(o.gfi_logb + o.gfi_n * fast_log(racc * o.gfi_s2) - fast_log((double)h + 0.01));  // gfi.py:292-294
+            } else {
+                // the path ends in another band: column `tgt` of the halo row's resolution tables
+                ix[i] = ok ? (IDX)o.res_idx[remote - 1][tgt] : (IDX)ND_I;
+                if (o.hand || o.gfi) {
+                    if (ok && !HandOps<TD>::is_nd(z[i])) {
+                        h = HandOps<TD>::sub(z[i], (TD)o.res_z[remote - 1][tgt]);
+                        if (h < (TD)0 && h != HandOps<TD>::nd()) h = (TD)0;
+                        if (o.gfi && !(h <= HandOps<TD>::nd())) {
+                            const double ra = (double)o.res_acc[remote - 1][tgt] * o.gfi_s2;
+                            g = (float)(o.gfi_logb + o.gfi_n * fast_log(ra) - fast_log_pos((double)h + 0.01));
+                        }
+                    }
                 }
             }
             hd[i] = h;
@@ -508,8 +516,7 @@ int run_tiles(const dtb_hand_args *a, const TileView &v, const RiverSrc &rs, con
             o.res_acc[k] = sm[k]->res_acc;
         }
     }
-    hand_tile_kernel<TD, IDX, ACC><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, (const TD *)a->dem, (const ACC *)a->acc, nstate, o);
-    DTB_LAUNCH_CHECK("hand_tile_kernel");
+    DTB_KERNEL("hand_tile_kernel", st, hand_tile_kernel<TD, IDX, ACC><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, (const TD *)a->dem, (const ACC *)a->acc, nstate, o));
     return DTB_OK;
 }
 
@@ -569,13 +576,13 @@ extern "C" int dtb_hand(const dtb_hand_args *a, void *ws, size_t ws_bytes, void 
 
     if (mode != DTB_HAND_FINISH) {
         DTB_CUDA(cudaMemsetAsync(active, 0, 256, st));
-        if (a->acc_dtype == DTB_I64) hand_entry_kernel<int64_t><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, nstate, active);
+        DTB_KERNEL("hand_entry_kernel", st, {
+            if (a->acc_dtype == DTB_I64) hand_entry_kernel<int64_t><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, nstate, active);
         else hand_entry_kernel<int32_t><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, nstate, active);
-        DTB_LAUNCH_CHECK("hand_entry_kernel");
+        });
         const int rounds = rounds_for(max_moves);
         for (int r = 1; r <= rounds; ++r) {
-            hand_node_jump_kernel<<<JUMP_BLOCKS, H_THREADS, 0, st>>>(nnodes, nstate, active, r, 2);
-            DTB_LAUNCH_CHECK("hand_node_jump_kernel");
+            DTB_KERNEL("hand_node_jump_kernel", st, hand_node_jump_kernel<<<JUMP_BLOCKS, H_THREADS, 0, st>>>(nnodes, nstate, active, r, 2));
         }
     }
     if (mode == DTB_HAND_SUMMARY) {

@@ -515,16 +515,13 @@ extern "C" int dtb_slope_d8(const void *dem, int dem_dtype, int64_t buf_rows, in
             attr_set = true;
         }
         const int grid = ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs;
-        slope_d8_tma_kernel<<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8);
-        DTB_LAUNCH_CHECK("slope_d8_tma_kernel");
+        DTB_KERNEL("slope_d8_tma_kernel", st, slope_d8_tma_kernel<<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8));
     } else if (dem_dtype == DTB_F32) {
-        slope_d8_generic_kernel<float><<<ntiles, NTHREADS, 0, st>>>((const float *)dem, buf_rows, row_begin, row_end, cols,
-                                                                    tiles_x, k, slope, d8);
-        DTB_LAUNCH_CHECK("slope_d8_generic_kernel<f32>");
+        DTB_KERNEL("slope_d8_generic_kernel<f32>", st, slope_d8_generic_kernel<float><<<ntiles, NTHREADS, 0, st>>>((const float *)dem, buf_rows, row_begin, row_end, cols,
+                                                                    tiles_x, k, slope, d8));
     } else {
-        slope_d8_generic_kernel<int16_t><<<ntiles, NTHREADS, 0, st>>>((const int16_t *)dem, buf_rows, row_begin, row_end,
-                                                                      cols, tiles_x, k, slope, d8);
-        DTB_LAUNCH_CHECK("slope_d8_generic_kernel<i16>");
+        DTB_KERNEL("slope_d8_generic_kernel<i16>", st, slope_d8_generic_kernel<int16_t><<<ntiles, NTHREADS, 0, st>>>((const int16_t *)dem, buf_rows, row_begin, row_end,
+                                                                      cols, tiles_x, k, slope, d8));
     }
     return DTB_OK;
 }

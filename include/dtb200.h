@@ -58,6 +58,13 @@ const char *dtb_last_cuda_error(void);
 /* number of kernels launched by the library since load / last reset (all threads) */
 int64_t dtb_launch_count(void);
 void dtb_reset_launch_count(void);
+/* Optional per-kernel timing: while enabled, every kernel launch of the library is bracketed by CUDA
+ * events on its stream.  dtb_profile_collect waits for the recorded events, writes one text line per
+ * kernel name ("name total_ms launches\n", in first-launch order) into buf (NUL-terminated, truncated
+ * to cap), clears the records and returns the untruncated length.  Used by bench.py for the roofline
+ * of the dominant kernel; off by default. */
+void dtb_profile_enable(int on);
+int64_t dtb_profile_collect(char *buf, int64_t cap);
 
 /* ---- slope + D8 (fused 3x3 stencil) -----------------------------------------------
  * Replaces slope_cpu + slope_gpu (slope.py:152-206, 209-259) and adds the D8 direction
