@@ -262,8 +262,12 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
     // in-tile state, slot layout of tiles.cuh: x = target (slot of the next cell while ACTIVE, global index of the
     // river cell, perimeter slot of the exit cell), y = [31..30 kind | 29..15 n_diag | 14..0 n_card]
     __shared__ uint2 st[TCELLS];
-    __shared__ unsigned long long exit_state[SLOTS];
-    __shared__ uint8_t exit_remote[SLOTS];  // 0: resolved inside the band, 1/2: by the band above/below
+    // what lies behind each exit cell of the perimeter: resolved once per slot, shared by every cell that
+    // leaves the tile through it (kind/moves, global river index, river elevation, ln b + n ln(A_r s^2))
+    __shared__ uint32_t exit_hi[SLOTS];
+    __shared__ long long exit_idx[SLOTS];
+    __shared__ TD exit_z[SLOTS];
+    __shared__ double exit_l1[SLOTS];
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
     const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
@@ -307,25 +311,24 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
     __syncthreads();
 
     // ---- in-tile pointer jumping (in place, asynchronous) ----
-    for (int round = 0; round < 13; ++round) {
-        unsigned m = activemask;
-        while (m) {
-            const int i = __ffs((int)m) - 1;
-            m &= m - 1;
-            const int p = i * H_THREADS + tid;
-            uint2 s = st[p];
+    // A field reaching 2^14 means the cell sits on / drains into an in-tile cycle (a simple path has < 4096
+    // moves): FAIL (flowhand.py:830/835).  Checking before every add keeps the 15-bit fields from carrying.
+    constexpr uint32_t CYC = 0x20004000u;
+    for (int round = 0; round < 16; ++round) {
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            if (!((activemask >> i) & 1u)) continue;
+            uint2 s = st[i * H_THREADS + tid];
             uint2 t = st[s.x];
             s.x = t.x;
             s.y += t.y;
-            if ((s.y >> 30) == 0u) {
+            if ((s.y >> 30) == 0u && !(s.y & CYC)) {
                 t = st[s.x];
                 s.x = t.x;
                 s.y += t.y;
             }
-            // a simple path inside the tile has < 4096 moves: more means the cell sits on / drains into an
-            // in-tile cycle (FAIL, flowhand.py:830/835); this also keeps the 15-bit counters from carrying
-            if ((s.y >> 30) == 0u && (s.y & 0x7FFFu) + ((s.y >> 15) & 0x7FFFu) >= (unsigned)TCELLS) s.y = (uint32_t)KIND_FAIL << 30;
-            st[p] = s;
+            if ((s.y >> 30) == 0u && (s.y & CYC)) s.y = (uint32_t)KIND_FAIL << 30;
+            st[i * H_THREADS + tid] = s;
             if (s.y >> 30) activemask &= ~(1u << i);
         }
         if (!__syncthreads_or(activemask != 0)) break;
@@ -365,8 +368,21 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
                 if (kind_of(e) != KIND_RIVER) { e = pack(KIND_FAIL, 0, 0, 0); remote = 0; }  // ACTIVE left over: cycle or > cap
             }
         }
-        exit_state[tid] = e;
-        exit_remote[tid] = (uint8_t)remote;
+        exit_hi[tid] = ((uint32_t)kind_of(e) << 30) | (nd_of(e) << 15) | nc_of(e);
+        if (kind_of(e) == KIND_RIVER) {
+            const int64_t loc = (int64_t)ptr_of(e);  // local index of the river cell, or (remote) a column of the halo tables
+            double racc = 1.0;
+            if (remote) {
+                exit_idx[tid] = o.res_idx[remote - 1][loc];
+                exit_z[tid] = (TD)o.res_z[remote - 1][loc];
+                if (o.gfi) racc = (double)o.res_acc[remote - 1][loc];
+            } else {
+                exit_idx[tid] = loc + o.idx_offset;
+                exit_z[tid] = (o.hand || o.gfi) ? dem[loc] : (TD)0;
+                if (o.gfi) racc = (double)acc[loc];  // river_accumulation, gfi.py:141-143
+            }
+            exit_l1[tid] = o.gfi ? o.gfi_logb + o.gfi_n * fast_log(racc * o.gfi_s2) : 0.0;
+        }
     }
     __syncthreads();
 
@@ -387,46 +403,30 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint2 s2 = st[(g4 + i) * H_THREADS + tid];
-            uint32_t kind = s2.y >> 30, nd = (s2.y >> 15) & 0x7FFFu, nc = s2.y & 0x7FFFu, tgt = s2.x;
-            unsigned remote = 0;
+            uint32_t kind = s2.y >> 30, nd = (s2.y >> 15) & 0x7FFFu, nc = s2.y & 0x7FFFu;
+            int64_t idx = (int64_t)ND_I;
+            TD zr = (TD)0;
+            double l1 = 0.0;
             if (kind == KIND_EXIT) {  // continue with the resolved path behind the tile's exit cell
-                const uint64_t e = exit_state[tgt];
-                remote = exit_remote[tgt];
-                kind = (uint32_t)kind_of(e);
-                nd += nd_of(e);
-                nc += nc_of(e);
-                tgt = ptr_of(e);
+                const uint32_t eh = exit_hi[s2.x];
+                kind = eh >> 30;
+                nd += (eh >> 15) & 0x7FFFu;
+                nc += eh & 0x7FFFu;
+                if (kind == KIND_RIVER) { idx = exit_idx[s2.x]; zr = exit_z[s2.x]; l1 = exit_l1[s2.x]; }
+            } else if (kind == KIND_RIVER) {  // river cell inside this tile: s2.x = its local index in the band
+                idx = (int64_t)s2.x + o.idx_offset;
+                if (o.hand || o.gfi) zr = dem[s2.x];
+                if (o.gfi) l1 = o.gfi_logb + o.gfi_n * fast_log((double)acc[s2.x] * o.gfi_s2);  // gfi.py:141-143
             }
             const bool ok = kind == KIND_RIVER && nc + nd <= o.max_moves;  // flowhand.py:835
             fd[i] = ok ? (float)((double)nc * o.px + (double)nd * o.pd) : ND_F;  // flowhand.py:840-843
+            ix[i] = ok ? (IDX)idx : (IDX)ND_I;
             TD h = HandOps<TD>::nd();
             float g = ND_F;
-            if (!remote) {
-                // river cell = local index `tgt` of this band
-                ix[i] = ok ? (IDX)((int64_t)tgt + o.idx_offset) : (IDX)ND_I;
-                if (o.hand || o.gfi) {
-                    if (ok && !HandOps<TD>::is_nd(z[i])) {  // flowhand.py:436-438
-                        h = HandOps<TD>::sub(z[i], dem[tgt]);
-                        if (h < (TD)0 && h != HandOps<TD>::nd()) h = (TD)0;
-                        if (o.gfi && !(h <= HandOps<TD>::nd())) {  // gfi.py:289
-                            const double ra = (double)acc[tgt] * o.gfi_s2;  // river_accumulation, gfi.py:141-143
-                            g = (float)(o.gfi_logb + o.gfi_n * fast_log(ra) - fast_log_pos((double)h + 0.01));  // gfi.py:292-294
-                        }
-                    }
-                }
-            } else {
-                // the path ends in another band: column `tgt` of the halo row's resolution tables
-                ix[i] = ok ? (IDX)o.res_idx[remote - 1][tgt] : (IDX)ND_I;
-                if (o.hand || o.gfi) {
-                    if (ok && !HandOps<TD>::is_nd(z[i])) {
-                        h = HandOps<TD>::sub(z[i], (TD)o.res_z[remote - 1][tgt]);
-                        if (h < (TD)0 && h != HandOps<TD>::nd()) h = (TD)0;
-                        if (o.gfi && !(h <= HandOps<TD>::nd())) {
-                            const double ra = (double)o.res_acc[remote - 1][tgt] * o.gfi_s2;
-                            g = (float)(o.gfi_logb + o.gfi_n * fast_log(ra) - fast_log_pos((double)h + 0.01));
-                        }
-                    }
-                }
+            if ((o.hand || o.gfi) && ok && !HandOps<TD>::is_nd(z[i])) {  // flowhand.py:436-438
+                h = HandOps<TD>::sub(z[i], zr);
+                if (h < (TD)0 && h != HandOps<TD>::nd()) h = (TD)0;
+                if (o.gfi && !(h <= HandOps<TD>::nd())) g = (float)(l1 - fast_log_pos((double)h + 0.01));  // gfi.py:289-294
             }
             hd[i] = h;
             gf[i] = g;
