@@ -35,8 +35,7 @@ CHAIN_BYTES = 55
 KERNEL_BYTES = {
     "slope_d8_tma_kernel": 9,      # dem 4 R, slope 4 W, d8 1 W
     "fa_tile_kernel": 5,           # d8 1 R, acc 4 W
-    "fa_tile_finish_kernel": 1,    # d8 1 R (+ the acc runs an entry path touches)
-    "hand_entry_kernel": 5,        # d8 1 R, acc 4 R (river mask)
+    "fa_tile_finish_kernel<hand>": 1,  # d8 1 R (+ the acc runs an entry path touches); fused with HAND's entry pass
     "hand_tile_kernel": 33,        # d8 1, acc 4, dem 4 R; gathers dem[idx] 4 + acc[idx] 4; idx, fdist, hand, gfi 16 W
 }
 SAMPLE_ROWS = SAMPLE_COLS = 3072  # bounded CPU sample
@@ -204,9 +203,10 @@ def run_ours(args):
             e[0].record()
             slope, d8 = device.slope_d8(dem, PX)
             e[1].record()
-            acc = device.flow_accumulation(d8, dtype=int_dt)
+            acc = device.flow_accumulation(d8, dtype=int_dt, fuse_hand_threshold=RIVER_THR)
             e[2].record()
-            out = device.hand(d8, dem, PX, acc=acc, river_threshold=RIVER_THR, gfi_params=(N_GFI, B_GFI, PX), idx_dtype=int_dt)
+            out = device.hand(d8, dem, PX, acc=acc, river_threshold=RIVER_THR, gfi_params=(N_GFI, B_GFI, PX), idx_dtype=int_dt,
+                              entry_done=True)
             e[3].record()
             return e, (slope, d8, acc, out)
 

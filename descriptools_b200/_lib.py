@@ -62,6 +62,7 @@ class HandArgs(Structure):
         ("gfi_b", c_double),
         ("gfi_size", c_double),
         ("band", POINTER(HandBand)),
+        ("entry_done", c_int),
     ]
 
 
@@ -83,6 +84,9 @@ class FlowaccArgs(Structure):
         ("term_below", c_void_p),
         ("mode", c_int),
         ("unfinalised_host", POINTER(c_int64)),
+        ("hand_ws", c_void_p),
+        ("hand_ws_bytes", c_size_t),
+        ("hand_river_threshold", c_int64),
     ]
 
 

@@ -223,6 +223,8 @@ class Band:
         a = self._fa_args(DTB_FA_FINISH if inflow is not None else DTB_FA_FULL)
         a.inflow_above = 0 if self.first else self.fa_inflow[0].data_ptr()
         a.inflow_below = 0 if self.last else self.fa_inflow[1].data_ptr()
+        # the last tile pass also does HAND's entry-node pass (river = acc > threshold) into the HAND workspace
+        a.hand_ws, a.hand_ws_bytes, a.hand_river_threshold = self.ws_hand.data_ptr(), self.ws_hand.numel(), self.thr
         self._check(self.lib.dtb_flowacc_band(ctypes.byref(a), self.ws_fa.data_ptr(), self.ws_fa.numel(), self._stream()),
                     "dtb_flowacc_band(finish)")
 
@@ -236,6 +238,7 @@ class Band:
         a.idx_dtype = idt
         a.gfi_n, a.gfi_b, a.gfi_size = self.n_gfi, self.b_gfi, self.px
         b.mode, b.row_offset = mode, self.r0
+        a.entry_done = 1
         b.above.halo = 0 if self.first else self.d8_buf[0].data_ptr()
         b.below.halo = 0 if self.last else self.d8_buf[self.rows + 1].data_ptr()
         a.band = ctypes.pointer(b)

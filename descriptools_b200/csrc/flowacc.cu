@@ -191,71 +191,145 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
 
 // ---- T2: add the resolved inflow of the entry nodes along their in-tile paths --------------------------
 // acc already holds the tile-local counts; only the 64-byte runs that an entry path touches are rewritten.
-template <typename ACC>
+// The walks run over a successor table built once per tile (slot layout, 16 bits per cell:
+// [14 diagonal move | 13..0 successor slot / W_EXIT / W_TERM]).
+// HAND = true fuses the first pass of the HAND stage (hand.cu, H1) into the same tile visit: with the river
+// mask defined as acc > threshold (example.py:52) every river cell lies on an entry path or has a local
+// count above the threshold, so once the inflow is added the tile knows its river cells and the entry nodes
+// can walk to their first river cell / failure / next entry node right away.
+constexpr uint32_t NX_DIAG = 0x4000u;
+
+template <typename ACC, bool HAND>
 __global__ void __launch_bounds__(FT_THREADS)
-fa_tile_finish_kernel(TileView v, const unsigned long long *__restrict__ nstate, ACC *__restrict__ acc,
-                      unsigned long long *__restrict__ counters)
+fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const unsigned long long *__restrict__ nstate,
+                      ACC *__restrict__ acc, unsigned long long *__restrict__ counters, int64_t thr,
+                      unsigned long long *__restrict__ hand_nstate, unsigned *__restrict__ hand_active)
 {
     typedef typename std::conditional<sizeof(ACC) == 8, unsigned long long, uint32_t>::type EXT;
     __shared__ __align__(16) uint8_t codes[(T + 2) * CP + 16];
+    __shared__ uint16_t nxt[TCELLS];
     __shared__ EXT ext[TCELLS];
+    __shared__ uint16_t rivm[HAND ? FT_THREADS : 1];
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
     const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
     const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
     const bool fast = stage_codes(v, r0, c0, codes, tid, FT_THREADS);
-#pragma unroll
-    for (int i = 0; i < CPT; ++i) ext[i * FT_THREADS + tid] = 0;
     __syncthreads();
 
+    const int lr = tid >> 2, lcb = (tid & 3) * CPT;
+    {
+        const uint8_t *crow = codes + (lr + 1) * CP + 16 + lcb;
+        const uint4 cw = *reinterpret_cast<const uint4 *>(crow);
+        const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            const int lc = lcb + i, p = lr * T + lc;
+            const unsigned code = (cws[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            uint32_t nx = W_TERM;
+            int dloc, dcode;
+            if (d8_delta(code, dloc, dcode) && crow[i + dcode] != 0) nx = (code & exit_codes(lr, lc)) ? W_EXIT : phys_of((uint32_t)(p + dloc));
+            nxt[i * FT_THREADS + tid] = (uint16_t)(nx | ((code & 0xAAu) ? NX_DIAG : 0u));
+            ext[i * FT_THREADS + tid] = 0;
+        }
+    }
+    __syncthreads();
+
+    // ---- entry nodes push their resolved inflow down their in-tile path ----
+    const uint32_t my_inmask = tid < USED_SLOTS ? (meta[(size_t)tile * SLOTS + tid] >> 16) & 0xFFu : 0u;
+    uint32_t my_slot = 0;
     unsigned unresolved = 0;
-    if (tid < USED_SLOTS) {
-        int lr, lc;
-        slot_cell(tid, lr, lc);
-        const uint8_t *cp = codes + (lr + 1) * CP + 16 + lc;
-        if (*cp != 0 && (in_mask(codes, lr, lc) & out_mask(lr, lc))) {
-            const uint64_t ns = nstate[(size_t)tile * SLOTS + tid];
-            if ((ns >> N_PEND_SHIFT) & N_PEND) ++unresolved;  // never finalised: node-level cycle
-            const EXT w = (EXT)(ns & N_CNT);
-            int p = lr * T + lc;
-            for (int steps = 0; w != 0 && steps < TCELLS; ++steps) {
-                atomicAdd(&ext[phys_of((uint32_t)p)], w);
-                const unsigned code = *cp;
-                int dloc, dcode;
-                if (!d8_delta(code, dloc, dcode) || cp[dcode] == 0 || (code & exit_codes(p >> 6, p & (T - 1)))) break;
-                p += dloc;
-                cp += dcode;
-            }
+    if (my_inmask) {
+        int plr, plc;
+        slot_cell(tid, plr, plc);
+        my_slot = phys_of((uint32_t)(plr * T + plc));
+        const uint64_t ns = nstate[(size_t)tile * SLOTS + tid];
+        if ((ns >> N_PEND_SHIFT) & N_PEND) ++unresolved;  // never finalised: node-level cycle
+        const EXT w = (EXT)(ns & N_CNT);
+        uint32_t q = my_slot;
+        for (int steps = 0; w != 0 && steps < TCELLS; ++steps) {
+            atomicAdd(&ext[q], w);
+            const uint32_t n = nxt[q] & W_NXT;
+            if (n >= W_EXIT) break;
+            q = n;
         }
     }
     unresolved = __reduce_add_sync(0xffffffffu, unresolved);
     if ((tid & 31) == 0 && unresolved) atomicAdd(&counters[0], (unsigned long long)unresolved);
     __syncthreads();
 
-    const int lr = tid >> 2, lcb = (tid & 3) * CPT;
+    // ---- acc += inflow on the touched runs; river bits of my 16 cells ----
     const int64_t gr = r0 + lr;
-    if (gr >= v.rows) return;
-    EXT e[CPT];
-    bool any = false;
+    unsigned riv = 0;
+    if (gr < v.rows) {
+        EXT e[CPT];
+        bool any = false;
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) { e[i] = ext[i * FT_THREADS + tid]; any |= e[i] != 0; }
-    if (!any) return;
-    ACC *dst = acc + gr * v.cols + c0 + lcb;
-    if (fast && ((reinterpret_cast<uintptr_t>(acc) & 15u) == 0)) {
-        constexpr int V = 16 / sizeof(ACC);
+        for (int i = 0; i < CPT; ++i) { e[i] = ext[i * FT_THREADS + tid]; any |= e[i] != 0; }
+        // cells off every entry path keep their tile-local count (< 4096): they can only be river cells for tiny thresholds
+        const bool need = any || (HAND && thr < (int64_t)TCELLS);
+        if (need) {
+            ACC *dst = acc + gr * v.cols + c0 + lcb;
+            if (fast && ((reinterpret_cast<uintptr_t>(acc) & 15u) == 0)) {
+                constexpr int V = 16 / sizeof(ACC);
 #pragma unroll
-        for (int i = 0; i < CPT; i += V) {
-            uint4 w = *reinterpret_cast<const uint4 *>(dst + i);
-            ACC *a = reinterpret_cast<ACC *>(&w);
+                for (int i = 0; i < CPT; i += V) {
+                    uint4 w = *reinterpret_cast<const uint4 *>(dst + i);
+                    ACC *a = reinterpret_cast<ACC *>(&w);
 #pragma unroll
-            for (int j = 0; j < V; ++j) a[j] += (ACC)e[i + j];
-            *reinterpret_cast<uint4 *>(dst + i) = w;
+                    for (int j = 0; j < V; ++j) {
+                        a[j] += (ACC)e[i + j];
+                        if (HAND) riv |= (unsigned)((int64_t)a[j] > thr) << (i + j);
+                    }
+                    if (any) *reinterpret_cast<uint4 *>(dst + i) = w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < CPT; ++i)
+                    if (c0 + lcb + i < v.cols) {
+                        const ACC a = dst[i] + (ACC)e[i];
+                        if (e[i] != 0) dst[i] = a;
+                        if (HAND) riv |= (unsigned)((int64_t)a > thr) << i;
+                    }
+            }
         }
-    } else {
-#pragma unroll
-        for (int i = 0; i < CPT; ++i)
-            if (e[i] != 0 && c0 + lcb + i < v.cols) dst[i] += (ACC)e[i];
     }
+    if (!HAND) return;
+    rivm[tid] = (uint16_t)riv;
+    __syncthreads();
+
+    // ---- HAND first pass: entry nodes walk to their first river cell / failure / next entry node ----
+    uint64_t hs = 0ull;  // inactive slot (never referenced)
+    int is_active = 0;
+    if (my_inmask) {
+        uint32_t q = my_slot, nc = 0, nd = 0;
+        hs = pack(KIND_FAIL, 0, 0, 0);  // in-tile cycle if the loop runs out
+        for (int steps = 0; steps <= TCELLS; ++steps) {
+            if ((rivm[q & (FT_THREADS - 1)] >> (q >> 8)) & 1u) {  // flowhand.py:622
+                const uint32_t pl = logical_of(q);
+                hs = pack(KIND_RIVER, nd, nc, (uint32_t)((r0 + (pl >> 6)) * v.cols + c0 + (pl & (T - 1))));
+                break;
+            }
+            const uint32_t n16 = nxt[q], n = n16 & W_NXT;
+            if (n == W_TERM) break;  // unknown code, off-raster or code-0 landing (flowhand.py:623-764, 826, 830)
+            if (n16 & NX_DIAG) ++nd; else ++nc;
+            if (n == W_EXIT) {
+                const uint32_t pl = logical_of(q);
+                const int qr = (int)(pl >> 6), qc = (int)(pl & (T - 1));
+                int dr, dc;
+                d8_offset(codes[(qr + 1) * CP + 16 + qc], dr, dc);
+                const int64_t tr = r0 + qr + dr, tc = c0 + qc + dc;
+                if (tr < 0) hs = pack(KIND_EXIT, nd, nc, LINK_OUT | (uint32_t)tc);
+                else if (tr >= v.rows) hs = pack(KIND_EXIT, nd, nc, LINK_OUT | LINK_BELOW | (uint32_t)tc);
+                else { hs = pack(KIND_ACTIVE, nd, nc, (uint32_t)node_of_cell(tr, tc, v.tiles_x)); is_active = 1; }
+                break;
+            }
+            q = n;
+        }
+    }
+    hand_nstate[(size_t)tile * SLOTS + tid] = hs;
+    const unsigned ballot = __ballot_sync(0xffffffffu, is_active);
+    if ((tid & 31) == 0 && ballot) atomicAdd(&hand_active[0], (unsigned)__popc(ballot));
 }
 
 // ---- N: entry-node forest ---------------------------------------------------------------------
@@ -513,7 +587,17 @@ int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
         return DTB_OK;
     }
 
-    DTB_KERNEL("fa_tile_finish_kernel", st, fa_tile_finish_kernel<ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, nstate, acc, counters));
+    if (a->hand_ws) {
+        // fused HAND first pass: node states and the ACTIVE counter live at the head of the HAND workspace (hand.cu)
+        unsigned *hactive = reinterpret_cast<unsigned *>(a->hand_ws);
+        unsigned long long *hstate = reinterpret_cast<unsigned long long *>((char *)a->hand_ws + 256);
+        DTB_CUDA(cudaMemsetAsync(hactive, 0, 256, st));
+        DTB_KERNEL("fa_tile_finish_kernel<hand>", st, fa_tile_finish_kernel<ACC, true><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(
+                       v, meta, nstate, acc, counters, a->hand_river_threshold, hstate, hactive));
+    } else {
+        DTB_KERNEL("fa_tile_finish_kernel", st, fa_tile_finish_kernel<ACC, false><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(
+                       v, meta, nstate, acc, counters, 0, nullptr, nullptr));
+    }
     // cyclic grids only (each kernel returns at once when counters[0] == 0)
     DTB_KERNEL("fa_flat_init_kernel", st, fa_flat_init_kernel<<<FLAT_BLOCKS, 256, 0, st>>>(v, a->inflow_above, a->inflow_below, flat, counters));
     DTB_KERNEL("fa_flat_sweep_kernel", st, fa_flat_sweep_kernel<ACC><<<FLAT_BLOCKS, 256, 0, st>>>(v, acc, flat, counters));
@@ -546,6 +630,9 @@ extern "C" int dtb_flowacc_band(const dtb_flowacc_args *a, void *ws, size_t ws_b
     if (ws_bytes < dtb_flowacc_workspace_bytes(a->rows, a->cols)) return DTB_ERR_WORKSPACE;
     if (a->cols >= (int64_t)1 << 30) return DTB_ERR_UNSUPPORTED;
     if (a->halo_below && a->rows % T != 0) return DTB_ERR_INVALID;  // band seams sit on tile seams
+    if (a->hand_ws && (a->mode == DTB_FA_SUMMARY || a->hand_ws_bytes < dtb_hand_workspace_bytes(a->rows, a->cols) ||
+                       a->rows * a->cols > 0xffffffffLL))
+        return DTB_ERR_INVALID;
     const NodeLayout L = layout(a->rows, a->cols);
     if (L.nnodes >= (int64_t)1 << 30) return DTB_ERR_UNSUPPORTED;  // node ids share a word with the LINK_OUT flags
     if (a->rows * a->cols >= (int64_t)1 << 43) return DTB_ERR_UNSUPPORTED;

@@ -36,27 +36,6 @@ namespace dtb {
 namespace {
 
 constexpr int H_THREADS = 256;
-constexpr uint64_t KIND_ACTIVE = 0, KIND_RIVER = 1, KIND_FAIL = 2, KIND_EXIT = 3;
-constexpr uint32_t CNT_SAT = 32767;
-constexpr int JUMP_BLOCKS = kNumSMs * 8;
-
-__device__ __forceinline__ uint64_t pack(uint64_t kind, uint32_t nd, uint32_t nc, uint32_t ptr)
-{
-    return (kind << 62) | ((uint64_t)nd << 47) | ((uint64_t)nc << 32) | (uint64_t)ptr;
-}
-__device__ __forceinline__ uint64_t kind_of(uint64_t s) { return s >> 62; }
-__device__ __forceinline__ uint32_t nd_of(uint64_t s) { return (uint32_t)(s >> 47) & 0x7FFFu; }
-__device__ __forceinline__ uint32_t nc_of(uint64_t s) { return (uint32_t)(s >> 32) & 0x7FFFu; }
-__device__ __forceinline__ uint32_t ptr_of(uint64_t s) { return (uint32_t)s; }
-__device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b) { return min(a + b, CNT_SAT); }
-// state of a path that continues with `t` after the moves recorded in `s`
-__device__ __forceinline__ uint64_t compose(uint64_t s, uint64_t t)
-{
-    const uint64_t kt = kind_of(t);
-    if (kt == KIND_FAIL) return pack(KIND_FAIL, 0, 0, 0);
-    return pack(kt, sat_add(nd_of(s), nd_of(t)), sat_add(nc_of(s), nc_of(t)), ptr_of(t));
-}
-
 struct RiverSrc {
     const int8_t *river;  // 0/1 mask (flowhand.py:609) or NULL
     const void *acc;      // river = acc > thr (example.py:52)
@@ -574,12 +553,15 @@ extern "C" int dtb_hand(const dtb_hand_args *a, void *ws, size_t ws_bytes, void 
     if (nnodes >= (int64_t)1 << 30) return DTB_ERR_UNSUPPORTED;
     RiverSrc rs{a->river, a->acc, a->river_threshold};
 
+    if (a->entry_done && a->river) return DTB_ERR_INVALID;  // the fused entry pass knows only acc > threshold
     if (mode != DTB_HAND_FINISH) {
-        DTB_CUDA(cudaMemsetAsync(active, 0, 256, st));
-        DTB_KERNEL("hand_entry_kernel", st, {
-            if (a->acc_dtype == DTB_I64) hand_entry_kernel<int64_t><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, nstate, active);
-        else hand_entry_kernel<int32_t><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, nstate, active);
-        });
+        if (!a->entry_done) {
+            DTB_CUDA(cudaMemsetAsync(active, 0, 256, st));
+            DTB_KERNEL("hand_entry_kernel", st, {
+                if (a->acc_dtype == DTB_I64) hand_entry_kernel<int64_t><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, nstate, active);
+                else hand_entry_kernel<int32_t><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, nstate, active);
+            });
+        }
         const int rounds = rounds_for(max_moves);
         for (int r = 1; r <= rounds; ++r) {
             DTB_KERNEL("hand_node_jump_kernel", st, hand_node_jump_kernel<<<JUMP_BLOCKS, H_THREADS, 0, st>>>(nnodes, nstate, active, r, 2));

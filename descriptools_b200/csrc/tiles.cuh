@@ -146,4 +146,28 @@ __device__ __forceinline__ int64_t node_of_cell(int64_t gr, int64_t gc, int tile
     return ((gr / T) * tiles_x + gc / T) * SLOTS + slot_of((int)(gr % T), (int)(gc % T));
 }
 
+// ---- packed path state of the HAND stage (hand.cu; also written by the fused finish pass of flowacc.cu) ----
+//     [63..62 kind | 61..47 diagonal moves | 46..32 cardinal moves | 31..0 target]
+constexpr uint64_t KIND_ACTIVE = 0, KIND_RIVER = 1, KIND_FAIL = 2, KIND_EXIT = 3;
+constexpr uint32_t CNT_SAT = 32767;
+constexpr int JUMP_BLOCKS = kNumSMs * 8;
+
+__device__ __forceinline__ uint64_t pack(uint64_t kind, uint32_t nd, uint32_t nc, uint32_t ptr)
+{
+    return (kind << 62) | ((uint64_t)nd << 47) | ((uint64_t)nc << 32) | (uint64_t)ptr;
+}
+__device__ __forceinline__ uint64_t kind_of(uint64_t s) { return s >> 62; }
+__device__ __forceinline__ uint32_t nd_of(uint64_t s) { return (uint32_t)(s >> 47) & 0x7FFFu; }
+__device__ __forceinline__ uint32_t nc_of(uint64_t s) { return (uint32_t)(s >> 32) & 0x7FFFu; }
+__device__ __forceinline__ uint32_t ptr_of(uint64_t s) { return (uint32_t)s; }
+__device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b) { return min(a + b, CNT_SAT); }
+// state of a path that continues with `t` after the moves recorded in `s`
+__device__ __forceinline__ uint64_t compose(uint64_t s, uint64_t t)
+{
+    const uint64_t kt = kind_of(t);
+    if (kt == KIND_FAIL) return pack(KIND_FAIL, 0, 0, 0);
+    return pack(kt, sat_add(nd_of(s), nd_of(t)), sat_add(nc_of(s), nc_of(t)), ptr_of(t));
+}
+
+
 }  // namespace dtb

@@ -55,18 +55,18 @@ def _int_dtype(t: torch.Tensor) -> int:
 
 
 class _Workspace:
-    """One cached scratch buffer per device, grown on demand (caller-owned from the ABI's view)."""
+    """Cached scratch buffers per (device, stage), grown on demand (caller-owned from the ABI's view)."""
 
     def __init__(self):
         self.buf = {}
 
-    def get(self, nbytes: int) -> torch.Tensor:
-        dev = torch.cuda.current_device()
-        b = self.buf.get(dev)
+    def get(self, nbytes: int, stage: str = "shared") -> torch.Tensor:
+        key = (torch.cuda.current_device(), stage)
+        b = self.buf.get(key)
         if b is None or b.numel() < nbytes:
-            self.buf[dev] = None
-            b = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{dev}")
-            self.buf[dev] = b
+            self.buf[key] = None
+            b = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{key[0]}")
+            self.buf[key] = b
         return b
 
     def release(self):
@@ -91,25 +91,40 @@ def slope_d8(dem: torch.Tensor, px: float, want_slope: bool = True, want_d8: boo
 
 
 def flow_accumulation(d8: torch.Tensor, dtype: torch.dtype = torch.int32, nodata_fill: int = -100,
-                      check_cycles: bool = False):
-    """D8 flow accumulation.  Returns acc, or (acc, n_cycle_cells) if check_cycles."""
+                      check_cycles: bool = False, fuse_hand_threshold: int | None = None):
+    """D8 flow accumulation.  Returns acc, or (acc, n_cycle_cells) if check_cycles.
+
+    fuse_hand_threshold = t: the final tile pass also runs HAND's entry-node pass for the river mask
+    acc > t and leaves the node states in the HAND workspace; follow with hand(..., entry_done=True).
+    """
+    from ._lib import FlowaccArgs
+
     d8 = _chk2d(d8, "d8")
     if d8.dtype != torch.uint8:
         raise TypeError("d8 must be uint8")
     rows, cols = d8.shape
     acc = torch.empty((rows, cols), dtype=dtype, device=d8.device)
     nbytes = lib.dtb_flowacc_workspace_bytes(rows, cols)
-    ws = workspace.get(nbytes)
+    ws = workspace.get(nbytes, "flowacc")
     left = ctypes.c_int64(0)
-    check(lib.dtb_flowacc(_ptr(d8), rows, cols, _ptr(acc), _int_dtype(acc), int(nodata_fill), _ptr(ws), nbytes,
-                          ctypes.byref(left) if check_cycles else None, _stream()), "dtb_flowacc")
+    a = FlowaccArgs()
+    a.d8, a.rows, a.cols = _ptr(d8), rows, cols
+    a.acc, a.acc_dtype, a.nodata_fill = _ptr(acc), _int_dtype(acc), int(nodata_fill)
+    if check_cycles:
+        a.unfinalised_host = ctypes.pointer(left)
+    if fuse_hand_threshold is not None:
+        hb = lib.dtb_hand_workspace_bytes(rows, cols)
+        hws = workspace.get(hb, "hand")
+        a.hand_ws, a.hand_ws_bytes, a.hand_river_threshold = _ptr(hws), hb, int(fuse_hand_threshold)
+    check(lib.dtb_flowacc_band(ctypes.byref(a), _ptr(ws), nbytes, _stream()), "dtb_flowacc_band")
     return (acc, int(left.value)) if check_cycles else acc
 
 
 def hand(fdr: torch.Tensor, dem: torch.Tensor | None, px: float, river: torch.Tensor | None = None,
          acc: torch.Tensor | None = None, river_threshold: int = 0, max_moves: int = 0,
          want_fdist: bool = True, want_idx: bool = True, want_hand: bool = True,
-         gfi_params: tuple[float, float, float] | None = None, idx_dtype: torch.dtype | None = None):
+         gfi_params: tuple[float, float, float] | None = None, idx_dtype: torch.dtype | None = None,
+         entry_done: bool = False):
     """Flow distance, river index, HAND and (optionally) fused GFI.
 
     flowhand.py:476-846 + 414-442 (+ gfi.py:118-147, 267-294 when gfi_params=(n, b, size)).
@@ -155,8 +170,9 @@ def hand(fdr: torch.Tensor, dem: torch.Tensor | None, px: float, river: torch.Te
         out["gfi"] = torch.empty((rows, cols), dtype=torch.float32, device=dev)
         a.gfi_n, a.gfi_b, a.gfi_size = (float(v) for v in gfi_params)
     a.fdist, a.idx, a.hand, a.gfi = _ptr(out.get("fdist")), _ptr(out.get("idx")), _ptr(out.get("hand")), _ptr(out.get("gfi"))
+    a.entry_done = 1 if entry_done else 0
     nbytes = lib.dtb_hand_workspace_bytes(rows, cols)
-    ws = workspace.get(nbytes)
+    ws = workspace.get(nbytes, "hand")
     check(lib.dtb_hand(ctypes.byref(a), _ptr(ws), nbytes, _stream()), "dtb_hand")
     return out
 
@@ -248,7 +264,7 @@ def fill_depressions(dem: torch.Tensor) -> int:
         raise ValueError("dem must be a contiguous float32 CUDA tensor")
     rows, cols = dem.shape
     nbytes = lib.dtb_fill_workspace_bytes(rows, cols)
-    ws = workspace.get(nbytes)
+    ws = workspace.get(nbytes, "fill")
     it = ctypes.c_int(0)
     check(lib.dtb_fill_depressions_f32(_ptr(dem), rows, cols, _ptr(ws), nbytes, ctypes.byref(it), _stream()),
           "dtb_fill_depressions_f32")

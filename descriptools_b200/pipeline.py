@@ -30,9 +30,10 @@ def run_device(dem: torch.Tensor, px: float, river_threshold: int, n_gfi: float 
     rows, cols = dem.shape
     int_dt = torch.int32 if rows * cols < 2**31 else torch.int64
     slope, d8 = device.slope_d8(dem, px)
-    acc = device.flow_accumulation(d8, dtype=int_dt, nodata_fill=-100)
+    # the last tile pass of the accumulation also does HAND's entry-node pass (river = acc > threshold)
+    acc = device.flow_accumulation(d8, dtype=int_dt, nodata_fill=-100, fuse_hand_threshold=river_threshold)
     out = device.hand(d8, dem, px, acc=acc, river_threshold=river_threshold, max_moves=max_moves,
-                      gfi_params=(n_gfi, scale_factor, size), idx_dtype=int_dt)
+                      gfi_params=(n_gfi, scale_factor, size), idx_dtype=int_dt, entry_done=True)
     out.update(slope=slope, d8=d8, acc=acc)
     return out
 
@@ -105,11 +106,11 @@ def pipeline(dem, px: float, river_threshold: int, n_gfi: float = 0.4, scale_fac
                                slope[r0:r1].data_ptr(), d8[r0:r1].data_ptr(), main.cuda_stream), "dtb_slope_d8")
         send_back("slope", slope, r0, r1)
         send_back("d8", d8, r0, r1)
-    acc = device.flow_accumulation(d8, dtype=int_dt, nodata_fill=-100)
+    acc = device.flow_accumulation(d8, dtype=int_dt, nodata_fill=-100, fuse_hand_threshold=river_threshold)
     keep.append(acc)
     send_back("acc", acc)
     out = device.hand(d8, dem_d, px, acc=acc, river_threshold=river_threshold, gfi_params=(n_gfi, scale_factor, size),
-                      idx_dtype=int_dt)
+                      idx_dtype=int_dt, entry_done=True)
     for name in ("idx", "fdist", "hand", "gfi"):
         keep.append(out[name])
         send_back(name, out[name])

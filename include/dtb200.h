@@ -120,6 +120,14 @@ typedef struct dtb_flowacc_args {
     int32_t *term_above, *term_below;
     int mode;
     int64_t *unfinalised_host;
+    /* Optional fusion with the HAND stage (modes FULL and FINISH): if hand_ws is a workspace of
+     * dtb_hand_workspace_bytes(rows, cols) bytes, the final tile pass also performs dtb_hand's first
+     * pass (entry-node walks) for the river mask acc > hand_river_threshold (example.py:52) and leaves
+     * the node states there; the following dtb_hand call on the same fdr / acc / threshold / workspace
+     * passes entry_done = 1 and skips that pass. */
+    void *hand_ws;
+    size_t hand_ws_bytes;
+    int64_t hand_river_threshold;
 } dtb_flowacc_args;
 int dtb_flowacc_band(const dtb_flowacc_args *args, void *ws, size_t ws_bytes, void *stream);
 
@@ -151,6 +159,7 @@ typedef struct dtb_hand_args {
     float *gfi;
     double gfi_n, gfi_b, gfi_size;
     const struct dtb_hand_band *band; /* NULL: the buffers hold the whole raster */
+    int entry_done;                   /* 1: the entry-node pass was done by dtb_flowacc_band (hand_ws) */
 } dtb_hand_args;
 
 /* Row-band form (multi-GPU).  One dtb_hand_seam per side of the band.
