@@ -45,18 +45,21 @@ def band_edges(rows: int, nbands: int) -> list[int]:
 
 # ---- boundary solvers (rank 0; pure torch, any device) -------------------------------------------
 def forest_accumulate(nxt: torch.Tensor, base: torch.Tensor) -> torch.Tensor:
-    """out[i] = base[i] + sum of out[j] over j with nxt[j] == i  (nxt < 0: none), by pointer doubling."""
+    """out[i] = base[i] + sum of out[j] over j with nxt[j] == i  (nxt < 0: none), by pointer doubling.
+
+    Whole-array ops only (no data-dependent shapes), so a pass of ROUNDS doublings enqueues without a host
+    sync; one check per pass decides whether a chain longer than 2**ROUNDS seam crossings needs another."""
+    ROUNDS = 5
     s, a = base.clone(), nxt.clone()
-    for _ in range(64):
-        live = a >= 0
-        if not bool(live.any()):
+    zero = torch.zeros_like(s)
+    for _ in range(13):
+        for _ in range(ROUNDS):
+            live = a >= 0
+            tgt = a.clamp(min=0)
+            s = s + torch.zeros_like(s).index_add_(0, tgt, torch.where(live, s, zero))
+            a = torch.where(live, a[tgt], a)
+        if not bool((a >= 0).any()):
             return s
-        tgt = a[live]
-        add = torch.zeros_like(s)
-        add.index_add_(0, tgt, s[live])
-        a2 = a.clone()
-        a2[live] = a[tgt]
-        s, a = s + add, a2
     raise RuntimeError("flow accumulation boundary graph has a cycle")
 
 
@@ -111,17 +114,15 @@ def solve_hand_boundary(summ: torch.Tensor) -> torch.Tensor:
     tgt = torch.where(ok, (b2.clamp(0, n - 1) * 2 + (1 - t_side)) * cols + t_col.clamp(max=cols - 1), torch.full_like(node, -1))
     kind = torch.where((kind == KIND_EXIT) & ~ok, torch.full_like(kind, KIND_FAIL), kind)
     src = node.clone()                                                       # whose payload the node ends up with
-    for _ in range(64):
-        live = kind == KIND_EXIT
-        if not bool(live.any()):
+    for _ in range(13):                                                      # 13 x 5 doublings > any move cap
+        for _ in range(5):                                                   # whole-array ops: no host sync inside
+            live = kind == KIND_EXIT
+            t = tgt.clamp(min=0)
+            nd = torch.where(live, (nd + nd[t]).clamp(max=CNT_SAT), nd)
+            nc = torch.where(live, (nc + nc[t]).clamp(max=CNT_SAT), nc)
+            kind, tgt, src = torch.where(live, kind[t], kind), torch.where(live, tgt[t], tgt), torch.where(live, src[t], src)
+        if not bool((kind == KIND_EXIT).any()):
             break
-        t = tgt[live]
-        nd2, nc2 = nd.clone(), nc.clone()
-        nd2[live] = (nd[live] + nd[t]).clamp(max=CNT_SAT)
-        nc2[live] = (nc[live] + nc[t]).clamp(max=CNT_SAT)
-        kind2, tgt2, src2 = kind.clone(), tgt.clone(), src.clone()
-        kind2[live], tgt2[live], src2[live] = kind[t], tgt[t], src[t]
-        kind, nd, nc, tgt, src = kind2, nd2, nc2, tgt2, src2
     kind = torch.where(kind == KIND_EXIT, torch.full_like(kind, KIND_FAIL), kind)   # cycle across seams
     state = ((kind << 62) | (nd << 47) | (nc << 32)).view(n, 2, cols)
     pay = pay[src].view(n, 2, cols, 3)

@@ -192,12 +192,12 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
 // ---- T2: add the resolved inflow of the entry nodes along their in-tile paths --------------------------
 // acc already holds the tile-local counts; only the 64-byte runs that an entry path touches are rewritten.
 // The walks run over a successor table built once per tile (slot layout, 16 bits per cell:
-// [14 diagonal move | 13..0 successor slot / W_EXIT / W_TERM]).
+// [15 river cell | 14 diagonal move | 13..0 successor slot / W_EXIT / W_TERM]).
 // HAND = true fuses the first pass of the HAND stage (hand.cu, H1) into the same tile visit: with the river
 // mask defined as acc > threshold (example.py:52) every river cell lies on an entry path or has a local
 // count above the threshold, so once the inflow is added the tile knows its river cells and the entry nodes
 // can walk to their first river cell / failure / next entry node right away.
-constexpr uint32_t NX_DIAG = 0x4000u;
+constexpr uint32_t NX_DIAG = 0x4000u, NX_RIVER = 0x8000u, NX_CYCLE = 0xFFFFFFFFu;
 
 template <typename ACC, bool HAND>
 __global__ void __launch_bounds__(FT_THREADS)
@@ -209,7 +209,6 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const unsig
     __shared__ __align__(16) uint8_t codes[(T + 2) * CP + 16];
     __shared__ uint16_t nxt[TCELLS];
     __shared__ EXT ext[TCELLS];
-    __shared__ uint16_t rivm[HAND ? FT_THREADS : 1];
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
     const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
@@ -236,8 +235,10 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const unsig
     __syncthreads();
 
     // ---- entry nodes push their resolved inflow down their in-tile path ----
+    // The same walk records where the path ends and how many cardinal / diagonal moves it takes: in a tile
+    // without river cells that already is the entry node's HAND state.
     const uint32_t my_inmask = tid < USED_SLOTS ? (meta[(size_t)tile * SLOTS + tid] >> 16) & 0xFFu : 0u;
-    uint32_t my_slot = 0;
+    uint32_t my_slot = 0, path_moves = 0, path_end = W_TERM, path_last = 0;  // moves: n_card | n_diag << 16
     unsigned unresolved = 0;
     if (my_inmask) {
         int plr, plc;
@@ -247,10 +248,13 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const unsig
         if ((ns >> N_PEND_SHIFT) & N_PEND) ++unresolved;  // never finalised: node-level cycle
         const EXT w = (EXT)(ns & N_CNT);
         uint32_t q = my_slot;
-        for (int steps = 0; w != 0 && steps < TCELLS; ++steps) {
+        path_end = NX_CYCLE;
+        for (int steps = 0; steps < TCELLS; ++steps) {
             atomicAdd(&ext[q], w);
-            const uint32_t n = nxt[q] & W_NXT;
-            if (n >= W_EXIT) break;
+            const uint32_t n16 = nxt[q], n = n16 & W_NXT;
+            if (n == W_TERM) { path_end = W_TERM; break; }
+            path_moves += 1u + ((n16 >> 14) & 1u) * 0xFFFFu;
+            if (n == W_EXIT) { path_end = W_EXIT; path_last = q; break; }
             q = n;
         }
     }
@@ -295,36 +299,45 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const unsig
         }
     }
     if (!HAND) return;
-    rivm[tid] = (uint16_t)riv;
-    __syncthreads();
+    // river cells get bit 15 of their successor entry; a tile without any keeps the states of the first walk
+    if (riv) {
+#pragma unroll
+        for (int i = 0; i < CPT; ++i)
+            if ((riv >> i) & 1u) nxt[i * FT_THREADS + tid] |= NX_RIVER;
+    }
+    const bool tile_has_river = __syncthreads_or(riv != 0);
 
     // ---- HAND first pass: entry nodes walk to their first river cell / failure / next entry node ----
     uint64_t hs = 0ull;  // inactive slot (never referenced)
     int is_active = 0;
     if (my_inmask) {
-        uint32_t q = my_slot, nc = 0, nd = 0;
-        hs = pack(KIND_FAIL, 0, 0, 0);  // in-tile cycle if the loop runs out
-        for (int steps = 0; steps <= TCELLS; ++steps) {
-            if ((rivm[q & (FT_THREADS - 1)] >> (q >> 8)) & 1u) {  // flowhand.py:622
-                const uint32_t pl = logical_of(q);
-                hs = pack(KIND_RIVER, nd, nc, (uint32_t)((r0 + (pl >> 6)) * v.cols + c0 + (pl & (T - 1))));
-                break;
+        uint32_t q = my_slot, moves = 0, end = NX_CYCLE;
+        if (!tile_has_river) {
+            moves = path_moves; end = path_end; q = path_last;
+        } else {
+            for (int steps = 0; steps <= TCELLS; ++steps) {
+                const uint32_t n16 = nxt[q], n = n16 & W_NXT;
+                if (n16 & NX_RIVER) { end = NX_RIVER; break; }  // flowhand.py:622
+                if (n == W_TERM) { end = W_TERM; break; }     // unknown code, off-raster or code-0 landing (flowhand.py:623-764, 826, 830)
+                moves += 1u + ((n16 >> 14) & 1u) * 0xFFFFu;
+                if (n == W_EXIT) { end = W_EXIT; break; }
+                q = n;
             }
-            const uint32_t n16 = nxt[q], n = n16 & W_NXT;
-            if (n == W_TERM) break;  // unknown code, off-raster or code-0 landing (flowhand.py:623-764, 826, 830)
-            if (n16 & NX_DIAG) ++nd; else ++nc;
-            if (n == W_EXIT) {
-                const uint32_t pl = logical_of(q);
-                const int qr = (int)(pl >> 6), qc = (int)(pl & (T - 1));
-                int dr, dc;
-                d8_offset(codes[(qr + 1) * CP + 16 + qc], dr, dc);
-                const int64_t tr = r0 + qr + dr, tc = c0 + qc + dc;
-                if (tr < 0) hs = pack(KIND_EXIT, nd, nc, LINK_OUT | (uint32_t)tc);
-                else if (tr >= v.rows) hs = pack(KIND_EXIT, nd, nc, LINK_OUT | LINK_BELOW | (uint32_t)tc);
-                else { hs = pack(KIND_ACTIVE, nd, nc, (uint32_t)node_of_cell(tr, tc, v.tiles_x)); is_active = 1; }
-                break;
-            }
-            q = n;
+        }
+        const uint32_t nc = moves & 0xFFFFu, nd = moves >> 16;
+        hs = pack(KIND_FAIL, 0, 0, 0);  // W_TERM, or an in-tile cycle
+        if (end == NX_RIVER) {
+            const uint32_t pl = logical_of(q);
+            hs = pack(KIND_RIVER, nd, nc, (uint32_t)((r0 + (pl >> 6)) * v.cols + c0 + (pl & (T - 1))));
+        } else if (end == W_EXIT) {
+            const uint32_t pl = logical_of(q);
+            const int qr = (int)(pl >> 6), qc = (int)(pl & (T - 1));
+            int dr, dc;
+            d8_offset(codes[(qr + 1) * CP + 16 + qc], dr, dc);
+            const int64_t tr = r0 + qr + dr, tc = c0 + qc + dc;
+            if (tr < 0) hs = pack(KIND_EXIT, nd, nc, LINK_OUT | (uint32_t)tc);
+            else if (tr >= v.rows) hs = pack(KIND_EXIT, nd, nc, LINK_OUT | LINK_BELOW | (uint32_t)tc);
+            else { hs = pack(KIND_ACTIVE, nd, nc, (uint32_t)node_of_cell(tr, tc, v.tiles_x)); is_active = 1; }
         }
     }
     hand_nstate[(size_t)tile * SLOTS + tid] = hs;
