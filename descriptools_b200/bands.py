@@ -44,60 +44,73 @@ def band_edges(rows: int, nbands: int) -> list[int]:
 
 
 # ---- boundary solvers (rank 0; pure torch, any device) -------------------------------------------
-def forest_accumulate(nxt: torch.Tensor, base: torch.Tensor) -> torch.Tensor:
-    """out[i] = base[i] + sum of out[j] over j with nxt[j] == i  (nxt < 0: none), by pointer doubling.
+# Whole-array ops only (no data-dependent shapes) and a fixed number of pointer-doubling rounds, so a solve
+# enqueues without any host sync.  Each solver also returns a 0-d flag tensor that is non-zero if a chain of
+# more than 2**ROUNDS seam crossings (or a cycle across seams) was left unresolved; the driver checks the
+# flags once per step and repeats the step with more rounds in that (pathological) case.
+ROUNDS = 6
 
-    Whole-array ops only (no data-dependent shapes), so a pass of ROUNDS doublings enqueues without a host
-    sync; one check per pass decides whether a chain longer than 2**ROUNDS seam crossings needs another."""
-    ROUNDS = 5
+
+def forest_accumulate(nxt: torch.Tensor, base: torch.Tensor, rounds: int = ROUNDS):
+    """out[i] = base[i] + sum of out[j] over j with nxt[j] == i  (nxt < 0: none), by pointer doubling.
+    Returns (out, unresolved flag)."""
     s, a = base.clone(), nxt.clone()
     zero = torch.zeros_like(s)
-    for _ in range(13):
-        for _ in range(ROUNDS):
-            live = a >= 0
-            tgt = a.clamp(min=0)
-            s = s + torch.zeros_like(s).index_add_(0, tgt, torch.where(live, s, zero))
-            a = torch.where(live, a[tgt], a)
-        if not bool((a >= 0).any()):
-            return s
-    raise RuntimeError("flow accumulation boundary graph has a cycle")
+    for _ in range(rounds):
+        live = a >= 0
+        tgt = a.clamp(min=0)
+        s = s + torch.zeros_like(s).index_add_(0, tgt, torch.where(live, s, zero))
+        a = torch.where(live, a[tgt], a)
+    return s, (a >= 0).any()
 
 
-def solve_flowacc_boundary(summ: torch.Tensor) -> torch.Tensor:
+_plan_cache = {}
+
+
+def _plan(n: int, cols: int, dev):
+    """static index tensors of the boundary graph: node (b, side, c) -> (b*2+side)*cols + c"""
+    key = (n, cols, str(dev))
+    p = _plan_cache.get(key)
+    if p is None:
+        b = torch.arange(n, device=dev).view(n, 1, 1).expand(n, 2, cols)
+        side = torch.arange(2, device=dev).view(1, 2, 1).expand(n, 2, cols)
+        c = torch.arange(cols, device=dev).view(1, 1, cols).expand(n, 2, cols)
+        b2 = torch.where(side == 0, b - 1, b + 1)           # band on the other side of the seam
+        p = dict(c=c.contiguous(), s2=(1 - side).contiguous(), b2ok=((b2 >= 0) & (b2 < n)).contiguous(),
+                 b2c=b2.clamp(0, n - 1).contiguous(), node=torch.arange(2 * n * cols, device=dev))
+        p["nb"], p["nside"] = p["node"] // (2 * cols), (p["node"] // cols) % 2
+        _plan_cache[key] = p
+    return p
+
+
+def solve_flowacc_boundary(summ: torch.Tensor, rounds: int = ROUNDS):
     """summ int64 [N, 6, cols]: exit_above, exit_below, term_above, term_below, d8 first row, d8 last row.
-    Returns inflow int64 [N, 2, cols]: (acc+1) carried by the halo row above / below each band."""
+    Returns (inflow int64 [N, 2, cols]: (acc+1) carried by the halo row above / below each band, flag)."""
     n, _, cols = summ.shape
-    dev = summ.device
-    base = summ[:, 0:2, :].reshape(-1).clone()                  # node (b, side, c) -> (b*2+side)*cols + c
+    p = _plan(n, cols, summ.device)
+    base = summ[:, 0:2, :]
     term = summ[:, 2:4, :]
     code = summ[:, 4:6, :]
-    b = torch.arange(n, device=dev).view(n, 1, 1).expand(n, 2, cols)
-    side = torch.arange(2, device=dev).view(1, 2, 1).expand(n, 2, cols)
-    c = torch.arange(cols, device=dev).view(1, 1, cols).expand(n, 2, cols)
     # column shift of the move across the seam: NW/SW -1, N/S 0, NE/SE +1 (flowhand.py:801-824)
-    dc = torch.zeros_like(code)
-    dc[(code == 32) | (code == 8)] = -1
-    dc[(code == 128) | (code == 2)] = 1
-    b2 = torch.where(side == 0, b - 1, b + 1)                   # band the exit lands in
-    s2 = 1 - side                                               # ... on its opposite boundary row
-    c2 = c + dc
-    is_exit = (summ[:, 0:2, :] > 0) & (b2 >= 0) & (b2 < n) & (c2 >= 0) & (c2 < cols)
-    b2c, c2c = b2.clamp(0, n - 1), c2.clamp(0, cols - 1)
-    t = term[b2c, s2, c2c]                                      # where the landing cell's in-band path leaves
-    t_side, t_col = (t >> 30) & 1, t & 0x3FFFFFFF
-    nxt = torch.where(is_exit & (t >= 0), (b2c * 2 + t_side) * cols + t_col, torch.full_like(t, -1)).reshape(-1)
-    f = forest_accumulate(nxt, base).view(n, 2, cols)
-    inflow = torch.zeros((n, 2, cols), dtype=torch.int64, device=dev)
+    dc = ((code == 128) | (code == 2)).to(torch.int64) - ((code == 32) | (code == 8)).to(torch.int64)
+    c2 = p["c"] + dc
+    is_exit = (base > 0) & p["b2ok"] & (c2 >= 0) & (c2 < cols)
+    t = term[p["b2c"], p["s2"], c2.clamp(0, cols - 1)]          # where the landing cell's in-band path leaves
+    nxt = torch.where(is_exit & (t >= 0), (p["b2c"] * 2 + ((t >> 30) & 1)) * cols + (t & 0x3FFFFFFF), torch.full_like(t, -1))
+    f, flag = forest_accumulate(nxt.reshape(-1), base.reshape(-1), rounds)
+    f = f.view(n, 2, cols)
+    inflow = torch.zeros((n, 2, cols), dtype=torch.int64, device=summ.device)
     inflow[1:, 0, :] = f[:-1, 1, :]                             # above band b = last row of band b-1
     inflow[:-1, 1, :] = f[1:, 0, :]                             # below band b = first row of band b+1
-    return inflow
+    return inflow, flag
 
 
-def solve_hand_boundary(summ: torch.Tensor) -> torch.Tensor:
+def solve_hand_boundary(summ: torch.Tensor, rounds: int = ROUNDS):
     """summ int64 [N, 8, cols]: (state, idx, z-bits, acc) of the first row, then of the last row.
-    Returns int64 [N, 8, cols]: resolved (state, idx, z-bits, acc) of the halo row above, then below."""
+    Returns (int64 [N, 8, cols]: resolved (state, idx, z-bits, acc) of the halo row above, then below; flag)."""
     n, _, cols = summ.shape
     dev = summ.device
+    p = _plan(n, cols, dev)
     st = torch.stack([summ[:, 0, :], summ[:, 4, :]], 1).reshape(-1)          # node (b, side, c)
     pay = torch.stack([summ[:, 1:4, :], summ[:, 5:8, :]], 1)                 # [N, 2, 3, cols]
     pay = pay.permute(0, 1, 3, 2).reshape(-1, 3)
@@ -105,25 +118,21 @@ def solve_hand_boundary(summ: torch.Tensor) -> torch.Tensor:
     nd = (st >> 47) & 0x7FFF
     nc = (st >> 32) & 0x7FFF
     ptr = st & 0xFFFFFFFF
-    kind = torch.where(st == 0, torch.full_like(kind, KIND_FAIL), kind)      # not an entry: never referenced
-    node = torch.arange(2 * n * cols, device=dev)
-    b, side = node // (2 * cols), (node // cols) % 2
+    kind = torch.where(st == 0, KIND_FAIL, kind)                             # not an entry: never referenced
     t_side, t_col = (ptr >> 30) & 1, ptr & 0x3FFFFFFF
-    b2 = torch.where(t_side == 0, b - 1, b + 1)
+    b2 = torch.where(t_side == 0, p["nb"] - 1, p["nb"] + 1)
     ok = (kind == KIND_EXIT) & (b2 >= 0) & (b2 < n) & (t_col < cols)
-    tgt = torch.where(ok, (b2.clamp(0, n - 1) * 2 + (1 - t_side)) * cols + t_col.clamp(max=cols - 1), torch.full_like(node, -1))
-    kind = torch.where((kind == KIND_EXIT) & ~ok, torch.full_like(kind, KIND_FAIL), kind)
-    src = node.clone()                                                       # whose payload the node ends up with
-    for _ in range(13):                                                      # 13 x 5 doublings > any move cap
-        for _ in range(5):                                                   # whole-array ops: no host sync inside
-            live = kind == KIND_EXIT
-            t = tgt.clamp(min=0)
-            nd = torch.where(live, (nd + nd[t]).clamp(max=CNT_SAT), nd)
-            nc = torch.where(live, (nc + nc[t]).clamp(max=CNT_SAT), nc)
-            kind, tgt, src = torch.where(live, kind[t], kind), torch.where(live, tgt[t], tgt), torch.where(live, src[t], src)
-        if not bool((kind == KIND_EXIT).any()):
-            break
-    kind = torch.where(kind == KIND_EXIT, torch.full_like(kind, KIND_FAIL), kind)   # cycle across seams
+    tgt = torch.where(ok, (b2.clamp(0, n - 1) * 2 + (1 - t_side)) * cols + t_col.clamp(max=cols - 1), -1)
+    kind = torch.where((kind == KIND_EXIT) & ~ok, KIND_FAIL, kind)
+    src = p["node"]                                                          # whose payload the node ends up with
+    for _ in range(rounds):
+        live = kind == KIND_EXIT
+        t = tgt.clamp(min=0)
+        nd = torch.where(live, (nd + nd[t]).clamp(max=CNT_SAT), nd)
+        nc = torch.where(live, (nc + nc[t]).clamp(max=CNT_SAT), nc)
+        kind, tgt, src = torch.where(live, kind[t], kind), torch.where(live, tgt[t], tgt), torch.where(live, src[t], src)
+    flag = (kind == KIND_EXIT).any()
+    kind = torch.where(kind == KIND_EXIT, KIND_FAIL, kind)                   # cycle across seams
     state = ((kind << 62) | (nd << 47) | (nc << 32)).view(n, 2, cols)
     pay = pay[src].view(n, 2, cols, 3)
     res = torch.zeros((n, 8, cols), dtype=torch.int64, device=dev)
@@ -133,7 +142,7 @@ def solve_hand_boundary(summ: torch.Tensor) -> torch.Tensor:
     res[1:, 1:4, :] = pay[:-1, 1].permute(0, 2, 1)
     res[:-1, 4, :] = state[1:, 0, :]                                         # below band b = first row of band b+1
     res[:-1, 5:8, :] = pay[1:, 0].permute(0, 2, 1)
-    return res
+    return res, flag
 
 
 # ---- one band on one device ------------------------------------------------------------------------
@@ -285,6 +294,7 @@ class LocalExchange:
 
     def __init__(self, nbands):
         self.nbands = nbands
+        self.flags = []
 
     def halo(self, items):
         """items[i] = (first_row, last_row, halo_above_dst, halo_below_dst) of band i"""
@@ -294,8 +304,9 @@ class LocalExchange:
             if i + 1 < len(items):
                 below.copy_(items[i + 1][0])
 
-    def solve(self, per_band, solver):
-        out = solver(torch.stack(per_band, 0))
+    def solve(self, per_band, solver, rounds=ROUNDS):
+        out, flag = solver(torch.stack(per_band, 0), rounds)
+        self.flags.append(flag)
         return [out[i] for i in range(len(per_band))]
 
 
@@ -308,6 +319,7 @@ class DistExchange:
         self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.nbands = self.world
+        self.flags = []
 
     def halo(self, items):
         (first_row, last_row, above, below), = items
@@ -320,20 +332,18 @@ class DistExchange:
             for w in d.batch_isend_irecv(ops):
                 w.wait()
 
-    def solve(self, per_band, solver):
+    def solve(self, per_band, solver, rounds=ROUNDS):
         """gather the summaries on rank 0, solve the boundary graph there, scatter the answers"""
         (mine,), d = per_band, self.dist
         mine = mine.contiguous()
         gathered = [torch.empty_like(mine) for _ in range(self.world)] if self.rank == 0 else None
         d.gather(mine, gathered, dst=0, group=self.group)
-        out = torch.empty_like(mine)
         parts = None
+        out = torch.empty(self._out_shape(mine, solver), dtype=mine.dtype, device=mine.device)
         if self.rank == 0:
-            res = solver(torch.stack(gathered, 0))
+            res, flag = solver(torch.stack(gathered, 0), rounds)
+            self.flags.append(flag)
             parts = [res[i].contiguous() for i in range(self.world)]
-            out = torch.empty_like(parts[0])
-        else:
-            out = torch.empty(self._out_shape(mine, solver), dtype=mine.dtype, device=mine.device)
         d.scatter(out, parts, src=0, group=self.group)
         return [out]
 
@@ -366,6 +376,27 @@ class BandRunner:
 
     def step(self, events=None):
         """One pass of the chain; `events` (4 CUDA events) are recorded at the stage boundaries."""
+        rounds = ROUNDS
+        while True:
+            self.x.flags.clear()
+            self._step(events, rounds)
+            if not self._unresolved():
+                return
+            rounds += 6  # a chain of more than 2**rounds seam crossings: repeat the step with more doubling rounds
+            if rounds > 66:
+                raise RuntimeError("band boundary graph did not resolve (cycle across band seams)")
+
+    def _unresolved(self) -> bool:
+        """one host sync per step: did every boundary solve resolve?  (all ranks must agree on repeating)"""
+        flags = self.x.flags
+        bad = torch.stack([f.to(torch.int32) for f in flags]).sum() if flags else None
+        if isinstance(self.x, DistExchange):
+            t = bad.reshape(1).clone() if bad is not None else torch.zeros(1, dtype=torch.int32, device=self.bands[0].dev)
+            self.x.dist.broadcast(t, src=0, group=self.x.group)
+            return bool(t.item())
+        return bool(bad.item()) if bad is not None else False
+
+    def _step(self, events, rounds):
         rec = (lambda i: events[i].record()) if events is not None else (lambda i: None)
         B = self.bands
         rec(0)
@@ -377,14 +408,14 @@ class BandRunner:
         if self.nbands == 1:
             B[0].flowacc_finish(None)
         else:
-            inflow = self.x.solve([b.flowacc_summary() for b in B], solve_flowacc_boundary)
+            inflow = self.x.solve([b.flowacc_summary() for b in B], solve_flowacc_boundary, rounds)
             for b, f in zip(B, inflow):
                 b.flowacc_finish(f)
         rec(2)
         if self.nbands == 1:
             B[0].hand_finish(None)
         else:
-            res = self.x.solve([b.hand_summary() for b in B], solve_hand_boundary)
+            res = self.x.solve([b.hand_summary() for b in B], solve_hand_boundary, rounds)
             for b, r in zip(B, res):
                 b.hand_finish(r)
         rec(3)

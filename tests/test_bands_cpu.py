@@ -156,6 +156,7 @@ def test_solvers_three_bands_match_oracle_serial():
         a, b = edges[i], edges[i + 1]
         summ.append(torch.from_numpy(flowacc_summary(d8[a:b], d8[a - 1] if i > 0 else None, d8[b] if i < 2 else None)))
     inflow = bands.LocalExchange(3).solve(summ, bands.solve_flowacc_boundary)
+    assert not bool(bands.solve_flowacc_boundary(torch.stack(summ, 0))[1])  # resolved within the default rounds
     off = {1: (0, 1), 2: (1, 1), 4: (1, 0), 8: (1, -1), 16: (0, -1), 32: (-1, -1), 64: (-1, 0), 128: (-1, 1)}
     n = 0
     for i in range(3):
