@@ -200,10 +200,11 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
 constexpr uint32_t NX_DIAG = 0x4000u, NX_RIVER = 0x8000u, NX_CYCLE = 0xFFFFFFFFu;
 
 template <typename ACC, bool HAND>
-__global__ void __launch_bounds__(FT_THREADS)
+__global__ void __launch_bounds__(FT_THREADS, 4)
 fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const unsigned long long *__restrict__ nstate,
                       ACC *__restrict__ acc, unsigned long long *__restrict__ counters, int64_t thr,
-                      unsigned long long *__restrict__ hand_nstate, unsigned *__restrict__ hand_active)
+                      unsigned long long *__restrict__ hand_nstate, unsigned *__restrict__ hand_active,
+                      uint16_t *__restrict__ hand_table)
 {
     typedef typename std::conditional<sizeof(ACC) == 8, unsigned long long, uint32_t>::type EXT;
     __shared__ __align__(16) uint8_t codes[(T + 2) * CP + 16];
@@ -217,6 +218,7 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const unsig
     __syncthreads();
 
     const int lr = tid >> 2, lcb = (tid & 3) * CPT;
+    unsigned validmask = 0;
     {
         const uint8_t *crow = codes + (lr + 1) * CP + 16 + lcb;
         const uint4 cw = *reinterpret_cast<const uint4 *>(crow);
@@ -230,6 +232,7 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const unsig
             if (d8_delta(code, dloc, dcode) && crow[i + dcode] != 0) nx = (code & exit_codes(lr, lc)) ? W_EXIT : phys_of((uint32_t)(p + dloc));
             nxt[i * FT_THREADS + tid] = (uint16_t)(nx | ((code & 0xAAu) ? NX_DIAG : 0u));
             ext[i * FT_THREADS + tid] = 0;
+            validmask |= (code != 0 ? 1u : 0u) << i;
         }
     }
     __syncthreads();
@@ -275,17 +278,24 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const unsig
         if (need) {
             ACC *dst = acc + gr * v.cols + c0 + lcb;
             if (fast && ((reinterpret_cast<uintptr_t>(acc) & 15u) == 0)) {
-                constexpr int V = 16 / sizeof(ACC);
+                constexpr int V = 16 / sizeof(ACC), NV = CPT / V;
+                uint4 w[NV];
 #pragma unroll
-                for (int i = 0; i < CPT; i += V) {
-                    uint4 w = *reinterpret_cast<const uint4 *>(dst + i);
-                    ACC *a = reinterpret_cast<ACC *>(&w);
+                for (int k = 0; k < NV; ++k) w[k] = __ldcg(reinterpret_cast<const uint4 *>(dst) + k);
+                // (the kernel is bound by the latency of these loads: __launch_bounds__(.., 4) gives the scheduler the
+                // registers to keep all of them in flight instead of interleaving them with the arithmetic)
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    ACC *a = reinterpret_cast<ACC *>(&w[k]);
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
-                        a[j] += (ACC)e[i + j];
-                        if (HAND) riv |= (unsigned)((int64_t)a[j] > thr) << (i + j);
+                        a[j] += (ACC)e[k * V + j];
+                        if (HAND) riv |= (unsigned)((int64_t)a[j] > thr) << (k * V + j);
                     }
-                    if (any) *reinterpret_cast<uint4 *>(dst + i) = w;
+                }
+                if (any) {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) reinterpret_cast<uint4 *>(dst)[k] = w[k];
                 }
             } else {
 #pragma unroll
@@ -299,6 +309,7 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const unsig
         }
     }
     if (!HAND) return;
+    riv &= validmask;  // a cell without a direction code is nodata for HAND (flowhand.py:601)
     // river cells get bit 15 of their successor entry; a tile without any keeps the states of the first walk
     if (riv) {
 #pragma unroll
@@ -306,6 +317,15 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const unsig
             if ((riv >> i) & 1u) nxt[i * FT_THREADS + tid] |= NX_RIVER;
     }
     const bool tile_has_river = __syncthreads_or(riv != 0);
+    {   // the table in cell order (thread t owns cells 16t..16t+15) for HAND's tile pass
+        uint32_t w[CPT / 2];
+#pragma unroll
+        for (int i = 0; i < CPT; i += 2)
+            w[i / 2] = (uint32_t)nxt[i * FT_THREADS + tid] | ((uint32_t)nxt[(i + 1) * FT_THREADS + tid] << 16);
+        uint4 *dst = reinterpret_cast<uint4 *>(hand_table + (size_t)tile * TCELLS + tid * CPT);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
 
     // ---- HAND first pass: entry nodes walk to their first river cell / failure / next entry node ----
     uint64_t hs = 0ull;  // inactive slot (never referenced)
@@ -606,10 +626,11 @@ int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
         unsigned long long *hstate = reinterpret_cast<unsigned long long *>((char *)a->hand_ws + 256);
         DTB_CUDA(cudaMemsetAsync(hactive, 0, 256, st));
         DTB_KERNEL("fa_tile_finish_kernel<hand>", st, fa_tile_finish_kernel<ACC, true><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(
-                       v, meta, nstate, acc, counters, a->hand_river_threshold, hstate, hactive));
+                       v, meta, nstate, acc, counters, a->hand_river_threshold, hstate, hactive,
+                       reinterpret_cast<uint16_t *>(hstate + L.nnodes)));
     } else {
         DTB_KERNEL("fa_tile_finish_kernel", st, fa_tile_finish_kernel<ACC, false><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(
-                       v, meta, nstate, acc, counters, 0, nullptr, nullptr));
+                       v, meta, nstate, acc, counters, 0, nullptr, nullptr, nullptr));
     }
     // cyclic grids only (each kernel returns at once when counters[0] == 0)
     DTB_KERNEL("fa_flat_init_kernel", st, fa_flat_init_kernel<<<FLAT_BLOCKS, 256, 0, st>>>(v, a->inflow_above, a->inflow_below, flat, counters));

@@ -231,13 +231,15 @@ __device__ __forceinline__ void load4(const V *src, V (&val)[4], bool vec, int64
     }
 }
 
-template <typename TD, typename IDX, typename ACC>
+template <typename TD, typename IDX, typename ACC, bool TABLE>
 __global__ void __launch_bounds__(H_THREADS)
 hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC *__restrict__ acc,
-                 const unsigned long long *__restrict__ nstate, HandOut o)
+                 const unsigned long long *__restrict__ nstate, const uint16_t *__restrict__ table, HandOut o)
 {
-    __shared__ __align__(16) uint8_t codes[(T + 2) * CP + 16];
-    __shared__ uint16_t rivm[H_THREADS];
+    // TABLE: the successor table the fused finish pass of flowacc.cu left behind (one 16-bit entry per cell in
+    // cell order: [15 river | 14 diagonal move | 13..0 successor slot / W_EXIT / W_TERM]) replaces staging the
+    // codes, reading the river source and decoding the moves again.
+    __shared__ __align__(16) uint8_t codes[TABLE ? 16 : (T + 2) * CP + 16];
     // in-tile state, slot layout of tiles.cuh: x = target (slot of the next cell while ACTIVE, global index of the
     // river cell, perimeter slot of the exit cell), y = [31..30 kind | 29..15 n_diag | 14..0 n_card]
     __shared__ uint2 st[TCELLS];
@@ -251,18 +253,42 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
     const int tile = blockIdx.x;
     const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
     const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
-    const bool fast = stage_codes(v, r0, c0, codes, tid, H_THREADS);
     const int lr = tid >> 2, lcb = (tid & 3) * CPT;
-    const unsigned myriv = river_bits<ACC>(rs, v, r0, c0, lr, lcb, fast);
-    rivm[tid] = (uint16_t)myriv;
-    __syncthreads();
-    auto C = [&](int r, int c) -> unsigned { return codes[(r + 1) * CP + 16 + c]; };
+    bool fast;
+    unsigned myriv = 0;
+    if (TABLE) {
+        fast = (v.cols % 16 == 0) && (c0 + T <= v.cols);
+    } else {
+        fast = stage_codes(v, r0, c0, codes, tid, H_THREADS);
+        myriv = river_bits<ACC>(rs, v, r0, c0, lr, lcb, fast);
+        __syncthreads();
+    }
+    auto C = [&](int r, int c) -> unsigned {
+        if (TABLE) return fetch_code(v, r0 + r, c0 + c);
+        return codes[(r + 1) * CP + 16 + c];
+    };
 
     // ---- initial state of my 16 cells ----
     // Inside the tile a path is at most 4095 moves, so the two 15-bit counters never carry and composing
     // "s then t" is one 32-bit add (s is ACTIVE = kind 0) plus taking t's target.
     unsigned activemask = 0;
-    {
+    if (TABLE) {
+        const uint4 *tp = reinterpret_cast<const uint4 *>(table + (size_t)tile * TCELLS + tid * CPT);
+        const uint4 ta = __ldg(tp), tb = __ldg(tp + 1);
+        const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            const uint32_t e = (tw[i >> 1] >> (16 * (i & 1))) & 0xFFFFu, n = e & 0x3FFFu;
+            uint2 s = make_uint2(0u, (uint32_t)KIND_FAIL << 30);  // W_TERM: code 0, unknown code, bad landing
+            if (e & 0x8000u) s = make_uint2((uint32_t)((r0 + lr) * v.cols + c0 + lcb + i), (uint32_t)KIND_RIVER << 30);
+            else if (n == 0x3FFEu) s = make_uint2((uint32_t)slot_of(lr, lcb + i), (uint32_t)KIND_EXIT << 30);
+            else if (n != 0x3FFFu) {
+                s = make_uint2(n, (e & 0x4000u) ? (1u << 15) : 1u);
+                activemask |= 1u << i;
+            }
+            st[i * H_THREADS + tid] = s;
+        }
+    } else {
         const uint8_t *crow = codes + (lr + 1) * CP + 16 + lcb;
         const uint4 cw = *reinterpret_cast<const uint4 *>(crow);
         const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
@@ -317,13 +343,21 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
     if (tid < USED_SLOTS) {
         int plr, plc;
         slot_cell(tid, plr, plc);
-        const unsigned code = C(plr, plc);
         uint64_t e = pack(KIND_FAIL, 0, 0, 0);
         unsigned remote = 0;
-        int dr, dc;
-        if (d8_offset(code, dr, dc)) {
+        int dr = 0, dc = 0;
+        bool is_exit;
+        if (TABLE) {
+            is_exit = (__ldg(table + (size_t)tile * TCELLS + plr * T + plc) & 0xBFFFu) == 0x3FFEu;  // W_EXIT, not a river cell
+            if (is_exit) d8_offset(C(plr, plc), dr, dc);
+        } else {
+            is_exit = d8_offset(C(plr, plc), dr, dc) &&
+                      ((unsigned)(plr + dr) >= (unsigned)T || (unsigned)(plc + dc) >= (unsigned)T) && C(plr + dr, plc + dc) != 0;
+        }
+        const unsigned code = is_exit ? C(plr, plc) : 0u;
+        {
             const int tr = plr + dr, tc = plc + dc;
-            if (((unsigned)tr >= (unsigned)T || (unsigned)tc >= (unsigned)T) && C(tr, tc) != 0) {
+            if (is_exit) {
                 const int64_t gr = r0 + tr, gc = c0 + tc;
                 const bool diag = d8_is_diag(code);
                 const uint64_t mv = pack(KIND_ACTIVE, diag ? 1u : 0u, diag ? 0u : 1u, 0);
@@ -495,7 +529,14 @@ int run_tiles(const dtb_hand_args *a, const TileView &v, const RiverSrc &rs, con
             o.res_acc[k] = sm[k]->res_acc;
         }
     }
-    DTB_KERNEL("hand_tile_kernel", st, hand_tile_kernel<TD, IDX, ACC><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, (const TD *)a->dem, (const ACC *)a->acc, nstate, o));
+    // the successor table of the fused finish pass sits behind the node states in the workspace
+    const uint16_t *table = reinterpret_cast<const uint16_t *>(nstate + tiles * SLOTS);
+    if (a->entry_done)
+        DTB_KERNEL("hand_tile_kernel<table>", st, hand_tile_kernel<TD, IDX, ACC, true><<<(unsigned)tiles, H_THREADS, 0, st>>>(
+                       v, rs, (const TD *)a->dem, (const ACC *)a->acc, nstate, table, o));
+    else
+        DTB_KERNEL("hand_tile_kernel", st, hand_tile_kernel<TD, IDX, ACC, false><<<(unsigned)tiles, H_THREADS, 0, st>>>(
+                       v, rs, (const TD *)a->dem, (const ACC *)a->acc, nstate, nullptr, o));
     return DTB_OK;
 }
 
@@ -522,7 +563,8 @@ extern "C" size_t dtb_hand_workspace_bytes(int64_t rows, int64_t cols)
 {
     if (rows <= 0 || cols <= 0) return 0;
     const int64_t tiles = ((rows + dtb::T - 1) / dtb::T) * ((cols + dtb::T - 1) / dtb::T);
-    return (size_t)tiles * dtb::SLOTS * 8 + 256;
+    // node states + the per-cell successor table of the fused flow-accumulation finish pass (flowacc.cu)
+    return 256 + (size_t)tiles * dtb::SLOTS * 8 + (size_t)tiles * dtb::TCELLS * 2;
 }
 
 extern "C" int dtb_hand(const dtb_hand_args *a, void *ws, size_t ws_bytes, void *stream)
