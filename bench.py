@@ -37,6 +37,7 @@ KERNEL_BYTES = {
     "fa_tile_kernel": 5,           # d8 1 R, acc 4 W
     "fa_tile_finish_kernel<hand>": 1,  # d8 1 R (+ the acc runs an entry path touches); fused with HAND's entry pass
     "hand_tile_kernel": 33,        # d8 1, acc 4, dem 4 R; gathers dem[idx] 4 + acc[idx] 4; idx, fdist, hand, gfi 16 W
+    "hand_tile_kernel<table>": 30, # successor table 2 R instead of d8 + acc (fused chain)
 }
 SAMPLE_ROWS = SAMPLE_COLS = 3072  # bounded CPU sample
 
