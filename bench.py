@@ -292,6 +292,12 @@ def run_ours(args):
     ms_step = ms / args.steps
     value = n_cells / (ms_step * 1e-3) / 1e6
     keep = None
+    per_rank_kernel_ms = None
+    if world > 1:  # load balance across bands: every rank's kernel time per step
+        mine = torch.tensor([sum(v[0] for v in kernel_ms.values()) / args.steps], device="cuda", dtype=torch.float64)
+        allk = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allk, mine)
+        per_rank_kernel_ms = [round(float(t[0]), 3) for t in allk]
 
     # ---- end-to-end through the host API: pinned DEM in, seven rasters out ----------------------
     e2e = None
@@ -386,6 +392,8 @@ def run_ours(args):
                 "frac": (dk.get("achieved_gbs") or 0.0) / peak, "traffic": traffic, "peak_kind": peak_kind + " (burst copy)",
                 "bytes_per_launch": (dk.get("bytes_per_cell") or 0) * cells_launch, "avg_launch_ms": dk.get("avg_launch_ms"),
                 "chain_frac": CHAIN_BYTES * n_cells / (ms_step * 1e-3) / 1e9 / peak_total, "stages": stages, "kernels": kernels}
+    if per_rank_kernel_ms is not None:
+        roofline["per_rank_kernel_ms"] = per_rank_kernel_ms
     if world == 1 and not args.no_cpu:
         roofline["stencil_10k"] = stencil_config1(peak)
 
