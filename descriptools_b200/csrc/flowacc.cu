@@ -45,7 +45,7 @@ constexpr int W_CNT_SHIFT = 14;
 constexpr int WALK_CAP = 8;
 
 template <typename ACC>
-__global__ void __launch_bounds__(FT_THREADS)
+__global__ void __launch_bounds__(FT_THREADS, 8)
 fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ link, uint32_t *__restrict__ meta,
                ACC *__restrict__ acc, ACC nodata_fill, unsigned long long *__restrict__ counters)
 {

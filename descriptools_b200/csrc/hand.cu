@@ -246,7 +246,7 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
     // what lies behind each exit cell of the perimeter: resolved once per slot, shared by every cell that
     // leaves the tile through it (kind/moves, global river index, river elevation, ln b + n ln(A_r s^2))
     __shared__ uint32_t exit_hi[SLOTS];
-    __shared__ long long exit_idx[SLOTS];
+    __shared__ IDX exit_idx[SLOTS];
     __shared__ TD exit_z[SLOTS];
     __shared__ double exit_l1[SLOTS];
     const int tid = threadIdx.x;
@@ -386,11 +386,11 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
             const int64_t loc = (int64_t)ptr_of(e);  // local index of the river cell, or (remote) a column of the halo tables
             double racc = 1.0;
             if (remote) {
-                exit_idx[tid] = o.res_idx[remote - 1][loc];
+                exit_idx[tid] = (IDX)o.res_idx[remote - 1][loc];
                 exit_z[tid] = (TD)o.res_z[remote - 1][loc];
                 if (o.gfi) racc = (double)o.res_acc[remote - 1][loc];
             } else {
-                exit_idx[tid] = loc + o.idx_offset;
+                exit_idx[tid] = (IDX)(loc + o.idx_offset);
                 exit_z[tid] = (o.hand || o.gfi) ? dem[loc] : (TD)0;
                 if (o.gfi) racc = (double)acc[loc];  // river_accumulation, gfi.py:141-143
             }
