@@ -412,3 +412,88 @@ def test_bands_weaving_valley_vs_oracle():
     np.testing.assert_array_equal(got["hand"], hand)
     np.testing.assert_allclose(got["fdist"], fdist, rtol=RTOL, atol=0)
     np.testing.assert_allclose(got["gfi"], oracle.gfi(hand, acc, idx, 0.4, 0.1, PX), rtol=RTOL, atol=ATOL)
+
+
+# ---- tiled kernels: paths the small cases above do not reach ----------------------------------------
+def test_chain_int64_counts_and_indices():
+    """the int64 instantiations (acc, idx; 64-bit inflow pushes in shared memory) against the oracle"""
+    from descriptools_b200 import device
+
+    dem = synth(330, 470, 5)
+    thr = 700
+    t = torch.from_numpy(dem).cuda()
+    slope, d8 = device.slope_d8(t, PX)
+    acc = device.flow_accumulation(d8, dtype=torch.int64, fuse_hand_threshold=thr)
+    out = device.hand(d8, t, PX, acc=acc, river_threshold=thr, gfi_params=(0.4, 0.1, PX), idx_dtype=torch.int64, entry_done=True)
+    _, d8_ref = oracle.slope_d8(dem, PX)
+    acc_ref, _ = oracle.flow_accumulation(d8_ref)
+    river = (acc_ref > thr).astype(np.int8)
+    fdist, idx, hand = oracle.flow_hand_index(dem, d8_ref, river, PX)
+    assert acc.dtype == torch.int64 and out["idx"].dtype == torch.int64
+    np.testing.assert_array_equal(acc.cpu().numpy(), acc_ref)
+    np.testing.assert_array_equal(out["idx"].cpu().numpy(), idx)
+    np.testing.assert_array_equal(out["hand"].cpu().numpy(), hand)
+    np.testing.assert_allclose(out["fdist"].cpu().numpy(), fdist, rtol=RTOL, atol=0)
+    np.testing.assert_allclose(out["gfi"].cpu().numpy(), oracle.gfi(hand, acc_ref, idx, 0.4, 0.1, PX), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("thr", [10, 4095, 4096, 30000])
+def test_fused_and_unfused_hand_agree(thr):
+    """river threshold below / at / above the tile size (4096 cells): the fused entry pass + successor table
+    must give exactly what the stand-alone HAND kernels give from the same accumulation"""
+    from descriptools_b200 import device
+
+    dem = synth(900, 1024, 77)
+    t = torch.from_numpy(dem).cuda()
+    _, d8 = device.slope_d8(t, PX)
+    acc_plain = device.flow_accumulation(d8)
+    plain = device.hand(d8, t, PX, acc=acc_plain, river_threshold=thr, gfi_params=(0.4, 0.1, PX))
+    acc_fused = device.flow_accumulation(d8, fuse_hand_threshold=thr)
+    fused = device.hand(d8, t, PX, acc=acc_fused, river_threshold=thr, gfi_params=(0.4, 0.1, PX), entry_done=True)
+    river = (acc_plain > thr).to(torch.int8)
+    masked = device.hand(d8, t, PX, river=river, acc=acc_plain, gfi_params=(0.4, 0.1, PX))
+    assert torch.equal(acc_plain, acc_fused)
+    for name in ("idx", "fdist", "hand", "gfi"):
+        assert torch.equal(plain[name], fused[name]), name
+        assert torch.equal(plain[name], masked[name]), name
+    acc_ref, _ = oracle.flow_accumulation(d8.cpu().numpy())
+    np.testing.assert_array_equal(acc_plain.cpu().numpy(), acc_ref)
+    _, idx_ref = oracle.flow_distance_index(d8.cpu().numpy(), (acc_ref > thr).astype(np.int8), PX)
+    np.testing.assert_array_equal(fused["idx"].cpu().numpy(), idx_ref)
+
+
+def test_serpentine_across_tiles():
+    """one channel snaking through every row of a 200 x 300 raster (19 000+ moves, hundreds of tile crossings):
+    accumulation along the stem, HAND to a single outlet river cell, and the 20 000-move cap with a shorter one"""
+    from descriptools_b200 import device
+
+    rows, cols = 200, 300
+    d8 = np.zeros((rows, cols), np.uint8)
+    for r in range(rows):
+        east = r % 2 == 0
+        d8[r, :] = 1 if east else 16
+        d8[r, cols - 1 if east else 0] = 4  # turn down at the end of the row
+    d8[rows - 1, cols - 1 if (rows - 1) % 2 == 0 else 0] = 4  # last cell drains off the raster
+    acc_ref, left = oracle.flow_accumulation(d8)
+    assert left == 0 and acc_ref.max() == rows * cols - 1
+    acc = device.flow_accumulation(torch.from_numpy(d8).cuda(), dtype=torch.int32)
+    np.testing.assert_array_equal(acc.cpu().numpy(), acc_ref)
+    river = np.zeros((rows, cols), np.int8)
+    river[rows - 1, 0 if (rows - 1) % 2 else cols - 1] = 1
+    for cap in (0, 12345):  # 0 = the reference's 20000
+        f_ref, i_ref = oracle.flow_distance_index(d8, river, PX, max_moves=cap or 20000)
+        out = device.hand(torch.from_numpy(d8).cuda(), None, PX, river=torch.from_numpy(river).cuda(), max_moves=cap, want_hand=False)
+        np.testing.assert_array_equal(out["idx"].cpu().numpy(), i_ref)
+        np.testing.assert_allclose(out["fdist"].cpu().numpy(), f_ref, rtol=RTOL, atol=0)
+        assert 0 < (i_ref >= 0).sum() < rows * cols  # the cap cuts the upstream part of the channel
+
+
+def test_flowacc_large_acyclic_partial_tiles():
+    from descriptools_b200 import device
+
+    dem = synth(1111, 777, 9)  # neither dimension a multiple of 64 or 16: generic staging path, clipped tiles
+    _, d8 = oracle.slope_d8(dem, PX)
+    acc_ref, left = oracle.flow_accumulation(d8)
+    acc, bad = device.flow_accumulation(torch.from_numpy(d8).cuda(), check_cycles=True)
+    assert left == 0 and bad == 0
+    np.testing.assert_array_equal(acc.cpu().numpy(), acc_ref)
