@@ -208,6 +208,9 @@ class Band:
         a.halo_below = 0 if self.last else self.d8_buf[self.rows + 1].data_ptr()
         a.acc, a.acc_dtype, a.nodata_fill = self.acc.data_ptr(), DTB_I64 if self.int_dt == torch.int64 else DTB_I32, -100
         a.mode = mode
+        # the tile passes keep their successor table in the HAND workspace, and the last one also does HAND's
+        # entry-node pass (river = acc > threshold) into it
+        a.hand_ws, a.hand_ws_bytes, a.hand_river_threshold = self.ws_hand.data_ptr(), self.ws_hand.numel(), self.thr
         return a
 
     def flowacc_summary(self) -> torch.Tensor:
@@ -233,8 +236,6 @@ class Band:
         a = self._fa_args(DTB_FA_FINISH if inflow is not None else DTB_FA_FULL)
         a.inflow_above = 0 if self.first else self.fa_inflow[0].data_ptr()
         a.inflow_below = 0 if self.last else self.fa_inflow[1].data_ptr()
-        # the last tile pass also does HAND's entry-node pass (river = acc > threshold) into the HAND workspace
-        a.hand_ws, a.hand_ws_bytes, a.hand_river_threshold = self.ws_hand.data_ptr(), self.ws_hand.numel(), self.thr
         self._check(self.lib.dtb_flowacc_band(ctypes.byref(a), self.ws_fa.data_ptr(), self.ws_fa.numel(), self._stream()),
                     "dtb_flowacc_band(finish)")
 

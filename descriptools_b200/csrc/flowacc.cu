@@ -43,11 +43,14 @@ constexpr int N_PEND_SHIFT = 48;
 constexpr uint32_t W_EXIT = 0x3FFEu, W_TERM = 0x3FFFu, W_NXT = 0x3FFFu, W_PEND_ONE = 1u << 28;
 constexpr int W_CNT_SHIFT = 14;
 constexpr int WALK_CAP = 8;
+// successor table, 16 bits per cell in cell order: [15 river cell | 14 diagonal move | 13..0 successor slot / W_EXIT / W_TERM]
+constexpr uint32_t NX_DIAG = 0x4000u, NX_RIVER = 0x8000u, NX_CYCLE = 0xFFFFFFFFu, NX_NODATA = W_TERM | NX_DIAG;
 
 template <typename ACC>
 __global__ void __launch_bounds__(FT_THREADS, 8)
 fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ link, uint32_t *__restrict__ meta,
-               ACC *__restrict__ acc, ACC nodata_fill, unsigned long long *__restrict__ counters)
+               ACC *__restrict__ acc, ACC nodata_fill, unsigned long long *__restrict__ counters,
+               uint16_t *__restrict__ table)
 {
     __shared__ __align__(16) uint8_t codes[(T + 2) * CP + 16];  // col T of the last row sits at (T+2)*CP
     __shared__ uint32_t word[TCELLS];
@@ -67,7 +70,7 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
     // ---- per-cell set-up: successor slot; in-tile in-degree by scatter (one shared RED per cell) ----
     const int lr = tid >> 2, lcb = (tid & 3) * CPT;
     unsigned validmask = 0;
-    uint32_t mynx[CPT];
+    uint32_t tab[CPT / 2];
     {
         const uint8_t *crow = codes + (lr + 1) * CP + 16 + lcb;
         const uint4 cw = *reinterpret_cast<const uint4 *>(crow);
@@ -79,15 +82,25 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
             uint32_t nx = W_TERM;
             int dloc, dcode;
             if (d8_delta(code, dloc, dcode) && crow[i + dcode] != 0) nx = (code & exit_codes(lr, lc)) ? W_EXIT : phys_of((uint32_t)(p + dloc));
-            mynx[i] = nx;
             word[i * FT_THREADS + tid] = nx;
             validmask |= (code != 0 ? 1u : 0u) << i;
+            // successor table entry (T2 and HAND's tile pass reuse it): diagonal flag of the move; a cell without a
+            // direction code is marked by the flag on a terminal entry (NX_NODATA)
+            const uint32_t t16 = nx | ((nx != W_TERM ? (code & 0xAAu) != 0 : code == 0) ? NX_DIAG : 0u);
+            if (i & 1) tab[i >> 1] |= t16 << 16; else tab[i >> 1] = t16;
         }
+    }
+    {   // cell order = thread order: thread t owns cells 16t..16t+15
+        uint4 *dst = reinterpret_cast<uint4 *>(table + (size_t)tile * TCELLS + tid * CPT);
+        dst[0] = make_uint4(tab[0], tab[1], tab[2], tab[3]);
+        dst[1] = make_uint4(tab[4], tab[5], tab[6], tab[7]);
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < CPT; ++i)
-        if (mynx[i] < W_EXIT) atomicAdd(&word[mynx[i]], W_PEND_ONE);
+    for (int i = 0; i < CPT; ++i) {
+        const uint32_t n = word[i * FT_THREADS + tid] & W_NXT;  // (other threads only touch the pending field)
+        if (n < W_EXIT) atomicAdd(&word[n], W_PEND_ONE);
+    }
     __syncthreads();
     unsigned srcmask = 0;
 #pragma unroll
@@ -191,48 +204,41 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
 
 // ---- T2: add the resolved inflow of the entry nodes along their in-tile paths --------------------------
 // acc already holds the tile-local counts; only the 64-byte runs that an entry path touches are rewritten.
-// The walks run over a successor table built once per tile (slot layout, 16 bits per cell:
-// [15 river cell | 14 diagonal move | 13..0 successor slot / W_EXIT / W_TERM]).
+// The walks run over the successor table T1 wrote for the tile (16 bits per cell, see NX_*).
 // HAND = true fuses the first pass of the HAND stage (hand.cu, H1) into the same tile visit: with the river
 // mask defined as acc > threshold (example.py:52) every river cell lies on an entry path or has a local
 // count above the threshold, so once the inflow is added the tile knows its river cells and the entry nodes
 // can walk to their first river cell / failure / next entry node right away.
-constexpr uint32_t NX_DIAG = 0x4000u, NX_RIVER = 0x8000u, NX_CYCLE = 0xFFFFFFFFu;
 
 template <typename ACC, bool HAND>
 __global__ void __launch_bounds__(FT_THREADS, 4)
-fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const unsigned long long *__restrict__ nstate,
-                      ACC *__restrict__ acc, unsigned long long *__restrict__ counters, int64_t thr,
-                      unsigned long long *__restrict__ hand_nstate, unsigned *__restrict__ hand_active,
-                      uint16_t *__restrict__ hand_table)
+fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const uint32_t *__restrict__ link,
+                      const unsigned long long *__restrict__ nstate, ACC *__restrict__ acc,
+                      unsigned long long *__restrict__ counters, int64_t thr, unsigned long long *__restrict__ hand_nstate,
+                      unsigned *__restrict__ hand_active, uint16_t *__restrict__ table)
 {
     typedef typename std::conditional<sizeof(ACC) == 8, unsigned long long, uint32_t>::type EXT;
-    __shared__ __align__(16) uint8_t codes[(T + 2) * CP + 16];
     __shared__ uint16_t nxt[TCELLS];
     __shared__ EXT ext[TCELLS];
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
     const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
     const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
-    const bool fast = stage_codes(v, r0, c0, codes, tid, FT_THREADS);
-    __syncthreads();
+    const bool fast = (v.cols % 16 == 0) && (c0 + T <= v.cols);
 
+    // the successor table T1 left for this tile -> shared memory (slot layout)
     const int lr = tid >> 2, lcb = (tid & 3) * CPT;
     unsigned validmask = 0;
     {
-        const uint8_t *crow = codes + (lr + 1) * CP + 16 + lcb;
-        const uint4 cw = *reinterpret_cast<const uint4 *>(crow);
-        const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
+        const uint4 *tp = reinterpret_cast<const uint4 *>(table + (size_t)tile * TCELLS + tid * CPT);
+        const uint4 ta = __ldcg(tp), tb = __ldcg(tp + 1);
+        const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
-            const int lc = lcb + i, p = lr * T + lc;
-            const unsigned code = (cws[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-            uint32_t nx = W_TERM;
-            int dloc, dcode;
-            if (d8_delta(code, dloc, dcode) && crow[i + dcode] != 0) nx = (code & exit_codes(lr, lc)) ? W_EXIT : phys_of((uint32_t)(p + dloc));
-            nxt[i * FT_THREADS + tid] = (uint16_t)(nx | ((code & 0xAAu) ? NX_DIAG : 0u));
+            const uint32_t e = (tw[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+            nxt[i * FT_THREADS + tid] = (uint16_t)e;
             ext[i * FT_THREADS + tid] = 0;
-            validmask |= (code != 0 ? 1u : 0u) << i;
+            validmask |= (e != NX_NODATA ? 1u : 0u) << i;
         }
     }
     __syncthreads();
@@ -317,12 +323,12 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const unsig
             if ((riv >> i) & 1u) nxt[i * FT_THREADS + tid] |= NX_RIVER;
     }
     const bool tile_has_river = __syncthreads_or(riv != 0);
-    {   // the table in cell order (thread t owns cells 16t..16t+15) for HAND's tile pass
+    if (riv) {  // patch the river bits into the persistent table (HAND's tile pass reads it)
         uint32_t w[CPT / 2];
 #pragma unroll
         for (int i = 0; i < CPT; i += 2)
             w[i / 2] = (uint32_t)nxt[i * FT_THREADS + tid] | ((uint32_t)nxt[(i + 1) * FT_THREADS + tid] << 16);
-        uint4 *dst = reinterpret_cast<uint4 *>(hand_table + (size_t)tile * TCELLS + tid * CPT);
+        uint4 *dst = reinterpret_cast<uint4 *>(table + (size_t)tile * TCELLS + tid * CPT);
         dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
         dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
@@ -350,14 +356,17 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const unsig
             const uint32_t pl = logical_of(q);
             hs = pack(KIND_RIVER, nd, nc, (uint32_t)((r0 + (pl >> 6)) * v.cols + c0 + (pl & (T - 1))));
         } else if (end == W_EXIT) {
-            const uint32_t pl = logical_of(q);
-            const int qr = (int)(pl >> 6), qc = (int)(pl & (T - 1));
-            int dr, dc;
-            d8_offset(codes[(qr + 1) * CP + 16 + qc], dr, dc);
-            const int64_t tr = r0 + qr + dr, tc = c0 + qc + dc;
-            if (tr < 0) hs = pack(KIND_EXIT, nd, nc, LINK_OUT | (uint32_t)tc);
-            else if (tr >= v.rows) hs = pack(KIND_EXIT, nd, nc, LINK_OUT | LINK_BELOW | (uint32_t)tc);
-            else { hs = pack(KIND_ACTIVE, nd, nc, (uint32_t)node_of_cell(tr, tc, v.tiles_x)); is_active = 1; }
+            // the path leaves through the exit T1 found for this entry: link = the entry node it lands on
+            const uint32_t l = link[(size_t)tile * SLOTS + tid];
+            if (!(l & LINK_OUT)) { hs = pack(KIND_ACTIVE, nd, nc, l); is_active = 1; }
+            else if (l != LINK_NONE) {
+                // out of the band: HAND wants the column of the halo cell it lands on (T1 stored the exit cell's column)
+                const int64_t xc = (int64_t)(l & 0x3FFFFFFFu);
+                const int64_t xr = (l & LINK_BELOW) ? v.rows - 1 : 0;
+                int dr, dc;
+                d8_offset(v.d8[xr * v.cols + xc], dr, dc);
+                hs = pack(KIND_EXIT, nd, nc, (l & (LINK_OUT | LINK_BELOW)) | (uint32_t)(xc + dc));
+            }
         }
     }
     hand_nstate[(size_t)tile * SLOTS + tid] = hs;
@@ -578,7 +587,10 @@ NodeLayout layout(int64_t rows, int64_t cols)
     L.off_meta = o; o += (size_t)L.nnodes * 4;
     L.off_nstate = o; o += (size_t)L.nnodes * 8;
     o = (o + 255) & ~(size_t)255;
-    L.off_flat = o; o += (size_t)rows * (size_t)cols * 8;  // only touched for cyclic grids
+    // flat per-cell state, only touched for cyclic grids; until then the region carries the 16-bit successor
+    // table between the two tile passes when the caller gave no HAND workspace to keep it in
+    const size_t flat_bytes = (size_t)rows * (size_t)cols * 8, table_bytes = (size_t)L.tiles * TCELLS * 2;
+    L.off_flat = o; o += flat_bytes > table_bytes ? flat_bytes : table_bytes;
     L.total = o;
     return L;
 }
@@ -597,10 +609,15 @@ int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
     TileView v{a->d8, a->halo_above, a->halo_below, a->rows, a->cols, (int)((a->cols + T - 1) / T)};
     ACC *acc = reinterpret_cast<ACC *>(a->acc);
     const unsigned nb_nodes = (unsigned)((L.nnodes + 255) / 256);
+    // successor table: behind the node states of the HAND workspace if there is one (HAND's tile pass reads it), else
+    // in the flat region of this workspace
+    unsigned *hactive = reinterpret_cast<unsigned *>(a->hand_ws);
+    unsigned long long *hstate = a->hand_ws ? reinterpret_cast<unsigned long long *>((char *)a->hand_ws + 256) : nullptr;
+    uint16_t *table = a->hand_ws ? reinterpret_cast<uint16_t *>(hstate + L.nnodes) : reinterpret_cast<uint16_t *>(flat);
 
     if (a->mode != DTB_FA_FINISH) {
         DTB_CUDA(cudaMemsetAsync(counters, 0, 256, st));
-        DTB_KERNEL("fa_tile_kernel", st, fa_tile_kernel<ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, exitw, link, meta, acc, (ACC)a->nodata_fill, counters));
+        DTB_KERNEL("fa_tile_kernel", st, fa_tile_kernel<ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, exitw, link, meta, acc, (ACC)a->nodata_fill, counters, table));
     }
     DTB_KERNEL("fa_node_init_kernel", st, fa_node_init_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, a->rows, a->cols, v.tiles_x, exitw, meta, a->inflow_above,
                                                  a->inflow_below, nstate));
@@ -622,15 +639,12 @@ int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
 
     if (a->hand_ws) {
         // fused HAND first pass: node states and the ACTIVE counter live at the head of the HAND workspace (hand.cu)
-        unsigned *hactive = reinterpret_cast<unsigned *>(a->hand_ws);
-        unsigned long long *hstate = reinterpret_cast<unsigned long long *>((char *)a->hand_ws + 256);
         DTB_CUDA(cudaMemsetAsync(hactive, 0, 256, st));
         DTB_KERNEL("fa_tile_finish_kernel<hand>", st, fa_tile_finish_kernel<ACC, true><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(
-                       v, meta, nstate, acc, counters, a->hand_river_threshold, hstate, hactive,
-                       reinterpret_cast<uint16_t *>(hstate + L.nnodes)));
+                       v, meta, link, nstate, acc, counters, a->hand_river_threshold, hstate, hactive, table));
     } else {
         DTB_KERNEL("fa_tile_finish_kernel", st, fa_tile_finish_kernel<ACC, false><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(
-                       v, meta, nstate, acc, counters, 0, nullptr, nullptr, nullptr));
+                       v, meta, link, nstate, acc, counters, 0, nullptr, nullptr, table));
     }
     // cyclic grids only (each kernel returns at once when counters[0] == 0)
     DTB_KERNEL("fa_flat_init_kernel", st, fa_flat_init_kernel<<<FLAT_BLOCKS, 256, 0, st>>>(v, a->inflow_above, a->inflow_below, flat, counters));
@@ -664,8 +678,7 @@ extern "C" int dtb_flowacc_band(const dtb_flowacc_args *a, void *ws, size_t ws_b
     if (ws_bytes < dtb_flowacc_workspace_bytes(a->rows, a->cols)) return DTB_ERR_WORKSPACE;
     if (a->cols >= (int64_t)1 << 30) return DTB_ERR_UNSUPPORTED;
     if (a->halo_below && a->rows % T != 0) return DTB_ERR_INVALID;  // band seams sit on tile seams
-    if (a->hand_ws && (a->mode == DTB_FA_SUMMARY || a->hand_ws_bytes < dtb_hand_workspace_bytes(a->rows, a->cols) ||
-                       a->rows * a->cols > 0xffffffffLL))
+    if (a->hand_ws && (a->hand_ws_bytes < dtb_hand_workspace_bytes(a->rows, a->cols) || a->rows * a->cols > 0xffffffffLL))
         return DTB_ERR_INVALID;
     const NodeLayout L = layout(a->rows, a->cols);
     if (L.nnodes >= (int64_t)1 << 30) return DTB_ERR_UNSUPPORTED;  // node ids share a word with the LINK_OUT flags

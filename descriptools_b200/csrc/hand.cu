@@ -282,7 +282,7 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
             uint2 s = make_uint2(0u, (uint32_t)KIND_FAIL << 30);  // W_TERM: code 0, unknown code, bad landing
             if (e & 0x8000u) s = make_uint2((uint32_t)((r0 + lr) * v.cols + c0 + lcb + i), (uint32_t)KIND_RIVER << 30);
             else if (n == 0x3FFEu) s = make_uint2((uint32_t)slot_of(lr, lcb + i), (uint32_t)KIND_EXIT << 30);
-            else if (n != 0x3FFFu) {
+            else if (n != 0x3FFFu) {  // 0x3FFF: terminal (valid outlet, or nodata when bit 14 is set)
                 s = make_uint2(n, (e & 0x4000u) ? (1u << 15) : 1u);
                 activemask |= 1u << i;
             }

@@ -120,7 +120,7 @@ typedef struct dtb_flowacc_args {
     int32_t *term_above, *term_below;
     int mode;
     int64_t *unfinalised_host;
-    /* Optional fusion with the HAND stage (modes FULL and FINISH): if hand_ws is a workspace of
+    /* Optional fusion with the HAND stage (pass the same hand_ws in every mode of one computation): if hand_ws is a workspace of
      * dtb_hand_workspace_bytes(rows, cols) bytes, the final tile pass also performs dtb_hand's first
      * pass (entry-node walks) for the river mask acc > hand_river_threshold (example.py:52) and leaves
      * the node states there; the following dtb_hand call on the same fdr / acc / threshold / workspace

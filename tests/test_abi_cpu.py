@@ -39,7 +39,8 @@ def test_argument_validation_needs_no_device():
     assert L.dtb_slope_d8(1, 7, 10, 10, 0, 10, 12.5, 1, None, None) == -1  # bad dtype
     assert L.dtb_flowacc(1, 10, 10, 1, 0, -100, 1, 8, None, None) == -3  # workspace too small
     # 1 tile: counters + 256 nodes x (exitw, link, meta, state) + the flat-sweep state used for cyclic grids
-    assert L.dtb_flowacc_workspace_bytes(10, 10) == 256 + 256 * (4 + 4 + 4 + 8) + 10 * 10 * 8
+    assert L.dtb_flowacc_workspace_bytes(10, 10) == 256 + 256 * (4 + 4 + 4 + 8) + max(10 * 10 * 8, 4096 * 2)
+    assert L.dtb_flowacc_workspace_bytes(1000, 1000) == 256 + 256 * 256 * (4 + 4 + 4 + 8) + 1000 * 1000 * 8
     assert L.dtb_hand_workspace_bytes(100, 70) == 256 + 2 * 2 * 256 * 8 + 2 * 2 * 4096 * 2
     assert L.dtb_hand(None, None, 0, None) == -1
     assert L.dtb_downslope(None, 0, None, 1, 1, 1.0, 1.0, 0, None, None) == -1
