@@ -51,9 +51,26 @@ def band_edges(rows: int, nbands: int) -> list[int]:
 ROUNDS = 6
 
 
+_forest_ws = {}
+
+
 def forest_accumulate(nxt: torch.Tensor, base: torch.Tensor, rounds: int = ROUNDS):
-    """out[i] = base[i] + sum of out[j] over j with nxt[j] == i  (nxt < 0: none), by pointer doubling.
-    Returns (out, unresolved flag)."""
+    """out[i] = base[i] + sum of out[j] over j with nxt[j] == i  (nxt < 0: none).  Returns (out, unresolved flag).
+    CUDA tensors: the library's last-arriver sweep (dtb_forest_accumulate); CPU tensors: pointer doubling in torch."""
+    if nxt.is_cuda:
+        from ._lib import check, lib
+
+        n = nxt.numel()
+        nxt, base = nxt.contiguous(), base.contiguous()
+        key = (nxt.device.index, n)
+        if key not in _forest_ws:
+            _forest_ws[key] = (torch.empty(lib.dtb_forest_workspace_bytes(n), dtype=torch.uint8, device=nxt.device),
+                               torch.empty(n, dtype=torch.int64, device=nxt.device),
+                               torch.zeros(1, dtype=torch.int32, device=nxt.device))
+        ws, out, flag = _forest_ws[key]
+        check(lib.dtb_forest_accumulate(nxt.data_ptr(), base.data_ptr(), n, out.data_ptr(), flag.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), torch.cuda.current_stream(nxt.device).cuda_stream), "dtb_forest_accumulate")
+        return out, flag[0] != 0
     s, a = base.clone(), nxt.clone()
     zero = torch.zeros_like(s)
     for _ in range(rounds):

@@ -569,6 +569,45 @@ fa_band_exit_scatter_kernel(TileView v, int side, int64_t tile0, const uint32_t 
     atomicAdd(reinterpret_cast<unsigned long long *>(&exit_out[c]), (unsigned long long)(nstate[node] & N_CNT));
 }
 
+// ---- generic forest accumulation (band boundary graph, bands.py) -------------------------------------
+// out[i] = base[i] + sum of out[j] over j with next[j] == i (next < 0: none): the same last-arriver sweep on
+// a caller-supplied forest.  state: [63 source | 62..44 pending | 43..0 count].
+__global__ void __launch_bounds__(256)
+forest_init_kernel(int64_t n, const long long *__restrict__ next, const long long *__restrict__ base, unsigned long long *state)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    atomicAdd(&state[i], (unsigned long long)base[i] & F_CNT);  // state was zeroed; tributaries may already have counted in
+    const long long t = next[i];
+    if (t >= 0 && t < n) atomicAdd(&state[t], F_PEND_ONE);
+}
+__global__ void __launch_bounds__(256)
+forest_sweep_kernel(int64_t n, const long long *__restrict__ next, unsigned long long *state, const unsigned long long *__restrict__ pend0)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    if ((pend0[i] >> 44) != 0ull) return;  // not a source (pending as counted before the sweep started)
+    uint64_t w = pend0[i] & F_CNT;
+    int64_t q = i;
+    for (;;) {
+        const long long t = next[q];
+        if (t < 0 || t >= n) break;
+        const uint64_t old = atomicAdd(&state[t], (unsigned long long)(w - F_PEND_ONE));
+        if (((old >> 44) & 0x7FFFFull) != 1ull) break;
+        w += old & F_CNT;
+        q = t;
+    }
+}
+__global__ void __launch_bounds__(256)
+forest_out_kernel(int64_t n, const unsigned long long *__restrict__ state, long long *__restrict__ out, int *__restrict__ unresolved)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t s = state[i];
+    out[i] = (long long)(s & F_CNT);
+    if ((s >> 44) & 0x7FFFFull) atomicOr(unresolved, 1);  // never finalised: the forest has a cycle
+}
+
 struct NodeLayout {
     int64_t tiles, nnodes;
     size_t off_counters, off_exitw, off_link, off_meta, off_nstate, off_flat, total;
@@ -700,4 +739,24 @@ extern "C" int dtb_flowacc(const uint8_t *d8, int64_t rows, int64_t cols, void *
     a.unfinalised_host = unfinalised_host;
     if (acc_dtype == DTB_I32 && rows * cols > 0x7fffffffLL) return DTB_ERR_UNSUPPORTED;
     return dtb_flowacc_band(&a, ws, ws_bytes, stream);
+}
+
+extern "C" size_t dtb_forest_workspace_bytes(int64_t n) { return n > 0 ? (size_t)n * 16 : 0; }
+
+extern "C" int dtb_forest_accumulate(const int64_t *next, const int64_t *base, int64_t n, int64_t *out, int *unresolved,
+                                     void *ws, size_t ws_bytes, void *stream)
+{
+    using namespace dtb;
+    if (!next || !base || !out || !unresolved || !ws || n <= 0) return DTB_ERR_INVALID;
+    if (ws_bytes < dtb_forest_workspace_bytes(n)) return DTB_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    unsigned long long *state = reinterpret_cast<unsigned long long *>(ws), *pend0 = state + n;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    DTB_CUDA(cudaMemsetAsync(state, 0, (size_t)n * 8, st));
+    DTB_CUDA(cudaMemsetAsync(unresolved, 0, sizeof(int), st));
+    DTB_KERNEL("forest_init_kernel", st, forest_init_kernel<<<nb, 256, 0, st>>>(n, (const long long *)next, (const long long *)base, state));
+    DTB_CUDA(cudaMemcpyAsync(pend0, state, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));  // snapshot: who is a source
+    DTB_KERNEL("forest_sweep_kernel", st, forest_sweep_kernel<<<nb, 256, 0, st>>>(n, (const long long *)next, state, pend0));
+    DTB_KERNEL("forest_out_kernel", st, forest_out_kernel<<<nb, 256, 0, st>>>(n, state, (long long *)out, unresolved));
+    return DTB_OK;
 }

@@ -131,6 +131,13 @@ typedef struct dtb_flowacc_args {
 } dtb_flowacc_args;
 int dtb_flowacc_band(const dtb_flowacc_args *args, void *ws, size_t ws_bytes, void *stream);
 
+/* Generic forest accumulation used by the band driver for the boundary graph between row bands:
+ * out[i] = base[i] + sum of out[j] over all j with next[j] == i (next[j] < 0: no successor).
+ * *unresolved (device int) becomes non-zero if the graph has a cycle.  ws: dtb_forest_workspace_bytes(n). */
+size_t dtb_forest_workspace_bytes(int64_t n);
+int dtb_forest_accumulate(const int64_t *next, const int64_t *base, int64_t n, int64_t *out,
+                          int *unresolved, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- flow distance + river-cell index + HAND (+ optional fused GFI) -------------------
  * Replaces flow_distance_index_cpu + flow_distance_index_gpu (flowhand.py:476-562,
  * 565-846, unpartitioned: out = 0) and hand_calculator (flowhand.py:414-442); with

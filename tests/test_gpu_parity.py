@@ -497,3 +497,23 @@ def test_flowacc_large_acyclic_partial_tiles():
     acc, bad = device.flow_accumulation(torch.from_numpy(d8).cuda(), check_cycles=True)
     assert left == 0 and bad == 0
     np.testing.assert_array_equal(acc.cpu().numpy(), acc_ref)
+
+
+def test_forest_accumulate_cuda_matches_torch():
+    """band boundary solver: the library's sweep == pointer doubling in torch, on a random forest"""
+    from descriptools_b200 import bands
+
+    rng = np.random.default_rng(3)
+    n = 50000
+    nxt = np.full(n, -1, np.int64)
+    for i in range(1, n):  # a random forest: every node points at a lower-numbered node or nowhere
+        if rng.random() < 0.9:
+            nxt[i] = rng.integers(max(0, i - 50), i)
+    base = rng.integers(0, 1 << 33, n).astype(np.int64)
+    ref, flag_ref = bands.forest_accumulate(torch.from_numpy(nxt), torch.from_numpy(base), rounds=20)
+    got, flag = bands.forest_accumulate(torch.from_numpy(nxt).cuda(), torch.from_numpy(base).cuda())
+    assert not bool(flag_ref) and not bool(flag)
+    assert torch.equal(got.cpu(), ref)
+    nxt[0] = 5  # 0 -> 5 -> ... -> 0: a cycle
+    _, flag = bands.forest_accumulate(torch.from_numpy(nxt).cuda(), torch.from_numpy(base).cuda())
+    assert bool(flag)
