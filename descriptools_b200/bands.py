@@ -167,7 +167,7 @@ class Band:
     """Device buffers and kernel calls of one row band (rows [r0, r1) of a `grows` x `cols` raster)."""
 
     def __init__(self, index: int, nbands: int, r0: int, r1: int, grows: int, cols: int, px: float, thr: int, n_gfi: float,
-                 b_gfi: float, device):
+                 b_gfi: float, device, force_int64: bool = False):
         from ._lib import lib
 
         self.lib = lib
@@ -176,7 +176,7 @@ class Band:
         self.px, self.thr, self.n_gfi, self.b_gfi = float(px), int(thr), float(n_gfi), float(b_gfi)
         self.dev = device
         self.first, self.last = index == 0, index == nbands - 1
-        self.int_dt = torch.int32 if grows * cols < 2**31 else torch.int64
+        self.int_dt = torch.int32 if grows * cols < 2**31 and not force_int64 else torch.int64
         rows = self.rows
         f32, u8, i64 = torch.float32, torch.uint8, torch.int64
         mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)
@@ -407,7 +407,8 @@ class DistExchange:
 class BandRunner:
     """Runs the chain over row bands.  `exchange=None` picks torch.distributed (one band per rank)."""
 
-    def __init__(self, rows, cols, px, river_threshold, n_gfi=0.4, b_gfi=0.1, nbands=None, exchange=None, device=None):
+    def __init__(self, rows, cols, px, river_threshold, n_gfi=0.4, b_gfi=0.1, nbands=None, exchange=None, device=None,
+                 force_int64=False):
         if exchange is None:
             exchange = DistExchange() if nbands is None else LocalExchange(nbands)
         self.x = exchange
@@ -417,8 +418,8 @@ class BandRunner:
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         mine = range(self.nbands) if isinstance(exchange, LocalExchange) else [exchange.rank]
-        self.bands = [Band(i, self.nbands, self.edges[i], self.edges[i + 1], rows, cols, px, river_threshold, n_gfi, b_gfi, device)
-                      for i in mine]
+        self.bands = [Band(i, self.nbands, self.edges[i], self.edges[i + 1], rows, cols, px, river_threshold, n_gfi, b_gfi, device,
+                           force_int64) for i in mine]
 
     def load(self, dem_rows: list[torch.Tensor]):
         """dem_rows[k]: the DEM rows of local band k (device or host tensor)"""

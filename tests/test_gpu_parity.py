@@ -368,11 +368,11 @@ def weaving_dem(rows, cols, seam, amp=20.0, period=90.0):
     return oracle.priority_flood_eps(z.astype(np.float32))
 
 
-def _run_bands(dem, k, thr):
+def _run_bands(dem, k, thr, force_int64=False):
     from descriptools_b200 import bands
 
     rows, cols = dem.shape
-    runner = bands.BandRunner(rows, cols, PX, thr, 0.4, 0.1, nbands=k)
+    runner = bands.BandRunner(rows, cols, PX, thr, 0.4, 0.1, nbands=k, force_int64=force_int64)
     runner.load([torch.from_numpy(dem[a:b]) for a, b in zip(runner.edges, runner.edges[1:])])
     runner.step()
     torch.cuda.synchronize()
@@ -517,3 +517,16 @@ def test_forest_accumulate_cuda_matches_torch():
     nxt[0] = 5  # 0 -> 5 -> ... -> 0: a cycle
     _, flag = bands.forest_accumulate(torch.from_numpy(nxt).cuda(), torch.from_numpy(base).cuda())
     assert bool(flag)
+
+
+def test_bands_int64_equal_single_gpu():
+    """the continental configuration's dtypes (int64 accumulation and indices) through the band path"""
+    from descriptools_b200 import pipeline
+
+    dem = synth(640, 336, 12)
+    thr = 250
+    ref = pipeline.run_device(torch.from_numpy(dem).cuda(), PX, thr)
+    got = _run_bands(dem, 3, thr, force_int64=True)
+    assert got["acc"].dtype == np.int64 and got["idx"].dtype == np.int64
+    for name in ("slope", "d8", "acc", "idx", "fdist", "hand", "gfi"):
+        np.testing.assert_array_equal(got[name], ref[name].cpu().numpy().astype(got[name].dtype), err_msg=name)
