@@ -342,15 +342,12 @@ def run_ours(args):
             pinned = {k: torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True) for k, t in outs.items()}
 
             def host_step():
-                band.dem.copy_(dem_host, non_blocking=True)
-                runner.step()
-                for k, t in band.outputs().items():
-                    pinned[k].copy_(t, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
+                runner.step_host([dem_host], [pinned])  # finished rasters stream back while the next stage computes
 
             host_step()
+            host_step()
             barrier()
-            k_e2e = max(1, min(args.steps, 2))
+            k_e2e = max(1, min(args.steps, 3))
             t0 = time.perf_counter()
             for _ in range(k_e2e):
                 host_step()

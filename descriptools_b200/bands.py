@@ -426,12 +426,13 @@ class BandRunner:
         for b, d in zip(self.bands, dem_rows):
             b.dem.copy_(d, non_blocking=True)
 
-    def step(self, events=None):
-        """One pass of the chain; `events` (4 CUDA events) are recorded at the stage boundaries."""
+    def step(self, events=None, hook=None):
+        """One pass of the chain; `events` (4 CUDA events) are recorded at the stage boundaries and `hook(i)` is
+        called after stage i (1 slope+D8, 2 flow accumulation, 3 HAND/GFI) has been enqueued."""
         rounds = ROUNDS
         while True:
             self.x.flags.clear()
-            self._step(events, rounds)
+            self._step(events, rounds, hook)
             if not self._unresolved():
                 return
             rounds += 6  # a chain of more than 2**rounds seam crossings: repeat the step with more doubling rounds
@@ -448,8 +449,38 @@ class BandRunner:
             return bool(t.item())
         return bool(bad.item()) if bad is not None else False
 
-    def _step(self, events, rounds):
-        rec = (lambda i: events[i].record()) if events is not None else (lambda i: None)
+    def step_host(self, dem_host: list, pinned_out: list):
+        """Host in / host out: dem_host[k] (pinned) is band k's DEM rows, pinned_out[k] a dict of pinned tensors for its
+        seven rasters.  Every finished raster streams back on a copy stream while the next stage computes."""
+        main = torch.cuda.current_stream(self.bands[0].dev)
+        if not hasattr(self, "_down"):
+            self._down = torch.cuda.Stream(device=self.bands[0].dev)
+        down = self._down
+        for b, h in zip(self.bands, dem_host):
+            b.dem.copy_(h, non_blocking=True)
+        ready = {1: ("slope", "d8"), 2: ("acc",), 3: ("idx", "fdist", "hand", "gfi")}
+
+        def hook(i):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            down.wait_event(ev)
+            with torch.cuda.stream(down):
+                for b, pin in zip(self.bands, pinned_out):
+                    o = b.outputs()
+                    for name in ready[i]:
+                        pin[name].copy_(o[name], non_blocking=True)
+
+        self.step(hook=hook)
+        down.synchronize()
+        main.synchronize()
+
+    def _step(self, events, rounds, hook=None):
+        def rec(i):
+            if events is not None:
+                events[i].record()
+            if hook is not None and i > 0:
+                hook(i)
+
         B = self.bands
         rec(0)
         self.x.halo([(b.dem_buf[1], b.dem_buf[b.rows], b.dem_buf[0], b.dem_buf[b.rows + 1]) for b in B])

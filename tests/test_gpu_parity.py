@@ -530,3 +530,19 @@ def test_bands_int64_equal_single_gpu():
     assert got["acc"].dtype == np.int64 and got["idx"].dtype == np.int64
     for name in ("slope", "d8", "acc", "idx", "fdist", "hand", "gfi"):
         np.testing.assert_array_equal(got[name], ref[name].cpu().numpy().astype(got[name].dtype), err_msg=name)
+
+
+def test_bands_step_host_matches_device_step():
+    from descriptools_b200 import bands
+
+    dem = synth(384, 272, 4)
+    thr = 150
+    rows, cols = dem.shape
+    runner = bands.BandRunner(rows, cols, PX, thr, 0.4, 0.1, nbands=2)
+    parts = [torch.from_numpy(dem[a:b].copy()).pin_memory() for a, b in zip(runner.edges, runner.edges[1:])]
+    pinned = [{k: torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory() for k, t in b.outputs().items()} for b in runner.bands]
+    runner.step_host(parts, pinned)
+    host = {k: np.concatenate([p[k].numpy() for p in pinned], 0) for k in pinned[0]}
+    ref = _run_bands(dem, 2, thr)
+    for k in ref:
+        np.testing.assert_array_equal(host[k], ref[k], err_msg=k)
