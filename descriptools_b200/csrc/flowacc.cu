@@ -42,7 +42,7 @@ constexpr int N_PEND_SHIFT = 48;
 // step both accumulates and returns the successor of the cell just finalised.
 constexpr uint32_t W_EXIT = 0x3FFEu, W_TERM = 0x3FFFu, W_NXT = 0x3FFFu, W_PEND_ONE = 1u << 28;
 constexpr int W_CNT_SHIFT = 14;
-constexpr int WALK_CAP = 8;
+constexpr int WALK_CAP = 4;
 // successor table, 16 bits per cell in cell order: [15 river cell | 14 diagonal move | 13..0 successor slot / W_EXIT / W_TERM]
 constexpr uint32_t NX_DIAG = 0x4000u, NX_RIVER = 0x8000u, NX_CYCLE = 0xFFFFFFFFu, NX_NODATA = W_TERM | NX_DIAG;
 
@@ -256,16 +256,18 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const uint3
         const uint64_t ns = nstate[(size_t)tile * SLOTS + tid];
         if ((ns >> N_PEND_SHIFT) & N_PEND) ++unresolved;  // never finalised: node-level cycle
         const EXT w = (EXT)(ns & N_CNT);
-        uint32_t q = my_slot;
-        path_end = NX_CYCLE;
-        for (int steps = 0; steps < TCELLS; ++steps) {
+        uint32_t q = my_slot, n16 = 0, ndiag = 0;
+        int steps = 0;
+        for (; steps < TCELLS; ++steps) {
             atomicAdd(&ext[q], w);
-            const uint32_t n16 = nxt[q], n = n16 & W_NXT;
-            if (n == W_TERM) { path_end = W_TERM; break; }
-            path_moves += 1u + ((n16 >> 14) & 1u) * 0xFFFFu;
-            if (n == W_EXIT) { path_end = W_EXIT; path_last = q; break; }
-            q = n;
+            n16 = nxt[q];
+            if ((n16 & W_NXT) >= W_EXIT) break;
+            ndiag += n16 >> 14;  // no river bits yet: bit 14 = diagonal move
+            q = n16 & W_NXT;
         }
+        path_end = steps == TCELLS ? NX_CYCLE : (n16 & W_NXT);
+        if (path_end == W_EXIT) { ++steps; ndiag += (n16 >> 14) & 1u; path_last = q; }  // the exit move itself
+        path_moves = (uint32_t)(steps - (int)ndiag) | (ndiag << 16);
     }
     unresolved = __reduce_add_sync(0xffffffffu, unresolved);
     if ((tid & 31) == 0 && unresolved) atomicAdd(&counters[0], (unsigned long long)unresolved);
