@@ -71,6 +71,7 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
     const int lr = tid >> 2, lcb = (tid & 3) * CPT;
     unsigned validmask = 0;
     uint32_t tab[CPT / 2];
+    const unsigned rowexit = (lr == 0 ? 0xE0u : 0u) | (lr == T - 1 ? 0x0Eu : 0u);
     {
         const uint8_t *crow = codes + (lr + 1) * CP + 16 + lcb;
         const uint4 cw = *reinterpret_cast<const uint4 *>(crow);
@@ -81,7 +82,10 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
             const unsigned code = (cws[i >> 2] >> (8 * (i & 3))) & 0xFFu;
             uint32_t nx = W_TERM;
             int dloc, dcode;
-            if (d8_delta(code, dloc, dcode) && crow[i + dcode] != 0) nx = (code & exit_codes(lr, lc)) ? W_EXIT : phys_of((uint32_t)(p + dloc));
+            // one-hot codes whose move leaves the tile from this cell: the row part is per thread, the column part
+            // only concerns the first / last cell of the row
+            const unsigned xm = rowexit | ((i == 0 && lcb == 0) ? 0x38u : 0u) | ((i == CPT - 1 && lcb == T - CPT) ? 0x83u : 0u);
+            if (d8_delta(code, dloc, dcode) && crow[i + dcode] != 0) nx = (code & xm) ? W_EXIT : phys_of((uint32_t)(p + dloc));
             word[i * FT_THREADS + tid] = nx;
             validmask |= (code != 0 ? 1u : 0u) << i;
             // successor table entry (T2 and HAND's tile pass reuse it): diagonal flag of the move; a cell without a
