@@ -176,13 +176,6 @@ __device__ __forceinline__ T hand_value(T z, bool resolved, const T *__restrict_
     return h;
 }
 
-// gfi.py:287-294
-template <typename T>
-__device__ __forceinline__ float gfi_value(T h, double racc, double n, double b, double s2)
-{
-    if (h <= HandOps<T>::nd()) return ND_F;
-    return (float)log(b * pow(racc * s2, n) / ((double)h + 0.01));
-}
 
 
 // ---- H3: per-tile resolution + epilogue ---------------------------------------------------------
