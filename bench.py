@@ -112,6 +112,12 @@ class ClockSampler:
                 "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def use_all_host_cores():
+    """the oracle port is OpenMP code; torchrun exports OMP_NUM_THREADS=1 to its children, which would silently turn
+    the CPU baseline into a single-thread run.  Must run before the oracle library is loaded."""
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
+
 def cpu_chain(dem, threads_note=True):
     """the oracle port over one DEM: slope+D8, accumulation, flow distance/index, HAND, GFI"""
     import numpy as np
@@ -137,6 +143,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_cores()
     import oracle
 
     oracle.build()
@@ -413,6 +420,7 @@ def run_ours(args):
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
     if world == 1 and not args.no_cpu:
+        use_all_host_cores()
         import oracle
 
         oracle.build()
