@@ -115,7 +115,14 @@ class ClockSampler:
 def use_all_host_cores():
     """the oracle port is OpenMP code; torchrun exports OMP_NUM_THREADS=1 to its children, which would silently turn
     the CPU baseline into a single-thread run.  Must run before the oracle library is loaded."""
-    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:  # libgomp may already be initialised (torch loads it): set the team size at run time as well
+        import ctypes
+
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except Exception:
+        pass
 
 
 def cpu_chain(dem, threads_note=True):
