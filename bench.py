@@ -112,62 +112,30 @@ class ClockSampler:
                 "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def use_all_host_cores():
-    """the oracle port is OpenMP code; torchrun exports OMP_NUM_THREADS=1 to its children, which would silently turn
-    the CPU baseline into a single-thread run.  Must run before the oracle library is loaded."""
-    n = os.cpu_count() or 1
-    os.environ["OMP_NUM_THREADS"] = str(n)
-    try:  # libgomp may already be initialised (torch loads it): set the team size at run time as well
-        import ctypes
-
-        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
-    except Exception:
-        pass
-
-
-def cpu_chain(dem, threads_note=True):
-    """the oracle port over one DEM: slope+D8, accumulation, flow distance/index, HAND, GFI"""
-    import numpy as np
-    import oracle
-
-    t0 = time.perf_counter()
-    slope, d8 = oracle.slope_d8(dem, PX)
-    acc, _ = oracle.flow_accumulation(d8)
-    river = (acc > RIVER_THR).astype(np.int8)
-    fdist, idx, hand = oracle.flow_hand_index(dem, d8, river, PX)
-    gfi = oracle.gfi(hand, acc, idx, N_GFI, B_GFI, PX)
-    return time.perf_counter() - t0
-
-
-def sample_dem():
-    """bounded CPU sample: a SAMPLE_ROWS x SAMPLE_COLS DEM of the same recipe, conditioned on the device"""
-    from descriptools_b200 import device
-
-    return device.conditioned_dem(SAMPLE_ROWS, SAMPLE_COLS).cpu().numpy()
+def cpu_reference(steps, warmup):
+    """the oracle port over the chain, timed in a process of its own (oracle/cpu_bench.py: no torch in the process,
+    OpenMP team = all host cores even under torchrun, which exports OMP_NUM_THREADS=1)"""
+    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
+    cmd = [sys.executable, os.path.join(REPO, "oracle", "cpu_bench.py"), str(SAMPLE_ROWS), str(SAMPLE_COLS), str(steps), str(warmup),
+           str(PX), str(RIVER_THR), str(N_GFI), str(B_GFI)]
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, check=True).stdout.strip().splitlines()[-1]
+    return json.loads(out)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    use_all_host_cores()
-    import oracle
-
-    oracle.build()
-    dem = sample_dem()
-    cores = os.cpu_count() or 1
-    for _ in range(args.warmup):
-        cpu_chain(dem)
-    t = [cpu_chain(dem) for _ in range(args.steps)]
-    dt = sum(t)
-    val = dem.size * args.steps / dt / 1e6
-    sample = f"{SAMPLE_ROWS}x{SAMPLE_COLS} f32 dtb-synth-v1 DEM per step, river = acc > {RIVER_THR}"
+    r = cpu_reference(args.steps, args.warmup)
+    dt = sum(r["seconds"])
+    val = r["cells"] * args.steps / dt / 1e6
+    sample = f"{SAMPLE_ROWS}x{SAMPLE_COLS} f32 dtb-synth-v1 DEM per step, river = acc > {RIVER_THR}; oracle/dt_oracle.c with OpenMP"
     print(json.dumps({
         "impl": "reference", "metric": "DEM Mcells/s slope->D8->flowacc->HAND->GFI", "value": val, "unit": "Mcells/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -427,15 +395,10 @@ def run_ours(args):
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
     if world == 1 and not args.no_cpu:
-        use_all_host_cores()
-        import oracle
-
-        oracle.build()
-        sdem = sample_dem()
-        cpu_chain(sdem)
-        dt = cpu_chain(sdem)
-        line["cpu_baseline"] = {"value": sdem.size / dt / 1e6, "unit": "Mcells/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                "sample": f"{SAMPLE_ROWS}x{SAMPLE_COLS} f32 dtb-synth-v1 DEM, same chain, oracle/dt_oracle.c with OpenMP"}
+        r = cpu_reference(1, 1)
+        line["cpu_baseline"] = {"value": r["cells"] / r["seconds"][0] / 1e6, "unit": "Mcells/s", "cores": r["cores"], "kind": "port",
+                                "sample": f"{SAMPLE_ROWS}x{SAMPLE_COLS} f32 dtb-synth-v1 DEM, same chain, oracle/dt_oracle.c with OpenMP "
+                                          "(separate process)"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

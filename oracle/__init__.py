@@ -47,6 +47,13 @@ def _lib(name: str) -> ctypes.CDLL:
     return _LIBS[name]
 
 
+def set_threads(n: int) -> int:
+    """OpenMP team size of the oracle's loops; returns the value in effect."""
+    lib = _lib("libdt_oracle.so")
+    lib.orc_set_threads(ctypes.c_int(int(n)))
+    return int(lib.orc_max_threads())
+
+
 def _p(a: np.ndarray):
     return a.ctypes.data_as(ctypes.c_void_p)
 

@@ -372,3 +372,14 @@ void orc_ti_mti(const int64_t *fac, const float *slope_rad, int64_t n, double px
 }
 
 int orc_abi_version(void) { return 1; }
+
+/* OpenMP team size of this library's loops (bench.py's CPU legs: torchrun exports OMP_NUM_THREADS=1, and the
+ * process may hold more than one OpenMP runtime, so the setting has to go through the one linked here). */
+#ifdef _OPENMP
+#include <omp.h>
+void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int orc_max_threads(void) { return omp_get_max_threads(); }
+#else
+void orc_set_threads(int n) { (void)n; }
+int orc_max_threads(void) { return 1; }
+#endif
