@@ -206,17 +206,19 @@ def run_ours(args):
         torch.cuda.synchronize()
         int_dt = torch.int32 if n_cells < 2**31 else torch.int64
 
+        outs = pipeline.alloc_outputs(rows, cols)  # the seven rasters, allocated once and rewritten by every pass
+
         def step(timed):
             e = [ev() for _ in range(4)]
             e[0].record()
-            slope, d8 = device.slope_d8(dem, PX)
+            slope, d8 = device.slope_d8(dem, PX, out=outs)
             e[1].record()
-            acc = device.flow_accumulation(d8, dtype=int_dt, fuse_hand_threshold=RIVER_THR)
+            acc = device.flow_accumulation(d8, dtype=int_dt, fuse_hand_threshold=RIVER_THR, out=outs)
             e[2].record()
             out = device.hand(d8, dem, PX, acc=acc, river_threshold=RIVER_THR, gfi_params=(N_GFI, B_GFI, PX), idx_dtype=int_dt,
-                              entry_done=True)
+                              entry_done=True, out=outs)
             e[3].record()
-            return e, (slope, d8, acc, out)
+            return e, None
 
         runner = None
     else:
@@ -296,7 +298,7 @@ def run_ours(args):
             dem_host = torch.empty((rows, cols), dtype=torch.float32, pin_memory=True)
             dem_host.copy_(dem)
             pinned = {k: torch.empty((rows, cols), dtype=getattr(torch, np.dtype(v).name), pin_memory=True) for k, v in dts.items()}
-            del dem
+            del dem, outs
             device.workspace.release()
             torch.cuda.empty_cache()
             for _ in range(2):  # warm-up (device allocations, workspaces, first touch of the pinned buffers)
@@ -312,6 +314,7 @@ def run_ours(args):
                    "d2h_bytes_per_step": int(sum(np.dtype(v).itemsize for v in dts.values())) * n_cells, "steps": k_e2e,
                    "ms_per_step": dt * 1e3}
             del pinned, dem_host
+            pipeline.release_buffers()
         except Exception as ex:  # host RAM too small for the pinned staging buffers
             e2e = {"value": None, "unit": "Mcells/s", "error": repr(ex)[:200]}
     elif runner is not None and args.no_e2e:

@@ -76,22 +76,33 @@ class _Workspace:
 workspace = _Workspace()
 
 
+def _out(out, name, shape, dtype, dev):
+    """a caller-supplied output raster (dict `out`, reused across calls: multi-GB allocations per call make the caching
+    allocator split and re-malloc blocks, and cudaMalloc / cudaFree synchronise the device) or a fresh one"""
+    if out is not None and name in out:
+        t = out[name]
+        if tuple(t.shape) != tuple(shape) or t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
+            raise ValueError(f"out[{name!r}] must be a contiguous CUDA tensor of shape {tuple(shape)} and dtype {dtype}")
+        return t
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
 def slope_d8(dem: torch.Tensor, px: float, want_slope: bool = True, want_d8: bool = True,
-             row_begin: int = 0, row_end: int | None = None):
+             row_begin: int = 0, row_end: int | None = None, out: dict | None = None):
     """Fused slope (%) + D8 over rows [row_begin,row_end) of `dem` (slope.py:152-259 + SURVEY A2)."""
     dem = _chk2d(dem, "dem")
     rows, cols = dem.shape
     row_end = rows if row_end is None else row_end
     nr = row_end - row_begin
-    slope = torch.empty((nr, cols), dtype=torch.float32, device=dem.device) if want_slope else None
-    d8 = torch.empty((nr, cols), dtype=torch.uint8, device=dem.device) if want_d8 else None
+    slope = _out(out, "slope", (nr, cols), torch.float32, dem.device) if want_slope else None
+    d8 = _out(out, "d8", (nr, cols), torch.uint8, dem.device) if want_d8 else None
     check(lib.dtb_slope_d8(_ptr(dem), _dem_dtype(dem), rows, cols, row_begin, row_end, float(px), _ptr(slope), _ptr(d8),
                            _stream()), "dtb_slope_d8")
     return slope, d8
 
 
 def flow_accumulation(d8: torch.Tensor, dtype: torch.dtype = torch.int32, nodata_fill: int = -100,
-                      check_cycles: bool = False, fuse_hand_threshold: int | None = None):
+                      check_cycles: bool = False, fuse_hand_threshold: int | None = None, out: dict | None = None):
     """D8 flow accumulation.  Returns acc, or (acc, n_cycle_cells) if check_cycles.
 
     fuse_hand_threshold = t: the final tile pass also runs HAND's entry-node pass for the river mask
@@ -103,7 +114,7 @@ def flow_accumulation(d8: torch.Tensor, dtype: torch.dtype = torch.int32, nodata
     if d8.dtype != torch.uint8:
         raise TypeError("d8 must be uint8")
     rows, cols = d8.shape
-    acc = torch.empty((rows, cols), dtype=dtype, device=d8.device)
+    acc = _out(out, "acc", (rows, cols), dtype, d8.device)
     nbytes = lib.dtb_flowacc_workspace_bytes(rows, cols)
     ws = workspace.get(nbytes, "flowacc")
     left = ctypes.c_int64(0)
@@ -124,7 +135,7 @@ def hand(fdr: torch.Tensor, dem: torch.Tensor | None, px: float, river: torch.Te
          acc: torch.Tensor | None = None, river_threshold: int = 0, max_moves: int = 0,
          want_fdist: bool = True, want_idx: bool = True, want_hand: bool = True,
          gfi_params: tuple[float, float, float] | None = None, idx_dtype: torch.dtype | None = None,
-         entry_done: bool = False):
+         entry_done: bool = False, out: dict | None = None):
     """Flow distance, river index, HAND and (optionally) fused GFI.
 
     flowhand.py:476-846 + 414-442 (+ gfi.py:118-147, 267-294 when gfi_params=(n, b, size)).
@@ -152,22 +163,22 @@ def hand(fdr: torch.Tensor, dem: torch.Tensor | None, px: float, river: torch.Te
         a.dem_dtype = _dem_dtype(dem)
     a.dem = _ptr(dem)
     a.rows, a.cols, a.px, a.max_moves = rows, cols, float(px), int(max_moves)
-    out = {}
+    given, out = out, {}
     if want_fdist:
-        out["fdist"] = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+        out["fdist"] = _out(given, "fdist", (rows, cols), torch.float32, dev)
     if want_idx:
         if idx_dtype is None:
             idx_dtype = torch.int32 if rows * cols < 2**31 else torch.int64
-        out["idx"] = torch.empty((rows, cols), dtype=idx_dtype, device=dev)
+        out["idx"] = _out(given, "idx", (rows, cols), idx_dtype, dev)
         a.idx_dtype = _int_dtype(out["idx"])
     if want_hand:
         if dem is None:
             raise ValueError("hand needs dem")
-        out["hand"] = torch.empty((rows, cols), dtype=dem.dtype, device=dev)
+        out["hand"] = _out(given, "hand", (rows, cols), dem.dtype, dev)
     if gfi_params is not None:
         if dem is None or acc is None:
             raise ValueError("fused gfi needs dem and acc")
-        out["gfi"] = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+        out["gfi"] = _out(given, "gfi", (rows, cols), torch.float32, dev)
         a.gfi_n, a.gfi_b, a.gfi_size = (float(v) for v in gfi_params)
     a.fdist, a.idx, a.hand, a.gfi = _ptr(out.get("fdist")), _ptr(out.get("idx")), _ptr(out.get("hand")), _ptr(out.get("gfi"))
     a.entry_done = 1 if entry_done else 0

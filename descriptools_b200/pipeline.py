@@ -19,8 +19,16 @@ from ._convert import dem_to_native
 STAGE_OUTPUTS = ("slope", "d8", "acc", "fdist", "idx", "hand", "gfi")
 
 
+def alloc_outputs(rows: int, cols: int, dem_dtype: torch.dtype = torch.float32, device=None) -> dict:
+    """the seven rasters of the chain, allocated once (pass as `out=` to run_device / pipeline to reuse them)"""
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    it = torch.int32 if rows * cols < 2**31 else torch.int64
+    dts = dict(slope=torch.float32, d8=torch.uint8, acc=it, fdist=torch.float32, idx=it, hand=dem_dtype, gfi=torch.float32)
+    return {k: torch.empty((rows, cols), dtype=v, device=dev) for k, v in dts.items()}
+
+
 def run_device(dem: torch.Tensor, px: float, river_threshold: int, n_gfi: float = 0.4, scale_factor: float = 0.1,
-               size: float | None = None, max_moves: int = 0) -> dict:
+               size: float | None = None, max_moves: int = 0, out: dict | None = None) -> dict:
     """slope(%) f32, d8 u8, acc i32/i64, fdist f32, idx i32/i64, hand (DEM dtype), gfi f32.
 
     river cells are `acc > river_threshold` (example.py:52); GFI uses `size` = px by default
@@ -29,13 +37,31 @@ def run_device(dem: torch.Tensor, px: float, river_threshold: int, n_gfi: float 
     size = px if size is None else size
     rows, cols = dem.shape
     int_dt = torch.int32 if rows * cols < 2**31 else torch.int64
-    slope, d8 = device.slope_d8(dem, px)
+    slope, d8 = device.slope_d8(dem, px, out=out)
     # the last tile pass of the accumulation also does HAND's entry-node pass (river = acc > threshold)
-    acc = device.flow_accumulation(d8, dtype=int_dt, nodata_fill=-100, fuse_hand_threshold=river_threshold)
+    acc = device.flow_accumulation(d8, dtype=int_dt, nodata_fill=-100, fuse_hand_threshold=river_threshold, out=out)
     out = device.hand(d8, dem, px, acc=acc, river_threshold=river_threshold, max_moves=max_moves,
-                      gfi_params=(n_gfi, scale_factor, size), idx_dtype=int_dt, entry_done=True)
+                      gfi_params=(n_gfi, scale_factor, size), idx_dtype=int_dt, entry_done=True, out=out)
     out.update(slope=slope, d8=d8, acc=acc)
     return out
+
+
+_buffers = {}
+
+
+def _device_buffers(rows, cols, dem_dtype, dev) -> dict:
+    """device rasters of the host pipeline, kept between calls (one set per shape; release_buffers() frees them)"""
+    key = (rows, cols, dem_dtype, str(dev))
+    if key not in _buffers:
+        _buffers.clear()
+        b = alloc_outputs(rows, cols, dem_dtype, dev)
+        b["dem"] = torch.empty((rows, cols), dtype=dem_dtype, device=dev)
+        _buffers[key] = b
+    return _buffers[key]
+
+
+def release_buffers() -> None:
+    _buffers.clear()
 
 
 def pipeline(dem, px: float, river_threshold: int, n_gfi: float = 0.4, scale_factor: float = 0.1,
@@ -83,10 +109,8 @@ def pipeline(dem, px: float, river_threshold: int, n_gfi: float = 0.4, scale_fac
                 host[name][r0:r1].copy_(t[r0:r1], non_blocking=True)
 
     # DEM up in row blocks; slope + D8 of a block runs once the block below it (its halo row) is resident
-    dem_d = torch.empty((rows, cols), dtype=dem_h.dtype, device=dev)
-    slope = torch.empty((rows, cols), dtype=torch.float32, device=dev)
-    d8 = torch.empty((rows, cols), dtype=torch.uint8, device=dev)
-    keep += [dem_d, slope, d8]
+    buf = _device_buffers(rows, cols, dem_h.dtype, dev)
+    dem_d, slope, d8 = buf["dem"], buf["slope"], buf["d8"]
     k = max(1, min(chunks, rows // 256 or 1))
     edges = [rows * i // k for i in range(k + 1)]
     arrived = []
@@ -106,11 +130,10 @@ def pipeline(dem, px: float, river_threshold: int, n_gfi: float = 0.4, scale_fac
                                slope[r0:r1].data_ptr(), d8[r0:r1].data_ptr(), main.cuda_stream), "dtb_slope_d8")
         send_back("slope", slope, r0, r1)
         send_back("d8", d8, r0, r1)
-    acc = device.flow_accumulation(d8, dtype=int_dt, nodata_fill=-100, fuse_hand_threshold=river_threshold)
-    keep.append(acc)
+    acc = device.flow_accumulation(d8, dtype=int_dt, nodata_fill=-100, fuse_hand_threshold=river_threshold, out=buf)
     send_back("acc", acc)
     out = device.hand(d8, dem_d, px, acc=acc, river_threshold=river_threshold, gfi_params=(n_gfi, scale_factor, size),
-                      idx_dtype=int_dt, entry_done=True)
+                      idx_dtype=int_dt, entry_done=True, out=buf)
     for name in ("idx", "fdist", "hand", "gfi"):
         keep.append(out[name])
         send_back(name, out[name])
