@@ -115,6 +115,10 @@ SIGNATURES = {
     "dtb_lnhlh": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_double, c_double, c_double, c_void_p, c_void_p]),
     "dtb_ti_mti": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "dtb_slope_to_radians": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "dtb_eval_counts": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_double, POINTER(c_double), c_int, c_int, POINTER(c_int64),
+                                c_void_p, c_size_t, c_void_p]),
+    "dtb_eval_class_map": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]),
+    "dtb_minmax_scale": (c_int, [c_void_p, c_int, c_int64, c_double, c_double, c_double, c_void_p, c_void_p]),
     "dtb_synth_dem_f32": (c_int, [c_int64, c_int64, c_int64, c_uint32, POINTER(c_float), c_float, c_float, c_float,
                                   c_float, c_void_p, c_void_p]),
     "dtb_fill_workspace_bytes": (c_size_t, [c_int64, c_int64]),

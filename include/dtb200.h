@@ -232,6 +232,24 @@ int dtb_ti_mti(const void *acc, int acc_dtype, const float *slope_rad, int64_t n
 /* example.py:63-64 glue: slope in percent -> radians with nodata patched back to -100 */
 int dtb_slope_to_radians(const float *slope_pct, int64_t n, float *slope_rad, void *stream);
 
+/* ---- threshold calibration against a benchmark flood map ------------------------------
+ * evaluation.py:5-9 (minMaxScale), :90-123 (binary_map), :126-171 (avaliacao), :12-87 (calibration is a host loop
+ * over dtb_eval_counts, descriptools_b200/evaluation.py).
+ * dtb_eval_counts: confusion counts (tn, fp, fn, tp) of up to 32 strictly ascending thresholds in ONE pass over
+ *   the rasters.  desc f32/f64; cells equal to `nodata` (the reference uses descriptor_matrix[0,0]) or NaN are never
+ *   flooded; flood int8 with avaliacao's remapping (1 -> 2, -100 -> 0); under != 0: flooded = desc <= threshold, else >=.
+ *   counts_host: k x 4 int64, valid on return (the call synchronises the stream).  ws >= 4*33*8 bytes.
+ * dtb_eval_class_map: binary map and / or class map (0 tn, 1 fp, 2 fn, 3 tp) for one threshold.
+ * dtb_minmax_scale: (mat - mn) / (mx - mn) in f64, nodata and NaN -> NaN. */
+enum { DTB_EV_F32 = 0, DTB_EV_F64 = 1, DTB_EV_I16 = 2 };
+int dtb_eval_counts(const void *desc, int desc_is_f64, const int8_t *flood, int64_t n, double nodata,
+                    const double *thresholds_host, int k, int under, int64_t *counts_host, void *ws,
+                    size_t ws_bytes, void *stream);
+int dtb_eval_class_map(const void *desc, int desc_is_f64, const int8_t *flood, int64_t n, double nodata,
+                       double threshold, int under, int8_t *binary, int8_t *cls, void *stream);
+int dtb_minmax_scale(const void *mat, int mat_dtype, int64_t n, double mn, double mx, double nodata,
+                     double *out, void *stream);
+
 /* ---- benchmark support: synthetic DEM "dtb-synth-v1" + depression filling ---------------
  * No reference counterpart (its fixtures were conditioned by an external GIS,
  * Example/example.py:33-39).  Bit-identical to oracle/dt_condition.cpp. */

@@ -546,3 +546,52 @@ def test_bands_step_host_matches_device_step():
     ref = _run_bands(dem, 2, thr)
     for k in ref:
         np.testing.assert_array_equal(host[k], ref[k], err_msg=k)
+
+
+# ---- evaluation.py: calibration against the benchmark flood map ---------------------
+def test_evaluation_kat1_hand_class(mods, ex):
+    """example.py:106-147 end to end on the device: flow_hand_index -> minMaxScale -> calibration -> binary_map ->
+    avaliacao reproduces Example/output/hand_class.tif (the reference's only golden output) and its indexes."""
+    import descriptools_b200.evaluation as evaluation
+    from helpers import avaliacao as avaliacao_ref, binary_map as binary_map_ref, calibration as calibration_ref, min_max_scale
+
+    _, _, hand = mods["flowhand"].flow_hand_index(ex["dem"], ex["fdr"], ex["river"], PX)
+    elements = np.unique(hand)
+    mn, mx = elements[1], elements[-1]
+    desc = evaluation.minMaxScale(hand, mn, mx, -100)
+    np.testing.assert_array_equal(desc, min_max_scale(hand, mn, mx, -100))
+    flood = ex["flood"].copy()
+    th = evaluation.calibration(desc, flood, "under")
+    assert th == calibration_ref(desc, ex["flood"].copy()) == pytest.approx(0.012)
+    assert set(np.unique(flood)) <= {0, 2}  # remapped in place like the reference
+    binary = evaluation.binary_map(desc, th, "under")
+    np.testing.assert_array_equal(binary, binary_map_ref(desc, th))
+    c, f, cls = evaluation.avaliacao(binary, flood)
+    c_ref, f_ref, cls_ref = avaliacao_ref(binary_map_ref(desc, th), ex["flood"].copy())
+    assert c == c_ref == pytest.approx(0.8581615676712259, abs=1e-12)
+    assert f == f_ref == pytest.approx(0.7240945135019289, abs=1e-12)
+    np.testing.assert_array_equal(cls, cls_ref)
+    np.testing.assert_array_equal(cls.astype(np.uint8), ex["hand_class"])
+
+
+def test_evaluation_counts_random_over_and_under():
+    import descriptools_b200.evaluation as evaluation
+    from helpers import binary_map as binary_map_ref
+
+    rng = np.random.default_rng(8)
+    desc = rng.random((300, 257))
+    desc[rng.random(desc.shape) < 0.1] = np.nan
+    desc[0, 0] = np.nan
+    flood = (rng.random(desc.shape) < 0.3).astype(np.int8)
+    flood[rng.random(desc.shape) < 0.05] = -100
+    for under in ("under", "over"):
+        th = 0.37
+        b = evaluation.binary_map(desc, th, under)
+        ref = binary_map_ref(desc, th, under == "under")
+        np.testing.assert_array_equal(b, ref)
+        c, f, cls = evaluation.avaliacao(b, flood.copy())
+        cmp_ = np.where(flood == 1, 2, np.where(flood == -100, 0, flood))
+        ref_cls = ref + cmp_
+        tn, fp, fn, tp = [(ref_cls == k).sum() for k in range(4)]
+        assert c == tp / (tp + fn) and f == tp / (tp + fn + fp)
+        np.testing.assert_array_equal(cls, ref_cls)
