@@ -5,13 +5,13 @@
 // the neighbour that last raised the running maximum in scan order NW,N,NE,W,E,SW,S,SE;
 // outlets point at their first undefined neighbour).  Bit-exact against oracle/dt_oracle.c.
 //
-// B200 design: persistent CTAs (2 per SM) walk 128x64-cell tiles in row-major order; each
-// tile plus its halo (a 136x66 f32 box starting 4 columns left of the tile: the TMA unit
+// B200 design: persistent CTAs (3 per SM) walk 128x32-cell tiles in row-major order; each
+// tile plus its halo (a 136x34 f32 box starting 4 columns left of the tile: the TMA unit
 // faults unless the box's innermost start coordinate is 16-byte aligned -- measured on B200,
 // scripts/tma_probe.cu) is staged in shared memory by TMA
 // (cp.async.bulk.tensor.2d, out-of-bounds elements filled with NaN, which stands in for
 // the reference's -100 padding ring) through a 3-stage mbarrier ring, so the next two
-// tiles are in flight while one is computed.  A thread owns 4 columns x 8 rows and slides
+// tiles are in flight while one is computed.  A thread owns 4 columns x 4 rows and slides
 // a 3-row register window down its strip: LDS.128+LDS.64 per row, every elevation
 // difference computed once and used by both endpoints (19 FSUB per 4 cells), results
 // leave as one STG.128 (slope) and one STG.32 (four D8 codes) per row.
@@ -33,7 +33,7 @@ namespace dtb {
 namespace {
 
 constexpr int TW = 128;           // tile width  (cells)
-constexpr int TH = 64;            // tile height (cells)
+constexpr int TH = 32;            // tile height (cells)
 constexpr int HALO_L = 4;         // staged columns start at c0-4 (TMA: 16-byte aligned box start)
 constexpr int BOXW = TW + 8;      // staged columns c0-4 .. c0+TW+3
 constexpr int BOXH = TH + 2;      // staged rows    r0-1 .. r0+TH
@@ -379,7 +379,7 @@ __device__ __forceinline__ void stencil_strip_fast(const float *tile, int gx, in
 }
 
 // ---- TMA persistent kernel (f32, cols % 4 == 0, 16-byte aligned bases) ----------------------
-__global__ void __launch_bounds__(NTHREADS, 2)
+__global__ void __launch_bounds__(NTHREADS, 3)
 slope_d8_tma_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_begin, int64_t row_end, int64_t cols,
                     int tiles_x, int ntiles, SlopeConsts k, float *__restrict__ slope, uint8_t *__restrict__ d8)
 {
@@ -514,7 +514,7 @@ extern "C" int dtb_slope_d8(const void *dem, int dem_dtype, int64_t buf_rows, in
             DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
             attr_set = true;
         }
-        const int grid = ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs;
+        const int grid = ntiles < 3 * kNumSMs ? ntiles : 3 * kNumSMs;
         DTB_KERNEL("slope_d8_tma_kernel", st, slope_d8_tma_kernel<<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8));
     } else if (dem_dtype == DTB_F32) {
         DTB_KERNEL("slope_d8_generic_kernel<f32>", st, slope_d8_generic_kernel<float><<<ntiles, NTHREADS, 0, st>>>((const float *)dem, buf_rows, row_begin, row_end, cols,
