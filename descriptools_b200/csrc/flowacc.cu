@@ -106,10 +106,12 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
         if (n < W_EXIT) atomicAdd(&word[n], W_PEND_ONE);
     }
     __syncthreads();
+    // Sources are spatially clustered (ridges), so the walks are dealt out across the CTA instead of by owner: for its
+    // k-th walk slot thread t takes cell k of thread (t + 37 k) mod 256 (still consecutive words for consecutive lanes).
+    // A cell without a direction code looks like a source with no successor: its walk is empty.
     unsigned srcmask = 0;
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) srcmask |= ((word[i * FT_THREADS + tid] >> 28) == 0u ? 1u : 0u) << i;
-    srcmask &= validmask;
+    for (int i = 0; i < CPT; ++i) srcmask |= ((word[i * FT_THREADS + ((tid + 37 * i) & (FT_THREADS - 1))] >> 28) == 0u ? 1u : 0u) << i;
     __syncthreads();  // every thread has read its pending fields before the sweep starts changing them
 
     // ---- sweep: every source walks until it is not the last tributary to arrive.  A walk that is still
@@ -118,7 +120,7 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
     while (srcmask) {
         const int i = __ffs((int)srcmask) - 1;
         srcmask &= srcmask - 1;
-        uint32_t n = word[i * FT_THREADS + tid] & W_NXT, carry = 0;
+        uint32_t n = word[i * FT_THREADS + ((tid + 37 * i) & (FT_THREADS - 1))] & W_NXT, carry = 0;
         int left = WALK_CAP;
         while (n < W_EXIT) {
             if (left-- == 0) {
