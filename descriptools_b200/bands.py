@@ -518,5 +518,34 @@ class BandRunner:
                 b.hand_finish(r)
         rec(3)
 
+    def downslope(self, delta: float, max_moves: int = 0) -> list[torch.Tensor]:
+        """Downslope index of every local band (downslope.py:317-376), after step() (it needs the D8 codes).
+
+        A downslope walk is cut by the drop it has reached, not by a band seam, and cannot be pointer-jumped, so the
+        reference's scheme -- tiles plus a global second pass over whatever left its tile (downslope.py:366-374) --
+        becomes: replicate DEM + D8 on every rank (one broadcast per band over NVLink, 5 bytes per cell) and let each
+        rank walk its own rows over the whole raster.  Exact, no iteration."""
+        from ._lib import check, lib
+
+        dev = self.bands[0].dev
+        full_dem = torch.empty((self.rows, self.cols), dtype=torch.float32, device=dev)
+        full_d8 = torch.empty((self.rows, self.cols), dtype=torch.uint8, device=dev)
+        mine = {b.index: b for b in self.bands}
+        for i in range(self.nbands):
+            a, e = self.edges[i], self.edges[i + 1]
+            if i in mine:
+                full_dem[a:e].copy_(mine[i].dem)
+                full_d8[a:e].copy_(mine[i].d8)
+            if isinstance(self.x, DistExchange):
+                self.x.dist.broadcast(full_dem[a:e], src=i, group=self.x.group)
+                self.x.dist.broadcast(full_d8[a:e], src=i, group=self.x.group)
+        outs = []
+        for b in self.bands:
+            out = torch.empty((b.rows, self.cols), dtype=torch.float32, device=dev)
+            check(lib.dtb_downslope_rows(full_dem.data_ptr(), 0, full_d8.data_ptr(), self.rows, self.cols, b.r0, b.r1, b.px,
+                                         float(delta), int(max_moves), out.data_ptr(), b._stream()), "dtb_downslope_rows")
+            outs.append(out)
+        return outs
+
     def outputs(self) -> list[dict]:
         return [b.outputs() for b in self.bands]

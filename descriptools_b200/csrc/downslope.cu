@@ -30,15 +30,17 @@ template <> struct Diff<int16_t> {
 
 template <typename T>
 __global__ void __launch_bounds__(DS_THREADS)
-downslope_kernel(const T *__restrict__ dem, const uint8_t *__restrict__ fdr, int64_t rows, int64_t cols, double px,
-                 double pd, double delta, int64_t max_moves, float *__restrict__ out)
+downslope_kernel(const T *__restrict__ dem, const uint8_t *__restrict__ fdr, int64_t rows, int64_t cols, int64_t row_begin,
+                 int64_t row_end, double px, double pd, double delta, int64_t max_moves, float *__restrict__ out)
 {
-    const int64_t n = rows * cols;
-    const int64_t i = (int64_t)blockIdx.x * DS_THREADS + threadIdx.x;
-    if (i >= n) return;
+    // cells of rows [row_begin, row_end) are computed (walks may wander over the whole raster); out starts at row_begin
+    const int64_t n = (row_end - row_begin) * cols;
+    const int64_t o = (int64_t)blockIdx.x * DS_THREADS + threadIdx.x;
+    if (o >= n) return;
+    const int64_t i = o + row_begin * cols;
     const T z0 = dem[i];
     if (z0 <= (T)ND_I) {  // downslope.py:459
-        out[i] = ND_F;
+        out[o] = ND_F;
         return;
     }
     int64_t y = i / cols, x = i - y * cols, pos = i, loop = 0;
@@ -59,28 +61,35 @@ downslope_kernel(const T *__restrict__ dem, const uint8_t *__restrict__ fdr, int
         if (++loop == max_moves) break;  // downslope.py:300-304
     }
     // downslope.py:306-312 (dist == 0 also covers the reference's 0/0 ZeroDivisionError case)
-    out[i] = (dist == 0.0) ? 0.0f : (float)(Diff<T>::sub(z0, zc) / dist);
+    out[o] = (dist == 0.0) ? 0.0f : (float)(Diff<T>::sub(z0, zc) / dist);
 }
 
 }  // namespace
 }  // namespace dtb
 
-extern "C" int dtb_downslope(const void *dem, int dem_dtype, const uint8_t *fdr, int64_t rows, int64_t cols, double px,
-                             double delta, int64_t max_moves, float *out, void *stream)
+extern "C" int dtb_downslope_rows(const void *dem, int dem_dtype, const uint8_t *fdr, int64_t rows, int64_t cols, int64_t row_begin,
+                                  int64_t row_end, double px, double delta, int64_t max_moves, float *out, void *stream)
 {
     using namespace dtb;
-    if (!dem || !fdr || !out || rows <= 0 || cols <= 0 || !(px > 0.0)) return DTB_ERR_INVALID;
+    if (!dem || !fdr || !out || rows <= 0 || cols <= 0 || !(px > 0.0) || row_begin < 0 || row_end > rows || row_begin > row_end)
+        return DTB_ERR_INVALID;
+    if (row_begin == row_end) return DTB_OK;
     if (max_moves <= 0) max_moves = 5000;
-    const int64_t n = rows * cols;
+    const int64_t n = (row_end - row_begin) * cols;
     const unsigned blocks = (unsigned)((n + DS_THREADS - 1) / DS_THREADS);
     cudaStream_t st = as_stream(stream);
     const double pd = px * sqrt(2.0);
     if (dem_dtype == DTB_F32)
-        downslope_kernel<float><<<blocks, DS_THREADS, 0, st>>>((const float *)dem, fdr, rows, cols, px, pd, delta, max_moves, out);
+        DTB_KERNEL("downslope_kernel<f32>", st, downslope_kernel<float><<<blocks, DS_THREADS, 0, st>>>((const float *)dem, fdr, rows, cols, row_begin, row_end, px, pd, delta, max_moves, out));
     else if (dem_dtype == DTB_I16)
-        downslope_kernel<int16_t><<<blocks, DS_THREADS, 0, st>>>((const int16_t *)dem, fdr, rows, cols, px, pd, delta, max_moves, out);
+        DTB_KERNEL("downslope_kernel<i16>", st, downslope_kernel<int16_t><<<blocks, DS_THREADS, 0, st>>>((const int16_t *)dem, fdr, rows, cols, row_begin, row_end, px, pd, delta, max_moves, out));
     else
         return DTB_ERR_INVALID;
-    DTB_LAUNCH_CHECK("downslope_kernel");
     return DTB_OK;
+}
+
+extern "C" int dtb_downslope(const void *dem, int dem_dtype, const uint8_t *fdr, int64_t rows, int64_t cols, double px,
+                             double delta, int64_t max_moves, float *out, void *stream)
+{
+    return dtb_downslope_rows(dem, dem_dtype, fdr, rows, cols, 0, rows, px, delta, max_moves, out, stream);
 }

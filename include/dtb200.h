@@ -213,6 +213,12 @@ int dtb_hand_from_index(const void *dem, int dem_dtype, const void *idx, int idx
 int dtb_downslope(const void *dem, int dem_dtype, const uint8_t *fdr, int64_t rows,
                   int64_t cols, double px, double delta, int64_t max_moves, float *out,
                   void *stream);
+/* rows [row_begin, row_end) only (out holds those rows); the walks still see the whole raster.  Row-band form: the
+ * band driver replicates dem + fdr on every rank (NVLink broadcast) and each rank computes its own rows -- the
+ * counterpart of the reference's "GPU pass per tile + global CPU pass over the -50 flags" (downslope.py:366-374). */
+int dtb_downslope_rows(const void *dem, int dem_dtype, const uint8_t *fdr, int64_t rows, int64_t cols,
+                       int64_t row_begin, int64_t row_end, double px, double delta, int64_t max_moves,
+                       float *out, void *stream);
 
 /* ---- pointwise indices -----------------------------------------------------------------
  * dtb_river_accumulation: gfi.py:118-147.  out has acc's dtype.

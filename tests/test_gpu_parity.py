@@ -595,3 +595,19 @@ def test_evaluation_counts_random_over_and_under():
         tn, fp, fn, tp = [(ref_cls == k).sum() for k in range(4)]
         assert c == tp / (tp + fn) and f == tp / (tp + fn + fp)
         np.testing.assert_array_equal(cls, ref_cls)
+
+
+def test_bands_downslope_equals_single_gpu():
+    from descriptools_b200 import bands, device
+
+    dem = synth(384, 300, 21)
+    rows, cols = dem.shape
+    t = torch.from_numpy(dem).cuda()
+    _, d8 = device.slope_d8(t, PX)
+    ref = device.downslope(t, d8, PX, 5.0).cpu().numpy()
+    np.testing.assert_array_equal(ref, oracle.downslope(dem, d8.cpu().numpy(), PX, 5.0))
+    runner = bands.BandRunner(rows, cols, PX, 200, nbands=3)
+    runner.load([torch.from_numpy(dem[a:b]) for a, b in zip(runner.edges, runner.edges[1:])])
+    runner.step()
+    got = torch.cat(runner.downslope(5.0), 0).cpu().numpy()
+    np.testing.assert_array_equal(got, ref)
