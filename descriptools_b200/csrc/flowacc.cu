@@ -216,18 +216,19 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
 // count above the threshold, so once the inflow is added the tile knows its river cells and the entry nodes
 // can walk to their first river cell / failure / next entry node right away.
 
-template <typename ACC, bool HAND>
-__global__ void __launch_bounds__(FT_THREADS, 4)
-fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const uint32_t *__restrict__ link,
-                      const unsigned long long *__restrict__ nstate, ACC *__restrict__ acc,
-                      unsigned long long *__restrict__ counters, int64_t thr, unsigned long long *__restrict__ hand_nstate,
-                      unsigned *__restrict__ hand_active, uint16_t *__restrict__ table)
+// REDO = true is the second run of the HAND part on a grid with D8 cycles: the flat sweep has rewritten acc since, so
+// the river bits of the table and the entry states are derived again from the final counts (nothing is added to acc).
+template <typename ACC, bool HAND, bool REDO>
+__device__ __forceinline__ void
+fa_finish_tile(const int tile, const TileView &v, const uint32_t *__restrict__ meta, const uint32_t *__restrict__ link,
+               const unsigned long long *__restrict__ nstate, ACC *__restrict__ acc,
+               unsigned long long *__restrict__ counters, int64_t thr, unsigned long long *__restrict__ hand_nstate,
+               unsigned *__restrict__ hand_active, uint16_t *__restrict__ table)
 {
     typedef typename std::conditional<sizeof(ACC) == 8, unsigned long long, uint32_t>::type EXT;
     __shared__ uint16_t nxt[TCELLS];
     __shared__ EXT ext[TCELLS];
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
     const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
     const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
     const bool fast = (v.cols % 16 == 0) && (c0 + T <= v.cols);
@@ -241,7 +242,8 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const uint3
         const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
-            const uint32_t e = (tw[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+            uint32_t e = (tw[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+            if (REDO) e &= ~NX_RIVER;  // river bits of the first run
             nxt[i * FT_THREADS + tid] = (uint16_t)e;
             ext[i * FT_THREADS + tid] = 0;
             validmask |= (e != NX_NODATA ? 1u : 0u) << i;
@@ -260,8 +262,8 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const uint3
         slot_cell(tid, plr, plc);
         my_slot = phys_of((uint32_t)(plr * T + plc));
         const uint64_t ns = nstate[(size_t)tile * SLOTS + tid];
-        if ((ns >> N_PEND_SHIFT) & N_PEND) ++unresolved;  // never finalised: node-level cycle
-        const EXT w = (EXT)(ns & N_CNT);
+        if (!REDO && ((ns >> N_PEND_SHIFT) & N_PEND)) ++unresolved;  // never finalised: node-level cycle
+        const EXT w = REDO ? (EXT)0 : (EXT)(ns & N_CNT);
         uint32_t q = my_slot, n16 = 0, ndiag = 0;
         int steps = 0;
         for (; steps < TCELLS; ++steps) {
@@ -288,7 +290,7 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const uint3
 #pragma unroll
         for (int i = 0; i < CPT; ++i) { e[i] = ext[i * FT_THREADS + tid]; any |= e[i] != 0; }
         // cells off every entry path keep their tile-local count (< 4096): they can only be river cells for tiny thresholds
-        const bool need = any || (HAND && thr < (int64_t)TCELLS);
+        const bool need = any || (HAND && (REDO || thr < (int64_t)TCELLS));
         if (need) {
             ACC *dst = acc + gr * v.cols + c0 + lcb;
             if (fast && ((reinterpret_cast<uintptr_t>(acc) & 15u) == 0)) {
@@ -331,7 +333,7 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const uint3
             if ((riv >> i) & 1u) nxt[i * FT_THREADS + tid] |= NX_RIVER;
     }
     const bool tile_has_river = __syncthreads_or(riv != 0);
-    if (riv) {  // patch the river bits into the persistent table (HAND's tile pass reads it)
+    if (riv || REDO) {  // patch the river bits into the persistent table (HAND's tile pass reads it)
         uint32_t w[CPT / 2];
 #pragma unroll
         for (int i = 0; i < CPT; i += 2)
@@ -380,6 +382,31 @@ fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const uint3
     hand_nstate[(size_t)tile * SLOTS + tid] = hs;
     const unsigned ballot = __ballot_sync(0xffffffffu, is_active);
     if ((tid & 31) == 0 && ballot) atomicAdd(&hand_active[0], (unsigned)__popc(ballot));
+}
+
+template <typename ACC, bool HAND>
+__global__ void __launch_bounds__(FT_THREADS, 4)
+fa_tile_finish_kernel(TileView v, const uint32_t *__restrict__ meta, const uint32_t *__restrict__ link,
+                      const unsigned long long *__restrict__ nstate, ACC *__restrict__ acc,
+                      unsigned long long *__restrict__ counters, int64_t thr, unsigned long long *__restrict__ hand_nstate,
+                      unsigned *__restrict__ hand_active, uint16_t *__restrict__ table)
+{
+    fa_finish_tile<ACC, HAND, false>((int)blockIdx.x, v, meta, link, nstate, acc, counters, thr, hand_nstate, hand_active, table);
+}
+
+// cyclic grids only: returns at once when counters[0] == 0 (the count of unfinalised cells / nodes)
+template <typename ACC>
+__global__ void __launch_bounds__(FT_THREADS, 4)
+fa_tile_rehand_kernel(TileView v, int64_t tiles, const uint32_t *__restrict__ meta, const uint32_t *__restrict__ link,
+                      const unsigned long long *__restrict__ nstate, ACC *__restrict__ acc,
+                      unsigned long long *__restrict__ counters, int64_t thr, unsigned long long *__restrict__ hand_nstate,
+                      unsigned *__restrict__ hand_active, uint16_t *__restrict__ table)
+{
+    if (counters[0] == 0ull) return;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        fa_finish_tile<ACC, true, true>((int)tile, v, meta, link, nstate, acc, counters, thr, hand_nstate, hand_active, table);
+        __syncthreads();
+    }
 }
 
 // ---- N: entry-node forest ---------------------------------------------------------------------
@@ -697,6 +724,9 @@ int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
     DTB_KERNEL("fa_flat_init_kernel", st, fa_flat_init_kernel<<<FLAT_BLOCKS, 256, 0, st>>>(v, a->inflow_above, a->inflow_below, flat, counters));
     DTB_KERNEL("fa_flat_sweep_kernel", st, fa_flat_sweep_kernel<ACC><<<FLAT_BLOCKS, 256, 0, st>>>(v, acc, flat, counters));
     DTB_KERNEL("fa_flat_fix_kernel", st, fa_flat_fix_kernel<ACC><<<FLAT_BLOCKS, 256, 0, st>>>(v, acc, flat, counters));
+    if (a->hand_ws)
+        DTB_KERNEL("fa_tile_rehand_kernel", st, fa_tile_rehand_kernel<ACC><<<FLAT_BLOCKS, FT_THREADS, 0, st>>>(
+                       v, L.tiles, meta, link, nstate, acc, counters, a->hand_river_threshold, hstate, hactive, table));
     if (a->unfinalised_host) {
         unsigned long long h[3];
         DTB_CUDA(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, st));

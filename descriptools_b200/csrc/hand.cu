@@ -224,10 +224,104 @@ __device__ __forceinline__ void load4(const V *src, V (&val)[4], bool vec, int64
     }
 }
 
+// What lies behind exit cell (plr, plc) of the tile at (r0, c0), leaving with direction (dr, dc) / code `code`:
+// the state of the entry node it lands on (or of the halo cell, for a band), composed with the exit move.
+template <typename TD, typename IDX, typename ACC>
+__device__ __forceinline__ void resolve_exit(const TileView &v, int64_t r0, int64_t c0, int slot, int plr, int plc, bool is_exit,
+                                             unsigned code, int dr, int dc, const TD *__restrict__ dem,
+                                             const ACC *__restrict__ acc, const unsigned long long *__restrict__ nstate,
+                                             const HandOut &o, uint32_t *exit_hi, IDX *exit_idx, TD *exit_z, double *exit_l1)
+{
+    uint64_t e = pack(KIND_FAIL, 0, 0, 0);
+    unsigned remote = 0;
+    if (is_exit) {
+        const int64_t gr = r0 + plr + dr, gc = c0 + plc + dc;
+        const bool diag = d8_is_diag(code);
+        const uint64_t mv = pack(KIND_ACTIVE, diag ? 1u : 0u, diag ? 0u : 1u, 0);
+        uint64_t ns = pack(KIND_FAIL, 0, 0, 0);
+        if (gr >= 0 && gr < v.rows) ns = nstate[node_of_cell(gr, gc, v.tiles_x)];
+        if (kind_of(ns) == KIND_EXIT || gr < 0 || gr >= v.rows) {
+            // the path leaves the band (now, or further down inside the band): continue with the
+            // resolved path of the halo cell it lands on
+            int side;
+            int64_t col;
+            uint64_t pre = mv;
+            if (gr < 0 || gr >= v.rows) { side = gr < 0 ? 0 : 1; col = gc; }
+            else { side = (ptr_of(ns) & LINK_BELOW) ? 1 : 0; col = ptr_of(ns) & 0x3FFFFFFFu; pre = compose(mv, ns); }
+            ns = o.res_state[side] ? o.res_state[side][col] : pack(KIND_FAIL, 0, 0, 0);
+            ns = (ns & ~0xFFFFFFFFull) | (uint64_t)(uint32_t)col;
+            e = compose(pack(KIND_ACTIVE, nd_of(pre), nc_of(pre), 0), ns);
+            remote = 1u + (unsigned)side;
+        } else {
+            e = compose(mv, ns);
+        }
+        if (kind_of(e) != KIND_RIVER) { e = pack(KIND_FAIL, 0, 0, 0); remote = 0; }  // ACTIVE left over: cycle or > cap
+    }
+    exit_hi[slot] = ((uint32_t)kind_of(e) << 30) | (nd_of(e) << 15) | nc_of(e);
+    if (kind_of(e) == KIND_RIVER) {
+        const int64_t loc = (int64_t)ptr_of(e);  // local index of the river cell, or (remote) a column of the halo tables
+        double racc = 1.0;
+        if (remote) {
+            exit_idx[slot] = (IDX)o.res_idx[remote - 1][loc];
+            exit_z[slot] = (TD)o.res_z[remote - 1][loc];
+            if (o.gfi) racc = (double)o.res_acc[remote - 1][loc];
+        } else {
+            exit_idx[slot] = (IDX)(loc + o.idx_offset);
+            exit_z[slot] = (o.hand || o.gfi) ? dem[loc] : (TD)0;
+            if (o.gfi) racc = (double)acc[loc];  // river_accumulation, gfi.py:141-143
+        }
+        exit_l1[slot] = o.gfi ? o.gfi_logb + o.gfi_n * fast_log(racc * o.gfi_s2) : 0.0;
+    }
+}
+
+template <typename TD, typename IDX> struct alignas(8) ExitRec {
+    uint32_t hi;  // [31..30 kind | 29..15 diagonal moves | 14..0 cardinal moves] from the exit cell on
+    TD z;         // elevation of the river cell
+    IDX idx;      // its global index
+    double l1;    // ln b + n ln(A_r size^2)
+};
+template <typename TD, typename IDX, typename ACC>
+__device__ __forceinline__ void resolve_exit(const TileView &v, int64_t r0, int64_t c0, int slot, int plr, int plc, bool is_exit,
+                                             unsigned code, int dr, int dc, const TD *__restrict__ dem,
+                                             const ACC *__restrict__ acc, const unsigned long long *__restrict__ nstate,
+                                             const HandOut &o, ExitRec<TD, IDX> *exits)
+{
+    uint32_t hi;
+    IDX idx = (IDX)ND_I;
+    TD z = (TD)0;
+    double l1 = 0.0;
+    resolve_exit<TD, IDX, ACC>(v, r0, c0, 0, plr, plc, is_exit, code, dr, dc, dem, acc, nstate, o, &hi, &idx, &z, &l1);
+    ExitRec<TD, IDX> x;
+    x.hi = hi;
+    x.z = z;
+    x.idx = idx;
+    x.l1 = l1;
+    exits[slot] = x;
+}
+
+// outputs of one cell from its resolved path
+template <typename TD, typename IDX>
+__device__ __forceinline__ void finish_cell(const HandOut &o, uint32_t kind, uint32_t nd, uint32_t nc, int64_t idx, TD zr, double l1,
+                                            TD z, float &fd, IDX &ix, TD &hd, float &gf)
+{
+    const bool ok = kind == KIND_RIVER && nc + nd <= o.max_moves;  // flowhand.py:835
+    fd = ok ? (float)((double)nc * o.px + (double)nd * o.pd) : ND_F;  // flowhand.py:840-843
+    ix = ok ? (IDX)idx : (IDX)ND_I;
+    TD h = HandOps<TD>::nd();
+    float g = ND_F;
+    if ((o.hand || o.gfi) && ok && !HandOps<TD>::is_nd(z)) {  // flowhand.py:436-438
+        h = HandOps<TD>::sub(z, zr);
+        if (h < (TD)0 && h != HandOps<TD>::nd()) h = (TD)0;
+        if (o.gfi && !(h <= HandOps<TD>::nd())) g = (float)(l1 - fast_log_pos((double)h + 0.01));  // gfi.py:289-294
+    }
+    hd = h;
+    gf = g;
+}
+
 template <typename TD, typename IDX, typename ACC, bool TABLE>
-__global__ void __launch_bounds__(H_THREADS)
-hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC *__restrict__ acc,
-                 const unsigned long long *__restrict__ nstate, const uint16_t *__restrict__ table, HandOut o)
+__device__ __forceinline__ void hand_tile_body(const int tile, const TileView &v, const RiverSrc &rs, const TD *__restrict__ dem,
+                                               const ACC *__restrict__ acc, const unsigned long long *__restrict__ nstate,
+                                               const uint16_t *__restrict__ table, const HandOut &o)
 {
     // TABLE: the successor table the fused finish pass of flowacc.cu left behind (one 16-bit entry per cell in
     // cell order: [15 river | 14 diagonal move | 13..0 successor slot / W_EXIT / W_TERM]) replaces staging the
@@ -243,7 +337,6 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
     __shared__ TD exit_z[SLOTS];
     __shared__ double exit_l1[SLOTS];
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
     const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
     const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
     const int lr = tid >> 2, lcb = (tid & 3) * CPT;
@@ -336,8 +429,6 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
     if (tid < USED_SLOTS) {
         int plr, plc;
         slot_cell(tid, plr, plc);
-        uint64_t e = pack(KIND_FAIL, 0, 0, 0);
-        unsigned remote = 0;
         int dr = 0, dc = 0;
         bool is_exit;
         if (TABLE) {
@@ -348,47 +439,7 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
                       ((unsigned)(plr + dr) >= (unsigned)T || (unsigned)(plc + dc) >= (unsigned)T) && C(plr + dr, plc + dc) != 0;
         }
         const unsigned code = is_exit ? C(plr, plc) : 0u;
-        {
-            const int tr = plr + dr, tc = plc + dc;
-            if (is_exit) {
-                const int64_t gr = r0 + tr, gc = c0 + tc;
-                const bool diag = d8_is_diag(code);
-                const uint64_t mv = pack(KIND_ACTIVE, diag ? 1u : 0u, diag ? 0u : 1u, 0);
-                uint64_t ns = pack(KIND_FAIL, 0, 0, 0);
-                if (gr >= 0 && gr < v.rows) ns = nstate[node_of_cell(gr, gc, v.tiles_x)];
-                if (kind_of(ns) == KIND_EXIT || gr < 0 || gr >= v.rows) {
-                    // the path leaves the band (now, or further down inside the band): continue with the
-                    // resolved path of the halo cell it lands on
-                    int side;
-                    int64_t col;
-                    uint64_t pre = mv;
-                    if (gr < 0 || gr >= v.rows) { side = gr < 0 ? 0 : 1; col = gc; }
-                    else { side = (ptr_of(ns) & LINK_BELOW) ? 1 : 0; col = ptr_of(ns) & 0x3FFFFFFFu; pre = compose(mv, ns); }
-                    ns = o.res_state[side] ? o.res_state[side][col] : pack(KIND_FAIL, 0, 0, 0);
-                    ns = (ns & ~0xFFFFFFFFull) | (uint64_t)(uint32_t)col;
-                    e = compose(pack(KIND_ACTIVE, nd_of(pre), nc_of(pre), 0), ns);
-                    remote = 1u + (unsigned)side;
-                } else {
-                    e = compose(mv, ns);
-                }
-                if (kind_of(e) != KIND_RIVER) { e = pack(KIND_FAIL, 0, 0, 0); remote = 0; }  // ACTIVE left over: cycle or > cap
-            }
-        }
-        exit_hi[tid] = ((uint32_t)kind_of(e) << 30) | (nd_of(e) << 15) | nc_of(e);
-        if (kind_of(e) == KIND_RIVER) {
-            const int64_t loc = (int64_t)ptr_of(e);  // local index of the river cell, or (remote) a column of the halo tables
-            double racc = 1.0;
-            if (remote) {
-                exit_idx[tid] = (IDX)o.res_idx[remote - 1][loc];
-                exit_z[tid] = (TD)o.res_z[remote - 1][loc];
-                if (o.gfi) racc = (double)o.res_acc[remote - 1][loc];
-            } else {
-                exit_idx[tid] = (IDX)(loc + o.idx_offset);
-                exit_z[tid] = (o.hand || o.gfi) ? dem[loc] : (TD)0;
-                if (o.gfi) racc = (double)acc[loc];  // river_accumulation, gfi.py:141-143
-            }
-            exit_l1[tid] = o.gfi ? o.gfi_logb + o.gfi_n * fast_log(racc * o.gfi_s2) : 0.0;
-        }
+        resolve_exit<TD, IDX, ACC>(v, r0, c0, tid, plr, plc, is_exit, code, dr, dc, dem, acc, nstate, o, exit_hi, exit_idx, exit_z, exit_l1);
     }
     __syncthreads();
 
@@ -424,18 +475,183 @@ hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC 
                 if (o.hand || o.gfi) zr = dem[s2.x];
                 if (o.gfi) l1 = o.gfi_logb + o.gfi_n * fast_log((double)acc[s2.x] * o.gfi_s2);  // gfi.py:141-143
             }
-            const bool ok = kind == KIND_RIVER && nc + nd <= o.max_moves;  // flowhand.py:835
-            fd[i] = ok ? (float)((double)nc * o.px + (double)nd * o.pd) : ND_F;  // flowhand.py:840-843
-            ix[i] = ok ? (IDX)idx : (IDX)ND_I;
-            TD h = HandOps<TD>::nd();
-            float g = ND_F;
-            if ((o.hand || o.gfi) && ok && !HandOps<TD>::is_nd(z[i])) {  // flowhand.py:436-438
-                h = HandOps<TD>::sub(z[i], zr);
-                if (h < (TD)0 && h != HandOps<TD>::nd()) h = (TD)0;
-                if (o.gfi && !(h <= HandOps<TD>::nd())) g = (float)(l1 - fast_log_pos((double)h + 0.01));  // gfi.py:289-294
+            finish_cell<TD, IDX>(o, kind, nd, nc, idx, zr, l1, z[i], fd[i], ix[i], hd[i], gf[i]);
+        }
+        if (o.fdist) store4<float>(o.fdist + obase, fd, vec, c_first, v.cols);
+        if (o.idx) store4<IDX>(reinterpret_cast<IDX *>(o.idx) + obase, ix, vec, c_first, v.cols);
+        if (o.hand) store4<TD>(reinterpret_cast<TD *>(o.hand) + obase, hd, vec, c_first, v.cols);
+        if (o.gfi) store4<float>(o.gfi + obase, gf, vec, c_first, v.cols);
+    }
+}
+
+// tiles == nullptr: one CTA per tile of the grid; otherwise the CTAs share the *ntiles tiles listed (the tiles the
+// compact pass below had to give up on)
+template <typename TD, typename IDX, typename ACC, bool TABLE>
+__global__ void __launch_bounds__(H_THREADS)
+hand_tile_kernel(TileView v, RiverSrc rs, const TD *__restrict__ dem, const ACC *__restrict__ acc,
+                 const unsigned long long *__restrict__ nstate, const uint16_t *__restrict__ table, HandOut o,
+                 const unsigned *__restrict__ tiles, const unsigned *__restrict__ ntiles)
+{
+    if (!tiles) {
+        hand_tile_body<TD, IDX, ACC, TABLE>((int)blockIdx.x, v, rs, dem, acc, nstate, table, o);
+        return;
+    }
+    const unsigned n = *ntiles;
+    for (unsigned k = blockIdx.x; k < n; k += gridDim.x) {
+        hand_tile_body<TD, IDX, ACC, TABLE>((int)tiles[k], v, rs, dem, acc, nstate, table, o);
+        __syncthreads();
+    }
+}
+
+// ---- H3, compact form (over the successor table): one 32-bit word per cell -----------------------------------
+//     [31 root | 30 target is a root | 29 guard | 28..21 diagonal moves | 20 guard | 19..12 cardinal moves | 11..0 target]
+// (target = a cell of the tile, slot layout).  A root (river cell, exit cell, dead end) points at itself and keeps
+// its kind in bits 30..29 (KIND_*) and, for an exit cell, its perimeter slot in bits 19..12.  Composing "s then t"
+// is s = (s & ~0xFFF) + t, which also hands t's "target is a root" flag to s: a cell is done when that flag is set.
+// Half the shared-memory traffic of the 64-bit form above -- this stage is bound by shared-memory wavefronts -- at
+// the price of 8-bit counters: a tile with an in-tile path of 256 or more moves of one kind (or an in-tile cycle)
+// is handed to the 64-bit kernel through a list.
+constexpr uint32_t C_ROOT = 0x80000000u, C_FLAG = 0x40000000u, C_GUARDS = (1u << 29) | (1u << 20), C_CARD = 1u << 12, C_DIAG = 1u << 21;
+constexpr int OVF_SLOT = 32;  // word of the workspace header that counts the listed tiles
+
+// Shared-memory position of a state word.  On top of the slot layout of tiles.cuh (cell p at (p % 16) * 256 + p / 16:
+// conflict-free when thread t works on cell 16 t + i) bits 4..3 are XORed with bits 3..2 of the cell number, which
+// keeps that property and also makes "lane l works on cell 4 l + k of a 128-cell span" conflict-free -- the
+// epilogue's mapping, where a warp reads and writes whole 256-byte raster rows.  An involution.
+__device__ __forceinline__ uint32_t swz(uint32_t q) { return q ^ (((q >> 10) & 3u) << 3); }
+
+template <typename TD, typename IDX, typename ACC>
+__global__ void __launch_bounds__(H_THREADS, 6)
+hand_tile_compact_kernel(TileView v, const TD *__restrict__ dem, const ACC *__restrict__ acc,
+                         const unsigned long long *__restrict__ nstate, const uint16_t *__restrict__ table, HandOut o,
+                         unsigned *__restrict__ ovf_tiles, unsigned *__restrict__ ovf_count)
+{
+    __shared__ uint32_t st[TCELLS];
+    __shared__ ExitRec<TD, IDX> exits[SLOTS];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
+    const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
+    const int lr = tid >> 2, lcb = (tid & 3) * CPT;
+    const bool fast = (v.cols % 16 == 0) && (c0 + T <= v.cols);
+
+    unsigned activemask = 0;
+    {
+        const uint4 *tp = reinterpret_cast<const uint4 *>(table + (size_t)tile * TCELLS + tid * CPT);
+        const uint4 ta = __ldg(tp), tb = __ldg(tp + 1);
+        const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+        // perimeter slot of my cells (tiles.cuh slot_of, with the per-thread part hoisted): on the first / last row of
+        // the tile every cell has one, elsewhere only column 0 (my cell 0) and column T-1 (my cell 15) do
+        const bool rowedge = lr == 0 || lr == T - 1;
+        const uint32_t slot_row = (uint32_t)(lr == T - 1 ? T + lcb : lcb);
+        const uint32_t slot_first = rowedge ? slot_row : (uint32_t)(2 * T + lr - 1);
+        const uint32_t slot_last = rowedge ? slot_row + 15u : (uint32_t)(2 * T + (T - 2) + lr - 1);
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            const uint32_t e = (tw[i >> 1] >> (16 * (i & 1))) & 0xFFFFu, n = e & 0x3FFFu;
+            const uint32_t self = swz((uint32_t)(i * H_THREADS + tid));
+            const uint32_t slot = i == 0 ? slot_first : (i == CPT - 1 ? slot_last : slot_row + (uint32_t)i);
+            // W_TERM: dead end (code 0, unknown code, bad landing); W_EXIT: leaves the tile; bit 15: river cell
+            uint32_t s = C_ROOT | self | (n == 0x3FFEu ? ((uint32_t)KIND_EXIT << 29) | (slot << 12) : (uint32_t)KIND_FAIL << 29);
+            if (e & 0x8000u) s = C_ROOT | ((uint32_t)KIND_RIVER << 29) | self;
+            else if (n < 0x3FFEu) {
+                s = ((e & 0x4000u) ? C_DIAG : C_CARD) | swz(n);
+                activemask |= 1u << i;
             }
-            hd[i] = h;
-            gf[i] = g;
+            st[self] = s;
+        }
+    }
+    __syncthreads();
+
+    // ---- in-tile pointer jumping (in place, asynchronous) ----
+    // Two hops per visit, branch-free (a finished first hop just repeats itself in the second).  A guard bit means 256
+    // moves of one kind or more: not representable here, the tile is listed (whatever its cells hold by then).
+    uint32_t over = 0;
+    for (int round = 0; round < 16; ++round) {
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            if (!((activemask >> i) & 1u)) continue;
+            const uint32_t me = swz((uint32_t)(i * H_THREADS + tid));
+            uint32_t s = st[me];
+            const uint32_t t1 = st[s & 0xFFFu];
+            s = (t1 & C_ROOT) ? (s | C_FLAG) : ((s & ~0xFFFu) + t1);
+            const uint32_t t2 = st[s & 0xFFFu];
+            if (!(s & (C_FLAG | C_GUARDS))) s = (t2 & C_ROOT) ? (s | C_FLAG) : ((s & ~0xFFFu) + t2);
+            st[me] = s;
+            over |= s;
+            if (s & (C_FLAG | C_GUARDS)) activemask &= ~(1u << i);
+        }
+        if (!__syncthreads_or(activemask != 0)) break;
+    }
+    if (__syncthreads_or((over & C_GUARDS) != 0u || activemask != 0)) {
+        if (tid == 0) ovf_tiles[atomicAdd(ovf_count, 1u)] = (unsigned)tile;
+        return;
+    }
+
+    // ---- resolved state behind every exit cell of the perimeter ----
+    if (tid < USED_SLOTS) {
+        int plr, plc;
+        slot_cell(tid, plr, plc);
+        const uint32_t w = st[swz(phys_of((uint32_t)(plr * T + plc)))];
+        const bool is_exit = (w >> 29) == (4u | (uint32_t)KIND_EXIT);
+        int dr = 0, dc = 0;
+        unsigned code = 0;
+        if (is_exit) {
+            code = fetch_code(v, r0 + plr, c0 + plc);
+            d8_offset(code, dr, dc);
+        }
+        resolve_exit<TD, IDX, ACC>(v, r0, c0, tid, plr, plc, is_exit, code, dr, dc, dem, acc, nstate, o, exits);
+    }
+    __syncthreads();
+
+    // ---- epilogue: idx, flow distance, HAND, GFI ----
+    // A warp takes two 64-cell rows per pass (lane l: 4 cells at column 4 (l % 16)), so every load / store
+    // instruction covers whole 128-byte lines.
+    const bool vec = fast && (((reinterpret_cast<uintptr_t>(dem) | reinterpret_cast<uintptr_t>(o.fdist) |
+                                reinterpret_cast<uintptr_t>(o.idx) | reinterpret_cast<uintptr_t>(o.hand) |
+                                reinterpret_cast<uintptr_t>(o.gfi)) & 15u) == 0);
+    const int ecol = 4 * (tid & 15);
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+        const int erow = 8 * (tid >> 5) + 2 * pass + ((tid >> 4) & 1);
+        const int64_t gr = r0 + erow;
+        if (gr >= v.rows) continue;
+        const int64_t c_first = c0 + ecol, obase = gr * v.cols + c_first;
+        const uint32_t p = (uint32_t)(erow * T + ecol);
+        alignas(16) TD z[4];
+        alignas(16) float fd[4], gf[4];
+        alignas(16) IDX ix[4];
+        alignas(16) TD hd[4];
+        if (o.hand || o.gfi) load4<TD>(dem + obase, z, vec, c_first, v.cols, HandOps<TD>::nd());
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t s = st[swz((((p & 15u) + i) << 8) | (p >> 4))];
+            uint32_t r = s, nd = 0, nc = 0;
+            if (!(s & C_ROOT)) {
+                r = st[s & 0xFFFu];
+                nd = (s >> 21) & 0xFFu;
+                nc = (s >> 12) & 0xFFu;
+            }
+            uint32_t kind = (r >> 29) & 3u;
+            int64_t idx = (int64_t)ND_I;
+            TD zr = (TD)0;
+            double l1 = 0.0;
+            if (kind == KIND_EXIT) {  // continue with the resolved path behind the tile's exit cell
+                const ExitRec<TD, IDX> x = exits[(r >> 12) & 0xFFu];  // (idx, z, l1 only meaningful for a river)
+                kind = x.hi >> 30;
+                nd += (x.hi >> 15) & 0x7FFFu;
+                nc += x.hi & 0x7FFFu;
+                idx = x.idx;
+                zr = x.z;
+                l1 = x.l1;
+            } else if (kind == KIND_RIVER) {  // river cell inside this tile
+                const uint32_t rp = logical_of(swz(r & 0xFFFu));
+                const int64_t loc = (r0 + (int64_t)(rp >> 6)) * v.cols + c0 + (int64_t)(rp & 63u);
+                idx = loc + o.idx_offset;
+                if (o.hand || o.gfi) zr = dem[loc];
+                if (o.gfi) l1 = o.gfi_logb + o.gfi_n * fast_log((double)acc[loc] * o.gfi_s2);  // gfi.py:141-143
+            }
+            finish_cell<TD, IDX>(o, kind, nd, nc, idx, zr, l1, z[i], fd[i], ix[i], hd[i], gf[i]);
         }
         if (o.fdist) store4<float>(o.fdist + obase, fd, vec, c_first, v.cols);
         if (o.idx) store4<IDX>(reinterpret_cast<IDX *>(o.idx) + obase, ix, vec, c_first, v.cols);
@@ -524,12 +740,19 @@ int run_tiles(const dtb_hand_args *a, const TileView &v, const RiverSrc &rs, con
     }
     // the successor table of the fused finish pass sits behind the node states in the workspace
     const uint16_t *table = reinterpret_cast<const uint16_t *>(nstate + tiles * SLOTS);
-    if (a->entry_done)
-        DTB_KERNEL("hand_tile_kernel<table>", st, hand_tile_kernel<TD, IDX, ACC, true><<<(unsigned)tiles, H_THREADS, 0, st>>>(
-                       v, rs, (const TD *)a->dem, (const ACC *)a->acc, nstate, table, o));
-    else
+    if (a->entry_done) {
+        // compact pass over every tile, then the 64-bit pass over the few tiles it could not represent
+        unsigned *ovf_count = reinterpret_cast<unsigned *>(const_cast<unsigned long long *>(nstate)) - 64 + OVF_SLOT;
+        unsigned *ovf_tiles = reinterpret_cast<unsigned *>(const_cast<uint16_t *>(table) + tiles * TCELLS);
+        DTB_CUDA(cudaMemsetAsync(ovf_count, 0, sizeof(unsigned), st));
+        DTB_KERNEL("hand_tile_kernel<table>", st, hand_tile_compact_kernel<TD, IDX, ACC><<<(unsigned)tiles, H_THREADS, 0, st>>>(
+                       v, (const TD *)a->dem, (const ACC *)a->acc, nstate, table, o, ovf_tiles, ovf_count));
+        const unsigned grid = (unsigned)(tiles < kNumSMs * 4 ? tiles : kNumSMs * 4);
+        DTB_KERNEL("hand_tile_kernel<listed>", st, hand_tile_kernel<TD, IDX, ACC, true><<<grid, H_THREADS, 0, st>>>(
+                       v, rs, (const TD *)a->dem, (const ACC *)a->acc, nstate, table, o, ovf_tiles, ovf_count));
+    } else
         DTB_KERNEL("hand_tile_kernel", st, hand_tile_kernel<TD, IDX, ACC, false><<<(unsigned)tiles, H_THREADS, 0, st>>>(
-                       v, rs, (const TD *)a->dem, (const ACC *)a->acc, nstate, nullptr, o));
+                       v, rs, (const TD *)a->dem, (const ACC *)a->acc, nstate, nullptr, o, nullptr, nullptr));
     return DTB_OK;
 }
 
@@ -557,7 +780,8 @@ extern "C" size_t dtb_hand_workspace_bytes(int64_t rows, int64_t cols)
     if (rows <= 0 || cols <= 0) return 0;
     const int64_t tiles = ((rows + dtb::T - 1) / dtb::T) * ((cols + dtb::T - 1) / dtb::T);
     // node states + the per-cell successor table of the fused flow-accumulation finish pass (flowacc.cu)
-    return 256 + (size_t)tiles * dtb::SLOTS * 8 + (size_t)tiles * dtb::TCELLS * 2;
+    // + the list of tiles the compact tile pass hands to the 64-bit one
+    return 256 + (size_t)tiles * dtb::SLOTS * 8 + (size_t)tiles * dtb::TCELLS * 2 + (size_t)tiles * 4;
 }
 
 extern "C" int dtb_hand(const dtb_hand_args *a, void *ws, size_t ws_bytes, void *stream)

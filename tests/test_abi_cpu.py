@@ -41,7 +41,7 @@ def test_argument_validation_needs_no_device():
     # 1 tile: counters + 256 nodes x (exitw, link, meta, state) + the flat-sweep state used for cyclic grids
     assert L.dtb_flowacc_workspace_bytes(10, 10) == 256 + 256 * (4 + 4 + 4 + 8) + max(10 * 10 * 8, 4096 * 2)
     assert L.dtb_flowacc_workspace_bytes(1000, 1000) == 256 + 256 * 256 * (4 + 4 + 4 + 8) + 1000 * 1000 * 8
-    assert L.dtb_hand_workspace_bytes(100, 70) == 256 + 2 * 2 * 256 * 8 + 2 * 2 * 4096 * 2
+    assert L.dtb_hand_workspace_bytes(100, 70) == 256 + 2 * 2 * 256 * 8 + 2 * 2 * 4096 * 2 + 2 * 2 * 4
     assert L.dtb_hand(None, None, 0, None) == -1
     assert L.dtb_downslope(None, 0, None, 1, 1, 1.0, 1.0, 0, None, None) == -1
     with pytest.raises(_lib.DtbError):
