@@ -535,7 +535,6 @@ hand_tile_compact_kernel(TileView v, const TD *__restrict__ dem, const ACC *__re
     const int lr = tid >> 2, lcb = (tid & 3) * CPT;
     const bool fast = (v.cols % 16 == 0) && (c0 + T <= v.cols);
 
-    unsigned activemask = 0;
     {
         const uint4 *tp = reinterpret_cast<const uint4 *>(table + (size_t)tile * TCELLS + tid * CPT);
         const uint4 ta = __ldg(tp), tb = __ldg(tp + 1);
@@ -554,36 +553,34 @@ hand_tile_compact_kernel(TileView v, const TD *__restrict__ dem, const ACC *__re
             // W_TERM: dead end (code 0, unknown code, bad landing); W_EXIT: leaves the tile; bit 15: river cell
             uint32_t s = C_ROOT | self | (n == 0x3FFEu ? ((uint32_t)KIND_EXIT << 29) | (slot << 12) : (uint32_t)KIND_FAIL << 29);
             if (e & 0x8000u) s = C_ROOT | ((uint32_t)KIND_RIVER << 29) | self;
-            else if (n < 0x3FFEu) {
-                s = ((e & 0x4000u) ? C_DIAG : C_CARD) | swz(n);
-                activemask |= 1u << i;
-            }
+            else if (n < 0x3FFEu) s = ((e & 0x4000u) ? C_DIAG : C_CARD) | swz(n);
             st[self] = s;
         }
     }
     __syncthreads();
 
     // ---- in-tile pointer jumping (in place, asynchronous) ----
-    // Two hops per visit, branch-free (a finished first hop just repeats itself in the second).  A guard bit means 256
+    // Two hops per visit.  A cell is done when its word says "root" or "target is a root"; a guard bit means 256
     // moves of one kind or more: not representable here, the tile is listed (whatever its cells hold by then).
     uint32_t over = 0;
     for (int round = 0; round < 16; ++round) {
+        uint32_t all = ~0u;  // AND of the words seen this round: bit 30 / 31 survive iff every cell is done
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
-            if (!((activemask >> i) & 1u)) continue;
             const uint32_t me = swz((uint32_t)(i * H_THREADS + tid));
             uint32_t s = st[me];
+            if (s & (C_ROOT | C_FLAG)) continue;
             const uint32_t t1 = st[s & 0xFFFu];
             s = (t1 & C_ROOT) ? (s | C_FLAG) : ((s & ~0xFFFu) + t1);
             const uint32_t t2 = st[s & 0xFFFu];
             if (!(s & (C_FLAG | C_GUARDS))) s = (t2 & C_ROOT) ? (s | C_FLAG) : ((s & ~0xFFFu) + t2);
             st[me] = s;
             over |= s;
-            if (s & (C_FLAG | C_GUARDS)) activemask &= ~(1u << i);
+            all &= s;
         }
-        if (!__syncthreads_or(activemask != 0)) break;
+        if (!__syncthreads_or(!(all & C_FLAG) && !(over & C_GUARDS))) break;
     }
-    if (__syncthreads_or((over & C_GUARDS) != 0u || activemask != 0)) {
+    if (__syncthreads_or((over & C_GUARDS) != 0u)) {
         if (tid == 0) ovf_tiles[atomicAdd(ovf_count, 1u)] = (unsigned)tile;
         return;
     }
