@@ -42,6 +42,7 @@ constexpr int N_PEND_SHIFT = 48;
 // step both accumulates and returns the successor of the cell just finalised.
 constexpr uint32_t W_EXIT = 0x3FFEu, W_TERM = 0x3FFFu, W_NXT = 0x3FFFu, W_PEND_ONE = 1u << 28;
 constexpr int W_CNT_SHIFT = 14;
+constexpr uint32_t W_CNT_ONE = 1u << W_CNT_SHIFT, W_CNT_MASK = 0x3FFFu << W_CNT_SHIFT;
 constexpr int WALK_CAP = 4;
 // successor table, 16 bits per cell in cell order: [15 river cell | 14 diagonal move | 13..0 successor slot / W_EXIT / W_TERM]
 constexpr uint32_t NX_DIAG = 0x4000u, NX_RIVER = 0x8000u, NX_CYCLE = 0xFFFFFFFFu, NX_NODATA = W_TERM | NX_DIAG;
@@ -76,21 +77,35 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
         const uint8_t *crow = codes + (lr + 1) * CP + 16 + lcb;
         const uint4 cw = *reinterpret_cast<const uint4 *>(crow);
         const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
+        // displacement of the move of one-hot code bit b (0=E 1=SE 2=S 3=SW 4=W 5=NW 6=N 7=NE), as unsigned bytes:
+        // cell index + 65 and staged-code offset + 81 (the NW entries are 0: they also fill the upper result bytes)
+        constexpr uint32_t LB0 = 66u | (130u << 8) | (129u << 16) | (128u << 24), LB1 = 64u | (0u << 8) | (1u << 16) | (2u << 24);
+        constexpr uint32_t CB0 = (uint32_t)(81 + 1) | ((uint32_t)(81 + CP + 1) << 8) | ((uint32_t)(81 + CP) << 16) | ((uint32_t)(81 + CP - 1) << 24);
+        constexpr uint32_t CB1 = (uint32_t)(81 - 1) | ((uint32_t)(81 - CP - 1) << 8) | ((uint32_t)(81 - CP) << 16) | ((uint32_t)(81 - CP + 1) << 24);
+        static_assert(CP == 80 && T == 64, "biased displacement tables");
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // cells with a code: one bit per non-zero byte
+            const uint32_t nz = (((cws[k] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | cws[k]) & 0x80808080u;
+            validmask |= ((((nz >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * k);
+        }
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
-            const int lc = lcb + i, p = lr * T + lc;
-            const unsigned code = (cws[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-            uint32_t nx = W_TERM;
-            int dloc, dcode;
+            const int p = lr * T + lcb + i;
+            const uint32_t code = (cws[i >> 2] >> (8 * (i & 3))) & 0xFFu;
             // one-hot codes whose move leaves the tile from this cell: the row part is per thread, the column part
             // only concerns the first / last cell of the row
             const unsigned xm = rowexit | ((i == 0 && lcb == 0) ? 0x38u : 0u) | ((i == CPT - 1 && lcb == T - CPT) ? 0x83u : 0u);
-            if (d8_delta(code, dloc, dcode) && crow[i + dcode] != 0) nx = (code & xm) ? W_EXIT : phys_of((uint32_t)(p + dloc));
-            word[i * FT_THREADS + tid] = nx;
-            validmask |= (code != 0 ? 1u : 0u) << i;
-            // successor table entry (T2 and HAND's tile pass reuse it): diagonal flag of the move; a cell without a
-            // direction code is marked by the flag on a terminal entry (NX_NODATA)
-            const uint32_t t16 = nx | ((nx != W_TERM ? (code & 0xAAu) != 0 : code == 0) ? NX_DIAG : 0u);
+            uint32_t hb;  // index of the highest set bit (all ones for 0)
+            asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(code));
+            const uint32_t sel = (hb & 7u) | 0x5550u;
+            const uint32_t oc = __byte_perm(CB0, CB1, sel), ol = __byte_perm(LB0, LB1, sel);
+            // a move: one-hot code whose landing cell has a code (the staged halo ring makes the read safe for any b)
+            const bool moves = __popc(code) == 1 && crow[i + (int)oc - 81] != 0;
+            const uint32_t mv = ((code & xm) ? W_EXIT : phys_of((uint32_t)(p - 65) + ol)) | ((code & 0xAAu) ? NX_DIAG : 0u);
+            // successor table entry (T2 and HAND's tile pass reuse it): successor + diagonal flag of the move; a cell
+            // without a direction code is marked by the flag on a terminal entry (NX_NODATA)
+            const uint32_t t16 = moves ? mv : (code ? W_TERM : NX_NODATA);
+            word[i * FT_THREADS + tid] = t16 & W_NXT;
             if (i & 1) tab[i >> 1] |= t16 << 16; else tab[i >> 1] = t16;
         }
     }
@@ -120,35 +135,42 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
     while (srcmask) {
         const int i = __ffs((int)srcmask) - 1;
         srcmask &= srcmask - 1;
+        // `carry` = cells finalised so far, kept in the position of the count field (<< 14)
         uint32_t n = word[i * FT_THREADS + ((tid + 37 * i) & (FT_THREADS - 1))] & W_NXT, carry = 0;
         int left = WALK_CAP;
         while (n < W_EXIT) {
             if (left-- == 0) {
-                queue[atomicAdd(&qn, 1u)] = (carry << 14) | n;  // carry < 4096 < 2^18
+                queue[atomicAdd(&qn, 1u)] = carry | n;  // count < 4096: carry < 2^26
                 break;
             }
-            const uint32_t old = atomicAdd(&word[n], ((carry + 1u) << W_CNT_SHIFT) - W_PEND_ONE);
-            if ((old >> 28) != 1u) break;  // other tributaries still pending
-            carry += ((old >> W_CNT_SHIFT) & 0x3FFFu) + 1u;
+            const uint32_t old = atomicAdd(&word[n], carry + (W_CNT_ONE - W_PEND_ONE));
+            if (old >= 2u * W_PEND_ONE) break;  // other tributaries still pending (the field was >= 1: mine)
+            carry += (old & W_CNT_MASK) + W_CNT_ONE;
             n = old & W_NXT;
         }
     }
     __syncthreads();
     for (uint32_t k = tid; k < qn; k += FT_THREADS) {
-        uint32_t n = queue[k] & W_NXT, carry = queue[k] >> 14;
+        uint32_t n = queue[k] & W_NXT, carry = queue[k] & ~W_NXT;
         while (n < W_EXIT) {
-            const uint32_t old = atomicAdd(&word[n], ((carry + 1u) << W_CNT_SHIFT) - W_PEND_ONE);
-            if ((old >> 28) != 1u) break;
-            carry += ((old >> W_CNT_SHIFT) & 0x3FFFu) + 1u;
+            const uint32_t old = atomicAdd(&word[n], carry + (W_CNT_ONE - W_PEND_ONE));
+            if (old >= 2u * W_PEND_ONE) break;
+            carry += (old & W_CNT_MASK) + W_CNT_ONE;
             n = old & W_NXT;
         }
     }
     __syncthreads();
     // a cell that was never finalised (pending left) means the grid has a D8 cycle
+    uint32_t my[CPT];
     {
+        uint32_t pend = 0;
         unsigned bad = 0;
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) bad += ((validmask >> i) & 1u) && (word[i * FT_THREADS + tid] >> 28) != 0u;
+        for (int i = 0; i < CPT; ++i) { my[i] = word[i * FT_THREADS + tid]; pend |= my[i]; }
+        if (pend >> 28) {  // (a cell without a code has no tributary in the tile: its field is 0)
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) bad += (my[i] >> 28) != 0u;
+        }
         bad = __reduce_add_sync(0xffffffffu, bad);
         if ((tid & 31) == 0 && bad) atomicAdd(&counters[0], (unsigned long long)bad);
     }
@@ -159,7 +181,7 @@ fa_tile_kernel(TileView v, uint32_t *__restrict__ exitw, uint32_t *__restrict__ 
         alignas(16) ACC out[CPT];
 #pragma unroll
         for (int i = 0; i < CPT; ++i)
-            out[i] = ((validmask >> i) & 1u) ? (ACC)((word[i * FT_THREADS + tid] >> W_CNT_SHIFT) & 0x3FFFu) : nodata_fill;
+            out[i] = ((validmask >> i) & 1u) ? (ACC)((my[i] >> W_CNT_SHIFT) & 0x3FFFu) : nodata_fill;
         ACC *dst = acc + gr * v.cols + c0 + lcb;
         if (fast && ((reinterpret_cast<uintptr_t>(acc) & 15u) == 0)) {
             constexpr int V = 16 / sizeof(ACC);
