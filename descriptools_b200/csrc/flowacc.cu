@@ -255,6 +255,13 @@ fa_finish_tile(const int tile, const TileView &v, const uint32_t *__restrict__ m
     const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
     const bool fast = (v.cols % 16 == 0) && (c0 + T <= v.cols);
 
+    // Everything this tile needs from the node arrays is requested up front, next to the table: the kernel is a chain
+    // of dependent latencies (table -> walk -> acc), these loads would add three more links to it.
+    const size_t node = (size_t)tile * SLOTS + tid;
+    const uint32_t my_meta = tid < USED_SLOTS ? meta[node] : 0u;
+    const uint64_t my_ns = tid < USED_SLOTS ? nstate[node] : 0ull;
+    const uint32_t my_link = (HAND && tid < USED_SLOTS) ? link[node] : LINK_NONE;
+
     // the successor table T1 left for this tile -> shared memory (slot layout)
     const int lr = tid >> 2, lcb = (tid & 3) * CPT;
     unsigned validmask = 0;
@@ -276,14 +283,14 @@ fa_finish_tile(const int tile, const TileView &v, const uint32_t *__restrict__ m
     // ---- entry nodes push their resolved inflow down their in-tile path ----
     // The same walk records where the path ends and how many cardinal / diagonal moves it takes: in a tile
     // without river cells that already is the entry node's HAND state.
-    const uint32_t my_inmask = tid < USED_SLOTS ? (meta[(size_t)tile * SLOTS + tid] >> 16) & 0xFFu : 0u;
+    const uint32_t my_inmask = (my_meta >> 16) & 0xFFu;
     uint32_t my_slot = 0, path_moves = 0, path_end = W_TERM, path_last = 0;  // moves: n_card | n_diag << 16
     unsigned unresolved = 0;
     if (my_inmask) {
         int plr, plc;
         slot_cell(tid, plr, plc);
         my_slot = phys_of((uint32_t)(plr * T + plc));
-        const uint64_t ns = nstate[(size_t)tile * SLOTS + tid];
+        const uint64_t ns = my_ns;
         if (!REDO && ((ns >> N_PEND_SHIFT) & N_PEND)) ++unresolved;  // never finalised: node-level cycle
         const EXT w = REDO ? (EXT)0 : (EXT)(ns & N_CNT);
         uint32_t q = my_slot, n16 = 0, ndiag = 0;
@@ -389,7 +396,7 @@ fa_finish_tile(const int tile, const TileView &v, const uint32_t *__restrict__ m
             hs = pack(KIND_RIVER, nd, nc, (uint32_t)((r0 + (pl >> 6)) * v.cols + c0 + (pl & (T - 1))));
         } else if (end == W_EXIT) {
             // the path leaves through the exit T1 found for this entry: link = the entry node it lands on
-            const uint32_t l = link[(size_t)tile * SLOTS + tid];
+            const uint32_t l = my_link;
             if (!(l & LINK_OUT)) { hs = pack(KIND_ACTIVE, nd, nc, l); is_active = 1; }
             else if (l != LINK_NONE) {
                 // out of the band: HAND wants the column of the halo cell it lands on (T1 stored the exit cell's column)
