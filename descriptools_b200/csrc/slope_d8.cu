@@ -325,7 +325,7 @@ __device__ __forceinline__ void stencil_strip_fast(const float *tile, int gx, in
         for (int j = 1; j <= 5; ++j) sW[j] = mid[j] - dn[j - 1];
 
         float s_out[4];
-        uint32_t codes = 0;
+        uint32_t bsel = 0;
         bool slow = bad_up | bad_mid | bad_dn;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -337,19 +337,22 @@ __device__ __forceinline__ void stencil_strip_fast(const float *tile, int gx, in
             const float t = ad * k.r32;
             const bool use_c = ac >= t;
             const float a = use_c ? ac : ad;
-            // neighbours below their class maximum: sign bit of (d - max); bit order NW,N,NE,W,E,SW,S,SE from bit 0
+            // neighbours below their class maximum: sign bit of (d - max); scan order NW,N,NE,W,E,SW,S,SE from bit 7 down
             unsigned lose = 0;
-            lose = __funnelshift_l(__float_as_uint(dSE - ad), lose, 1);
-            lose = __funnelshift_l(__float_as_uint(dS - ac), lose, 1);
-            lose = __funnelshift_l(__float_as_uint(dSW - ad), lose, 1);
-            lose = __funnelshift_l(__float_as_uint(dE - ac), lose, 1);
-            lose = __funnelshift_l(__float_as_uint(dW - ac), lose, 1);
-            lose = __funnelshift_l(__float_as_uint(dNE - ad), lose, 1);
-            lose = __funnelshift_l(__float_as_uint(dN - ac), lose, 1);
             lose = __funnelshift_l(__float_as_uint(dNW - ad), lose, 1);
+            lose = __funnelshift_l(__float_as_uint(dN - ac), lose, 1);
+            lose = __funnelshift_l(__float_as_uint(dNE - ad), lose, 1);
+            lose = __funnelshift_l(__float_as_uint(dW - ac), lose, 1);
+            lose = __funnelshift_l(__float_as_uint(dE - ac), lose, 1);
+            lose = __funnelshift_l(__float_as_uint(dSW - ad), lose, 1);
+            lose = __funnelshift_l(__float_as_uint(dS - ac), lose, 1);
+            lose = __funnelshift_l(__float_as_uint(dSE - ad), lose, 1);
             const unsigned win = ~lose & (use_c ? 0x5Au : 0xA5u);
-            const unsigned b = (unsigned)__ffs((int)win) - 1u;  // first maximum in scan order (strict '<', slope.py:250,255)
-            codes |= (__byte_perm(0x10804020u, 0x02040801u, b) & 0xFFu) << (8 * c);
+            // highest set bit = first maximum in scan order (strict '<', slope.py:250,255); one nibble per cell, turned
+            // into the four code bytes by a single byte permute below (no winner: the row takes the slow path)
+            unsigned hb;
+            asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(win));
+            bsel += hb << (4 * c);
             const double y = (double)a * (use_c ? k.kc : k.kd);
             s_out[c] = (float)y;
             // range (no positive gradient, subnormal / huge), cardinal-diagonal near-tie, product within 16 ulp(f64)
@@ -358,6 +361,7 @@ __device__ __forceinline__ void stencil_strip_fast(const float *tile, int gx, in
                     ((((uint32_t)__double2loint(y) + 0x10u - 0x10000000u) & 0x1FFFFFE0u) == 0u);
         }
         float4 s4 = make_float4(s_out[0], s_out[1], s_out[2], s_out[3]);
+        uint32_t codes = __byte_perm(0x01080402u, 0x20408010u, bsel);  // SE,S,SW,E | W,NE,N,NW
         if (slow) slow_row(tile, ry0 + 1 + i, 4 * gx + HALO_L, k.px, k.pd, s4, codes);
         const int64_t orow = out_row0 + ry0 + i;
         if (orow >= 0 && orow < out_rows && c_first < cols) {
