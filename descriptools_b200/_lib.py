@@ -106,6 +106,8 @@ SIGNATURES = {
     "dtb_flowacc_band": (c_int, [POINTER(FlowaccArgs), c_void_p, c_size_t, c_void_p]),
     "dtb_forest_workspace_bytes": (c_size_t, [c_int64]),
     "dtb_forest_accumulate": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dtb_hand_boundary_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "dtb_hand_boundary_solve": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dtb_hand_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "dtb_hand": (c_int, [POINTER(HandArgs), c_void_p, c_size_t, c_void_p]),
     "dtb_hand_from_index": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p]),

@@ -82,6 +82,7 @@ def forest_accumulate(nxt: torch.Tensor, base: torch.Tensor, rounds: int = ROUND
 
 
 _plan_cache = {}
+_hand_ws = {}
 
 
 def _plan(n: int, cols: int, dev):
@@ -127,6 +128,19 @@ def solve_hand_boundary(summ: torch.Tensor, rounds: int = ROUNDS):
     Returns (int64 [N, 8, cols]: resolved (state, idx, z-bits, acc) of the halo row above, then below; flag)."""
     n, _, cols = summ.shape
     dev = summ.device
+    if summ.is_cuda:  # the library's pointer jumping (dtb_hand_boundary_solve); the torch form below serves CPU tensors
+        from ._lib import check, lib
+
+        summ = summ.contiguous()
+        key = (dev.index, n, cols)
+        if key not in _hand_ws:
+            _hand_ws[key] = (torch.empty(lib.dtb_hand_boundary_workspace_bytes(n, cols), dtype=torch.uint8, device=dev),
+                             torch.empty((n, 8, cols), dtype=torch.int64, device=dev),
+                             torch.zeros(1, dtype=torch.int32, device=dev))
+        ws, res, flag = _hand_ws[key]
+        check(lib.dtb_hand_boundary_solve(summ.data_ptr(), n, cols, int(rounds), res.data_ptr(), flag.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), torch.cuda.current_stream(dev).cuda_stream), "dtb_hand_boundary_solve")
+        return res, flag[0] != 0
     p = _plan(n, cols, dev)
     st = torch.stack([summ[:, 0, :], summ[:, 4, :]], 1).reshape(-1)          # node (b, side, c)
     pay = torch.stack([summ[:, 1:4, :], summ[:, 5:8, :]], 1)                 # [N, 2, 3, cols]

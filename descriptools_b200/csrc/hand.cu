@@ -701,6 +701,79 @@ hand_from_index_kernel(const T *__restrict__ dem, const IDX *__restrict__ idx, i
     hand[p] = hand_value<T>(dem[p], i != ND_I, dem, i != ND_I ? i : 0);
 }
 
+// ---- band boundary graph (multi-GPU): what lies behind the halo rows of every band -------------------
+// Node (b, side, c) = cell c of the first (side 0) / last (side 1) row of band b, with the summary state
+// hand_band_summary_kernel left for it: RIVER / FAIL, or EXIT = "leaves band b towards side t of column col", i.e.
+// continues at node (b -+ 1, other side, col).  Same in-place asynchronous pointer jumping as H2; a resolved node
+// carries in its pointer field the node whose payload (river index, elevation, accumulation) it ends on.
+__global__ void __launch_bounds__(H_THREADS)
+hb_init_kernel(const long long *__restrict__ summ, int64_t n, int64_t cols, unsigned long long *__restrict__ w,
+               unsigned *__restrict__ active)
+{
+    const int64_t node = (int64_t)blockIdx.x * H_THREADS + threadIdx.x;
+    int live = 0;
+    if (node < 2 * n * cols) {
+        const int64_t b = node / (2 * cols), rem = node - b * 2 * cols, side = rem / cols, c = rem - side * cols;
+        const uint64_t st = (uint64_t)summ[(b * 8 + side * 4) * cols + c];
+        uint64_t s = pack(KIND_FAIL, nd_of(st), nc_of(st), (uint32_t)node);  // 0 = not an entry (never referenced)
+        if (st != 0ull && kind_of(st) == KIND_RIVER) s = pack(KIND_RIVER, nd_of(st), nc_of(st), (uint32_t)node);
+        else if (st != 0ull && kind_of(st) == KIND_EXIT) {
+            const int64_t t_side = (ptr_of(st) >> 30) & 1u, t_col = ptr_of(st) & 0x3FFFFFFFu;
+            const int64_t b2 = t_side ? b + 1 : b - 1;
+            if (b2 >= 0 && b2 < n && t_col < cols) {
+                s = pack(KIND_EXIT, nd_of(st), nc_of(st), (uint32_t)((b2 * 2 + (1 - t_side)) * cols + t_col));
+                live = 1;
+            }
+        }
+        w[node] = s;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, live);
+    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&active[0], (unsigned)__popc(ballot));
+}
+
+__global__ void __launch_bounds__(H_THREADS)
+hb_jump_kernel(int64_t nnodes, unsigned long long *w, unsigned *__restrict__ active, int rnd)
+{
+    if (active[rnd - 1] == 0) return;
+    unsigned still = 0;
+    for (int64_t q = (int64_t)blockIdx.x * H_THREADS + threadIdx.x; q < nnodes; q += (int64_t)gridDim.x * H_THREADS) {
+        uint64_t s = __ldcg(&w[q]);
+        if (kind_of(s) != KIND_EXIT) continue;
+        for (int j = 0; j < 2 && kind_of(s) == KIND_EXIT; ++j) {
+            const uint64_t t = __ldcg(&w[ptr_of(s)]);
+            s = pack(kind_of(t), sat_add(nd_of(s), nd_of(t)), sat_add(nc_of(s), nc_of(t)), ptr_of(t));
+        }
+        __stcg(&w[q], s);
+        still += kind_of(s) == KIND_EXIT;
+    }
+    still = __reduce_add_sync(0xffffffffu, still);
+    if ((threadIdx.x & 31) == 0 && still) atomicAdd(&active[rnd], still);
+}
+
+__global__ void __launch_bounds__(H_THREADS)
+hb_out_kernel(const long long *__restrict__ summ, int64_t n, int64_t cols, const unsigned long long *__restrict__ w,
+              long long *__restrict__ res, int *__restrict__ flag)
+{
+    const int64_t i = (int64_t)blockIdx.x * H_THREADS + threadIdx.x;
+    if (i >= 2 * n * cols) return;
+    const int64_t b = i / (2 * cols), rem = i - b * 2 * cols, out = rem / cols, c = rem - out * cols;  // out 0: above, 1: below
+    const int64_t nb = out ? b + 1 : b - 1;
+    long long v[4] = {(long long)pack(KIND_FAIL, 0, 0, 0), 0, 0, 0};
+    if (nb >= 0 && nb < n) {
+        uint64_t s = w[(nb * 2 + (1 - out)) * cols + c];  // above band b = last row of band b-1; below = first row of band b+1
+        if (kind_of(s) == KIND_EXIT) {  // still travelling: a cycle across seams, or more seam crossings than the rounds cover
+            s = pack(KIND_FAIL, nd_of(s), nc_of(s), ptr_of(s));
+            *flag = 1;
+        }
+        const int64_t src = (int64_t)ptr_of(s), sb = src / (2 * cols), srem = src - sb * 2 * cols, ss = srem / cols, sc = srem - ss * cols;
+        v[0] = (long long)(s & ~0xFFFFFFFFull);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) v[k] = summ[(sb * 8 + ss * 4 + k) * cols + sc];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) res[(b * 8 + out * 4 + k) * cols + c] = v[k];
+}
+
 inline int rounds_for(int64_t max_moves)
 {
     int r = 0;
@@ -866,5 +939,34 @@ extern "C" int dtb_hand_from_index(const void *dem, int dem_dtype, const void *i
     else
         return DTB_ERR_INVALID;
     DTB_LAUNCH_CHECK("hand_from_index_kernel");
+    return DTB_OK;
+}
+
+extern "C" size_t dtb_hand_boundary_workspace_bytes(int64_t nbands, int64_t cols)
+{
+    if (nbands <= 0 || cols <= 0) return 0;
+    return 256 + (size_t)(2 * nbands * cols) * 8;
+}
+
+extern "C" int dtb_hand_boundary_solve(const int64_t *summ, int64_t nbands, int64_t cols, int rounds, int64_t *res,
+                                       int *unresolved, void *ws, size_t ws_bytes, void *stream)
+{
+    using namespace dtb;
+    if (!summ || !res || !unresolved || !ws || nbands <= 0 || cols <= 0 || rounds < 1 || rounds > 32) return DTB_ERR_INVALID;
+    if (cols >= (int64_t)1 << 30 || 2 * nbands * cols > 0xffffffffLL) return DTB_ERR_UNSUPPORTED;
+    if (ws_bytes < dtb_hand_boundary_workspace_bytes(nbands, cols)) return DTB_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    unsigned *active = reinterpret_cast<unsigned *>(ws);
+    unsigned long long *w = reinterpret_cast<unsigned long long *>((char *)ws + 256);
+    const int64_t nn = 2 * nbands * cols;
+    const unsigned blocks = (unsigned)((nn + H_THREADS - 1) / H_THREADS);
+    DTB_CUDA(cudaMemsetAsync(active, 0, 256, st));
+    DTB_CUDA(cudaMemsetAsync(unresolved, 0, sizeof(int), st));
+    DTB_KERNEL("hb_init_kernel", st, hb_init_kernel<<<blocks, H_THREADS, 0, st>>>(reinterpret_cast<const long long *>(summ), nbands, cols, w, active));
+    const unsigned jb = blocks < (unsigned)JUMP_BLOCKS ? blocks : (unsigned)JUMP_BLOCKS;
+    for (int r = 1; r <= rounds; ++r)
+        DTB_KERNEL("hb_jump_kernel", st, hb_jump_kernel<<<jb, H_THREADS, 0, st>>>(nn, w, active, r));
+    DTB_KERNEL("hb_out_kernel", st, hb_out_kernel<<<blocks, H_THREADS, 0, st>>>(reinterpret_cast<const long long *>(summ), nbands, cols, w,
+                                                                             reinterpret_cast<long long *>(res), unresolved));
     return DTB_OK;
 }

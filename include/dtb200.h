@@ -138,6 +138,17 @@ size_t dtb_forest_workspace_bytes(int64_t n);
 int dtb_forest_accumulate(const int64_t *next, const int64_t *base, int64_t n, int64_t *out,
                           int *unresolved, void *ws, size_t ws_bytes, void *stream);
 
+/* HAND across band seams (multi-GPU driver, rank 0): summ [nbands][8][cols] holds, for the first and then the last
+ * row of every band, the summary (state, river index, elevation bits, accumulation) dtb_hand(DTB_HAND_SUMMARY)
+ * wrote; res [nbands][8][cols] receives the resolved path behind the halo row above and then below every band --
+ * the res_* arrays of dtb_hand_seam for the DTB_HAND_FINISH call.  `rounds` launches of in-place pointer jumping
+ * (each at least quadruples the seam crossings covered); *unresolved (device int) becomes non-zero if a path is
+ * still crossing seams after that (a cycle across bands): it is reported as FAIL.  The reference has no counterpart
+ * (flowhand.py:282-402 walks its partitions serially). */
+size_t dtb_hand_boundary_workspace_bytes(int64_t nbands, int64_t cols);
+int dtb_hand_boundary_solve(const int64_t *summ, int64_t nbands, int64_t cols, int rounds, int64_t *res,
+                            int *unresolved, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- flow distance + river-cell index + HAND (+ optional fused GFI) -------------------
  * Replaces flow_distance_index_cpu + flow_distance_index_gpu (flowhand.py:476-562,
  * 565-846, unpartitioned: out = 0) and hand_calculator (flowhand.py:414-442); with

@@ -668,3 +668,37 @@ def test_fused_hand_random_codes_with_cycles():
     dem = (rng.standard_normal(d8.shape) * 10 + 100).astype(np.float32)
     dem[rng.random(d8.shape) < 0.02] = -100
     _hand_fused_vs_oracle(d8, dem, 3)
+
+
+def test_hand_boundary_solver_cuda_equals_torch():
+    """dtb_hand_boundary_solve (rank 0 of the band driver) against the torch pointer doubling the CPU / gloo tests
+    use: random boundary graphs with chains over several seams, dead ends and cycles across seams"""
+    from descriptools_b200 import bands
+
+    rng = np.random.default_rng(11)
+    for n, cols, p_exit in ((2, 257, 0.5), (5, 1000, 0.7), (8, 640, 0.3)):
+        kind = rng.choice([0, 1, 2, 3], size=(n, 2, cols), p=[0.1, 0.72 * (1 - p_exit), 0.18 * (1 - p_exit), 0.9 * p_exit])
+        nd = rng.integers(0, 300, (n, 2, cols))
+        nc = rng.integers(0, 300, (n, 2, cols))
+        t_side = rng.integers(0, 2, (n, 2, cols))
+        t_col = rng.integers(0, cols, (n, 2, cols))
+        state = (kind.astype(np.int64) << 62) | (nd.astype(np.int64) << 47) | (nc.astype(np.int64) << 32)
+        state = np.where(kind == 3, state | (1 << 31) | (t_side.astype(np.int64) << 30) | t_col, state)
+        state = np.where(kind == 0, 0, state)  # not an entry
+        summ = np.zeros((n, 8, cols), np.int64)
+        summ[:, 0], summ[:, 4] = state[:, 0], state[:, 1]
+        summ[:, 1:4] = rng.integers(1, 1 << 40, (n, 3, cols))
+        summ[:, 5:8] = rng.integers(1, 1 << 40, (n, 3, cols))
+        t = torch.from_numpy(summ)
+        ref, flag_ref = bands.solve_hand_boundary(t)
+        got, flag = bands.solve_hand_boundary(t.cuda())
+        ref, got = ref.numpy(), got.cpu().numpy()
+        assert bool(flag) == bool(flag_ref)
+        for row in (0, 4):
+            k_ref, k_got = (ref[:, row] >> 62) & 3, (got[:, row] >> 62) & 3
+            np.testing.assert_array_equal(k_got, k_ref)
+            river = k_ref == 1
+            assert river.any()
+            np.testing.assert_array_equal(got[:, row][river], ref[:, row][river])
+            for k in (1, 2, 3):
+                np.testing.assert_array_equal(got[:, row + k][river], ref[:, row + k][river])
