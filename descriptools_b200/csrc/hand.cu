@@ -301,18 +301,18 @@ __device__ __forceinline__ void resolve_exit(const TileView &v, int64_t r0, int6
 
 // outputs of one cell from its resolved path
 template <typename TD, typename IDX>
-__device__ __forceinline__ void finish_cell(const HandOut &o, uint32_t kind, uint32_t nd, uint32_t nc, int64_t idx, TD zr, double l1,
-                                            TD z, float &fd, IDX &ix, TD &hd, float &gf)
+__device__ __forceinline__ void finish_cell(const HandOut &o, const bool want_h, const bool want_g, uint32_t kind, uint32_t nd,
+                                            uint32_t nc, int64_t idx, TD zr, double l1, TD z, float &fd, IDX &ix, TD &hd, float &gf)
 {
     const bool ok = kind == KIND_RIVER && nc + nd <= o.max_moves;  // flowhand.py:835
     fd = ok ? (float)((double)nc * o.px + (double)nd * o.pd) : ND_F;  // flowhand.py:840-843
     ix = ok ? (IDX)idx : (IDX)ND_I;
     TD h = HandOps<TD>::nd();
     float g = ND_F;
-    if ((o.hand || o.gfi) && ok && !HandOps<TD>::is_nd(z)) {  // flowhand.py:436-438
+    if (want_h && ok && !HandOps<TD>::is_nd(z)) {  // flowhand.py:436-438
         h = HandOps<TD>::sub(z, zr);
         if (h < (TD)0 && h != HandOps<TD>::nd()) h = (TD)0;
-        if (o.gfi && !(h <= HandOps<TD>::nd())) g = (float)(l1 - fast_log_pos((double)h + 0.01));  // gfi.py:289-294
+        if (want_g && !(h <= HandOps<TD>::nd())) g = (float)(l1 - fast_log_pos((double)h + 0.01));  // gfi.py:289-294
     }
     hd = h;
     gf = g;
@@ -475,7 +475,7 @@ __device__ __forceinline__ void hand_tile_body(const int tile, const TileView &v
                 if (o.hand || o.gfi) zr = dem[s2.x];
                 if (o.gfi) l1 = o.gfi_logb + o.gfi_n * fast_log((double)acc[s2.x] * o.gfi_s2);  // gfi.py:141-143
             }
-            finish_cell<TD, IDX>(o, kind, nd, nc, idx, zr, l1, z[i], fd[i], ix[i], hd[i], gf[i]);
+            finish_cell<TD, IDX>(o, o.hand || o.gfi, o.gfi != nullptr, kind, nd, nc, idx, zr, l1, z[i], fd[i], ix[i], hd[i], gf[i]);
         }
         if (o.fdist) store4<float>(o.fdist + obase, fd, vec, c_first, v.cols);
         if (o.idx) store4<IDX>(reinterpret_cast<IDX *>(o.idx) + obase, ix, vec, c_first, v.cols);
@@ -520,8 +520,12 @@ constexpr int OVF_SLOT = 32;  // word of the workspace header that counts the li
 // epilogue's mapping, where a warp reads and writes whole 256-byte raster rows.  An involution.
 __device__ __forceinline__ uint32_t swz(uint32_t q) { return q ^ (((q >> 10) & 3u) << 3); }
 
-template <typename TD, typename IDX, typename ACC>
-__global__ void __launch_bounds__(H_THREADS, 6)
+#ifndef H3C_MINB
+#define H3C_MINB 6
+#endif
+// ALL: every output raster is wanted (the chain) -- spares the per-cell tests of the output pointers
+template <typename TD, typename IDX, typename ACC, bool ALL>
+__global__ void __launch_bounds__(H_THREADS, H3C_MINB)
 hand_tile_compact_kernel(TileView v, const TD *__restrict__ dem, const ACC *__restrict__ acc,
                          const unsigned long long *__restrict__ nstate, const uint16_t *__restrict__ table, HandOut o,
                          unsigned *__restrict__ ovf_tiles, unsigned *__restrict__ ovf_count)
@@ -534,6 +538,7 @@ hand_tile_compact_kernel(TileView v, const TD *__restrict__ dem, const ACC *__re
     const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
     const int lr = tid >> 2, lcb = (tid & 3) * CPT;
     const bool fast = (v.cols % 16 == 0) && (c0 + T <= v.cols);
+    const bool w_fd = ALL || o.fdist, w_ix = ALL || o.idx, w_hd = ALL || o.hand, w_gf = ALL || o.gfi;
 
     {
         const uint4 *tp = reinterpret_cast<const uint4 *>(table + (size_t)tile * TCELLS + tid * CPT);
@@ -619,7 +624,7 @@ hand_tile_compact_kernel(TileView v, const TD *__restrict__ dem, const ACC *__re
         alignas(16) float fd[4], gf[4];
         alignas(16) IDX ix[4];
         alignas(16) TD hd[4];
-        if (o.hand || o.gfi) load4<TD>(dem + obase, z, vec, c_first, v.cols, HandOps<TD>::nd());
+        if (w_hd || w_gf) load4<TD>(dem + obase, z, vec, c_first, v.cols, HandOps<TD>::nd());
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t s = st[swz((((p & 15u) + i) << 8) | (p >> 4))];
@@ -645,15 +650,15 @@ hand_tile_compact_kernel(TileView v, const TD *__restrict__ dem, const ACC *__re
                 const uint32_t rp = logical_of(swz(r & 0xFFFu));
                 const int64_t loc = (r0 + (int64_t)(rp >> 6)) * v.cols + c0 + (int64_t)(rp & 63u);
                 idx = loc + o.idx_offset;
-                if (o.hand || o.gfi) zr = dem[loc];
-                if (o.gfi) l1 = o.gfi_logb + o.gfi_n * fast_log((double)acc[loc] * o.gfi_s2);  // gfi.py:141-143
+                if (w_hd || w_gf) zr = dem[loc];
+                if (w_gf) l1 = o.gfi_logb + o.gfi_n * fast_log((double)acc[loc] * o.gfi_s2);  // gfi.py:141-143
             }
-            finish_cell<TD, IDX>(o, kind, nd, nc, idx, zr, l1, z[i], fd[i], ix[i], hd[i], gf[i]);
+            finish_cell<TD, IDX>(o, w_hd || w_gf, w_gf, kind, nd, nc, idx, zr, l1, z[i], fd[i], ix[i], hd[i], gf[i]);
         }
-        if (o.fdist) store4<float>(o.fdist + obase, fd, vec, c_first, v.cols);
-        if (o.idx) store4<IDX>(reinterpret_cast<IDX *>(o.idx) + obase, ix, vec, c_first, v.cols);
-        if (o.hand) store4<TD>(reinterpret_cast<TD *>(o.hand) + obase, hd, vec, c_first, v.cols);
-        if (o.gfi) store4<float>(o.gfi + obase, gf, vec, c_first, v.cols);
+        if (w_fd) store4<float>(o.fdist + obase, fd, vec, c_first, v.cols);
+        if (w_ix) store4<IDX>(reinterpret_cast<IDX *>(o.idx) + obase, ix, vec, c_first, v.cols);
+        if (w_hd) store4<TD>(reinterpret_cast<TD *>(o.hand) + obase, hd, vec, c_first, v.cols);
+        if (w_gf) store4<float>(o.gfi + obase, gf, vec, c_first, v.cols);
     }
 }
 
@@ -815,8 +820,12 @@ int run_tiles(const dtb_hand_args *a, const TileView &v, const RiverSrc &rs, con
         unsigned *ovf_count = reinterpret_cast<unsigned *>(const_cast<unsigned long long *>(nstate)) - 64 + OVF_SLOT;
         unsigned *ovf_tiles = reinterpret_cast<unsigned *>(const_cast<uint16_t *>(table) + tiles * TCELLS);
         DTB_CUDA(cudaMemsetAsync(ovf_count, 0, sizeof(unsigned), st));
-        DTB_KERNEL("hand_tile_kernel<table>", st, hand_tile_compact_kernel<TD, IDX, ACC><<<(unsigned)tiles, H_THREADS, 0, st>>>(
-                       v, (const TD *)a->dem, (const ACC *)a->acc, nstate, table, o, ovf_tiles, ovf_count));
+        if (a->fdist && a->idx && a->hand && a->gfi)
+            DTB_KERNEL("hand_tile_kernel<table>", st, hand_tile_compact_kernel<TD, IDX, ACC, true><<<(unsigned)tiles, H_THREADS, 0, st>>>(
+                           v, (const TD *)a->dem, (const ACC *)a->acc, nstate, table, o, ovf_tiles, ovf_count));
+        else
+            DTB_KERNEL("hand_tile_kernel<table>", st, hand_tile_compact_kernel<TD, IDX, ACC, false><<<(unsigned)tiles, H_THREADS, 0, st>>>(
+                           v, (const TD *)a->dem, (const ACC *)a->acc, nstate, table, o, ovf_tiles, ovf_count));
         const unsigned grid = (unsigned)(tiles < kNumSMs * 4 ? tiles : kNumSMs * 4);
         DTB_KERNEL("hand_tile_kernel<listed>", st, hand_tile_kernel<TD, IDX, ACC, true><<<grid, H_THREADS, 0, st>>>(
                        v, rs, (const TD *)a->dem, (const ACC *)a->acc, nstate, table, o, ovf_tiles, ovf_count));
