@@ -7,8 +7,11 @@ the fused HAND/GFI epilogue) over buffers that never leave HBM.
 
     run_device(dem_cuda_tensor, ...) -> dict of CUDA tensors        (what bench.py times as `value`)
     pipeline(dem_numpy, ...)         -> dict of NumPy arrays        (host in / host out, `e2e`)
+    pipeline_files(dem.tif, out_dir) -> GeoTIFF in, GeoTIFFs out            (raster.py codec, section 8 f3)
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
@@ -145,3 +148,47 @@ def pipeline(dem, px: float, river_threshold: int, n_gfi: float = 0.4, scale_fac
 def output_dtypes(dem_dtype: np.dtype, n_cells: int) -> dict:
     it = np.int32 if n_cells < 2**31 else np.int64
     return dict(slope=np.float32, d8=np.uint8, acc=it, fdist=np.float32, idx=it, hand=np.dtype(dem_dtype), gfi=np.float32)
+
+
+def pipeline_files(dem_path, out_dir, river_threshold: int, px: float | None = None, n_gfi: float = 0.4,
+                   scale_factor: float = 0.1, size: float | None = None, outputs=STAGE_OUTPUTS, compress: str = "lzw",
+                   blocksize: int = 256, block_bytes: int = 256 << 20, threads: int = 0) -> dict:
+    """The chain from a DEM GeoTIFF to one GeoTIFF per descriptor (`out_dir/<name>.tif`), what a user of the
+    reference does around the descriptor calls with rasterio (example.py:33, :42-43, :201-217).
+
+    The DEM is decoded in row blocks into pinned memory and copied to the device as it is decoded
+    (raster.read_to_device); its nodata value (GDAL_NODATA tag) becomes the path's sentinel -100 on the device
+    (example.py:42-43 does that on the host, from the corner cell); `px` defaults to the file's pixel size.
+    Results are encoded block by block as they are copied back (raster.write_from_device), tiled and compressed,
+    with the DEM's georeferencing; nodata is -100 (0 for the D8 codes, like 12_fdr.tif).
+    Returns {name: path}.
+    """
+    import torch
+
+    from . import raster
+
+    device.require_cuda()
+    with raster.open(dem_path) as src:
+        geo = dict(crs=src.crs, transform=src.transform)
+        if px is None:
+            px = src.res[0]
+        dem = raster.read_to_device(src, block_bytes=block_bytes, threads=threads)
+        nodata = src.nodata
+    if dem.dtype not in (torch.float32, torch.int16):
+        # the kernels take the two DEM types the reference is used with (f32 rasters, int16 after example.py:33)
+        dem = dem.to(torch.float32)
+    if nodata is not None:
+        dem.masked_fill_(dem == nodata, -100)
+    if dem.dtype == torch.float32:
+        dem.masked_fill_(torch.isnan(dem), -100)
+    res = run_device(dem, float(px), int(river_threshold), n_gfi, scale_factor, size)
+    os.makedirs(out_dir, exist_ok=True)
+    paths = {}
+    for name in outputs:
+        t = res[name]
+        kind = "f" if t.dtype.is_floating_point else "i"
+        paths[name] = os.path.join(out_dir, name + ".tif")
+        raster.write_from_device(paths[name], t, block_bytes=block_bytes, threads=threads, compress=compress,
+                                 predictor=1 if compress in (None, "none") else (3 if kind == "f" else 2),
+                                 tiled=True, blockxsize=blocksize, blockysize=blocksize, nodata=0 if name == "d8" else -100, **geo)
+    return paths

@@ -1,0 +1,520 @@
+"""raster.py -- the GeoTIFF files either side of the descriptor path.
+
+The reference does its raster I/O with rasterio (Example/example.py:33-39, :106, :201-217):
+
+    dem  = rio.open('input/12_dem.tif').read(1)
+    meta = rio.open('input/12_dem.tif').meta
+    meta.update(dtype=rio.uint8); meta.update(nodata=0)
+    with rio.open(out_file, "w", **meta) as dist:
+        dist.write(class_map.astype(rio.uint8))
+
+This module keeps that calling convention (`import descriptools_b200.raster as rio`) over the native
+multi-threaded codec libdtb200_io.so (include/dtb200_io.h, csrc/geotiff.cpp) and adds what a 40 000 x 40 000
+raster needs: row blocks decoded straight into pinned host memory while the previous block is on its way to
+the device (`read_to_device`), and the mirror image for results (`write_from_device`).  torch only owns the
+pinned / device buffers and the copy stream.  Single-band rasters only (all the reference uses).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from collections import namedtuple
+from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdtb200_io.so")
+
+# rasterio exposes dtype names as module attributes (example.py:205, :217)
+uint8, int8, uint16, int16, uint32, int32 = "uint8", "int8", "uint16", "int16", "uint32", "int32"
+uint64, int64, float32, float64 = "uint64", "int64", "float32", "float64"
+
+_DTYPES = ("uint8", "int8", "uint16", "int16", "uint32", "int32", "uint64", "int64", "float32", "float64")
+_COMPRESSION = {"none": 1, "lzw": 5, "deflate": 8, "packbits": 32773}
+_COMPRESSION_NAME = {v: k for k, v in _COMPRESSION.items()}
+# TIFF field types used for the georeferencing tags
+_T_ASCII, _T_SHORT, _T_DOUBLE = 2, 3, 12
+_GEO_TAGS = (33550, 33922, 34264, 34735, 34736, 34737)  # scale, tiepoint, transformation, GeoKey directory / doubles / ascii
+_TAG_GDAL_METADATA, _TAG_GDAL_NODATA = 42112, 42113
+
+
+class RasterError(RuntimeError):
+    pass
+
+
+class _Info(Structure):
+    _fields_ = [("rows", c_int64), ("cols", c_int64), ("dtype", c_int32), ("compression", c_int32), ("predictor", c_int32),
+                ("tile_rows", c_int32), ("tile_cols", c_int32), ("rows_per_strip", c_int32), ("bigtiff", c_int32),
+                ("big_endian", c_int32), ("has_nodata", c_int32), ("has_georef", c_int32), ("nodata", c_double),
+                ("pixel_scale", c_double * 3), ("tiepoint", c_double * 6)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python __graft_entry__.py` (or make -C descriptools_b200/csrc) first")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.dtbio_abi_version.restype = c_int
+    lib.dtbio_error_string.restype = c_char_p
+    lib.dtbio_error_string.argtypes = [c_int]
+    lib.dtbio_last_error.restype = c_char_p
+    lib.dtbio_dtype_size.restype = c_int64
+    lib.dtbio_dtype_size.argtypes = [c_int]
+    lib.dtbio_open.argtypes = [c_char_p, POINTER(c_void_p)]
+    lib.dtbio_get_info.argtypes = [c_void_p, POINTER(_Info)]
+    lib.dtbio_get_tag.argtypes = [c_void_p, c_int, POINTER(c_int), POINTER(c_int64), POINTER(c_void_p)]
+    lib.dtbio_read_rows.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int]
+    lib.dtbio_create.argtypes = [c_char_p, POINTER(_Info), POINTER(c_void_p)]
+    lib.dtbio_writer_info.argtypes = [c_void_p, POINTER(_Info)]
+    lib.dtbio_set_tag.argtypes = [c_void_p, c_int, c_int, c_int64, c_void_p]
+    lib.dtbio_write_rows.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int]
+    lib.dtbio_bytes_written.restype = c_int64
+    lib.dtbio_bytes_written.argtypes = [c_void_p]
+    lib.dtbio_close_reader.argtypes = [c_void_p]
+    lib.dtbio_close_writer.argtypes = [c_void_p]
+    if lib.dtbio_abi_version() != 1:
+        raise ImportError("libdtb200_io.so has an unexpected ABI version")
+    return lib
+
+
+lib = _load()
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        detail = lib.dtbio_last_error().decode("utf-8", "replace")
+        raise RasterError(f"{what}: {lib.dtbio_error_string(rc).decode()}" + (f" ({detail})" if detail else ""))
+
+
+class Affine(namedtuple("Affine", "a b c d e f")):
+    """x = a*col + b*row + c, y = d*col + e*row + f (the six numbers rasterio's `transform` carries)"""
+    __slots__ = ()
+
+    def __mul__(self, colrow):
+        col, row = colrow
+        return (self.a * col + self.b * row + self.c, self.d * col + self.e * row + self.f)
+
+
+_IDENTITY = Affine(1.0, 0.0, 0.0, 0.0, 1.0, 0.0)  # what a raster without georeferencing reports (rasterio does the same)
+
+
+class GeoKeys:
+    """Coordinate reference system as stored in the file: the GeoKey directory (tag 34735) with its double
+    and ASCII parameter tags, carried verbatim from a source raster to the rasters derived from it."""
+
+    def __init__(self, directory=(), doubles=(), ascii_params=""):
+        self.directory = tuple(int(v) for v in directory)
+        self.doubles = tuple(float(v) for v in doubles)
+        self.ascii_params = str(ascii_params)
+
+    def __eq__(self, other):
+        return isinstance(other, GeoKeys) and (self.directory, self.doubles, self.ascii_params) == (other.directory, other.doubles, other.ascii_params)
+
+    def __hash__(self):
+        return hash((self.directory, self.doubles, self.ascii_params))
+
+    def __bool__(self):
+        return bool(self.directory)
+
+    def key(self, key_id: int):
+        """value of one GeoKey (e.g. 3072 ProjectedCSTypeGeoKey -> EPSG code), None if absent"""
+        d = self.directory
+        for i in range(4, len(d) - 3, 4):
+            if d[i] == key_id:
+                loc, cnt, off = d[i + 1], d[i + 2], d[i + 3]
+                if loc == 0:
+                    return off
+                if loc == 34736:
+                    return self.doubles[off] if cnt == 1 else self.doubles[off:off + cnt]
+                if loc == 34737:
+                    return self.ascii_params[off:off + cnt].rstrip("|")
+        return None
+
+    def to_epsg(self):
+        return self.key(3072) or self.key(2048)
+
+    def __repr__(self):
+        cite = self.key(1026) or self.key(3073) or self.key(2049) or ""
+        return f"GeoKeys({len(self.directory) // 4 - 1} keys{', ' + repr(cite[:60]) if cite else ''})"
+
+
+def _format_nodata(v, dtype: str) -> str:
+    if v is None:
+        return ""
+    if np.dtype(dtype).kind in "iu" and float(v) == int(v):
+        return str(int(v))
+    return repr(float(v))
+
+
+def _only_band_one(indexes) -> None:
+    if indexes in (1, None):
+        return
+    if isinstance(indexes, int) or list(indexes) != [1]:
+        raise RasterError("single-band raster: only band 1 exists")
+
+
+class DatasetReader:
+    """`rio.open(path)`: `.read(1)`, `.meta`, `.profile`, and row-block reads into caller-owned memory."""
+
+    mode = "r"
+
+    def __init__(self, path):
+        self.name = os.fspath(path)
+        h = c_void_p()
+        _check(lib.dtbio_open(self.name.encode(), byref(h)), f"open {self.name}")
+        self._h = h
+        info = _Info()
+        _check(lib.dtbio_get_info(self._h, byref(info)), "dtbio_get_info")
+        self._info = info
+        self.height, self.width, self.count = int(info.rows), int(info.cols), 1
+        self.shape = (self.height, self.width)
+        self.dtypes = (_DTYPES[info.dtype],)
+        self.indexes = (1,)
+        self.nodata = float(info.nodata) if info.has_nodata else None
+        self.nodatavals = (self.nodata,)
+        self.compression = _COMPRESSION_NAME.get(int(info.compression), str(int(info.compression)))
+        self.is_tiled = info.tile_rows > 0
+        self.block_shapes = [(int(info.tile_rows), int(info.tile_cols)) if self.is_tiled else (int(info.rows_per_strip), self.width)]
+        self.closed = False
+
+    # -- metadata -------------------------------------------------------------------------------------
+    def tag(self, tag_id: int):
+        """raw TIFF tag of the first IFD: tuple of numbers, or str for ASCII; None if absent"""
+        t, n, p = c_int(), c_int64(), c_void_p()
+        if lib.dtbio_get_tag(self._h, tag_id, byref(t), byref(n), byref(p)) != 0:
+            return None
+        np_t = {1: np.uint8, 2: None, 3: np.uint16, 4: np.uint32, 6: np.int8, 7: np.uint8, 8: np.int16, 9: np.int32, 11: np.float32,
+                12: np.float64, 16: np.uint64, 17: np.int64, 5: np.uint32, 10: np.int32, 13: np.uint32, 18: np.uint64}[t.value]
+        if np_t is None:
+            return ctypes.string_at(p.value, n.value).split(b"\0")[0].decode("latin-1")
+        k = n.value * (2 if t.value in (5, 10) else 1)
+        if k == 0:
+            return ()
+        arr = np.frombuffer(ctypes.string_at(p.value, k * np.dtype(np_t).itemsize), dtype=np_t)
+        return tuple(arr.tolist())
+
+    @property
+    def transform(self) -> Affine:
+        m = self.tag(34264)
+        if m and len(m) >= 16:
+            return Affine(m[0], m[1], m[3], m[4], m[5], m[7])
+        if not self._info.has_georef:
+            return _IDENTITY
+        s, t = self._info.pixel_scale, self._info.tiepoint
+        return Affine(s[0], 0.0, t[3] - t[0] * s[0], 0.0, -s[1], t[4] + t[1] * s[1])
+
+    @property
+    def res(self):
+        tr = self.transform
+        return (abs(tr.a), abs(tr.e))
+
+    @property
+    def crs(self):
+        d = self.tag(34735)
+        if not d:
+            return None
+        return GeoKeys(d, self.tag(34736) or (), self.tag(34737) or "")
+
+    @property
+    def meta(self) -> dict:
+        """the dictionary example.py:202-206 copies from the DEM to the class map"""
+        return dict(driver="GTiff", dtype=self.dtypes[0], nodata=self.nodata, width=self.width, height=self.height, count=1,
+                    crs=self.crs, transform=self.transform)
+
+    @property
+    def profile(self) -> dict:
+        p = self.meta
+        if self.is_tiled:
+            p.update(tiled=True, blockysize=int(self._info.tile_rows), blockxsize=int(self._info.tile_cols))
+        else:
+            p.update(tiled=False, blockysize=int(self._info.rows_per_strip))
+        p.update(compress=self.compression, predictor=int(self._info.predictor), bigtiff=bool(self._info.bigtiff), interleave="band")
+        md = self.tag(_TAG_GDAL_METADATA)
+        if md:
+            p["gdal_metadata"] = md
+        return p
+
+    # -- pixels ---------------------------------------------------------------------------------------
+    def read_rows(self, row0: int, nrows: int, out=None, threads: int = 0):
+        """rows [row0, row0+nrows) into `out` (a C-contiguous-by-row NumPy array or a CPU torch tensor -- pinned
+        for the device path -- of the file's dtype and at least (nrows, width)); returns it"""
+        dt = np.dtype(self.dtypes[0])
+        if out is None:
+            out = np.empty((nrows, self.width), dtype=dt)
+        if hasattr(out, "data_ptr"):  # torch CPU tensor
+            if out.is_cuda:
+                raise RasterError("read_rows decodes into host memory; use read_to_device for a CUDA tensor")
+            ptr, stride, ok = out.data_ptr(), out.stride(0) * out.element_size(), out.stride(1) == 1 and out.element_size() == dt.itemsize
+            rows_ok = out.shape[0] >= nrows and out.shape[1] >= self.width
+        else:
+            ptr, stride = out.ctypes.data, out.strides[0]
+            ok = out.ndim == 2 and out.strides[1] == dt.itemsize and out.dtype.itemsize == dt.itemsize and out.flags.writeable
+            rows_ok = out.shape[0] >= nrows and out.shape[1] >= self.width
+        if not ok or not rows_ok:
+            raise RasterError("read_rows: `out` must be 2-D, unit column stride, element size of the file's dtype and large enough")
+        _check(lib.dtbio_read_rows(self._h, row0, nrows, c_void_p(ptr), stride, threads), f"read {self.name}")
+        return out
+
+    def read(self, indexes=None, out=None, threads: int = 0):
+        """band 1 as a 2-D array (`read(1)`, example.py:33) or a (1, rows, cols) array (`read()` / `read([1])`)"""
+        _only_band_one(indexes)
+        a = self.read_rows(0, self.height, out, threads)
+        return a if indexes == 1 else a.reshape((1,) + tuple(a.shape))
+
+    def close(self):
+        if not self.closed:
+            lib.dtbio_close_reader(self._h)
+            self.closed = True
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DatasetWriter:
+    """`rio.open(path, "w", **meta)`: `.write(array)` (example.py:216-217) or ordered row blocks."""
+
+    mode = "w"
+
+    def __init__(self, path, driver="GTiff", width=None, height=None, count=1, dtype=None, crs=None, transform=None, nodata=None,
+                 compress=None, predictor=1, tiled=False, blockxsize=256, blockysize=None, bigtiff=False, gdal_metadata=None,
+                 threads: int = 0, **ignored):
+        if driver not in ("GTiff", None):
+            raise RasterError("only the GTiff driver is written")
+        if count != 1:
+            raise RasterError("single-band rasters only")
+        if width is None or height is None or dtype is None:
+            raise RasterError("width, height and dtype are required to create a raster")
+        self.name = os.fspath(path)
+        self.width, self.height, self.count = int(width), int(height), 1
+        self.shape = (self.height, self.width)
+        dtype = np.dtype(dtype).name
+        if dtype not in _DTYPES:
+            raise RasterError(f"dtype {dtype} cannot be stored")
+        self.dtypes = (dtype,)
+        comp = _COMPRESSION[(compress or "none").lower()] if isinstance(compress, (str, type(None))) else int(compress)
+        info = _Info()
+        info.rows, info.cols, info.dtype = self.height, self.width, _DTYPES.index(dtype)
+        info.compression, info.predictor = comp, int(predictor)
+        if tiled:
+            info.tile_rows, info.tile_cols = int(blockysize or 256), int(blockxsize)
+        else:
+            info.rows_per_strip = int(blockysize or 0)
+        bt = str(bigtiff).upper()
+        info.bigtiff = 1 if bt in ("TRUE", "YES", "1") else 0
+        h = c_void_p()
+        _check(lib.dtbio_create(self.name.encode(), byref(info), byref(h)), f"create {self.name}")
+        self._h, self._threads, self.closed = h, threads, False
+        _check(lib.dtbio_writer_info(self._h, byref(info)), "dtbio_writer_info")
+        self.is_tiled, self.bigtiff = info.tile_rows > 0, bool(info.bigtiff)
+        # row blocks handed to write_rows start and end on multiples of this (or on the last row)
+        self.chunk_rows = int(info.tile_rows) if self.is_tiled else int(info.rows_per_strip)
+        self.nodata, self.crs, self.transform = nodata, crs, transform
+        try:
+            if transform is not None and tuple(transform)[:6] != _IDENTITY:
+                a, b, c, d, e, f = [float(v) for v in tuple(transform)[:6]]
+                if b == 0.0 and d == 0.0:
+                    self._set(33550, _T_DOUBLE, np.array([a, -e, 0.0]))
+                    self._set(33922, _T_DOUBLE, np.array([0.0, 0.0, 0.0, c, f, 0.0]))
+                else:
+                    self._set(34264, _T_DOUBLE, np.array([a, b, 0, c, d, e, 0, f, 0, 0, 0, 0, 0, 0, 0, 1.0]))
+            if crs:
+                if not isinstance(crs, GeoKeys):
+                    raise RasterError("crs must be the GeoKeys object of a raster opened with this module")
+                self._set(34735, _T_SHORT, np.array(crs.directory, dtype=np.uint16))
+                if crs.doubles:
+                    self._set(34736, _T_DOUBLE, np.array(crs.doubles))
+                if crs.ascii_params:
+                    self._set(34737, _T_ASCII, crs.ascii_params)
+            if nodata is not None:
+                self._set(_TAG_GDAL_NODATA, _T_ASCII, _format_nodata(nodata, dtype))
+            if gdal_metadata:
+                self._set(_TAG_GDAL_METADATA, _T_ASCII, gdal_metadata)
+        except Exception:
+            self.close()
+            raise
+
+    def _set(self, tag, ttype, value):
+        if ttype == _T_ASCII:
+            raw = value.encode("latin-1") + b"\0"
+            _check(lib.dtbio_set_tag(self._h, tag, ttype, len(raw), ctypes.c_char_p(raw)), "dtbio_set_tag")
+        else:
+            arr = np.ascontiguousarray(value, dtype=np.uint16 if ttype == _T_SHORT else np.float64)
+            _check(lib.dtbio_set_tag(self._h, tag, ttype, arr.size, c_void_p(arr.ctypes.data)), "dtbio_set_tag")
+
+    def write_rows(self, row0: int, block, threads: int | None = None):
+        """rows [row0, row0+len(block)) from a NumPy array or CPU torch tensor of the raster's dtype; row0 and
+        the end of the block must fall on chunk boundaries (multiples of `blockysize`) or on the last row"""
+        dt = np.dtype(self.dtypes[0])
+        if hasattr(block, "data_ptr"):
+            if block.is_cuda:
+                raise RasterError("write_rows encodes from host memory; use write_from_device for a CUDA tensor")
+            ok = block.dim() == 2 and block.stride(1) == 1 and block.element_size() == dt.itemsize and block.shape[1] == self.width
+            ptr, stride, n = block.data_ptr(), block.stride(0) * block.element_size(), block.shape[0]
+        else:
+            block = np.asarray(block)
+            if block.ndim == 2 and block.dtype != dt:
+                block = block.astype(dt)
+            ok = block.ndim == 2 and block.strides[1] == dt.itemsize and block.shape[1] == self.width
+            ptr, stride, n = block.ctypes.data, block.strides[0], block.shape[0]
+        if not ok:
+            raise RasterError("write_rows: block must be 2-D with the raster's width and unit column stride")
+        _check(lib.dtbio_write_rows(self._h, row0, n, c_void_p(ptr), stride, self._threads if threads is None else threads), f"write {self.name}")
+
+    def write(self, arr, indexes=None):
+        a = np.asarray(arr)
+        if a.ndim == 3:
+            if a.shape[0] != 1:
+                raise RasterError("single-band rasters only")
+            a = a[0]
+        if a.shape != self.shape:
+            raise RasterError(f"array shape {a.shape} does not match the raster {self.shape}")
+        _only_band_one(indexes)
+        self.write_rows(0, np.ascontiguousarray(a, dtype=self.dtypes[0]))
+
+    @property
+    def bytes_written(self) -> int:
+        return int(lib.dtbio_bytes_written(self._h))
+
+    def close(self):
+        if not self.closed:
+            self.closed = True
+            _check(lib.dtbio_close_writer(self._h), f"close {self.name}")
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, *exc):
+        if exc_type is not None:
+            # leave no half-written file behind; the library unlinks it when chunks are missing
+            self.closed = True
+            lib.dtbio_close_writer(self._h)
+            return False
+        self.close()
+
+    def __del__(self):
+        if not getattr(self, "closed", True):
+            self.closed = True
+            lib.dtbio_close_writer(self._h)
+
+
+def open(path, mode: str = "r", **kwargs):  # noqa: A001  (rasterio's name)
+    """`rio.open(path)` -> DatasetReader; `rio.open(path, "w", **meta)` -> DatasetWriter (example.py:33, :216)"""
+    if mode == "r":
+        if kwargs:
+            raise RasterError("unexpected keyword arguments for read mode: " + ", ".join(kwargs))
+        return DatasetReader(path)
+    if mode == "w":
+        return DatasetWriter(path, **kwargs)
+    raise RasterError(f"mode {mode!r} is not supported (use 'r' or 'w')")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# file <-> device streaming
+# ---------------------------------------------------------------------------------------------------------
+def _block_rows(src_rows: int, chunk_rows: int, cols: int, itemsize: int, target_bytes: int) -> int:
+    """rows per streamed block: about `target_bytes`, a multiple of the file's chunk height"""
+    want = max(1, target_bytes // max(1, cols * itemsize))
+    chunk_rows = max(1, chunk_rows)
+    return min(max(chunk_rows, want // chunk_rows * chunk_rows), max(src_rows, 1))
+
+
+def read_to_device(src, device=None, out=None, block_bytes: int = 256 << 20, threads: int = 0, stream=None):
+    """Decode a raster into a CUDA tensor: two pinned staging blocks; while block k is copied to the device on
+    `stream` (default: a private copy stream) the codec's thread team decodes block k+1.  Returns the tensor
+    (dtype of the file); the current stream waits for the last copy.  `src` is a path or a DatasetReader."""
+    import torch
+
+    from . import device as _device
+
+    dev = torch.device(device) if device is not None else _device.require_cuda()
+    reader = src if isinstance(src, DatasetReader) else DatasetReader(src)
+    try:
+        tdt = getattr(torch, reader.dtypes[0])
+        rows, cols = reader.shape
+        if out is None:
+            out = torch.empty((rows, cols), dtype=tdt, device=dev)
+        elif tuple(out.shape) != (rows, cols) or out.dtype != tdt or not out.is_cuda:
+            raise RasterError("read_to_device: `out` must be a CUDA tensor of the raster's shape and dtype")
+        br = _block_rows(rows, reader.block_shapes[0][0], cols, out.element_size(), block_bytes)
+        stage = [torch.empty((br, cols), dtype=tdt).pin_memory() for _ in range(2 if rows > br else 1)]
+        free = [None] * len(stage)
+        copy = stream if stream is not None else torch.cuda.Stream(device=out.device)
+        copy.wait_stream(torch.cuda.current_stream(out.device))  # `out` may reuse memory the current stream still works on
+        for k, r0 in enumerate(range(0, rows, br)):
+            n = min(br, rows - r0)
+            s = k % len(stage)
+            if free[s] is not None:
+                free[s].synchronize()  # the copy that last read this staging block has finished
+            reader.read_rows(r0, n, stage[s], threads)
+            with torch.cuda.stream(copy):
+                out[r0:r0 + n].copy_(stage[s][:n], non_blocking=True)
+                free[s] = torch.cuda.Event()
+                free[s].record(copy)
+        torch.cuda.current_stream(out.device).wait_stream(copy)
+        for ev in free:
+            if ev is not None:
+                ev.synchronize()  # the staging blocks die with this frame
+        return out
+    finally:
+        if reader is not src:
+            reader.close()
+
+
+def write_from_device(path, tensor, block_bytes: int = 256 << 20, threads: int = 0, **meta):
+    """Mirror of read_to_device: a 2-D CUDA tensor goes to a GeoTIFF in row blocks; block k+1 is copied to its
+    pinned staging buffer while the thread team encodes block k.  `meta` as for `open(path, "w", ...)`
+    (width / height / dtype default to the tensor's).  Returns the number of bytes written."""
+    import torch
+
+    if not tensor.is_cuda or tensor.dim() != 2:
+        raise RasterError("write_from_device needs a 2-D CUDA tensor")
+    rows, cols = tensor.shape
+    meta = dict(meta)
+    meta.setdefault("width", cols)
+    meta.setdefault("height", rows)
+    meta.setdefault("dtype", str(tensor.dtype).replace("torch.", ""))
+    if np.dtype(meta["dtype"]).name != str(tensor.dtype).replace("torch.", ""):
+        raise RasterError("write_from_device: dtype of the file must be the tensor's (convert on the device first)")
+    w = DatasetWriter(path, threads=threads, **meta)
+    try:
+        br = _block_rows(rows, w.chunk_rows, cols, tensor.element_size(), block_bytes)
+        stage = [torch.empty((br, cols), dtype=tensor.dtype).pin_memory() for _ in range(2 if rows > br else 1)]
+        copy = torch.cuda.Stream(device=tensor.device)
+        copy.wait_stream(torch.cuda.current_stream(tensor.device))
+        starts = list(range(0, rows, br))
+        done = []
+
+        def fetch(k):
+            r0 = starts[k]
+            n = min(br, rows - r0)
+            with torch.cuda.stream(copy):
+                stage[k % len(stage)][:n].copy_(tensor[r0:r0 + n], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            done.append(ev)
+
+        fetch(0)
+        for k, r0 in enumerate(starts):
+            n = min(br, rows - r0)
+            done[k].synchronize()
+            if k + 1 < len(starts) and len(stage) > 1:
+                fetch(k + 1)  # lands in the other staging block while this one is encoded
+            w.write_rows(r0, stage[k % len(stage)][:n])
+            if k + 1 < len(starts) and len(stage) == 1:
+                fetch(k + 1)
+        total = w.bytes_written
+        w.close()
+        return total
+    except Exception:
+        w.closed = True
+        lib.dtbio_close_writer(w._h)
+        raise

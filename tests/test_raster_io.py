@@ -1,0 +1,325 @@
+"""GeoTIFF codec (include/dtb200_io.h, descriptools_b200/raster.py).
+
+The checker is libtiff as bundled with Pillow: files written by the codec must read back identically through
+Pillow, files written by Pillow (strips, LZW / Deflate / PackBits, with and without the horizontal predictor)
+must decode identically through the codec, and -- in the build container, where the reference checkout is
+mounted -- the reference's own GDAL-written fixtures (LZW 128 x 128 tiles, Example/input/*.tif) must decode
+to exactly what tests/golden/example_inputs.npz was made from.
+"""
+import ctypes
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+import descriptools_b200.raster as rio
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_EXAMPLE = "/root/reference/Example"
+
+PIL_MODES = {"uint8": "L", "uint16": "I;16", "int32": "I", "float32": "F"}
+
+
+def _rand(shape, dtype, seed=0, smooth=True):
+    rng = np.random.default_rng(seed)
+    dt = np.dtype(dtype)
+    if dt.kind == "f":
+        a = rng.standard_normal(shape).cumsum(axis=1) if smooth else rng.standard_normal(shape)
+        return a.astype(dt)
+    info = np.iinfo(dt)
+    if smooth:
+        a = rng.integers(-3, 4, size=shape).cumsum(axis=1) + (0 if info.min < 0 else 200)
+        return np.clip(a, info.min, info.max).astype(dt)
+    return rng.integers(info.min, info.max, size=shape, dtype=dt, endpoint=True)
+
+
+def _pil_read(path):
+    from PIL import Image
+
+    Image.MAX_IMAGE_PIXELS = None
+    with Image.open(path) as im:
+        return np.array(im)
+
+
+def test_library_exports_every_declared_symbol():
+    src = open(os.path.join(REPO, "include", "dtb200_io.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(dtbio_[a-z0-9_]+)\s*\(", src)))
+    assert len(names) >= 14
+    raw = ctypes.CDLL(rio.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"libdtb200_io.so does not export {n}"
+    assert rio.lib.dtbio_abi_version() == 1
+    assert [rio.lib.dtbio_dtype_size(i) for i in range(10)] == [1, 1, 2, 2, 4, 4, 8, 8, 4, 8]
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "int8", "uint16", "int16", "uint32", "int32", "uint64", "int64", "float32", "float64"])
+@pytest.mark.parametrize("layout", ["strips", "tiles"])
+@pytest.mark.parametrize("compress,predictor", [("none", 1), ("lzw", 1), ("lzw", 2), ("deflate", 1), ("deflate", 2), ("lzw", 3), ("deflate", 3)])
+def test_round_trip_every_dtype_layout_and_codec(tmp_path, dtype, layout, compress, predictor):
+    if predictor == 3 and np.dtype(dtype).kind != "f":
+        pytest.skip("floating-point predictor")
+    a = _rand((157, 203), dtype, seed=3)  # ragged against 64 x 48 tiles and 7-row strips
+    path = tmp_path / "t.tif"
+    kw = dict(tiled=True, blockxsize=48, blockysize=64) if layout == "tiles" else dict(blockysize=7)
+    with rio.open(path, "w", driver="GTiff", width=203, height=157, count=1, dtype=dtype, compress=compress, predictor=predictor,
+                  nodata=-100 if np.dtype(dtype).kind != "u" else 0, **kw) as dst:
+        dst.write(a)
+    with rio.open(path) as src:
+        assert src.shape == a.shape and src.dtypes == (dtype,) and src.compression == compress
+        assert src.nodata == (-100 if np.dtype(dtype).kind != "u" else 0)
+        assert src.block_shapes == ([(64, 48)] if layout == "tiles" else [(7, 203)])
+        np.testing.assert_array_equal(src.read(1), a)
+        np.testing.assert_array_equal(src.read(), a[None])
+        # a row block that starts and ends inside chunks, into a wider buffer
+        buf = np.full((40, 256), 77, dtype=dtype)
+        src.read_rows(59, 40, buf, threads=3)
+        np.testing.assert_array_equal(buf[:, :203], a[59:99])
+        assert (buf[:, 203:] == 77).all()
+    if dtype in PIL_MODES:  # libtiff agrees (it has no mode for the other sample types through Pillow)
+        np.testing.assert_array_equal(_pil_read(path), a)
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "uint16", "int32", "float32"])
+@pytest.mark.parametrize("compression,predictor", [("raw", False), ("tiff_lzw", False), ("tiff_lzw", True), ("tiff_adobe_deflate", False),
+                                                   ("tiff_adobe_deflate", True), ("packbits", False)])
+def test_reads_what_libtiff_writes(tmp_path, dtype, compression, predictor):
+    from PIL import Image
+
+    if predictor and dtype == "float32":
+        pytest.skip("Pillow cannot ask libtiff for the floating-point predictor")
+    a = _rand((301, 333), dtype, seed=5, smooth=(compression != "raw"))
+    path = str(tmp_path / "p.tif")
+    kw = {} if compression == "raw" else {"compression": compression}
+    if predictor:
+        kw["tiffinfo"] = {317: 2}
+    Image.fromarray(a).save(path, **kw)
+    with rio.open(path) as src:
+        assert src.dtypes == (dtype,)
+        np.testing.assert_array_equal(src.read(1, threads=2), a)
+        np.testing.assert_array_equal(src.read_rows(300, 1), a[300:])
+
+
+def test_lzw_table_resets_and_incompressible_data(tmp_path):
+    # 256 KiB of noise per tile: the 12-bit table fills and is cleared dozens of times per chunk
+    a = _rand((512, 512), "uint8", seed=9, smooth=False)
+    path = tmp_path / "noise.tif"
+    with rio.open(path, "w", width=512, height=512, dtype="uint8", compress="lzw", tiled=True, blockxsize=512, blockysize=512) as dst:
+        dst.write(a)
+    np.testing.assert_array_equal(rio.open(path).read(1), a)
+    np.testing.assert_array_equal(_pil_read(path), a)
+    # and the other extreme: one value, codes grow to the longest strings
+    z = np.zeros((512, 512), np.uint8)
+    with rio.open(path, "w", width=512, height=512, dtype="uint8", compress="lzw", blockysize=512) as dst:
+        dst.write(z)
+    assert os.path.getsize(path) < 2000
+    np.testing.assert_array_equal(rio.open(path).read(1), z)
+    np.testing.assert_array_equal(_pil_read(path), z)
+
+
+def test_georeferencing_and_meta_follow_the_example(tmp_path):
+    """example.py:201-217: meta of the DEM, dtype / nodata updated, written with the class map"""
+    crs = rio.GeoKeys((1, 1, 0, 3, 1024, 0, 1, 1, 1025, 0, 1, 1, 3072, 0, 1, 32722), (), "")
+    tr = rio.Affine(12.5, 0.0, 605681.5, 0.0, -12.5, 7010736.25)
+    dem = _rand((64, 80), "float32", seed=1)
+    p1, p2 = tmp_path / "dem.tif", tmp_path / "class.tif"
+    with rio.open(p1, "w", driver="GTiff", width=80, height=64, count=1, dtype=rio.float32, crs=crs, transform=tr,
+                  nodata=-3.4028230607370965e38, compress="lzw", tiled=True, blockxsize=32, blockysize=32) as dst:
+        dst.write(dem.reshape(1, 64, 80))
+    meta = rio.open(p1).meta
+    assert meta["dtype"] == "float32" and meta["width"] == 80 and meta["height"] == 64 and meta["count"] == 1
+    assert meta["crs"] == crs and meta["crs"].to_epsg() == 32722 and meta["transform"] == tr
+    assert meta["nodata"] == pytest.approx(-3.4028230607370965e38)
+    meta.update(dtype=rio.uint8)
+    meta.update(nodata=0)
+    cls = (dem > 0).astype("uint8").reshape(1, 64, 80)
+    with rio.open(p2, "w", **meta) as dist:
+        dist.write(cls.astype(rio.uint8))
+    with rio.open(p2) as src:
+        assert src.meta == dict(meta, dtype="uint8", nodata=0.0)
+        assert src.transform * (0, 0) == (605681.5, 7010736.25) and src.res == (12.5, 12.5)
+        assert not src.is_tiled and src.compression == "none"  # rasterio's default layout for a bare meta
+        np.testing.assert_array_equal(src.read(1), cls[0])
+    from PIL import Image
+
+    with Image.open(p2) as im:  # a foreign reader sees the same tags
+        assert im.tag_v2[33550] == (12.5, 12.5, 0.0) and im.tag_v2[33922] == (0.0, 0.0, 0.0, 605681.5, 7010736.25, 0.0)
+        assert im.tag_v2[42113] == "0" and tuple(im.tag_v2[34735]) == crs.directory
+
+
+def test_bigtiff_and_big_endian_files(tmp_path):
+    a = _rand((90, 70), "int16", seed=2)
+    path = tmp_path / "big.tif"
+    with rio.open(path, "w", width=70, height=90, dtype="int16", compress="deflate", predictor=2, tiled=True, blockxsize=32, blockysize=32,
+                  bigtiff="YES") as dst:
+        assert dst.bigtiff
+        dst.write(a)
+    assert open(path, "rb").read(4) == b"II\x2b\x00"
+    with rio.open(path) as src:
+        assert src.profile["bigtiff"] and src.profile["predictor"] == 2 and src.profile["blockxsize"] == 32
+        np.testing.assert_array_equal(src.read(1), a)
+    np.testing.assert_array_equal(_pil_read(path), a)
+    # hand-made big-endian classic TIFF: one uncompressed strip of int16
+    be = tmp_path / "mm.tif"
+    data = a.astype(">i2").tobytes()
+    entries = [(256, 3, 1, 70), (257, 3, 1, 90), (258, 3, 1, 16), (259, 3, 1, 1), (262, 3, 1, 1), (273, 4, 1, 8), (277, 3, 1, 1),
+               (278, 3, 1, 90), (279, 4, 1, len(data)), (339, 3, 1, 2)]
+    ifd = struct.pack(">H", len(entries))
+    for tag, typ, cnt, val in entries:
+        ifd += struct.pack(">HHI", tag, typ, cnt) + (struct.pack(">HH", val, 0) if typ == 3 else struct.pack(">I", val))
+    ifd += struct.pack(">I", 0)
+    with open(be, "wb") as f:
+        f.write(b"MM" + struct.pack(">HI", 42, 8 + len(data)) + data + ifd)
+    with rio.open(be) as src:
+        assert src.dtypes == ("int16",)
+        np.testing.assert_array_equal(src.read(1), a)
+    np.testing.assert_array_equal(_pil_read(be), a)
+
+
+def test_row_blocks_in_any_order_and_writer_rules(tmp_path):
+    a = _rand((200, 96), "float32", seed=4)
+    path = tmp_path / "blocks.tif"
+    w = rio.open(path, "w", width=96, height=200, dtype="float32", compress="lzw", predictor=3, tiled=True, blockxsize=64, blockysize=64)
+    assert w.chunk_rows == 64
+    with pytest.raises(rio.RasterError, match="chunk boundary"):
+        w.write_rows(10, a[10:74])
+    with pytest.raises(rio.RasterError, match="chunk boundary"):
+        w.write_rows(0, a[:70])
+    w.write_rows(128, a[128:])  # last block first, ragged end
+    w.write_rows(0, a[:128])
+    with pytest.raises(rio.RasterError, match="twice"):
+        w.write_rows(64, a[64:128])
+    w.close()
+    np.testing.assert_array_equal(rio.open(path).read(1), a)
+    np.testing.assert_array_equal(_pil_read(path), a)
+    # a writer closed with chunks missing reports it and leaves no file behind
+    w = rio.open(path, "w", width=96, height=200, dtype="float32", blockysize=50)
+    w.write_rows(0, a[:50])
+    with pytest.raises(rio.RasterError, match="never written"):
+        w.close()
+    assert not os.path.exists(path)
+
+
+def test_errors_are_reported_not_guessed(tmp_path):
+    with pytest.raises(rio.RasterError, match="cannot open"):
+        rio.open(tmp_path / "absent.tif")
+    junk = tmp_path / "junk.tif"
+    junk.write_bytes(b"not a tiff at all")
+    with pytest.raises(rio.RasterError, match="not a TIFF"):
+        rio.open(junk)
+    from PIL import Image
+
+    rgb = tmp_path / "rgb.tif"
+    Image.fromarray(np.zeros((8, 8, 3), np.uint8)).save(rgb)
+    with pytest.raises(rio.RasterError, match="sample per pixel"):
+        rio.open(rgb)
+    # a truncated file: the tile data is gone but the IFD survives at the front? (ours sits at the end: cut it)
+    good = tmp_path / "good.tif"
+    with rio.open(good, "w", width=64, height=64, dtype="uint8", compress="lzw") as dst:
+        dst.write(np.zeros((64, 64), np.uint8))
+    cut = tmp_path / "cut.tif"
+    cut.write_bytes(good.read_bytes()[:40])
+    with pytest.raises(rio.RasterError):
+        rio.open(cut)
+    with pytest.raises(rio.RasterError, match="band 1"):
+        rio.open(good).read(2)
+    with pytest.raises(rio.RasterError, match="shape"):
+        with rio.open(tmp_path / "x.tif", "w", width=4, height=4, dtype="uint8") as dst:
+            dst.write(np.zeros((5, 4), np.uint8))
+    assert not os.path.exists(tmp_path / "x.tif")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLE), reason="reference checkout not mounted (build container only)")
+def test_reference_fixtures_decode_to_the_golden_inputs(tmp_path):
+    """Example/input/*.tif are GDAL-written LZW tiles; example.py:33-52 turns them into the arrays
+    tests/golden/example_inputs.npz holds.  KAT-1 (output/hand_class.tif) is read and re-written too."""
+    from helpers import example_inputs
+
+    ex = example_inputs()
+    with np.errstate(invalid="ignore"):
+        dem = rio.open(f"{REF_EXAMPLE}/input/12_dem.tif").read(1).astype("int16")   # example.py:33
+        fdr = rio.open(f"{REF_EXAMPLE}/input/12_fdr.tif").read(1)                   # :36
+        fac = rio.open(f"{REF_EXAMPLE}/input/12_fac.tif").read(1).astype("int")     # :39
+    dem = np.where(dem == dem[0, 0], -100, dem)                                     # :42-43
+    fac = np.where(fac == fac[0, 0], -100, fac)
+    flood = rio.open(f"{REF_EXAMPLE}/input/WB_12_100y.tif").read(1).astype("int8")   # :106
+    np.testing.assert_array_equal(dem, ex["dem"])
+    np.testing.assert_array_equal(fdr, ex["fdr"])
+    np.testing.assert_array_equal(fac, ex["fac"])
+    np.testing.assert_array_equal(flood, ex["flood"])
+    for name in ("12_dem", "12_fdr", "12_fac", "WB_12_100y"):
+        np.testing.assert_array_equal(rio.open(f"{REF_EXAMPLE}/input/{name}.tif").read(1), _pil_read(f"{REF_EXAMPLE}/input/{name}.tif"))
+    src = rio.open(f"{REF_EXAMPLE}/input/12_dem.tif")
+    assert src.crs.to_epsg() == 32722 and src.block_shapes == [(128, 128)] and src.compression == "lzw"
+    # example.py:201-217 on the reference's own class map: same pixels, same georeferencing, same layout
+    kat = rio.open(f"{REF_EXAMPLE}/output/hand_class.tif")
+    np.testing.assert_array_equal(kat.read(1), ex["hand_class"])
+    meta = src.meta
+    meta.update(dtype=rio.uint8)
+    meta.update(nodata=0)
+    out = tmp_path / "hand_class.tif"
+    with rio.open(out, "w", **meta) as dist:
+        dist.write(ex["hand_class"].reshape(1, *ex["hand_class"].shape).astype(rio.uint8))
+    mine = rio.open(out)
+    assert mine.transform == kat.transform and mine.nodata == kat.nodata and mine.block_shapes == kat.block_shapes
+    assert os.path.getsize(out) == pytest.approx(os.path.getsize(f"{REF_EXAMPLE}/output/hand_class.tif"), rel=0.001)
+    np.testing.assert_array_equal(_pil_read(out), ex["hand_class"])
+    # re-encode the DEM the way GDAL stored it and compare sizes (same algorithm, same tile size)
+    re_dem = tmp_path / "dem.tif"
+    with rio.open(re_dem, "w", **src.profile) as dst:
+        dst.write(src.read(1))
+    assert rio.open(re_dem).profile == src.profile
+    assert os.path.getsize(re_dem) == pytest.approx(os.path.getsize(f"{REF_EXAMPLE}/input/12_dem.tif"), rel=0.02)
+    np.testing.assert_array_equal(_pil_read(re_dem), _pil_read(f"{REF_EXAMPLE}/input/12_dem.tif"))
+
+
+@pytest.mark.gpu
+def test_file_to_device_and_back(tmp_path):
+    import torch
+
+    a = _rand((1000, 777), "float32", seed=6)
+    p = tmp_path / "in.tif"
+    with rio.open(p, "w", width=777, height=1000, dtype="float32", compress="lzw", tiled=True, blockxsize=128, blockysize=128, nodata=-100) as dst:
+        dst.write(a)
+    t = rio.read_to_device(p, block_bytes=1 << 20)  # 1 MiB blocks: 3 x 256 rows + a ragged one, both staging buffers reused
+    torch.cuda.synchronize()
+    assert t.is_cuda and t.dtype == torch.float32
+    np.testing.assert_array_equal(t.cpu().numpy(), a)
+    t2 = rio.read_to_device(p)  # single block
+    np.testing.assert_array_equal(t2.cpu().numpy(), a)
+    q = tmp_path / "out.tif"
+    n = rio.write_from_device(q, t * 2, block_bytes=1 << 20, compress="deflate", predictor=3, tiled=True, blockxsize=128, blockysize=128,
+                              **{k: v for k, v in rio.open(p).meta.items() if k in ("crs", "transform", "nodata")})
+    assert 0 < n <= os.path.getsize(q)
+    assert rio.open(q).transform == rio.open(p).transform and rio.open(q).nodata == -100
+    np.testing.assert_array_equal(rio.open(q).read(1), a * 2)
+    s = tmp_path / "strips.tif"
+    rio.write_from_device(s, (t > 0).to(torch.uint8), block_bytes=100_000)
+    np.testing.assert_array_equal(_pil_read(s), (a > 0).astype(np.uint8))
+
+
+@pytest.mark.gpu
+def test_pipeline_from_file_to_files(tmp_path):
+    """GeoTIFF DEM in, one GeoTIFF per descriptor out == the array pipeline on the same DEM"""
+    import oracle
+    from descriptools_b200 import pipeline
+
+    dem = oracle.conditioned_dem(300, 420, seed=11)
+    hole = np.zeros(dem.shape, bool)
+    hole[40:70, 100:160] = True
+    stored = np.where(hole, np.float32(-3.4028230607370965e38), dem)  # the file carries GDAL's nodata, not -100
+    crs = rio.GeoKeys((1, 1, 0, 1, 3072, 0, 1, 32722))
+    p = tmp_path / "dem.tif"
+    with rio.open(p, "w", width=420, height=300, dtype="float32", compress="lzw", tiled=True, blockxsize=128, blockysize=128,
+                  nodata=-3.4028230607370965e38, crs=crs, transform=rio.Affine(12.5, 0, 1000.0, 0, -12.5, 9000.0)) as dst:
+        dst.write(stored)
+    paths = pipeline.pipeline_files(p, tmp_path / "out", river_threshold=300, block_bytes=200_000)
+    want = pipeline.pipeline(np.where(hole, np.float32(-100), dem), 12.5, 300)
+    assert sorted(paths) == sorted(pipeline.STAGE_OUTPUTS)
+    for name, path in paths.items():
+        with rio.open(path) as src:
+            assert src.crs == crs and src.res == (12.5, 12.5) and src.nodata == (0 if name == "d8" else -100)
+            assert src.compression == "lzw" and src.block_shapes == [(256, 256)]
+            np.testing.assert_array_equal(src.read(1), want[name], err_msg=name)
