@@ -8,6 +8,7 @@
 // or encoded by a team of threads, one chunk at a time each, straight into / out of the caller's (pinned)
 // buffer; the Python side (descriptools_b200/raster.py) overlaps that with the host<->device copies.
 #include "../../include/dtb200_io.h"
+#include "lzw.cuh"  // the decoder shared with the device tile decoder (tiffdecode.cu)
 
 #include <fcntl.h>
 #include <sys/stat.h>
@@ -96,73 +97,8 @@ int sample_format_of(int dtype) {
 
 // ---------------------------------------------------------------------------------------------------
 // LZW, the TIFF flavour: MSB-first codes of 9..12 bits, Clear = 256, EOI = 257, the code width grows one
-// code early (TIFF 6.0 section 13).
+// code early (TIFF 6.0 section 13).  The decoder lives in lzw.cuh.
 // ---------------------------------------------------------------------------------------------------
-struct LzwEntry {
-    uint16_t prefix;
-    uint16_t len;
-    uint8_t first;
-    uint8_t last;
-};
-
-// returns the number of bytes produced (<= cap) or -1 on a corrupt stream
-int64_t lzw_decode(const uint8_t *in, size_t n, uint8_t *out, size_t cap, LzwEntry *tab) {
-    if (n >= 2 && in[0] == 0 && (in[1] & 1)) return -2;  // pre-6.0 LSB-first variant
-    uint64_t acc = 0;
-    int have = 0;
-    size_t ip = 0, op = 0;
-    int nbits = 9, next = 258, old = -1;
-    for (int i = 0; i < 256; ++i) tab[i] = LzwEntry{0, 1, (uint8_t)i, (uint8_t)i};
-    auto emit = [&](int code) {
-        size_t len = tab[code].len;
-        size_t end = op + len;
-        int c = code;
-        // walk the chain backwards; bytes that would fall past the buffer are dropped
-        size_t pos = end;
-        while (pos > op) {
-            --pos;
-            if (pos < cap) out[pos] = tab[c].last;
-            c = tab[c].prefix;
-        }
-        op = end < cap ? end : cap;
-    };
-    while (op < cap) {
-        while (have < nbits) {
-            if (ip >= n) return (int64_t)op;  // ran out of input: hand back what there is
-            acc = (acc << 8) | in[ip++];
-            have += 8;
-        }
-        int code = (int)((acc >> (have - nbits)) & ((1u << nbits) - 1));
-        have -= nbits;
-        if (code == 257) break;
-        if (code == 256) {
-            nbits = 9;
-            next = 258;
-            old = -1;
-            continue;
-        }
-        if (old < 0) {
-            if (code > 255) return -1;
-            out[op++] = (uint8_t)code;
-            old = code;
-            continue;
-        }
-        if (code < next) {
-            if (next < 4096) tab[next] = LzwEntry{(uint16_t)old, (uint16_t)(tab[old].len + 1), tab[old].first, tab[code].first};
-            emit(code);
-        } else if (code == next && next < 4096) {
-            tab[next] = LzwEntry{(uint16_t)old, (uint16_t)(tab[old].len + 1), tab[old].first, tab[old].first};
-            emit(code);
-        } else {
-            return -1;
-        }
-        if (next < 4096) ++next;
-        if (next >= (1 << nbits) - 1 && nbits < 12) ++nbits;
-        old = code;
-    }
-    return (int64_t)op;
-}
-
 struct LzwEncoder {
     static const int HBITS = 14, HSIZE = 1 << HBITS;
     std::vector<int32_t> keys;
@@ -529,7 +465,7 @@ int interpret(dtbio_reader *r) {
 
 struct Scratch {
     std::vector<uint8_t> comp, raw, tmp;
-    std::vector<LzwEntry> lzw;
+    std::vector<dtb::LzwSlot> lzw;
     LzwEncoder *enc = nullptr;
     ~Scratch() { delete enc; }
 };
@@ -570,8 +506,8 @@ int decode_chunk(dtbio_reader *r, int64_t chunk, int64_t row0, int64_t row1, uin
         s.raw.resize(raw_bytes);
         int64_t got = 0;
         if (comp == DTBIO_COMP_LZW) {
-            s.lzw.resize(4096);
-            got = lzw_decode(s.comp.data(), len, s.raw.data(), raw_bytes, s.lzw.data());
+            s.lzw.resize(dtb::kLzwTableSlots);
+            got = dtb::lzw_decode(s.comp.data(), len, s.raw.data(), raw_bytes, s.lzw.data());
             if (got == -2) return fail(DTBIO_ERR_UNSUPPORTED, "old-style (pre TIFF 6.0) LZW");
         } else if (comp == DTBIO_COMP_DEFLATE) {
             uLongf n = (uLongf)raw_bytes;

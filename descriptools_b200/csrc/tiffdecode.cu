@@ -1,0 +1,288 @@
+// tiffdecode.cu -- GeoTIFF chunks decoded on the device.
+//
+// The reference lets GDAL decode its rasters on one host thread (rio.open(p).read(1), example.py:33-39).  A
+// 40 000 x 40 000 DEM is ~10^5 independent LZW tiles: here the compressed tiles travel over PCIe as they lie in
+// the file (a fraction of the decoded bytes) and every tile is decoded by one warp -- lane 0 runs the serial LZW
+// recurrence (lzw.cuh, the same function the host codec uses) into a per-warp scratch chunk that stays in L2, then
+// the 32 lanes undo the predictor one row each and store the rows to the raster together.  Thousands of tiles are
+// in flight at once; nothing here is bandwidth-bound, the point is to take the decode off the host cores and to
+// halve the bytes crossing PCIe.
+//
+// Everything a lane does is in three __host__ __device__ phase functions; dtb_selftest_tiff_decode_host() runs
+// the same functions lane by lane on the CPU so the tile geometry, predictor and store logic are tested without a
+// device (tests/test_raster_io.py).  The package itself never calls the self-test.
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "lzw.cuh"
+
+namespace dtb {
+namespace {
+
+constexpr int TD_WARPS = 4;  // warps per CTA
+constexpr int TD_LANES = 32;
+constexpr int TD_CTAS_PER_SM = 8;
+
+struct ChunkGeom {
+    int64_t cy, cx;        // chunk row / column
+    int64_t data_rows;     // rows of the chunk inside the raster
+    int64_t stored_rows;   // rows the chunk is stored with (tiles are whole)
+    int64_t row_bytes;     // chunk_cols * bps
+    int64_t raw_bytes;     // row_bytes * stored_rows
+    int64_t x0, ncols;     // first raster column, columns inside the raster
+};
+
+__host__ __device__ inline int64_t td_across(const dtb_tiff_layout &L)
+{
+    return L.tiled ? (L.cols + L.chunk_cols - 1) / L.chunk_cols : 1;
+}
+
+__host__ __device__ inline ChunkGeom td_geom(const dtb_tiff_layout &L, int64_t chunk)
+{
+    ChunkGeom g;
+    const int64_t across = td_across(L);
+    const int64_t cw = L.tiled ? L.chunk_cols : L.cols;
+    g.cy = chunk / across;
+    g.cx = chunk % across;
+    const int64_t left = L.rows - g.cy * L.chunk_rows;
+    g.data_rows = left < L.chunk_rows ? left : L.chunk_rows;
+    g.stored_rows = L.tiled ? L.chunk_rows : g.data_rows;
+    g.row_bytes = cw * L.bps;
+    g.raw_bytes = g.row_bytes * g.stored_rows;
+    g.x0 = g.cx * cw;
+    g.ncols = (L.cols - g.x0) < cw ? (L.cols - g.x0) : cw;
+    return g;
+}
+
+__host__ __device__ inline size_t td_scratch_bytes(const dtb_tiff_layout &L)
+{
+    const int64_t cw = L.tiled ? L.chunk_cols : L.cols;
+    const size_t raw = (size_t)cw * L.bps * (size_t)L.chunk_rows;
+    return ((raw + 15) & ~(size_t)15) + sizeof(LzwSlot) * kLzwTableSlots;
+}
+
+// status word: 0 = ok, else ((chunk + 1) << 3) | reason   (reason 1 corrupt, 2 old-style LZW, 3 short chunk)
+__host__ __device__ inline long long td_status(int64_t chunk, int reason) { return (long long)(((chunk + 1) << 3) | reason); }
+
+// ---- phase 1 (lane 0): compressed bytes -> scratch chunk.  Returns bytes produced or a negative reason. ----
+__host__ __device__ inline int64_t td_phase1(const dtb_tiff_layout &L, const ChunkGeom &g, const uint8_t *comp, uint64_t len,
+                                             uint8_t *buf, LzwSlot *tab)
+{
+    if (L.compression == 5) return lzw_decode(comp, (size_t)len, buf, (size_t)g.raw_bytes, tab);
+    return -1;
+}
+
+// stored chunks: all lanes copy the bytes into the scratch chunk (the predictor works in place)
+__host__ __device__ inline void td_copy_stored(const uint8_t *comp, uint64_t n, uint8_t *buf, int lane)
+{
+    for (uint64_t i = (uint64_t)lane; i < n; i += TD_LANES) buf[i] = comp[i];
+}
+
+template <typename T>
+__host__ __device__ inline void td_hacc(uint8_t *row, int64_t width)
+{
+    T *p = reinterpret_cast<T *>(row);
+    T run = p[0];
+    for (int64_t i = 1; i < width; ++i) {
+        run = (T)(run + p[i]);
+        p[i] = run;
+    }
+}
+
+__host__ __device__ inline void td_swap(uint8_t *row, int64_t width, int bps)
+{
+    for (int64_t i = 0; i < width; ++i) {
+        uint8_t *s = row + i * bps;
+        for (int a = 0, b = bps - 1; a < b; ++a, --b) {
+            const uint8_t t = s[a];
+            s[a] = s[b];
+            s[b] = t;
+        }
+    }
+}
+
+// ---- phase 2 (one row per lane): byte order and predictor, in place -------------------------------------------
+__host__ __device__ inline void td_phase2(const dtb_tiff_layout &L, const ChunkGeom &g, uint8_t *buf, int lane)
+{
+    const int64_t width = g.row_bytes / L.bps;
+    for (int64_t r = lane; r < g.data_rows; r += TD_LANES) {
+        uint8_t *row = buf + r * g.row_bytes;
+        if (L.big_endian && L.predictor != 3 && L.bps > 1) td_swap(row, width, L.bps);
+        if (L.predictor == 2) {
+            switch (L.bps) {
+                case 1: td_hacc<uint8_t>(row, width); break;
+                case 2: td_hacc<uint16_t>(row, width); break;
+                case 4: td_hacc<uint32_t>(row, width); break;
+                case 8: td_hacc<unsigned long long>(row, width); break;
+            }
+        } else if (L.predictor == 3) {
+            // floating-point predictor: byte planes, differenced byte by byte over the whole row
+            uint8_t run = row[0];
+            for (int64_t i = 1; i < g.row_bytes; ++i) {
+                run = (uint8_t)(run + row[i]);
+                row[i] = run;
+            }
+        }
+    }
+}
+
+// ---- phase 3 (all lanes per row): scratch rows -> raster ---------------------------------------------------------
+__host__ __device__ inline void td_phase3(const dtb_tiff_layout &L, const ChunkGeom &g, const uint8_t *buf, uint8_t *out, int lane)
+{
+    const int64_t width = g.row_bytes / L.bps;
+    const int64_t bytes = g.ncols * L.bps;
+    for (int64_t r = 0; r < g.data_rows; ++r) {
+        const uint8_t *row = buf + r * g.row_bytes;
+        uint8_t *dst = out + ((g.cy * L.chunk_rows + r) * L.cols + g.x0) * L.bps;
+        if (L.predictor == 3) {
+            // sample i, byte b (little-endian) sits in plane bps-1-b at position i
+            for (int64_t i = lane; i < g.ncols; i += TD_LANES)
+                for (int b = 0; b < L.bps; ++b) dst[i * L.bps + b] = row[(int64_t)(L.bps - 1 - b) * width + i];
+        } else if ((((uintptr_t)dst | (uintptr_t)row | (uintptr_t)bytes) & 3u) == 0) {
+            const uint32_t *s = reinterpret_cast<const uint32_t *>(row);
+            uint32_t *d = reinterpret_cast<uint32_t *>(dst);
+            for (int64_t i = lane; i < bytes / 4; i += TD_LANES) d[i] = s[i];
+        } else {
+            for (int64_t i = lane; i < bytes; i += TD_LANES) dst[i] = row[i];
+        }
+    }
+}
+
+// an absent chunk (offset or byte count 0: GDAL's SPARSE_OK) reads as zeros
+__host__ __device__ inline void td_zero(const dtb_tiff_layout &L, const ChunkGeom &g, uint8_t *out, int lane)
+{
+    const int64_t bytes = g.ncols * L.bps;
+    for (int64_t r = 0; r < g.data_rows; ++r) {
+        uint8_t *dst = out + ((g.cy * L.chunk_rows + r) * L.cols + g.x0) * L.bps;
+        for (int64_t i = lane; i < bytes; i += TD_LANES) dst[i] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(TD_WARPS *TD_LANES)
+tiff_decode_kernel(dtb_tiff_layout L, const uint8_t *__restrict__ comp, const uint64_t *__restrict__ comp_off,
+                   const uint64_t *__restrict__ comp_len, int64_t first_chunk, int64_t n_chunks, uint8_t *__restrict__ out,
+                   uint8_t *__restrict__ ws, int64_t n_warps, unsigned long long *__restrict__ status)
+{
+    const int lane = threadIdx.x % TD_LANES;
+    const int64_t warp = (int64_t)blockIdx.x * TD_WARPS + threadIdx.x / TD_LANES;
+    if (warp >= n_warps) return;
+    const size_t per = td_scratch_bytes(L);
+    uint8_t *buf = ws + (size_t)warp * per;
+    LzwSlot *tab = reinterpret_cast<LzwSlot *>(buf + (per - sizeof(LzwSlot) * kLzwTableSlots));
+    for (int64_t c = warp; c < n_chunks; c += n_warps) {
+        const ChunkGeom g = td_geom(L, first_chunk + c);
+        const uint64_t off = comp_off[c], len = comp_len[c];
+        if (len == 0) {
+            td_zero(L, g, out, lane);
+            continue;
+        }
+        long long got = 0;
+        if (L.compression == 1) {
+            got = (long long)(len < (uint64_t)g.raw_bytes ? len : (uint64_t)g.raw_bytes);
+            td_copy_stored(comp + off, (uint64_t)got, buf, lane);
+        } else {
+            if (lane == 0) got = td_phase1(L, g, comp + off, len, buf, tab);
+            got = __shfl_sync(0xffffffffu, got, 0);
+        }
+        if (got < g.row_bytes * g.data_rows) {
+            if (lane == 0) atomicCAS(status, 0ull, (unsigned long long)td_status(first_chunk + c, got == -2 ? 2 : got < 0 ? 1 : 3));
+            continue;  // uniform across the warp
+        }
+        __syncwarp();
+        td_phase2(L, g, buf, lane);
+        __syncwarp();
+        td_phase3(L, g, buf, out, lane);
+        __syncwarp();  // the scratch chunk is reused by this warp's next chunk
+    }
+}
+
+int td_validate(const dtb_tiff_layout *L)
+{
+    if (!L || L->rows <= 0 || L->cols <= 0 || L->chunk_rows <= 0) return DTB_ERR_INVALID;
+    if (L->bps != 1 && L->bps != 2 && L->bps != 4 && L->bps != 8) return DTB_ERR_INVALID;
+    if (L->predictor < 1 || L->predictor > 3) return DTB_ERR_INVALID;
+    if (L->tiled && L->chunk_cols <= 0) return DTB_ERR_INVALID;
+    if (L->compression != 1 && L->compression != 5) return DTB_ERR_UNSUPPORTED;
+    return DTB_OK;
+}
+
+}  // namespace
+}  // namespace dtb
+
+using namespace dtb;
+
+extern "C" {
+
+size_t dtb_tiff_decode_workspace_bytes(const dtb_tiff_layout *lay, int64_t n_chunks)
+{
+    if (td_validate(lay) != DTB_OK || n_chunks <= 0) return 0;
+    const int64_t cap = (int64_t)kNumSMs * TD_CTAS_PER_SM * TD_WARPS;
+    const int64_t warps = n_chunks < cap ? n_chunks : cap;
+    return (size_t)warps * td_scratch_bytes(*lay) + 256;
+}
+
+int dtb_tiff_decode_chunks(const dtb_tiff_layout *lay, const uint8_t *comp, const uint64_t *comp_off, const uint64_t *comp_len,
+                           int64_t first_chunk, int64_t n_chunks, void *out, void *ws, size_t ws_bytes,
+                           unsigned long long *status, void *stream)
+{
+    const int v = td_validate(lay);
+    if (v != DTB_OK) return v;
+    if (n_chunks == 0) return DTB_OK;
+    if (!comp || !comp_off || !comp_len || !out || !ws || !status || n_chunks < 0 || first_chunk < 0) return DTB_ERR_INVALID;
+    const int64_t total = td_across(*lay) * ((lay->rows + lay->chunk_rows - 1) / lay->chunk_rows);
+    if (first_chunk + n_chunks > total) return DTB_ERR_INVALID;
+    const size_t per = td_scratch_bytes(*lay);
+    if (ws_bytes < per + 256) return DTB_ERR_WORKSPACE;
+    int64_t warps = (int64_t)((ws_bytes - 256) / per);
+    const int64_t cap = (int64_t)kNumSMs * TD_CTAS_PER_SM * TD_WARPS;
+    if (warps > cap) warps = cap;
+    if (warps > n_chunks) warps = n_chunks;
+    // scratch chunks start 256-byte aligned
+    uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    const unsigned blocks = (unsigned)((warps + TD_WARPS - 1) / TD_WARPS);
+    cudaStream_t st = as_stream(stream);
+    DTB_KERNEL("tiff_decode_kernel", st,
+               tiff_decode_kernel<<<blocks, TD_WARPS * TD_LANES, 0, st>>>(*lay, comp, comp_off, comp_len, first_chunk, n_chunks,
+                                                                         (uint8_t *)out, base, warps, status));
+    return DTB_OK;
+}
+
+int dtb_selftest_tiff_decode_host(const dtb_tiff_layout *lay, const uint8_t *comp_host, const uint64_t *comp_off_host,
+                                  const uint64_t *comp_len_host, int64_t first_chunk, int64_t n_chunks, void *out_host,
+                                  unsigned long long *status_host)
+{
+    const int v = td_validate(lay);
+    if (v != DTB_OK) return v;
+    if (!comp_host || !comp_off_host || !comp_len_host || !out_host || !status_host || n_chunks < 0) return DTB_ERR_INVALID;
+    const dtb_tiff_layout &L = *lay;
+    std::vector<uint8_t> scratch(td_scratch_bytes(L));
+    uint8_t *buf = scratch.data();
+    LzwSlot *tab = reinterpret_cast<LzwSlot *>(buf + (scratch.size() - sizeof(LzwSlot) * kLzwTableSlots));
+    *status_host = 0;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const ChunkGeom g = td_geom(L, first_chunk + c);
+        const uint64_t off = comp_off_host[c], len = comp_len_host[c];
+        if (len == 0) {
+            for (int lane = 0; lane < TD_LANES; ++lane) td_zero(L, g, (uint8_t *)out_host, lane);
+            continue;
+        }
+        long long got;
+        if (L.compression == 1) {
+            got = (long long)(len < (uint64_t)g.raw_bytes ? len : (uint64_t)g.raw_bytes);
+            for (int lane = 0; lane < TD_LANES; ++lane) td_copy_stored(comp_host + off, (uint64_t)got, buf, lane);
+        } else {
+            got = td_phase1(L, g, comp_host + off, len, buf, tab);
+        }
+        if (got < g.row_bytes * g.data_rows) {
+            if (*status_host == 0) *status_host = (unsigned long long)td_status(first_chunk + c, got == -2 ? 2 : got < 0 ? 1 : 3);
+            continue;
+        }
+        for (int lane = 0; lane < TD_LANES; ++lane) td_phase2(L, g, buf, lane);
+        for (int lane = 0; lane < TD_LANES; ++lane) td_phase3(L, g, buf, (uint8_t *)out_host, lane);
+    }
+    return DTB_OK;
+}
+
+}  // extern "C"

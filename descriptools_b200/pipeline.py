@@ -152,12 +152,12 @@ def output_dtypes(dem_dtype: np.dtype, n_cells: int) -> dict:
 
 def pipeline_files(dem_path, out_dir, river_threshold: int, px: float | None = None, n_gfi: float = 0.4,
                    scale_factor: float = 0.1, size: float | None = None, outputs=STAGE_OUTPUTS, compress: str = "lzw",
-                   blocksize: int = 256, block_bytes: int = 256 << 20, threads: int = 0) -> dict:
+                   blocksize: int = 256, block_bytes: int = 256 << 20, threads: int = 0, decode: str = "host") -> dict:
     """The chain from a DEM GeoTIFF to one GeoTIFF per descriptor (`out_dir/<name>.tif`), what a user of the
     reference does around the descriptor calls with rasterio (example.py:33, :42-43, :201-217).
 
     The DEM is decoded in row blocks into pinned memory and copied to the device as it is decoded
-    (raster.read_to_device); its nodata value (GDAL_NODATA tag) becomes the path's sentinel -100 on the device
+    (raster.read_to_device; `decode="device"` sends the compressed tiles instead and decodes them on the GPU); its nodata value (GDAL_NODATA tag) becomes the path's sentinel -100 on the device
     (example.py:42-43 does that on the host, from the corner cell); `px` defaults to the file's pixel size.
     Results are encoded block by block as they are copied back (raster.write_from_device), tiled and compressed,
     with the DEM's georeferencing; nodata is -100 (0 for the D8 codes, like 12_fdr.tif).
@@ -172,7 +172,7 @@ def pipeline_files(dem_path, out_dir, river_threshold: int, px: float | None = N
         geo = dict(crs=src.crs, transform=src.transform)
         if px is None:
             px = src.res[0]
-        dem = raster.read_to_device(src, block_bytes=block_bytes, threads=threads)
+        dem = raster.read_to_device(src, block_bytes=block_bytes, threads=threads, decode=decode)
         nodata = src.nodata
     if dem.dtype not in (torch.float32, torch.int16):
         # the kernels take the two DEM types the reference is used with (f32 rasters, int16 after example.py:33)

@@ -427,17 +427,121 @@ def _block_rows(src_rows: int, chunk_rows: int, cols: int, itemsize: int, target
     return min(max(chunk_rows, want // chunk_rows * chunk_rows), max(src_rows, 1))
 
 
-def read_to_device(src, device=None, out=None, block_bytes: int = 256 << 20, threads: int = 0, stream=None):
-    """Decode a raster into a CUDA tensor: two pinned staging blocks; while block k is copied to the device on
-    `stream` (default: a private copy stream) the codec's thread team decodes block k+1.  Returns the tensor
-    (dtype of the file); the current stream waits for the last copy.  `src` is a path or a DatasetReader."""
+def chunk_table(reader: "DatasetReader"):
+    """(layout, offsets, byte counts) of a raster's chunks: what dtb_tiff_decode_chunks (include/dtb200.h) needs.
+    offsets / counts are uint64 arrays in chunk order (tiles row-major, or strips top to bottom)."""
+    from ._lib import TiffLayout
+
+    info = reader._info
+    lay = TiffLayout()
+    lay.rows, lay.cols, lay.bps = reader.height, reader.width, np.dtype(reader.dtypes[0]).itemsize
+    lay.predictor, lay.compression, lay.big_endian = int(info.predictor), int(info.compression), int(info.big_endian)
+    lay.tiled = 1 if reader.is_tiled else 0
+    lay.chunk_rows = int(info.tile_rows if reader.is_tiled else info.rows_per_strip)
+    lay.chunk_cols = int(info.tile_cols) if reader.is_tiled else reader.width
+    across = -(-reader.width // lay.chunk_cols) if reader.is_tiled else 1
+    n = across * -(-reader.height // lay.chunk_rows)
+    off = np.array(reader.tag(324 if reader.is_tiled else 273), dtype=np.uint64)[:n]
+    cnt = reader.tag(325 if reader.is_tiled else 279)
+    if cnt is None:  # uncompressed files may omit the byte counts
+        rows_in = np.minimum(lay.chunk_rows, reader.height - (np.arange(n) // across) * lay.chunk_rows)
+        cnt = rows_in * lay.chunk_cols * lay.bps
+    cnt = np.array(cnt, dtype=np.uint64)[:n]
+    cnt[off == 0] = 0
+    return lay, across, off, cnt
+
+
+def _read_to_device_chunks(reader, out, block_bytes: int, copy):
+    """read_to_device(decode="device"): the compressed chunks go over PCIe as they lie in the file and are decoded
+    by dtb_tiff_decode_chunks, one warp per chunk.  File spans are read into two pinned staging buffers; reading
+    span k+1 overlaps the copy and decode of span k on `copy`."""
+    import torch
+
+    from ._lib import check
+    from ._lib import lib as cuda_lib
+
+    lay, across, off, cnt = chunk_table(reader)
+    if lay.compression not in (1, 5):
+        raise RasterError(f"decode='device' handles stored and LZW chunks, not {reader.compression}; use decode='host'")
+    dev = out.device
+    n = off.size
+    chunk_raw = lay.chunk_rows * lay.chunk_cols * lay.bps
+    per_group = max(1, block_bytes // max(1, chunk_raw) // across) * across  # whole chunk-rows, about block_bytes decoded
+    groups = [(g0, min(n, g0 + per_group)) for g0 in range(0, n, per_group)]
+    spans = []
+    for g0, g1 in groups:
+        live = cnt[g0:g1] > 0
+        lo = int(off[g0:g1][live].min()) if live.any() else 0
+        hi = int((off[g0:g1] + cnt[g0:g1])[live].max()) if live.any() else 0
+        spans.append((lo, hi))
+    biggest = max(1, max(hi - lo for lo, hi in spans))
+    stage = [torch.empty(biggest, dtype=torch.uint8).pin_memory() for _ in range(min(2, len(groups)))]
+    comp = [torch.empty(biggest, dtype=torch.uint8, device=dev) for _ in stage]
+    ws_bytes = int(cuda_lib.dtb_tiff_decode_workspace_bytes(ctypes.byref(lay), per_group))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    status = torch.zeros(1, dtype=torch.int64, device=dev)
+    copy.wait_stream(torch.cuda.current_stream(dev))
+    free = [None] * len(stage)
+    fd = os.open(reader.name, os.O_RDONLY)
+    try:
+        for k, ((g0, g1), (lo, hi)) in enumerate(zip(groups, spans)):
+            s = k % len(stage)
+            if free[s] is not None:
+                free[s].synchronize()  # the copy out of this staging buffer (and the decode behind it) has finished
+            view = memoryview(stage[s].numpy())[:hi - lo]
+            got = 0
+            while got < hi - lo:
+                m = os.preadv(fd, [view[got:]], lo + got)
+                if m <= 0:
+                    raise RasterError(f"{reader.name}: file ends inside a chunk")
+                got += m
+            rel = off[g0:g1] - np.uint64(lo)
+            rel[cnt[g0:g1] == 0] = 0
+            table = torch.from_numpy(np.concatenate([rel, cnt[g0:g1]]).view(np.int64))
+            with torch.cuda.stream(copy):
+                comp[s][:hi - lo].copy_(stage[s][:hi - lo], non_blocking=True)
+                table_d = table.to(dev)  # small and pageable: synchronous with respect to the host, ordered on `copy`
+                check(cuda_lib.dtb_tiff_decode_chunks(ctypes.byref(lay), comp[s].data_ptr(), table_d.data_ptr(),
+                                                      table_d.data_ptr() + 8 * (g1 - g0), g0, g1 - g0, out.data_ptr(),
+                                                      ws.data_ptr(), ws_bytes, status.data_ptr(), copy.cuda_stream),
+                      "dtb_tiff_decode_chunks")
+                free[s] = torch.cuda.Event()
+                free[s].record(copy)
+    finally:
+        os.close(fd)
+    copy.synchronize()
+    code = int(status.item())
+    if code:
+        reason = {1: "corrupt LZW stream", 2: "pre-6.0 LZW", 3: "chunk decodes short"}.get(code & 7, "decode error")
+        raise RasterError(f"{reader.name}: chunk {(code >> 3) - 1}: {reason}")
+    torch.cuda.current_stream(dev).wait_stream(copy)
+    return out
+
+
+def read_to_device(src, device=None, out=None, block_bytes: int = 256 << 20, threads: int = 0, stream=None, decode: str = "host"):
+    """Decode a raster into a CUDA tensor.  Returns the tensor (dtype of the file); the current stream waits for
+    the last copy.  `src` is a path or a DatasetReader.
+
+    decode="host": two pinned staging blocks; while block k is copied to the device on `stream` (default: a private
+    copy stream) the codec's thread team decodes block k+1.
+    decode="device": the compressed chunks are copied instead and decoded on the device (stored and LZW files;
+    anything else raises -- nothing falls back silently)."""
     import torch
 
     from . import device as _device
 
+    if decode not in ("host", "device"):
+        raise RasterError("decode must be 'host' or 'device'")
     dev = torch.device(device) if device is not None else _device.require_cuda()
     reader = src if isinstance(src, DatasetReader) else DatasetReader(src)
     try:
+        if decode == "device":
+            tdt = getattr(torch, reader.dtypes[0])
+            if out is None:
+                out = torch.empty(reader.shape, dtype=tdt, device=dev)
+            elif tuple(out.shape) != reader.shape or out.dtype != tdt or not out.is_cuda or not out.is_contiguous():
+                raise RasterError("read_to_device: `out` must be a contiguous CUDA tensor of the raster's shape and dtype")
+            return _read_to_device_chunks(reader, out, block_bytes, stream if stream is not None else torch.cuda.Stream(device=out.device))
         tdt = getattr(torch, reader.dtypes[0])
         rows, cols = reader.shape
         if out is None:

@@ -267,6 +267,42 @@ int dtb_eval_class_map(const void *desc, int desc_is_f64, const int8_t *flood, i
 int dtb_minmax_scale(const void *mat, int mat_dtype, int64_t n, double mn, double mx, double nodata,
                      double *out, void *stream);
 
+/* ---- raster files: GeoTIFF chunks decoded on the device ---------
+ * Replaces the pixel decode inside rasterio's `rio.open(p).read(1)` (Example/example.py:33-39) for tiled or
+ * striped single-band files that are stored or LZW-compressed (what GDAL wrote for 12_dem / 12_fdr / 12_fac):
+ * the compressed chunks are copied to the device as they lie in the file and one warp decodes each chunk
+ * (LZW, byte order, predictor 2 / 3) into the raster.  File parsing stays on the host (include/dtb200_io.h).
+ *   lay          geometry of the file: chunk i covers chunk-row i / across, chunk-column i % across
+ *                (across = ceil(cols / chunk_cols) for tiles, 1 for strips); tiles are stored whole, the last
+ *                strip holds only the rows that exist.
+ *   comp         device buffer with the compressed bytes; chunk first_chunk + i is comp[comp_off[i] ..
+ *                comp_off[i] + comp_len[i]); comp_off / comp_len are DEVICE arrays; comp_len[i] == 0 = absent
+ *                chunk (reads as zeros).
+ *   out          device pointer to the WHOLE raster (rows x cols samples of bps bytes, dense).
+ *   ws           dtb_tiff_decode_workspace_bytes(lay, n_chunks) bytes (one scratch chunk + string table per
+ *                resident warp; fewer bytes = fewer warps, at least one).
+ *   status       device word, zeroed by the caller: stays 0, or receives ((chunk + 1) << 3) | reason for the
+ *                first chunk that failed (1 corrupt stream, 2 pre-6.0 LZW, 3 chunk decodes short).
+ * dtb_selftest_tiff_decode_host runs the kernel's per-lane code on the CPU over HOST pointers; it exists for
+ * the CPU test-suite (no device there) and is not called by the package. */
+typedef struct dtb_tiff_layout {
+    int64_t rows, cols;
+    int32_t bps;         /* bytes per sample: 1, 2, 4, 8                     */
+    int32_t predictor;   /* 1 none, 2 horizontal differencing, 3 floating point */
+    int32_t compression; /* 1 stored, 5 LZW                                   */
+    int32_t tiled;       /* 1 tiles, 0 strips                                 */
+    int32_t chunk_rows;  /* TileLength or RowsPerStrip                        */
+    int32_t chunk_cols;  /* TileWidth (ignored for strips)                    */
+    int32_t big_endian;  /* samples stored most significant byte first        */
+} dtb_tiff_layout;
+size_t dtb_tiff_decode_workspace_bytes(const dtb_tiff_layout *lay, int64_t n_chunks);
+int dtb_tiff_decode_chunks(const dtb_tiff_layout *lay, const uint8_t *comp, const uint64_t *comp_off,
+                           const uint64_t *comp_len, int64_t first_chunk, int64_t n_chunks, void *out, void *ws,
+                           size_t ws_bytes, unsigned long long *status, void *stream);
+int dtb_selftest_tiff_decode_host(const dtb_tiff_layout *lay, const uint8_t *comp_host, const uint64_t *comp_off_host,
+                                  const uint64_t *comp_len_host, int64_t first_chunk, int64_t n_chunks, void *out_host,
+                                  unsigned long long *status_host);
+
 /* ---- benchmark support: synthetic DEM "dtb-synth-v1" + depression filling ---------------
  * No reference counterpart (its fixtures were conditioned by an external GIS,
  * Example/example.py:33-39).  Bit-identical to oracle/dt_condition.cpp. */

@@ -231,6 +231,105 @@ def test_errors_are_reported_not_guessed(tmp_path):
     assert not os.path.exists(tmp_path / "x.tif")
 
 
+def _decode_like_the_device(path, first=0, count=None):
+    """the tile-decoding kernel's per-lane code (csrc/tiffdecode.cu), run lane by lane on the CPU by the library's self-test
+    entry point: same geometry, LZW, byte order, predictor and store code the warps execute"""
+    from descriptools_b200 import _lib
+
+    with rio.open(path) as r:
+        lay, across, off, cnt = rio.chunk_table(r)
+        shape, dtype = r.shape, r.dtypes[0]
+    data = np.fromfile(path, dtype=np.uint8)
+    out = np.full(shape, 7, dtype=dtype)
+    status = ctypes.c_ulonglong(99)
+    n = off.size - first if count is None else count
+    rc = _lib.lib.dtb_selftest_tiff_decode_host(ctypes.byref(lay), data.ctypes.data, off[first:].ctypes.data, cnt[first:].ctypes.data,
+                                                first, n, out.ctypes.data, ctypes.byref(status))
+    assert rc == 0
+    return out, status.value, (lay, across)
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "int16", "uint32", "int64", "float32", "float64"])
+@pytest.mark.parametrize("layout", ["strips", "tiles"])
+@pytest.mark.parametrize("compress,predictor", [("none", 1), ("lzw", 1), ("lzw", 2), ("lzw", 3), ("none", 2)])
+def test_device_decoder_lane_code_on_the_cpu(tmp_path, dtype, layout, compress, predictor):
+    if predictor == 3 and np.dtype(dtype).kind != "f":
+        pytest.skip("floating-point predictor")
+    a = _rand((157, 203), dtype, seed=8)
+    path = tmp_path / "t.tif"
+    kw = dict(tiled=True, blockxsize=48, blockysize=64) if layout == "tiles" else dict(blockysize=7)
+    with rio.open(path, "w", width=203, height=157, dtype=dtype, compress=compress, predictor=predictor, **kw) as dst:
+        dst.write(a)
+    out, status, (lay, across) = _decode_like_the_device(path)
+    assert status == 0
+    np.testing.assert_array_equal(out, a)
+    # a range of chunks in the middle: only their cells are touched
+    first = across * 1 if layout == "tiles" else 5
+    count = across if layout == "tiles" else 9
+    out, status, _ = _decode_like_the_device(path, first, count)
+    r0, r1 = (64, 128) if layout == "tiles" else (35, 98)
+    assert status == 0
+    np.testing.assert_array_equal(out[r0:r1], a[r0:r1])
+    assert (out[:r0] == 7).all() and (out[r1:] == 7).all()
+
+
+def test_device_decoder_lane_code_big_endian_and_damage(tmp_path):
+    from PIL import Image
+
+    a = _rand((90, 70), "uint16", seed=2)
+    be = str(tmp_path / "mm.tif")
+    data = a.astype(">u2").tobytes()
+    entries = [(256, 3, 1, 70), (257, 3, 1, 90), (258, 3, 1, 16), (259, 3, 1, 1), (262, 3, 1, 1), (273, 4, 1, 8), (277, 3, 1, 1),
+               (278, 3, 1, 90), (279, 4, 1, len(data)), (339, 3, 1, 1)]
+    ifd = struct.pack(">H", len(entries))
+    for tag, typ, cnt, val in entries:
+        ifd += struct.pack(">HHI", tag, typ, cnt) + (struct.pack(">HH", val, 0) if typ == 3 else struct.pack(">I", val))
+    with open(be, "wb") as f:
+        f.write(b"MM" + struct.pack(">HI", 42, 8 + len(data)) + data + ifd + struct.pack(">I", 0))
+    out, status, _ = _decode_like_the_device(be)
+    assert status == 0
+    np.testing.assert_array_equal(out, a)
+    # libtiff's LZW with the horizontal predictor (strips), decoded by the lane code
+    p = str(tmp_path / "p.tif")
+    Image.fromarray(a).save(p, compression="tiff_lzw", tiffinfo={317: 2})
+    out, status, _ = _decode_like_the_device(p)
+    assert status == 0
+    np.testing.assert_array_equal(out, a)
+    # damage: truncate every chunk's byte count -> the first chunk is reported as short, nothing crashes
+    good = tmp_path / "good.tif"
+    with rio.open(good, "w", width=70, height=90, dtype="uint16", compress="lzw", tiled=True, blockxsize=32, blockysize=32) as dst:
+        dst.write(a)
+    from descriptools_b200 import _lib
+
+    with rio.open(good) as r:
+        lay, across, off, cnt = rio.chunk_table(r)
+    raw = np.fromfile(good, dtype=np.uint8)
+    out = np.zeros((90, 70), np.uint16)
+    st = ctypes.c_ulonglong(0)
+    half = (cnt // 2).astype(np.uint64)
+    assert _lib.lib.dtb_selftest_tiff_decode_host(ctypes.byref(lay), raw.ctypes.data, off.ctypes.data, half.ctypes.data, 0, off.size,
+                                                  out.ctypes.data, ctypes.byref(st)) == 0
+    assert st.value == ((0 + 1) << 3) | 3
+    # an absent chunk (byte count 0) reads as zeros, like GDAL's sparse files
+    cnt2 = cnt.copy()
+    cnt2[4] = 0
+    out = np.full((90, 70), 9, np.uint16)
+    _lib.lib.dtb_selftest_tiff_decode_host(ctypes.byref(lay), raw.ctypes.data, off.ctypes.data, cnt2.ctypes.data, 0, off.size,
+                                           out.ctypes.data, ctypes.byref(st))
+    want = a.copy()
+    want[32:64, 32:64] = 0
+    assert st.value == 0
+    np.testing.assert_array_equal(out, want)
+    # argument checks need no device
+    lay.compression = 8
+    assert _lib.lib.dtb_tiff_decode_workspace_bytes(ctypes.byref(lay), 4) == 0
+    assert _lib.lib.dtb_tiff_decode_chunks(ctypes.byref(lay), 1, 1, 1, 0, 1, 1, 1, 1 << 20, 1, None) == -4
+    lay.compression = 5
+    assert _lib.lib.dtb_tiff_decode_workspace_bytes(ctypes.byref(lay), 4) == 4 * (32 * 32 * 2 + 8 * 4096) + 256
+    assert _lib.lib.dtb_tiff_decode_chunks(ctypes.byref(lay), 1, 1, 1, 0, 1, 1, 1, 100, 1, None) == -3
+    assert _lib.lib.dtb_tiff_decode_chunks(ctypes.byref(lay), 1, 1, 1, 8, 2, 1, 1, 1 << 20, 1, None) == -1  # 9 chunks only
+
+
 @pytest.mark.skipif(not os.path.isdir(REF_EXAMPLE), reason="reference checkout not mounted (build container only)")
 def test_reference_fixtures_decode_to_the_golden_inputs(tmp_path):
     """Example/input/*.tif are GDAL-written LZW tiles; example.py:33-52 turns them into the arrays
@@ -323,3 +422,46 @@ def test_pipeline_from_file_to_files(tmp_path):
             assert src.crs == crs and src.res == (12.5, 12.5) and src.nodata == (0 if name == "d8" else -100)
             assert src.compression == "lzw" and src.block_shapes == [(256, 256)]
             np.testing.assert_array_equal(src.read(1), want[name], err_msg=name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,layout,compress,predictor", [("float32", "tiles", "lzw", 1), ("float32", "tiles", "lzw", 3), ("int16", "strips", "lzw", 2),
+                                                             ("uint8", "tiles", "lzw", 1), ("int32", "tiles", "none", 1), ("float64", "strips", "none", 1),
+                                                             ("int64", "tiles", "lzw", 2)])
+def test_tiles_decoded_on_the_device(tmp_path, dtype, layout, compress, predictor):
+    import torch
+
+    a = _rand((1000, 777), dtype, seed=12)
+    p = tmp_path / "in.tif"
+    kw = dict(tiled=True, blockxsize=128, blockysize=128) if layout == "tiles" else dict(blockysize=16)
+    with rio.open(p, "w", width=777, height=1000, dtype=dtype, compress=compress, predictor=predictor, **kw) as dst:
+        dst.write(a)
+    from descriptools_b200 import _lib
+
+    before = _lib.launch_count()
+    t = rio.read_to_device(p, decode="device", block_bytes=1 << 20)  # several spans: both staging buffers are reused
+    torch.cuda.synchronize()
+    assert _lib.launch_count() > before
+    np.testing.assert_array_equal(t.cpu().numpy(), a)
+    t = rio.read_to_device(p, decode="device")  # one span
+    np.testing.assert_array_equal(t.cpu().numpy(), a)
+
+
+@pytest.mark.gpu
+def test_device_decoder_reports_damage_and_refuses_what_it_cannot_do(tmp_path):
+    a = _rand((300, 300), "uint8", seed=13, smooth=False)
+    p = tmp_path / "d.tif"
+    with rio.open(p, "w", width=300, height=300, dtype="uint8", compress="deflate", tiled=True, blockxsize=64, blockysize=64) as dst:
+        dst.write(a)
+    with pytest.raises(rio.RasterError, match="deflate"):
+        rio.read_to_device(p, decode="device")
+    q = tmp_path / "l.tif"
+    with rio.open(q, "w", width=300, height=300, dtype="uint8", compress="lzw", tiled=True, blockxsize=64, blockysize=64) as dst:
+        dst.write(a)
+    raw = bytearray(q.read_bytes())
+    with rio.open(q) as r:
+        _, _, off, cnt = rio.chunk_table(r)
+    raw[int(off[3]) + 2:int(off[3]) + int(cnt[3])] = b"\xff" * (int(cnt[3]) - 2)  # codes far beyond the table
+    q.write_bytes(bytes(raw))
+    with pytest.raises(rio.RasterError, match="chunk 3"):
+        rio.read_to_device(q, decode="device")
