@@ -465,7 +465,7 @@ int interpret(dtbio_reader *r) {
 
 struct Scratch {
     std::vector<uint8_t> comp, raw, tmp;
-    std::vector<dtb::LzwSlot> lzw;
+    std::vector<dtb::LzwWideSlot> lzw;
     LzwEncoder *enc = nullptr;
     ~Scratch() { delete enc; }
 };

@@ -2,15 +2,17 @@
 //
 // The reference lets GDAL decode its rasters on one host thread (rio.open(p).read(1), example.py:33-39).  A
 // 40 000 x 40 000 DEM is ~10^5 independent LZW tiles: here the compressed tiles travel over PCIe as they lie in
-// the file (a fraction of the decoded bytes) and every tile is decoded by one warp -- lane 0 runs the serial LZW
-// recurrence (lzw.cuh, the same function the host codec uses) into a per-warp scratch chunk that stays in L2, then
-// the 32 lanes undo the predictor one row each and store the rows to the raster together.  Thousands of tiles are
+// the file (a fraction of the decoded bytes) and every tile is decoded by one warp -- the lanes run the serial LZW
+// recurrence in lock step (lzw.cuh, the same function the host codec uses: uniform control flow, broadcast loads,
+// string copies spread over the lanes) into a per-warp scratch chunk, then undo the predictor one row each and
+// store the rows to the raster together.  Thousands of tiles are
 // in flight at once; nothing here is bandwidth-bound, the point is to take the decode off the host cores and to
 // halve the bytes crossing PCIe.
 //
 // Everything a lane does is in three __host__ __device__ phase functions; dtb_selftest_tiff_decode_host() runs
 // the same functions lane by lane on the CPU so the tile geometry, predictor and store logic are tested without a
 // device (tests/test_raster_io.py).  The package itself never calls the self-test.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -23,7 +25,7 @@ namespace {
 
 constexpr int TD_WARPS = 4;  // warps per CTA
 constexpr int TD_LANES = 32;
-constexpr int TD_CTAS_PER_SM = 8;
+constexpr int TD_CTAS_PER_SM = 8;  // 64 registers x 128 threads: 8 CTAs fill the register file
 
 struct ChunkGeom {
     int64_t cy, cx;        // chunk row / column
@@ -60,17 +62,18 @@ __host__ __device__ inline size_t td_scratch_bytes(const dtb_tiff_layout &L)
 {
     const int64_t cw = L.tiled ? L.chunk_cols : L.cols;
     const size_t raw = (size_t)cw * L.bps * (size_t)L.chunk_rows;
-    return ((raw + 15) & ~(size_t)15) + sizeof(LzwSlot) * kLzwTableSlots;
+    return ((raw + 15) & ~(size_t)15) + sizeof(LzwPackedSlot) * kLzwTableSlots;
 }
 
 // status word: 0 = ok, else ((chunk + 1) << 3) | reason   (reason 1 corrupt, 2 old-style LZW, 3 short chunk)
 __host__ __device__ inline long long td_status(int64_t chunk, int reason) { return (long long)(((chunk + 1) << 3) | reason); }
 
-// ---- phase 1 (lane 0): compressed bytes -> scratch chunk.  Returns bytes produced or a negative reason. ----
+// ---- phase 1 (all lanes in lock step): compressed bytes -> scratch chunk.  Returns bytes produced or a negative
+// reason, the same value in every lane.  [lane0, lane1) of nlanes: see lzw.cuh. ----
 __host__ __device__ inline int64_t td_phase1(const dtb_tiff_layout &L, const ChunkGeom &g, const uint8_t *comp, uint64_t len,
-                                             uint8_t *buf, LzwSlot *tab)
+                                             uint8_t *buf, LzwPackedSlot *tab, int lane0, int lane1)
 {
-    if (L.compression == 5) return lzw_decode(comp, (size_t)len, buf, (size_t)g.raw_bytes, tab);
+    if (L.compression == 5) return lzw_decode(comp, (size_t)len, buf, (size_t)g.raw_bytes, tab, lane0, lane1, TD_LANES);
     return -1;
 }
 
@@ -170,7 +173,7 @@ tiff_decode_kernel(dtb_tiff_layout L, const uint8_t *__restrict__ comp, const ui
     if (warp >= n_warps) return;
     const size_t per = td_scratch_bytes(L);
     uint8_t *buf = ws + (size_t)warp * per;
-    LzwSlot *tab = reinterpret_cast<LzwSlot *>(buf + (per - sizeof(LzwSlot) * kLzwTableSlots));
+    LzwPackedSlot *tab = reinterpret_cast<LzwPackedSlot *>(buf + (per - sizeof(LzwPackedSlot) * kLzwTableSlots));
     for (int64_t c = warp; c < n_chunks; c += n_warps) {
         const ChunkGeom g = td_geom(L, first_chunk + c);
         const uint64_t off = comp_off[c], len = comp_len[c];
@@ -183,8 +186,7 @@ tiff_decode_kernel(dtb_tiff_layout L, const uint8_t *__restrict__ comp, const ui
             got = (long long)(len < (uint64_t)g.raw_bytes ? len : (uint64_t)g.raw_bytes);
             td_copy_stored(comp + off, (uint64_t)got, buf, lane);
         } else {
-            if (lane == 0) got = td_phase1(L, g, comp + off, len, buf, tab);
-            got = __shfl_sync(0xffffffffu, got, 0);
+            got = td_phase1(L, g, comp + off, len, buf, tab, lane, lane + 1);
         }
         if (got < g.row_bytes * g.data_rows) {
             if (lane == 0) atomicCAS(status, 0ull, (unsigned long long)td_status(first_chunk + c, got == -2 ? 2 : got < 0 ? 1 : 3));
@@ -198,6 +200,18 @@ tiff_decode_kernel(dtb_tiff_layout L, const uint8_t *__restrict__ comp, const ui
     }
 }
 
+// resident CTAs per SM: TD_CTAS_PER_SM, or the tuning override DTB_TIFF_CTAS_PER_SM=1..8 (fewer warps keep the string
+// tables in L2, more warps hide more latency)
+int64_t td_warp_cap()
+{
+    int ctas = TD_CTAS_PER_SM;
+    if (const char *e = getenv("DTB_TIFF_CTAS_PER_SM")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= TD_CTAS_PER_SM) ctas = v;
+    }
+    return (int64_t)kNumSMs * ctas * TD_WARPS;
+}
+
 int td_validate(const dtb_tiff_layout *L)
 {
     if (!L || L->rows <= 0 || L->cols <= 0 || L->chunk_rows <= 0) return DTB_ERR_INVALID;
@@ -205,6 +219,8 @@ int td_validate(const dtb_tiff_layout *L)
     if (L->predictor < 1 || L->predictor > 3) return DTB_ERR_INVALID;
     if (L->tiled && L->chunk_cols <= 0) return DTB_ERR_INVALID;
     if (L->compression != 1 && L->compression != 5) return DTB_ERR_UNSUPPORTED;
+    const int64_t cw = L->tiled ? L->chunk_cols : L->cols;
+    if ((size_t)cw * L->bps * (size_t)L->chunk_rows > LzwPackedSlot::kMaxChunkBytes) return DTB_ERR_UNSUPPORTED;  // 20-bit offsets
     return DTB_OK;
 }
 
@@ -218,7 +234,7 @@ extern "C" {
 size_t dtb_tiff_decode_workspace_bytes(const dtb_tiff_layout *lay, int64_t n_chunks)
 {
     if (td_validate(lay) != DTB_OK || n_chunks <= 0) return 0;
-    const int64_t cap = (int64_t)kNumSMs * TD_CTAS_PER_SM * TD_WARPS;
+    const int64_t cap = (int64_t)kNumSMs * TD_CTAS_PER_SM * TD_WARPS;  // the most any setting uses
     const int64_t warps = n_chunks < cap ? n_chunks : cap;
     return (size_t)warps * td_scratch_bytes(*lay) + 256;
 }
@@ -236,7 +252,7 @@ int dtb_tiff_decode_chunks(const dtb_tiff_layout *lay, const uint8_t *comp, cons
     const size_t per = td_scratch_bytes(*lay);
     if (ws_bytes < per + 256) return DTB_ERR_WORKSPACE;
     int64_t warps = (int64_t)((ws_bytes - 256) / per);
-    const int64_t cap = (int64_t)kNumSMs * TD_CTAS_PER_SM * TD_WARPS;
+    const int64_t cap = td_warp_cap();
     if (warps > cap) warps = cap;
     if (warps > n_chunks) warps = n_chunks;
     // scratch chunks start 256-byte aligned
@@ -259,7 +275,7 @@ int dtb_selftest_tiff_decode_host(const dtb_tiff_layout *lay, const uint8_t *com
     const dtb_tiff_layout &L = *lay;
     std::vector<uint8_t> scratch(td_scratch_bytes(L));
     uint8_t *buf = scratch.data();
-    LzwSlot *tab = reinterpret_cast<LzwSlot *>(buf + (scratch.size() - sizeof(LzwSlot) * kLzwTableSlots));
+    LzwPackedSlot *tab = reinterpret_cast<LzwPackedSlot *>(buf + (scratch.size() - sizeof(LzwPackedSlot) * kLzwTableSlots));
     *status_host = 0;
     for (int64_t c = 0; c < n_chunks; ++c) {
         const ChunkGeom g = td_geom(L, first_chunk + c);
@@ -273,7 +289,7 @@ int dtb_selftest_tiff_decode_host(const dtb_tiff_layout *lay, const uint8_t *com
             got = (long long)(len < (uint64_t)g.raw_bytes ? len : (uint64_t)g.raw_bytes);
             for (int lane = 0; lane < TD_LANES; ++lane) td_copy_stored(comp_host + off, (uint64_t)got, buf, lane);
         } else {
-            got = td_phase1(L, g, comp_host + off, len, buf, tab);
+            got = td_phase1(L, g, comp_host + off, len, buf, tab, 0, TD_LANES);
         }
         if (got < g.row_bytes * g.data_rows) {
             if (*status_host == 0) *status_host = (unsigned long long)td_status(first_chunk + c, got == -2 ? 2 : got < 0 ? 1 : 3);

@@ -272,7 +272,7 @@ int dtb_minmax_scale(const void *mat, int mat_dtype, int64_t n, double mn, doubl
  * striped single-band files that are stored or LZW-compressed (what GDAL wrote for 12_dem / 12_fdr / 12_fac):
  * the compressed chunks are copied to the device as they lie in the file and one warp decodes each chunk
  * (LZW, byte order, predictor 2 / 3) into the raster.  File parsing stays on the host (include/dtb200_io.h).
- *   lay          geometry of the file: chunk i covers chunk-row i / across, chunk-column i % across
+ *   lay          geometry of the file (a chunk decodes to at most 1 MiB: DTB_ERR_UNSUPPORTED otherwise); chunk i covers chunk-row i / across, chunk-column i % across
  *                (across = ceil(cols / chunk_cols) for tiles, 1 for strips); tiles are stored whole, the last
  *                strip holds only the rows that exist.
  *   comp         device buffer with the compressed bytes; chunk first_chunk + i is comp[comp_off[i] ..
