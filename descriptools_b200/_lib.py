@@ -133,6 +133,12 @@ SIGNATURES = {
                                        c_size_t, c_void_p, c_void_p]),
     "dtb_selftest_tiff_decode_host": (c_int, [POINTER(TiffLayout), c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                                               c_void_p]),
+    "dtb_tiff_encode_bound": (c_size_t, [POINTER(TiffLayout)]),
+    "dtb_tiff_encode_workspace_bytes": (c_size_t, [POINTER(TiffLayout), c_int64]),
+    "dtb_tiff_encode_chunks": (c_int, [POINTER(TiffLayout), c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
+                                       c_void_p]),
+    "dtb_tiff_pack_chunks": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dtb_selftest_tiff_encode_host": (c_int, [POINTER(TiffLayout), c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "dtb_synth_dem_f32": (c_int, [c_int64, c_int64, c_int64, c_uint32, POINTER(c_float), c_float, c_float, c_float,
                                   c_float, c_void_p, c_void_p]),
     "dtb_fill_workspace_bytes": (c_size_t, [c_int64, c_int64]),

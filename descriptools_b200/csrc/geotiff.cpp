@@ -8,7 +8,7 @@
 // or encoded by a team of threads, one chunk at a time each, straight into / out of the caller's (pinned)
 // buffer; the Python side (descriptools_b200/raster.py) overlaps that with the host<->device copies.
 #include "../../include/dtb200_io.h"
-#include "lzw.cuh"  // the decoder shared with the device tile decoder (tiffdecode.cu)
+#include "lzw.cuh"  // the decoder shared with the device tile decoder (tiffcodec.cu)
 
 #include <fcntl.h>
 #include <sys/stat.h>
@@ -421,6 +421,8 @@ int interpret(dtbio_reader *r) {
     in.compression = comp;
     in.predictor = (int)tag_uint(r, 317, 1);
     if (in.predictor < 1 || in.predictor > 3) return fail(DTBIO_ERR_UNSUPPORTED, "unknown predictor");
+    // the predictor belongs to the LZW / Deflate codecs; libtiff and GDAL ignore the tag on stored and PackBits data
+    if (comp == DTBIO_COMP_NONE || comp == DTBIO_COMP_PACKBITS) in.predictor = 1;
     if (in.predictor == 3 && in.dtype != DTBIO_F32 && in.dtype != DTBIO_F64) return fail(DTBIO_ERR_FORMAT, "floating-point predictor on integer samples");
     if (tag_uint(r, 266, 1) != 1) return fail(DTBIO_ERR_UNSUPPORTED, "FillOrder 2");
     in.bigtiff = r->big;
@@ -782,6 +784,7 @@ int dtbio_create(const char *path, const dtbio_info *info, dtbio_writer **out) {
     if (comp != DTBIO_COMP_NONE && comp != DTBIO_COMP_LZW && comp != DTBIO_COMP_DEFLATE) return fail(DTBIO_ERR_UNSUPPORTED, "the writer compresses with LZW or Deflate only");
     int pred = info->predictor == 0 ? 1 : info->predictor;
     if (pred < 1 || pred > 3) return fail(DTBIO_ERR_INVALID, "bad predictor");
+    if (comp == DTBIO_COMP_NONE) pred = 1;  // a predictor without a codec is not part of the format (GDAL drops it too)
     if (pred == 3 && info->dtype != DTBIO_F32 && info->dtype != DTBIO_F64) return fail(DTBIO_ERR_INVALID, "predictor 3 needs floating-point samples");
     if ((info->tile_rows > 0) != (info->tile_cols > 0)) return fail(DTBIO_ERR_INVALID, "give both tile sizes or neither");
     if (info->tile_rows > 0 && ((info->tile_rows % 16) || (info->tile_cols % 16))) return fail(DTBIO_ERR_INVALID, "tile sizes must be multiples of 16");
@@ -840,6 +843,26 @@ int dtbio_write_rows(dtbio_writer *w, int64_t row0, int64_t nrows, const void *s
     return run_team(n, t, [&](int64_t i, int worker) {
         return encode_chunk(w, cy0 * L.across + i, row0, (const uint8_t *)src, stride, scratch[(size_t)worker]);
     });
+}
+
+int dtbio_write_encoded(dtbio_writer *w, int64_t first_chunk, int64_t n_chunks, const void *blob, int64_t blob_bytes,
+                        const int64_t *offsets, const int64_t *sizes) {
+    if (!w || n_chunks < 0 || first_chunk < 0 || blob_bytes < 0) return fail(DTBIO_ERR_INVALID, "bad argument");
+    if (n_chunks == 0) return DTBIO_OK;
+    if (!blob || !offsets || !sizes) return fail(DTBIO_ERR_INVALID, "null argument");
+    if (first_chunk + n_chunks > w->lay.n_chunks()) return fail(DTBIO_ERR_INVALID, "chunk range outside the raster");
+    for (int64_t i = 0; i < n_chunks; ++i) {
+        if (sizes[i] <= 0 || offsets[i] < 0 || offsets[i] + sizes[i] > blob_bytes) return fail(DTBIO_ERR_INVALID, "chunk " + std::to_string(first_chunk + i) + " lies outside the blob");
+        if (w->counts[(size_t)(first_chunk + i)]) return fail(DTBIO_ERR_ORDER, "chunk written twice");
+    }
+    uint64_t at = w->pos.fetch_add(((uint64_t)blob_bytes + 1) & ~(uint64_t)1);
+    if (!w->big && at + (uint64_t)blob_bytes > 0xFFFFFFF0ull) return fail(DTBIO_ERR_UNSUPPORTED, "classic TIFF would exceed 4 GB: create the file with bigtiff = 1");
+    if (!pwrite_all(w->fd, blob, (size_t)blob_bytes, at)) return fail(DTBIO_ERR_IO, std::string("write failed: ") + strerror(errno));
+    for (int64_t i = 0; i < n_chunks; ++i) {
+        w->offsets[(size_t)(first_chunk + i)] = at + (uint64_t)offsets[i];
+        w->counts[(size_t)(first_chunk + i)] = (uint64_t)sizes[i];
+    }
+    return DTBIO_OK;
 }
 
 int dtbio_writer_info(const dtbio_writer *w, dtbio_info *info) {

@@ -1,5 +1,5 @@
 // lzw.cuh -- TIFF-flavoured LZW decoding, one source for the host codec (geotiff.cpp) and the device tile
-// decoder (tiffdecode.cu).
+// decoder (tiffcodec.cu).
 //
 // TIFF 6.0 section 13: MSB-first codes of 9..12 bits, Clear = 256, EndOfInformation = 257, the code width
 // grows one code early.  The string table does not store strings: every string the coder can name has
@@ -157,6 +157,86 @@ DTB_LZW_HD int64_t lzw_decode(const uint8_t *in, size_t n, uint8_t *out, size_t 
         op += k;
     }
     return (int64_t)op;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Encoder for the device (and its CPU replay).  Any parse into table strings is a valid stream as long as the
+// code numbering stays in step with the decoder's (one new entry per code), so the dictionary may forget:
+// it is a 2-way bucketed hash of (prefix code, byte) -> code that simply overwrites on conflict, and a table
+// reset is a bump of the generation number stored in every slot instead of a sweep.  Slots are 64-bit words
+// [63..32 generation | 31..12 prefix << 8 | byte | 11..0 code]; `tab` holds kLzwHashSlots of them, zeroed once;
+// `gen` lives across calls (per warp) and starts at 0.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kLzwHashSlots = 8192;
+
+// worst case: every byte its own 12-bit code, plus Clear / EOI codes and the final flush
+DTB_LZW_HD size_t lzw_encode_bound(size_t n) { return n + n / 2 + n / 2048 + 16; }
+
+// Returns the number of bytes written to `out`, or -1 if `cap` is too small.
+DTB_LZW_HD int64_t lzw_encode(const uint8_t *in, size_t n, uint8_t *out, size_t cap, uint64_t *tab, uint32_t &gen)
+{
+    uint64_t acc = 0;
+    int have = 0;
+    size_t op = 0;
+    bool overflow = false;
+    int nbits = 9, next = 258, maxcode = 511;
+    auto put = [&](int code) {
+        acc = (acc << nbits) | (uint64_t)code;
+        have += nbits;
+        while (have >= 8) {
+            if (op < cap) out[op] = (uint8_t)(acc >> (have - 8));  // every lane stores the same byte
+            else overflow = true;
+            ++op;
+            have -= 8;
+        }
+    };
+    ++gen;
+    put(256);
+    if (n > 0) {
+        int ent = in[0];
+        for (size_t i = 1; i < n; ++i) {
+            const uint32_t c = in[i];
+            const uint32_t key = ((uint32_t)ent << 8) | c;
+            const uint64_t tag = ((uint64_t)gen << 20) | key;
+            const uint32_t b = ((key * 2654435761u) >> 20) & (uint32_t)(kLzwHashSlots / 2 - 1);
+            const uint64_t s0 = tab[2 * b], s1 = tab[2 * b + 1];
+            if ((s0 >> 12) == tag) { ent = (int)(s0 & 0xFFFu); continue; }
+            if ((s1 >> 12) == tag) { ent = (int)(s1 & 0xFFFu); continue; }
+            put(ent);
+            const uint64_t slot = (tag << 12) | (uint64_t)next;
+            // a way left over from an earlier generation first, else the one the byte picks
+            const uint32_t way = (uint32_t)(s0 >> 32) != gen ? 0u : (uint32_t)(s1 >> 32) != gen ? 1u : (c & 1u);
+            tab[2 * b + way] = slot;
+            ent = (int)c;
+            ++next;
+            if (next == 4094) {  // table full: Clear, and forget everything by moving to the next generation
+                put(256);
+                ++gen;
+                nbits = 9;
+                next = 258;
+                maxcode = 511;
+            } else if (next > maxcode) {
+                ++nbits;
+                maxcode = (1 << nbits) - 1;
+            }
+        }
+        put(ent);
+        // the decoder makes one more entry for that code before it reads EOI
+        ++next;
+        if (next == 4094) {
+            put(256);
+            nbits = 9;
+        } else if (next > maxcode) {
+            ++nbits;
+        }
+    }
+    put(257);
+    if (have > 0) {
+        if (op < cap) out[op] = (uint8_t)((acc << (8 - have)) & 0xFFu);
+        else overflow = true;
+        ++op;
+    }
+    return overflow ? -1 : (int64_t)op;
 }
 
 }  // namespace dtb

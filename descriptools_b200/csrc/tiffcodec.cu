@@ -1,4 +1,4 @@
-// tiffdecode.cu -- GeoTIFF chunks decoded on the device.
+// tiffcodec.cu -- GeoTIFF chunks decoded and encoded on the device.
 //
 // The reference lets GDAL decode its rasters on one host thread (rio.open(p).read(1), example.py:33-39).  A
 // 40 000 x 40 000 DEM is ~10^5 independent LZW tiles: here the compressed tiles travel over PCIe as they lie in
@@ -9,9 +9,14 @@
 // in flight at once; nothing here is bandwidth-bound, the point is to take the decode off the host cores and to
 // halve the bytes crossing PCIe.
 //
-// Everything a lane does is in three __host__ __device__ phase functions; dtb_selftest_tiff_decode_host() runs
-// the same functions lane by lane on the CPU so the tile geometry, predictor and store logic are tested without a
-// device (tests/test_raster_io.py).  The package itself never calls the self-test.
+// The way back (example.py:216-217 writes one class map; the chain writes seven rasters) mirrors it: a warp gathers
+// its tile from the raster, applies the predictor, LZW-encodes it (lzw.cuh: forgetful 2-way hash dictionary, table
+// resets by generation number) into a worst-case slot; a second kernel packs the streams back to back so that one
+// device-to-host copy and one file write carry a whole group of tiles.
+//
+// Everything a lane does is in __host__ __device__ phase functions; dtb_selftest_tiff_decode_host() /
+// dtb_selftest_tiff_encode_host() run the same functions lane by lane on the CPU so the tile geometry, predictor,
+// coder and store logic are tested without a device (tests/test_raster_io.py).  The package never calls them.
 #include <stdlib.h>
 #include <string.h>
 
@@ -200,6 +205,125 @@ tiff_decode_kernel(dtb_tiff_layout L, const uint8_t *__restrict__ comp, const ui
     }
 }
 
+
+// =====================================================================================================
+// encoding
+// =====================================================================================================
+__host__ __device__ inline size_t te_raw_bytes(const dtb_tiff_layout &L)
+{
+    const int64_t cw = L.tiled ? L.chunk_cols : L.cols;
+    return (size_t)cw * L.bps * (size_t)L.chunk_rows;
+}
+
+// bytes reserved per encoded chunk
+__host__ __device__ inline size_t te_bound(const dtb_tiff_layout &L)
+{
+    const size_t raw = te_raw_bytes(L);
+    return ((L.compression == 5 ? lzw_encode_bound(raw) : raw) + 15) & ~(size_t)15;
+}
+
+__host__ __device__ inline size_t te_scratch_bytes(const dtb_tiff_layout &L)
+{
+    return ((te_raw_bytes(L) + 15) & ~(size_t)15) + sizeof(uint64_t) * kLzwHashSlots;
+}
+
+// ---- phase 1 (all lanes per row): raster -> scratch chunk.  A partial tile is padded by repeating its last
+// column / row (never read back, compresses well); predictor 3 lays the row out as byte planes, most significant
+// byte of every sample first. ----
+__host__ __device__ inline void te_gather(const dtb_tiff_layout &L, const ChunkGeom &g, const uint8_t *raster, uint8_t *buf, int lane)
+{
+    const int64_t width = g.row_bytes / L.bps;
+    for (int64_t r = 0; r < g.stored_rows; ++r) {
+        const int64_t rr = r < g.data_rows ? r : g.data_rows - 1;
+        const uint8_t *src = raster + ((g.cy * L.chunk_rows + rr) * L.cols + g.x0) * L.bps;
+        uint8_t *row = buf + r * g.row_bytes;
+        for (int64_t i = lane; i < width; i += TD_LANES) {
+            const int64_t ii = i < g.ncols ? i : g.ncols - 1;
+            for (int b = 0; b < L.bps; ++b) {
+                const uint8_t v = src[ii * L.bps + b];
+                if (L.predictor == 3) row[(int64_t)(L.bps - 1 - b) * width + i] = v;
+                else row[i * L.bps + b] = v;
+            }
+        }
+    }
+}
+
+template <typename T>
+__host__ __device__ inline void te_hdiff(uint8_t *row, int64_t width)
+{
+    T *p = reinterpret_cast<T *>(row);
+    for (int64_t i = width - 1; i >= 1; --i) p[i] = (T)(p[i] - p[i - 1]);
+}
+
+// ---- phase 2 (one row per lane): predictor, in place ----
+__host__ __device__ inline void te_predict(const dtb_tiff_layout &L, const ChunkGeom &g, uint8_t *buf, int lane)
+{
+    const int64_t width = g.row_bytes / L.bps;
+    for (int64_t r = lane; r < g.stored_rows; r += TD_LANES) {
+        uint8_t *row = buf + r * g.row_bytes;
+        if (L.predictor == 2) {
+            switch (L.bps) {
+                case 1: te_hdiff<uint8_t>(row, width); break;
+                case 2: te_hdiff<uint16_t>(row, width); break;
+                case 4: te_hdiff<uint32_t>(row, width); break;
+                case 8: te_hdiff<unsigned long long>(row, width); break;
+            }
+        } else if (L.predictor == 3) {
+            for (int64_t i = g.row_bytes - 1; i >= 1; --i) row[i] = (uint8_t)(row[i] - row[i - 1]);
+        }
+    }
+}
+
+// ---- phase 3: scratch chunk -> encoded slot; returns the encoded size (the same in every lane) ----
+__host__ __device__ inline int64_t te_encode(const dtb_tiff_layout &L, const ChunkGeom &g, const uint8_t *buf, uint8_t *slot, size_t bound,
+                                             uint64_t *tab, uint32_t &gen, int lane0, int lane1)
+{
+    if (L.compression == 5) return lzw_encode(buf, (size_t)g.raw_bytes, slot, bound, tab, gen);
+    for (int l = lane0; l < lane1; ++l)
+        for (int64_t i = l; i < g.raw_bytes; i += TD_LANES) slot[i] = buf[i];
+    return g.raw_bytes;
+}
+
+__global__ void __launch_bounds__(TD_WARPS *TD_LANES)
+tiff_encode_kernel(dtb_tiff_layout L, const uint8_t *__restrict__ raster, int64_t first_chunk, int64_t n_chunks,
+                   uint8_t *__restrict__ enc, long long *__restrict__ sizes, uint8_t *__restrict__ ws, int64_t n_warps)
+{
+    const int lane = threadIdx.x % TD_LANES;
+    const int64_t warp = (int64_t)blockIdx.x * TD_WARPS + threadIdx.x / TD_LANES;
+    if (warp >= n_warps) return;
+    const size_t per = te_scratch_bytes(L), bound = te_bound(L);
+    uint8_t *buf = ws + (size_t)warp * per;
+    uint64_t *tab = reinterpret_cast<uint64_t *>(buf + (per - sizeof(uint64_t) * kLzwHashSlots));
+    for (int i = lane; i < kLzwHashSlots; i += TD_LANES) tab[i] = 0;  // generations restart with every launch
+    uint32_t gen = 0;
+    __syncwarp();
+    for (int64_t c = warp; c < n_chunks; c += n_warps) {
+        const ChunkGeom g = td_geom(L, first_chunk + c);
+        te_gather(L, g, raster, buf, lane);
+        __syncwarp();
+        te_predict(L, g, buf, lane);
+        __syncwarp();
+        const int64_t n = te_encode(L, g, buf, enc + (size_t)c * bound, bound, tab, gen, lane, lane + 1);
+        if (lane == 0) sizes[c] = n;
+        __syncwarp();  // the scratch chunk is reused by this warp's next chunk
+    }
+}
+
+constexpr int TP_THREADS = 256;
+
+// encoded slots -> one contiguous blob (chunk c at blob + offsets[c])
+__global__ void __launch_bounds__(TP_THREADS)
+tiff_pack_kernel(const uint8_t *__restrict__ enc, size_t bound, const long long *__restrict__ sizes,
+                 const long long *__restrict__ offsets, int64_t n_chunks, uint8_t *__restrict__ blob)
+{
+    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const uint8_t *src = enc + (size_t)c * bound;
+        uint8_t *dst = blob + offsets[c];
+        const long long n = sizes[c];
+        for (long long i = threadIdx.x; i < n; i += TP_THREADS) dst[i] = src[i];
+    }
+}
+
 // resident CTAs per SM: TD_CTAS_PER_SM, or the tuning override DTB_TIFF_CTAS_PER_SM=1..8 (fewer warps keep the string
 // tables in L2, more warps hide more latency)
 int64_t td_warp_cap()
@@ -212,13 +336,30 @@ int64_t td_warp_cap()
     return (int64_t)kNumSMs * ctas * TD_WARPS;
 }
 
-int td_validate(const dtb_tiff_layout *L)
+int td_validate_common(const dtb_tiff_layout *L)
 {
     if (!L || L->rows <= 0 || L->cols <= 0 || L->chunk_rows <= 0) return DTB_ERR_INVALID;
     if (L->bps != 1 && L->bps != 2 && L->bps != 4 && L->bps != 8) return DTB_ERR_INVALID;
     if (L->predictor < 1 || L->predictor > 3) return DTB_ERR_INVALID;
     if (L->tiled && L->chunk_cols <= 0) return DTB_ERR_INVALID;
     if (L->compression != 1 && L->compression != 5) return DTB_ERR_UNSUPPORTED;
+    if (L->compression == 1 && L->predictor != 1) return DTB_ERR_INVALID;  // the predictor belongs to the codec
+    return DTB_OK;
+}
+
+int te_validate(const dtb_tiff_layout *L)
+{
+    const int v = td_validate_common(L);
+    if (v != DTB_OK) return v;
+    if (L->big_endian) return DTB_ERR_UNSUPPORTED;  // files are written little-endian
+    if (L->predictor == 3 && L->bps < 4) return DTB_ERR_INVALID;
+    return DTB_OK;
+}
+
+int td_validate(const dtb_tiff_layout *L)
+{
+    const int v = td_validate_common(L);
+    if (v != DTB_OK) return v;
     const int64_t cw = L->tiled ? L->chunk_cols : L->cols;
     if ((size_t)cw * L->bps * (size_t)L->chunk_rows > LzwPackedSlot::kMaxChunkBytes) return DTB_ERR_UNSUPPORTED;  // 20-bit offsets
     return DTB_OK;
@@ -297,6 +438,73 @@ int dtb_selftest_tiff_decode_host(const dtb_tiff_layout *lay, const uint8_t *com
         }
         for (int lane = 0; lane < TD_LANES; ++lane) td_phase2(L, g, buf, lane);
         for (int lane = 0; lane < TD_LANES; ++lane) td_phase3(L, g, buf, (uint8_t *)out_host, lane);
+    }
+    return DTB_OK;
+}
+
+size_t dtb_tiff_encode_bound(const dtb_tiff_layout *lay) { return te_validate(lay) == DTB_OK ? te_bound(*lay) : 0; }
+
+size_t dtb_tiff_encode_workspace_bytes(const dtb_tiff_layout *lay, int64_t n_chunks)
+{
+    if (te_validate(lay) != DTB_OK || n_chunks <= 0) return 0;
+    const int64_t cap = (int64_t)kNumSMs * TD_CTAS_PER_SM * TD_WARPS;
+    const int64_t warps = n_chunks < cap ? n_chunks : cap;
+    return (size_t)warps * te_scratch_bytes(*lay) + 256;
+}
+
+int dtb_tiff_encode_chunks(const dtb_tiff_layout *lay, const void *raster, int64_t first_chunk, int64_t n_chunks, uint8_t *enc,
+                           long long *sizes, void *ws, size_t ws_bytes, void *stream)
+{
+    const int v = te_validate(lay);
+    if (v != DTB_OK) return v;
+    if (n_chunks == 0) return DTB_OK;
+    if (!raster || !enc || !sizes || !ws || n_chunks < 0 || first_chunk < 0) return DTB_ERR_INVALID;
+    const int64_t total = td_across(*lay) * ((lay->rows + lay->chunk_rows - 1) / lay->chunk_rows);
+    if (first_chunk + n_chunks > total) return DTB_ERR_INVALID;
+    const size_t per = te_scratch_bytes(*lay);
+    if (ws_bytes < per + 256) return DTB_ERR_WORKSPACE;
+    int64_t warps = (int64_t)((ws_bytes - 256) / per);
+    const int64_t cap = td_warp_cap();
+    if (warps > cap) warps = cap;
+    if (warps > n_chunks) warps = n_chunks;
+    uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    const unsigned blocks = (unsigned)((warps + TD_WARPS - 1) / TD_WARPS);
+    cudaStream_t st = as_stream(stream);
+    DTB_KERNEL("tiff_encode_kernel", st,
+               tiff_encode_kernel<<<blocks, TD_WARPS * TD_LANES, 0, st>>>(*lay, (const uint8_t *)raster, first_chunk, n_chunks, enc,
+                                                                         sizes, base, warps));
+    return DTB_OK;
+}
+
+int dtb_tiff_pack_chunks(const uint8_t *enc, size_t bound, const long long *sizes, const long long *offsets, int64_t n_chunks,
+                         uint8_t *blob, void *stream)
+{
+    if (n_chunks == 0) return DTB_OK;
+    if (!enc || !sizes || !offsets || !blob || n_chunks < 0 || bound == 0) return DTB_ERR_INVALID;
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    const unsigned blocks = (unsigned)(n_chunks < cap ? n_chunks : cap);
+    cudaStream_t st = as_stream(stream);
+    DTB_KERNEL("tiff_pack_kernel", st, tiff_pack_kernel<<<blocks, TP_THREADS, 0, st>>>(enc, bound, sizes, offsets, n_chunks, blob));
+    return DTB_OK;
+}
+
+int dtb_selftest_tiff_encode_host(const dtb_tiff_layout *lay, const void *raster_host, int64_t first_chunk, int64_t n_chunks,
+                                  uint8_t *enc_host, long long *sizes_host)
+{
+    const int v = te_validate(lay);
+    if (v != DTB_OK) return v;
+    if (!raster_host || !enc_host || !sizes_host || n_chunks < 0) return DTB_ERR_INVALID;
+    const dtb_tiff_layout &L = *lay;
+    const size_t per = te_scratch_bytes(L), bound = te_bound(L);
+    std::vector<uint8_t> scratch(per, 0);
+    uint8_t *buf = scratch.data();
+    uint64_t *tab = reinterpret_cast<uint64_t *>(buf + (per - sizeof(uint64_t) * kLzwHashSlots));
+    uint32_t gen = 0;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const ChunkGeom g = td_geom(L, first_chunk + c);
+        for (int lane = 0; lane < TD_LANES; ++lane) te_gather(L, g, (const uint8_t *)raster_host, buf, lane);
+        for (int lane = 0; lane < TD_LANES; ++lane) te_predict(L, g, buf, lane);
+        sizes_host[c] = te_encode(L, g, buf, enc_host + (size_t)c * bound, bound, tab, gen, 0, TD_LANES);
     }
     return DTB_OK;
 }

@@ -152,14 +152,15 @@ def output_dtypes(dem_dtype: np.dtype, n_cells: int) -> dict:
 
 def pipeline_files(dem_path, out_dir, river_threshold: int, px: float | None = None, n_gfi: float = 0.4,
                    scale_factor: float = 0.1, size: float | None = None, outputs=STAGE_OUTPUTS, compress: str = "lzw",
-                   blocksize: int = 256, block_bytes: int = 256 << 20, threads: int = 0, decode: str = "host") -> dict:
+                   blocksize: int = 256, block_bytes: int = 256 << 20, threads: int = 0, decode: str = "host", encode: str = "host") -> dict:
     """The chain from a DEM GeoTIFF to one GeoTIFF per descriptor (`out_dir/<name>.tif`), what a user of the
     reference does around the descriptor calls with rasterio (example.py:33, :42-43, :201-217).
 
     The DEM is decoded in row blocks into pinned memory and copied to the device as it is decoded
     (raster.read_to_device; `decode="device"` sends the compressed tiles instead and decodes them on the GPU); its nodata value (GDAL_NODATA tag) becomes the path's sentinel -100 on the device
     (example.py:42-43 does that on the host, from the corner cell); `px` defaults to the file's pixel size.
-    Results are encoded block by block as they are copied back (raster.write_from_device), tiled and compressed,
+    Results are encoded block by block as they are copied back (raster.write_from_device; `encode="device"` encodes the
+    tiles on the GPU and copies only the compressed bytes), tiled and compressed,
     with the DEM's georeferencing; nodata is -100 (0 for the D8 codes, like 12_fdr.tif).
     Returns {name: path}.
     """
@@ -188,7 +189,7 @@ def pipeline_files(dem_path, out_dir, river_threshold: int, px: float | None = N
         t = res[name]
         kind = "f" if t.dtype.is_floating_point else "i"
         paths[name] = os.path.join(out_dir, name + ".tif")
-        raster.write_from_device(paths[name], t, block_bytes=block_bytes, threads=threads, compress=compress,
+        raster.write_from_device(paths[name], t, block_bytes=block_bytes, threads=threads, encode=encode, compress=compress,
                                  predictor=1 if compress in (None, "none") else (3 if kind == "f" else 2),
                                  tiled=True, blockxsize=blocksize, blockysize=blocksize, nodata=0 if name == "d8" else -100, **geo)
     return paths

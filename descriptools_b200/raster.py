@@ -68,6 +68,7 @@ def _load():
     lib.dtbio_writer_info.argtypes = [c_void_p, POINTER(_Info)]
     lib.dtbio_set_tag.argtypes = [c_void_p, c_int, c_int, c_int64, c_void_p]
     lib.dtbio_write_rows.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int]
+    lib.dtbio_write_encoded.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]
     lib.dtbio_bytes_written.restype = c_int64
     lib.dtbio_bytes_written.argtypes = [c_void_p]
     lib.dtbio_close_reader.argtypes = [c_void_p]
@@ -315,6 +316,7 @@ class DatasetWriter:
         self._h, self._threads, self.closed = h, threads, False
         _check(lib.dtbio_writer_info(self._h, byref(info)), "dtbio_writer_info")
         self.is_tiled, self.bigtiff = info.tile_rows > 0, bool(info.bigtiff)
+        self._compression, self._predictor, self._tile_cols = int(info.compression), int(info.predictor), int(info.tile_cols)
         # row blocks handed to write_rows start and end on multiples of this (or on the last row)
         self.chunk_rows = int(info.tile_rows) if self.is_tiled else int(info.rows_per_strip)
         self.nodata, self.crs, self.transform = nodata, crs, transform
@@ -368,6 +370,31 @@ class DatasetWriter:
         if not ok:
             raise RasterError("write_rows: block must be 2-D with the raster's width and unit column stride")
         _check(lib.dtbio_write_rows(self._h, row0, n, c_void_p(ptr), stride, self._threads if threads is None else threads), f"write {self.name}")
+
+    def chunk_layout(self):
+        """(layout, chunks across, chunks in all) for dtb_tiff_encode_chunks (include/dtb200.h)"""
+        from ._lib import TiffLayout
+
+        lay = TiffLayout()
+        lay.rows, lay.cols, lay.bps = self.height, self.width, np.dtype(self.dtypes[0]).itemsize
+        lay.predictor, lay.compression, lay.big_endian = self._predictor, self._compression, 0
+        lay.tiled, lay.chunk_rows = (1 if self.is_tiled else 0), self.chunk_rows
+        lay.chunk_cols = self._tile_cols if self.is_tiled else self.width
+        across = -(-self.width // lay.chunk_cols) if self.is_tiled else 1
+        return lay, across, across * -(-self.height // lay.chunk_rows)
+
+    def write_encoded(self, first_chunk: int, blob, offsets, sizes):
+        """chunks encoded on the device: `blob` (uint8 NumPy array or CPU tensor) holds chunk first_chunk + i at
+        offsets[i] .. offsets[i] + sizes[i]; one file write for the whole group"""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        sizes = np.ascontiguousarray(sizes, dtype=np.int64)
+        if hasattr(blob, "data_ptr"):
+            ptr, nbytes = blob.data_ptr(), blob.numel() * blob.element_size()
+        else:
+            blob = np.ascontiguousarray(blob)
+            ptr, nbytes = blob.ctypes.data, blob.nbytes
+        _check(lib.dtbio_write_encoded(self._h, first_chunk, sizes.size, c_void_p(ptr), nbytes, c_void_p(offsets.ctypes.data),
+                                       c_void_p(sizes.ctypes.data)), f"write {self.name}")
 
     def write(self, arr, indexes=None):
         a = np.asarray(arr)
@@ -573,12 +600,79 @@ def read_to_device(src, device=None, out=None, block_bytes: int = 256 << 20, thr
             reader.close()
 
 
-def write_from_device(path, tensor, block_bytes: int = 256 << 20, threads: int = 0, **meta):
-    """Mirror of read_to_device: a 2-D CUDA tensor goes to a GeoTIFF in row blocks; block k+1 is copied to its
-    pinned staging buffer while the thread team encodes block k.  `meta` as for `open(path, "w", ...)`
-    (width / height / dtype default to the tensor's).  Returns the number of bytes written."""
+def _write_from_device_chunks(w: "DatasetWriter", tensor, block_bytes: int) -> None:
+    """write_from_device(encode="device"): groups of whole chunk-rows are encoded by dtb_tiff_encode_chunks (one warp
+    per chunk), packed back to back by dtb_tiff_pack_chunks, copied to a pinned buffer and written with one call
+    (dtbio_write_encoded).  The next group is encoded while this one is copied and written."""
     import torch
 
+    from ._lib import check
+    from ._lib import lib as cuda_lib
+
+    lay, across, n = w.chunk_layout()
+    bound = int(cuda_lib.dtb_tiff_encode_bound(ctypes.byref(lay)))
+    if bound == 0:
+        raise RasterError("encode='device' writes stored or LZW chunks (predictor 1-3, little-endian); use encode='host' for the rest")
+    dev = tensor.device
+    chunk_raw = lay.chunk_rows * lay.chunk_cols * lay.bps
+    per_group = max(1, block_bytes // max(1, chunk_raw) // across) * across
+    groups = [(g0, min(n, g0 + per_group)) for g0 in range(0, n, per_group)]
+    nbuf = min(2, len(groups))
+    ws_bytes = int(cuda_lib.dtb_tiff_encode_workspace_bytes(ctypes.byref(lay), per_group))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)  # one workspace: the encode kernels run in order on one stream
+    enc = [torch.empty(per_group * bound, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+    sizes_d = [torch.empty(per_group, dtype=torch.int64, device=dev) for _ in range(nbuf)]
+    blob_d = torch.empty(per_group * bound, dtype=torch.uint8, device=dev)
+    blob_h = torch.empty(per_group * bound, dtype=torch.uint8).pin_memory()
+    work, io = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    work.wait_stream(torch.cuda.current_stream(dev))
+    encoded, reusable = [None] * len(groups), [None] * nbuf
+
+    def launch(k):
+        g0, g1 = groups[k]
+        b = k % nbuf
+        if reusable[b] is not None:
+            work.wait_event(reusable[b])  # the pack kernel that read this slot buffer has run
+        check(cuda_lib.dtb_tiff_encode_chunks(ctypes.byref(lay), tensor.data_ptr(), g0, g1 - g0, enc[b].data_ptr(), sizes_d[b].data_ptr(),
+                                              ws.data_ptr(), ws_bytes, work.cuda_stream), "dtb_tiff_encode_chunks")
+        encoded[k] = torch.cuda.Event()
+        encoded[k].record(work)
+
+    launch(0)
+    for k, (g0, g1) in enumerate(groups):
+        b = k % nbuf
+        if k + 1 < len(groups):
+            launch(k + 1)
+        io.wait_event(encoded[k])
+        with torch.cuda.stream(io):
+            sizes = sizes_d[b][:g1 - g0].cpu().numpy()  # synchronises `io`: the group is encoded
+            if (sizes <= 0).any():
+                raise RasterError(f"{w.name}: a chunk did not fit its encode slot")
+            aligned = (sizes + 1) & ~1
+            offsets = np.cumsum(aligned) - aligned
+            total = int(aligned.sum())
+            offsets_d = torch.from_numpy(offsets).to(dev)
+            check(cuda_lib.dtb_tiff_pack_chunks(enc[b].data_ptr(), bound, sizes_d[b].data_ptr(), offsets_d.data_ptr(), g1 - g0,
+                                                blob_d.data_ptr(), io.cuda_stream), "dtb_tiff_pack_chunks")
+            reusable[b] = torch.cuda.Event()
+            reusable[b].record(io)
+            blob_h[:total].copy_(blob_d[:total], non_blocking=True)
+        io.synchronize()
+        w.write_encoded(g0, blob_h[:total], offsets, sizes)
+    torch.cuda.current_stream(dev).wait_stream(work)
+
+
+def write_from_device(path, tensor, block_bytes: int = 256 << 20, threads: int = 0, encode: str = "host", **meta):
+    """Mirror of read_to_device: a 2-D CUDA tensor goes to a GeoTIFF.  `meta` as for `open(path, "w", ...)`
+    (width / height / dtype default to the tensor's).  Returns the number of bytes written.
+
+    encode="host": row blocks; block k+1 is copied to its pinned staging buffer while the thread team encodes block k.
+    encode="device": the chunks are encoded on the device and only the compressed bytes cross PCIe (stored and LZW
+    files; anything else raises -- nothing falls back silently)."""
+    import torch
+
+    if encode not in ("host", "device"):
+        raise RasterError("encode must be 'host' or 'device'")
     if not tensor.is_cuda or tensor.dim() != 2:
         raise RasterError("write_from_device needs a 2-D CUDA tensor")
     rows, cols = tensor.shape
@@ -590,6 +684,13 @@ def write_from_device(path, tensor, block_bytes: int = 256 << 20, threads: int =
         raise RasterError("write_from_device: dtype of the file must be the tensor's (convert on the device first)")
     w = DatasetWriter(path, threads=threads, **meta)
     try:
+        if encode == "device":
+            if not tensor.is_contiguous():
+                raise RasterError("write_from_device(encode='device') needs a contiguous tensor")
+            _write_from_device_chunks(w, tensor, block_bytes)
+            total = w.bytes_written
+            w.close()
+            return total
         br = _block_rows(rows, w.chunk_rows, cols, tensor.element_size(), block_bytes)
         stage = [torch.empty((br, cols), dtype=tensor.dtype).pin_memory() for _ in range(2 if rows > br else 1)]
         copy = torch.cuda.Stream(device=tensor.device)

@@ -303,6 +303,23 @@ int dtb_selftest_tiff_decode_host(const dtb_tiff_layout *lay, const uint8_t *com
                                   const uint64_t *comp_len_host, int64_t first_chunk, int64_t n_chunks, void *out_host,
                                   unsigned long long *status_host);
 
+/* The way back -- replaces the pixel encode inside `rio.open(out, "w", **meta).write(...)` (example.py:216-217):
+ * dtb_tiff_encode_chunks: one warp gathers chunk first_chunk + i from the raster (partial tiles padded by edge
+ *   replication), applies lay->predictor and encodes it (lay->compression 5 LZW, 1 stored; little-endian only) into
+ *   enc + i * dtb_tiff_encode_bound(lay); sizes[i] receives the encoded byte count (DEVICE array).
+ * dtb_tiff_pack_chunks: copies the n_chunks streams to blob + offsets[i] (DEVICE arrays; the caller computes the
+ *   offsets from the sizes), so that one device-to-host copy and one write carry the group
+ *   (dtbio_write_encoded, include/dtb200_io.h).
+ * dtb_selftest_tiff_encode_host: the encode kernel's per-lane code on the CPU over HOST pointers (CPU test-suite). */
+size_t dtb_tiff_encode_bound(const dtb_tiff_layout *lay);
+size_t dtb_tiff_encode_workspace_bytes(const dtb_tiff_layout *lay, int64_t n_chunks);
+int dtb_tiff_encode_chunks(const dtb_tiff_layout *lay, const void *raster, int64_t first_chunk, int64_t n_chunks, uint8_t *enc,
+                           long long *sizes, void *ws, size_t ws_bytes, void *stream);
+int dtb_tiff_pack_chunks(const uint8_t *enc, size_t bound, const long long *sizes, const long long *offsets, int64_t n_chunks,
+                         uint8_t *blob, void *stream);
+int dtb_selftest_tiff_encode_host(const dtb_tiff_layout *lay, const void *raster_host, int64_t first_chunk, int64_t n_chunks,
+                                  uint8_t *enc_host, long long *sizes_host);
+
 /* ---- benchmark support: synthetic DEM "dtb-synth-v1" + depression filling ---------------
  * No reference counterpart (its fixtures were conditioned by an external GIS,
  * Example/example.py:33-39).  Bit-identical to oracle/dt_condition.cpp. */

@@ -98,6 +98,11 @@ int dtbio_set_tag(dtbio_writer *w, int tag, int type, int64_t count, const void 
  * rows_per_strip) and the block must end on one or at the last row; blocks may arrive in any order and
  * each chunk exactly once. */
 int dtbio_write_rows(dtbio_writer *w, int64_t row0, int64_t nrows, const void *src, int64_t src_stride_bytes, int threads);
+/* Chunks encoded elsewhere (dtb_tiff_encode_chunks, include/dtb200.h): chunk first_chunk + i is the sizes[i] bytes at
+ * blob + offsets[i]; the blob (blob_bytes long) is written with one call and the chunk table points into it.
+ * The streams must match the writer's compression / predictor / chunk geometry. */
+int dtbio_write_encoded(dtbio_writer *w, int64_t first_chunk, int64_t n_chunks, const void *blob, int64_t blob_bytes,
+                        const int64_t *offsets, const int64_t *sizes);
 /* number of bytes in the file so far (header + chunks written) */
 int64_t dtbio_bytes_written(const dtbio_writer *w);
 

@@ -149,6 +149,21 @@ def test_georeferencing_and_meta_follow_the_example(tmp_path):
         assert im.tag_v2[42113] == "0" and tuple(im.tag_v2[34735]) == crs.directory
 
 
+def test_predictor_without_a_codec_is_dropped(tmp_path):
+    """libtiff and GDAL apply the predictor only inside LZW / Deflate; a stored file never carries one"""
+    a = _rand((40, 50), "int16", seed=7)
+    p = tmp_path / "s.tif"
+    with rio.open(p, "w", width=50, height=40, dtype="int16", compress="none", predictor=2) as dst:
+        dst.write(a)
+    assert rio.open(p).profile["predictor"] == 1
+    np.testing.assert_array_equal(_pil_read(p), a)
+    from descriptools_b200 import _lib
+
+    lay = _lib.TiffLayout(rows=40, cols=50, bps=2, predictor=2, compression=1, tiled=0, chunk_rows=8, chunk_cols=50, big_endian=0)
+    assert _lib.lib.dtb_tiff_encode_bound(ctypes.byref(lay)) == 0
+    assert _lib.lib.dtb_tiff_decode_workspace_bytes(ctypes.byref(lay), 5) == 0
+
+
 def test_bigtiff_and_big_endian_files(tmp_path):
     a = _rand((90, 70), "int16", seed=2)
     path = tmp_path / "big.tif"
@@ -232,7 +247,7 @@ def test_errors_are_reported_not_guessed(tmp_path):
 
 
 def _decode_like_the_device(path, first=0, count=None):
-    """the tile-decoding kernel's per-lane code (csrc/tiffdecode.cu), run lane by lane on the CPU by the library's self-test
+    """the tile-decoding kernel's per-lane code (csrc/tiffcodec.cu), run lane by lane on the CPU by the library's self-test
     entry point: same geometry, LZW, byte order, predictor and store code the warps execute"""
     from descriptools_b200 import _lib
 
@@ -251,7 +266,7 @@ def _decode_like_the_device(path, first=0, count=None):
 
 @pytest.mark.parametrize("dtype", ["uint8", "int16", "uint32", "int64", "float32", "float64"])
 @pytest.mark.parametrize("layout", ["strips", "tiles"])
-@pytest.mark.parametrize("compress,predictor", [("none", 1), ("lzw", 1), ("lzw", 2), ("lzw", 3), ("none", 2)])
+@pytest.mark.parametrize("compress,predictor", [("none", 1), ("lzw", 1), ("lzw", 2), ("lzw", 3)])
 def test_device_decoder_lane_code_on_the_cpu(tmp_path, dtype, layout, compress, predictor):
     if predictor == 3 and np.dtype(dtype).kind != "f":
         pytest.skip("floating-point predictor")
@@ -271,6 +286,73 @@ def test_device_decoder_lane_code_on_the_cpu(tmp_path, dtype, layout, compress, 
     assert status == 0
     np.testing.assert_array_equal(out[r0:r1], a[r0:r1])
     assert (out[:r0] == 7).all() and (out[r1:] == 7).all()
+
+
+def _encode_like_the_device(path, a, **kw):
+    """the tile-encoding kernel's per-lane code (csrc/tiffcodec.cu) on the CPU, then the file is put together the way
+    write_from_device(encode="device") does it: one blob of streams, dtbio_write_encoded"""
+    from descriptools_b200 import _lib
+
+    w = rio.open(path, "w", width=a.shape[1], height=a.shape[0], dtype=a.dtype.name, **kw)
+    lay, across, n = w.chunk_layout()
+    bound = _lib.lib.dtb_tiff_encode_bound(ctypes.byref(lay))
+    assert bound > 0
+    enc = np.zeros(n * bound, np.uint8)
+    sizes = np.zeros(n, np.int64)
+    a = np.ascontiguousarray(a)
+    assert _lib.lib.dtb_selftest_tiff_encode_host(ctypes.byref(lay), a.ctypes.data, 0, n, enc.ctypes.data, sizes.ctypes.data) == 0
+    assert (sizes > 0).all() and (sizes <= bound).all()
+    half = n // 2  # two groups, the second one first
+    for c0, c1 in ((half, n), (0, half)):
+        al = (sizes[c0:c1] + 1) & ~1
+        offs = np.cumsum(al) - al
+        blob = np.zeros(int(al.sum()), np.uint8)
+        for i in range(c0, c1):
+            blob[offs[i - c0]:offs[i - c0] + sizes[i]] = enc[i * bound:i * bound + sizes[i]]
+        w.write_encoded(c0, blob, offs, sizes[c0:c1])
+    w.close()
+    return sizes
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "int16", "uint32", "int64", "float32", "float64"])
+@pytest.mark.parametrize("layout", ["strips", "tiles"])
+@pytest.mark.parametrize("compress,predictor", [("none", 1), ("lzw", 1), ("lzw", 2), ("lzw", 3)])
+def test_device_encoder_lane_code_on_the_cpu(tmp_path, dtype, layout, compress, predictor):
+    if predictor == 3 and np.dtype(dtype).kind != "f":
+        pytest.skip("floating-point predictor")
+    a = _rand((157, 203), dtype, seed=21)
+    path = tmp_path / "e.tif"
+    kw = dict(tiled=True, blockxsize=48, blockysize=64) if layout == "tiles" else dict(blockysize=7)
+    _encode_like_the_device(path, a, compress=compress, predictor=predictor, nodata=0, **kw)
+    with rio.open(path) as src:
+        assert src.compression == compress and src.profile["predictor"] == predictor
+        np.testing.assert_array_equal(src.read(1), a)       # the host codec reads it
+    if dtype in PIL_MODES:
+        np.testing.assert_array_equal(_pil_read(path), a)   # libtiff reads it
+    out, status, _ = _decode_like_the_device(path)          # the device decoder's lane code reads it
+    assert status == 0
+    np.testing.assert_array_equal(out, a)
+
+
+def test_device_encoder_table_resets_and_compression_ratio(tmp_path):
+    noise = _rand((512, 512), "uint8", seed=9, smooth=False)   # the dictionary fills and is cleared ~70 times per tile
+    p = tmp_path / "n.tif"
+    sizes = _encode_like_the_device(p, noise, compress="lzw", tiled=True, blockxsize=512, blockysize=512)
+    assert sizes[0] <= 512 * 512 * 1.5 + 200
+    np.testing.assert_array_equal(_pil_read(p), noise)
+    np.testing.assert_array_equal(rio.open(p).read(1), noise)
+    flat = np.zeros((512, 512), np.uint8)                      # longest strings
+    sizes = _encode_like_the_device(p, flat, compress="lzw", blockysize=512)
+    assert sizes[0] < 2000
+    np.testing.assert_array_equal(_pil_read(p), flat)
+    # the forgetful dictionary costs little against the exact one of the host codec
+    dem = _rand((512, 512), "float32", seed=4)
+    q = tmp_path / "h.tif"
+    with rio.open(q, "w", width=512, height=512, dtype="float32", compress="lzw", predictor=3, tiled=True, blockxsize=256, blockysize=256) as d:
+        d.write(dem)
+    _encode_like_the_device(p, dem, compress="lzw", predictor=3, tiled=True, blockxsize=256, blockysize=256)
+    np.testing.assert_array_equal(rio.open(p).read(1), dem)
+    assert os.path.getsize(p) < 1.05 * os.path.getsize(q)
 
 
 def test_device_decoder_lane_code_big_endian_and_damage(tmp_path):
@@ -414,14 +496,15 @@ def test_pipeline_from_file_to_files(tmp_path):
     with rio.open(p, "w", width=420, height=300, dtype="float32", compress="lzw", tiled=True, blockxsize=128, blockysize=128,
                   nodata=-3.4028230607370965e38, crs=crs, transform=rio.Affine(12.5, 0, 1000.0, 0, -12.5, 9000.0)) as dst:
         dst.write(stored)
-    paths = pipeline.pipeline_files(p, tmp_path / "out", river_threshold=300, block_bytes=200_000)
     want = pipeline.pipeline(np.where(hole, np.float32(-100), dem), 12.5, 300)
-    assert sorted(paths) == sorted(pipeline.STAGE_OUTPUTS)
-    for name, path in paths.items():
-        with rio.open(path) as src:
-            assert src.crs == crs and src.res == (12.5, 12.5) and src.nodata == (0 if name == "d8" else -100)
-            assert src.compression == "lzw" and src.block_shapes == [(256, 256)]
-            np.testing.assert_array_equal(src.read(1), want[name], err_msg=name)
+    for where in ("host", "device"):
+        paths = pipeline.pipeline_files(p, tmp_path / ("out_" + where), river_threshold=300, block_bytes=200_000, decode=where, encode=where)
+        assert sorted(paths) == sorted(pipeline.STAGE_OUTPUTS)
+        for name, path in paths.items():
+            with rio.open(path) as src:
+                assert src.crs == crs and src.res == (12.5, 12.5) and src.nodata == (0 if name == "d8" else -100)
+                assert src.compression == "lzw" and src.block_shapes == [(256, 256)]
+                np.testing.assert_array_equal(src.read(1), want[name], err_msg=f"{name} ({where})")
 
 
 @pytest.mark.gpu
@@ -465,3 +548,32 @@ def test_device_decoder_reports_damage_and_refuses_what_it_cannot_do(tmp_path):
     q.write_bytes(bytes(raw))
     with pytest.raises(rio.RasterError, match="chunk 3"):
         rio.read_to_device(q, decode="device")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,layout,compress,predictor", [("float32", "tiles", "lzw", 3), ("float32", "tiles", "lzw", 1), ("int32", "tiles", "lzw", 2),
+                                                             ("uint8", "strips", "lzw", 1), ("int16", "tiles", "none", 1), ("float64", "strips", "lzw", 3)])
+def test_tiles_encoded_on_the_device(tmp_path, dtype, layout, compress, predictor):
+    import torch
+
+    from descriptools_b200 import _lib
+
+    a = _rand((1000, 777), dtype, seed=14)
+    t = torch.from_numpy(a).cuda()
+    p = tmp_path / "out.tif"
+    kw = dict(tiled=True, blockxsize=128, blockysize=128) if layout == "tiles" else dict(blockysize=16)
+    before = _lib.launch_count()
+    n = rio.write_from_device(p, t, encode="device", block_bytes=1 << 20, compress=compress, predictor=predictor, nodata=-100,
+                              transform=rio.Affine(2.0, 0, 10.0, 0, -2.0, 99.0), **kw)   # several groups: both slot buffers are reused
+    assert _lib.launch_count() >= before + 2 and 0 < n <= os.path.getsize(p)
+    with rio.open(p) as src:
+        assert src.compression == compress and src.res == (2.0, 2.0) and src.nodata == -100
+        np.testing.assert_array_equal(src.read(1), a)
+    if dtype in PIL_MODES:
+        np.testing.assert_array_equal(_pil_read(p), a)
+    np.testing.assert_array_equal(rio.read_to_device(p, decode="device").cpu().numpy(), a)
+    rio.write_from_device(p, t, encode="device", compress=compress, predictor=predictor, **kw)  # one group
+    np.testing.assert_array_equal(rio.open(p).read(1), a)
+    with pytest.raises(rio.RasterError, match="encode='host'"):
+        rio.write_from_device(p, t, encode="device", compress="deflate")
+    assert not os.path.exists(p)
