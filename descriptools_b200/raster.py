@@ -454,6 +454,18 @@ def _block_rows(src_rows: int, chunk_rows: int, cols: int, itemsize: int, target
     return min(max(chunk_rows, want // chunk_rows * chunk_rows), max(src_rows, 1))
 
 
+_WARPS_IN_FLIGHT = 148 * 8 * 4  # the codec kernels keep one chunk per resident warp (csrc/tiffcodec.cu)
+
+
+def _chunks_per_group(n: int, across: int, chunk_raw: int, block_bytes: int) -> int:
+    """chunks handed to one codec launch: whole chunk-rows, about `block_bytes` of decoded data but never fewer than fill
+    the device (one warp per chunk) while leaving two groups to overlap with the copies, and at most 4 GiB decoded"""
+    by_bytes = block_bytes // max(1, chunk_raw)
+    fill = min(_WARPS_IN_FLIGHT, -(-n // 2))
+    want = min(max(by_bytes, fill, 1), max(1, (4 << 30) // max(1, chunk_raw)))
+    return min(n, max(1, -(-want // across)) * across)
+
+
 def chunk_table(reader: "DatasetReader"):
     """(layout, offsets, byte counts) of a raster's chunks: what dtb_tiff_decode_chunks (include/dtb200.h) needs.
     offsets / counts are uint64 arrays in chunk order (tiles row-major, or strips top to bottom)."""
@@ -478,7 +490,7 @@ def chunk_table(reader: "DatasetReader"):
     return lay, across, off, cnt
 
 
-def _read_to_device_chunks(reader, out, block_bytes: int, copy):
+def _read_to_device_chunks(reader, out, block_bytes: int, copy, group_chunks=None):
     """read_to_device(decode="device"): the compressed chunks go over PCIe as they lie in the file and are decoded
     by dtb_tiff_decode_chunks, one warp per chunk.  File spans are read into two pinned staging buffers; reading
     span k+1 overlaps the copy and decode of span k on `copy`."""
@@ -493,7 +505,7 @@ def _read_to_device_chunks(reader, out, block_bytes: int, copy):
     dev = out.device
     n = off.size
     chunk_raw = lay.chunk_rows * lay.chunk_cols * lay.bps
-    per_group = max(1, block_bytes // max(1, chunk_raw) // across) * across  # whole chunk-rows, about block_bytes decoded
+    per_group = group_chunks or _chunks_per_group(n, across, chunk_raw, block_bytes)
     groups = [(g0, min(n, g0 + per_group)) for g0 in range(0, n, per_group)]
     spans = []
     for g0, g1 in groups:
@@ -545,14 +557,15 @@ def _read_to_device_chunks(reader, out, block_bytes: int, copy):
     return out
 
 
-def read_to_device(src, device=None, out=None, block_bytes: int = 256 << 20, threads: int = 0, stream=None, decode: str = "host"):
+def read_to_device(src, device=None, out=None, block_bytes: int = 256 << 20, threads: int = 0, stream=None, decode: str = "host",
+                   group_chunks: int | None = None):
     """Decode a raster into a CUDA tensor.  Returns the tensor (dtype of the file); the current stream waits for
     the last copy.  `src` is a path or a DatasetReader.
 
     decode="host": two pinned staging blocks; while block k is copied to the device on `stream` (default: a private
     copy stream) the codec's thread team decodes block k+1.
     decode="device": the compressed chunks are copied instead and decoded on the device (stored and LZW files;
-    anything else raises -- nothing falls back silently)."""
+    anything else raises -- nothing falls back silently); `group_chunks` overrides the number of chunks per launch."""
     import torch
 
     from . import device as _device
@@ -568,7 +581,8 @@ def read_to_device(src, device=None, out=None, block_bytes: int = 256 << 20, thr
                 out = torch.empty(reader.shape, dtype=tdt, device=dev)
             elif tuple(out.shape) != reader.shape or out.dtype != tdt or not out.is_cuda or not out.is_contiguous():
                 raise RasterError("read_to_device: `out` must be a contiguous CUDA tensor of the raster's shape and dtype")
-            return _read_to_device_chunks(reader, out, block_bytes, stream if stream is not None else torch.cuda.Stream(device=out.device))
+            return _read_to_device_chunks(reader, out, block_bytes, stream if stream is not None else torch.cuda.Stream(device=out.device),
+                                          group_chunks)
         tdt = getattr(torch, reader.dtypes[0])
         rows, cols = reader.shape
         if out is None:
@@ -600,7 +614,7 @@ def read_to_device(src, device=None, out=None, block_bytes: int = 256 << 20, thr
             reader.close()
 
 
-def _write_from_device_chunks(w: "DatasetWriter", tensor, block_bytes: int) -> None:
+def _write_from_device_chunks(w: "DatasetWriter", tensor, block_bytes: int, group_chunks=None) -> None:
     """write_from_device(encode="device"): groups of whole chunk-rows are encoded by dtb_tiff_encode_chunks (one warp
     per chunk), packed back to back by dtb_tiff_pack_chunks, copied to a pinned buffer and written with one call
     (dtbio_write_encoded).  The next group is encoded while this one is copied and written."""
@@ -615,15 +629,14 @@ def _write_from_device_chunks(w: "DatasetWriter", tensor, block_bytes: int) -> N
         raise RasterError("encode='device' writes stored or LZW chunks (predictor 1-3, little-endian); use encode='host' for the rest")
     dev = tensor.device
     chunk_raw = lay.chunk_rows * lay.chunk_cols * lay.bps
-    per_group = max(1, block_bytes // max(1, chunk_raw) // across) * across
+    per_group = group_chunks or _chunks_per_group(n, across, chunk_raw, block_bytes)
     groups = [(g0, min(n, g0 + per_group)) for g0 in range(0, n, per_group)]
     nbuf = min(2, len(groups))
     ws_bytes = int(cuda_lib.dtb_tiff_encode_workspace_bytes(ctypes.byref(lay), per_group))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)  # one workspace: the encode kernels run in order on one stream
     enc = [torch.empty(per_group * bound, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
     sizes_d = [torch.empty(per_group, dtype=torch.int64, device=dev) for _ in range(nbuf)]
-    blob_d = torch.empty(per_group * bound, dtype=torch.uint8, device=dev)
-    blob_h = torch.empty(per_group * bound, dtype=torch.uint8).pin_memory()
+    blob = {"d": None, "h": None}  # packed streams of one group, device and pinned host; grown to what the data needs
     work, io = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     work.wait_stream(torch.cuda.current_stream(dev))
     encoded, reusable = [None] * len(groups), [None] * nbuf
@@ -652,17 +665,22 @@ def _write_from_device_chunks(w: "DatasetWriter", tensor, block_bytes: int) -> N
             offsets = np.cumsum(aligned) - aligned
             total = int(aligned.sum())
             offsets_d = torch.from_numpy(offsets).to(dev)
+            if blob["d"] is None or blob["d"].numel() < total:
+                room = min(per_group * bound, total + total // 4 + 4096)
+                blob["d"] = torch.empty(room, dtype=torch.uint8, device=dev)
+                blob["h"] = torch.empty(room, dtype=torch.uint8).pin_memory()
             check(cuda_lib.dtb_tiff_pack_chunks(enc[b].data_ptr(), bound, sizes_d[b].data_ptr(), offsets_d.data_ptr(), g1 - g0,
-                                                blob_d.data_ptr(), io.cuda_stream), "dtb_tiff_pack_chunks")
+                                                blob["d"].data_ptr(), io.cuda_stream), "dtb_tiff_pack_chunks")
             reusable[b] = torch.cuda.Event()
             reusable[b].record(io)
-            blob_h[:total].copy_(blob_d[:total], non_blocking=True)
+            blob["h"][:total].copy_(blob["d"][:total], non_blocking=True)
         io.synchronize()
-        w.write_encoded(g0, blob_h[:total], offsets, sizes)
+        w.write_encoded(g0, blob["h"][:total], offsets, sizes)
     torch.cuda.current_stream(dev).wait_stream(work)
 
 
-def write_from_device(path, tensor, block_bytes: int = 256 << 20, threads: int = 0, encode: str = "host", **meta):
+def write_from_device(path, tensor, block_bytes: int = 256 << 20, threads: int = 0, encode: str = "host",
+                      group_chunks: int | None = None, **meta):
     """Mirror of read_to_device: a 2-D CUDA tensor goes to a GeoTIFF.  `meta` as for `open(path, "w", ...)`
     (width / height / dtype default to the tensor's).  Returns the number of bytes written.
 
@@ -687,7 +705,7 @@ def write_from_device(path, tensor, block_bytes: int = 256 << 20, threads: int =
         if encode == "device":
             if not tensor.is_contiguous():
                 raise RasterError("write_from_device(encode='device') needs a contiguous tensor")
-            _write_from_device_chunks(w, tensor, block_bytes)
+            _write_from_device_chunks(w, tensor, block_bytes, group_chunks)
             total = w.bytes_written
             w.close()
             return total
