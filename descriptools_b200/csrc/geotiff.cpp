@@ -23,7 +23,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -35,6 +38,18 @@ thread_local std::string g_err;
 int fail(int code, const std::string &msg) {
     g_err = msg;
     return code;
+}
+
+// no C++ exception crosses the C ABI (a damaged file can ask for absurd allocations)
+template <typename F>
+int guarded(F body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        return fail(DTBIO_ERR_IO, "out of memory");
+    } catch (const std::exception &e) {
+        return fail(DTBIO_ERR_IO, e.what());
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -256,7 +271,7 @@ int run_team(int64_t n, int threads, Fn fn) {
         for (;;) {
             int64_t i = next.fetch_add(1);
             if (i >= n || status.load() != DTBIO_OK) return;
-            int rc = fn(i, worker);
+            int rc = guarded([&] { return fn(i, worker); });
             if (rc != DTBIO_OK) {
                 std::lock_guard<std::mutex> g(m);
                 if (status.load() == DTBIO_OK) {
@@ -333,6 +348,7 @@ struct Layout {
 // reader
 // =====================================================================================================
 struct dtbio_reader {
+    ~dtbio_reader() { if (fd >= 0) close(fd); }
     int fd = -1;
     uint64_t file_size = 0;
     bool big = false, swap = false;
@@ -441,6 +457,8 @@ int interpret(dtbio_reader *r) {
         r->counts = r->tags.count(279) ? &r->tags[279] : nullptr;
     }
     r->lay.set(in.rows, in.cols, DT_SIZE[in.dtype], in.tile_rows, in.tile_cols, in.rows_per_strip);
+    if ((double)r->lay.ch * (double)r->lay.cw * r->lay.bps > 2147483647.0)
+        return fail(DTBIO_ERR_UNSUPPORTED, "a chunk of more than 2 GiB (one strip for a huge raster?)");
     if (!r->offsets || r->offsets->count < (uint64_t)r->lay.n_chunks()) return fail(DTBIO_ERR_FORMAT, "chunk offsets missing or too few");
     if (r->counts && r->counts->count < (uint64_t)r->lay.n_chunks()) return fail(DTBIO_ERR_FORMAT, "chunk byte counts too few");
     if (!r->counts && in.compression != DTBIO_COMP_NONE) return fail(DTBIO_ERR_FORMAT, "compressed file without chunk byte counts");
@@ -548,6 +566,7 @@ int decode_chunk(dtbio_reader *r, int64_t chunk, int64_t row0, int64_t row1, uin
 // writer
 // =====================================================================================================
 struct dtbio_writer {
+    ~dtbio_writer() { if (fd >= 0) close(fd); }
     int fd = -1;
     std::string path;
     dtbio_info info{};
@@ -730,18 +749,22 @@ int dtbio_open(const char *path, dtbio_reader **out) {
     if (fd < 0) return fail(DTBIO_ERR_IO, std::string("cannot open ") + path + ": " + strerror(errno));
     struct stat st;
     if (fstat(fd, &st) != 0) { close(fd); return fail(DTBIO_ERR_IO, "fstat failed"); }
-    dtbio_reader *r = new dtbio_reader();
-    r->fd = fd;
-    r->file_size = (uint64_t)st.st_size;
-    int rc = read_ifd(r);
-    if (rc == DTBIO_OK) rc = interpret(r);
-    if (rc != DTBIO_OK) {
-        close(fd);
-        delete r;
-        return rc;
-    }
-    *out = r;
-    return DTBIO_OK;
+    return guarded([&]() -> int {
+        std::unique_ptr<dtbio_reader> r;
+        try {
+            r.reset(new dtbio_reader());
+        } catch (...) {
+            close(fd);
+            throw;
+        }
+        r->fd = fd;  // closed by the reader from here on
+        r->file_size = (uint64_t)st.st_size;
+        int rc = read_ifd(r.get());
+        if (rc == DTBIO_OK) rc = interpret(r.get());
+        if (rc != DTBIO_OK) return rc;
+        *out = r.release();
+        return DTBIO_OK;
+    });
 }
 
 int dtbio_get_info(const dtbio_reader *r, dtbio_info *info) {
@@ -768,10 +791,12 @@ int dtbio_read_rows(dtbio_reader *r, int64_t row0, int64_t nrows, void *dst, int
     if (nrows == 0) return DTBIO_OK;
     int64_t cy0 = row0 / L.ch, cy1 = (row0 + nrows - 1) / L.ch + 1;
     int64_t n = (cy1 - cy0) * L.across;
-    int t = team_size(threads, n);
-    std::vector<Scratch> scratch((size_t)t);
-    return run_team(n, t, [&](int64_t i, int worker) {
-        return decode_chunk(r, cy0 * L.across + i, row0, row0 + nrows, (uint8_t *)dst, stride, scratch[(size_t)worker]);
+    return guarded([&]() -> int {
+        int t = team_size(threads, n);
+        std::vector<Scratch> scratch((size_t)t);
+        return run_team(n, t, [&](int64_t i, int worker) {
+            return decode_chunk(r, cy0 * L.across + i, row0, row0 + nrows, (uint8_t *)dst, stride, scratch[(size_t)worker]);
+        });
     });
 }
 
@@ -788,7 +813,8 @@ int dtbio_create(const char *path, const dtbio_info *info, dtbio_writer **out) {
     if (pred == 3 && info->dtype != DTBIO_F32 && info->dtype != DTBIO_F64) return fail(DTBIO_ERR_INVALID, "predictor 3 needs floating-point samples");
     if ((info->tile_rows > 0) != (info->tile_cols > 0)) return fail(DTBIO_ERR_INVALID, "give both tile sizes or neither");
     if (info->tile_rows > 0 && ((info->tile_rows % 16) || (info->tile_cols % 16))) return fail(DTBIO_ERR_INVALID, "tile sizes must be multiples of 16");
-    dtbio_writer *w = new dtbio_writer();
+    return guarded([&]() -> int {
+    std::unique_ptr<dtbio_writer> w(new dtbio_writer());
     w->info = *info;
     w->info.compression = comp;
     w->info.predictor = pred;
@@ -805,25 +831,25 @@ int dtbio_create(const char *path, const dtbio_info *info, dtbio_writer **out) {
     w->counts.assign((size_t)w->lay.n_chunks(), 0);
     w->path = path;
     w->fd = open(path, O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
-    if (w->fd < 0) {
-        delete w;
-        return fail(DTBIO_ERR_IO, std::string("cannot create ") + path + ": " + strerror(errno));
-    }
+    if (w->fd < 0) return fail(DTBIO_ERR_IO, std::string("cannot create ") + path + ": " + strerror(errno));
     w->pos.store(16);  // header is patched in at close
-    *out = w;
+    *out = w.release();
     return DTBIO_OK;
+    });
 }
 
 int dtbio_set_tag(dtbio_writer *w, int tag, int type, int64_t count, const void *data) {
     if (!w || count < 0 || (count > 0 && !data)) return fail(DTBIO_ERR_INVALID, "null argument");
     int ts = type_size(type);
     if (ts == 0 || tag <= 0 || tag > 65535) return fail(DTBIO_ERR_INVALID, "bad tag or field type");
-    Tag t;
-    t.type = type;
-    t.count = (uint64_t)count;
-    t.data.assign((const uint8_t *)data, (const uint8_t *)data + (size_t)count * ts);
-    w->extra[tag] = std::move(t);
-    return DTBIO_OK;
+    return guarded([&]() -> int {
+        Tag t;
+        t.type = type;
+        t.count = (uint64_t)count;
+        t.data.assign((const uint8_t *)data, (const uint8_t *)data + (size_t)count * ts);
+        w->extra[tag] = std::move(t);
+        return DTBIO_OK;
+    });
 }
 
 int dtbio_write_rows(dtbio_writer *w, int64_t row0, int64_t nrows, const void *src, int64_t stride, int threads) {
@@ -838,10 +864,12 @@ int dtbio_write_rows(dtbio_writer *w, int64_t row0, int64_t nrows, const void *s
     int64_t n = (cy1 - cy0) * L.across;
     for (int64_t i = 0; i < n; ++i)
         if (w->counts[(size_t)(cy0 * L.across + i)]) return fail(DTBIO_ERR_ORDER, "chunk written twice");
-    int t = team_size(threads, n);
-    std::vector<Scratch> scratch((size_t)t);
-    return run_team(n, t, [&](int64_t i, int worker) {
-        return encode_chunk(w, cy0 * L.across + i, row0, (const uint8_t *)src, stride, scratch[(size_t)worker]);
+    return guarded([&]() -> int {
+        int t = team_size(threads, n);
+        std::vector<Scratch> scratch((size_t)t);
+        return run_team(n, t, [&](int64_t i, int worker) {
+            return encode_chunk(w, cy0 * L.across + i, row0, (const uint8_t *)src, stride, scratch[(size_t)worker]);
+        });
     });
 }
 
@@ -874,17 +902,20 @@ int dtbio_writer_info(const dtbio_writer *w, dtbio_info *info) {
 int64_t dtbio_bytes_written(const dtbio_writer *w) { return w ? (int64_t)w->pos.load() : 0; }
 
 int dtbio_close_reader(dtbio_reader *r) {
-    if (!r) return DTBIO_OK;
-    if (r->fd >= 0) close(r->fd);
-    delete r;
+    delete r;  // closes the file
     return DTBIO_OK;
 }
 
 int dtbio_close_writer(dtbio_writer *w) {
     if (!w) return DTBIO_OK;
-    int rc = finish(w);
+    int rc = guarded([&]() -> int { return finish(w); });
     if (close(w->fd) != 0 && rc == DTBIO_OK) rc = fail(DTBIO_ERR_IO, std::string("close failed: ") + strerror(errno));
-    if (rc != DTBIO_OK) unlink(w->path.c_str());
+    w->fd = -1;
+    if (rc != DTBIO_OK) {
+        std::string keep = g_err;
+        unlink(w->path.c_str());
+        g_err = keep;
+    }
     delete w;
     return rc;
 }

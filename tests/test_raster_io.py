@@ -412,6 +412,31 @@ def test_device_decoder_lane_code_big_endian_and_damage(tmp_path):
     assert _lib.lib.dtb_tiff_decode_chunks(ctypes.byref(lay), 1, 1, 1, 8, 2, 1, 1, 1 << 20, 1, None) == -1  # 9 chunks only
 
 
+def test_damaged_headers_come_back_as_errors(tmp_path):
+    """a file may claim anything: absurd chunk sizes and truncated data are reported, no exception crosses the C ABI"""
+    def tiff(entries, data=b"\x80\x00\x40\x40"):
+        ifd = struct.pack("<H", len(entries))
+        for tag, typ, cnt, val in entries:
+            ifd += struct.pack("<HHI", tag, typ, cnt) + (struct.pack("<HH", val, 0) if typ == 3 else struct.pack("<I", val))
+        return b"II" + struct.pack("<HI", 42, 8 + len(data)) + data + ifd + struct.pack("<I", 0)
+
+    p = tmp_path / "bad.tif"
+    p.write_bytes(tiff([(256, 4, 1, 70000), (257, 4, 1, 70000), (258, 3, 1, 32), (259, 3, 1, 5), (277, 3, 1, 1), (322, 4, 1, 1 << 30),
+                        (323, 4, 1, 1 << 30), (324, 4, 1, 8), (325, 4, 1, 4), (339, 3, 1, 3)]))
+    with pytest.raises(rio.RasterError, match="2 GiB"):
+        rio.open(p)
+    p.write_bytes(tiff([(256, 4, 1, 20000), (257, 4, 1, 20000), (258, 3, 1, 32), (259, 3, 1, 5), (277, 3, 1, 1), (273, 4, 1, 8),
+                        (278, 4, 1, 20000), (279, 4, 1, 4), (339, 3, 1, 3)]))
+    with rio.open(p) as r:  # one 1.6 GB strip, four bytes of data
+        with pytest.raises(rio.RasterError, match="decodes short"):
+            r.read_rows(0, 2, threads=2)
+    p.write_bytes(tiff([(256, 4, 1, 64), (257, 4, 1, 64), (258, 3, 1, 8), (259, 3, 1, 5), (277, 3, 1, 1), (273, 4, 1, 4000),
+                        (278, 4, 1, 64), (279, 4, 1, 100)]))
+    with rio.open(p) as r:
+        with pytest.raises(rio.RasterError, match="outside the file"):
+            r.read(1)
+
+
 @pytest.mark.skipif(not os.path.isdir(REF_EXAMPLE), reason="reference checkout not mounted (build container only)")
 def test_reference_fixtures_decode_to_the_golden_inputs(tmp_path):
     """Example/input/*.tif are GDAL-written LZW tiles; example.py:33-52 turns them into the arrays
