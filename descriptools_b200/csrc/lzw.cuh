@@ -162,18 +162,28 @@ DTB_LZW_HD int64_t lzw_decode(const uint8_t *in, size_t n, uint8_t *out, size_t 
 // ---------------------------------------------------------------------------------------------------------
 // Encoder for the device (and its CPU replay).  Any parse into table strings is a valid stream as long as the
 // code numbering stays in step with the decoder's (one new entry per code), so the dictionary may forget:
-// it is a 2-way bucketed hash of (prefix code, byte) -> code that simply overwrites on conflict, and a table
-// reset is a bump of the generation number stored in every slot instead of a sweep.  Slots are 64-bit words
-// [63..32 generation | 31..12 prefix << 8 | byte | 11..0 code]; `tab` holds kLzwHashSlots of them, zeroed once;
-// `gen` lives across calls (per warp) and starts at 0.
+// it is a 2-way bucketed hash of (prefix code, byte) -> code that overwrites on conflict.  A slot is 32 bits,
+// [31..12 prefix << 8 | byte | 11..0 code], all ones = empty (code 4095 is never assigned); a bucket is one aligned
+// 64-bit word, so a lookup is one load.  `tab` holds kLzwHashSlots slots (32 KB: small enough to live in shared
+// memory, one table per warp) and is wiped by the lanes together at every table reset.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kLzwHashSlots = 8192;
 
 // worst case: every byte its own 12-bit code, plus Clear / EOI codes and the final flush
 DTB_LZW_HD size_t lzw_encode_bound(size_t n) { return n + n / 2 + n / 2048 + 16; }
 
-// Returns the number of bytes written to `out`, or -1 if `cap` is too small.
-DTB_LZW_HD int64_t lzw_encode(const uint8_t *in, size_t n, uint8_t *out, size_t cap, uint64_t *tab, uint32_t &gen)
+DTB_LZW_HD void lzw_hash_wipe(uint64_t *buckets, int lane0, int lane1, int nlanes)
+{
+    DTB_LZW_WARP_SYNC();  // every earlier store to the table is ordered before the wipe
+    for (int l = lane0; l < lane1; ++l)
+        for (int i = l; i < kLzwHashSlots / 2; i += nlanes) buckets[i] = ~(uint64_t)0;
+    DTB_LZW_WARP_SYNC();  // and the wipe before the lookups that follow
+}
+
+// Returns the number of bytes written to `out`, or -1 if `cap` is too small.  `buckets`: kLzwHashSlots / 2 words of
+// 64 bits (two slots each).  [lane0, lane1) of nlanes as for lzw_decode.
+DTB_LZW_HD int64_t lzw_encode(const uint8_t *in, size_t n, uint8_t *out, size_t cap, uint64_t *buckets, int lane0 = 0, int lane1 = 1,
+                              int nlanes = 1)
 {
     uint64_t acc = 0;
     int have = 0;
@@ -190,28 +200,28 @@ DTB_LZW_HD int64_t lzw_encode(const uint8_t *in, size_t n, uint8_t *out, size_t 
             have -= 8;
         }
     };
-    ++gen;
+    lzw_hash_wipe(buckets, lane0, lane1, nlanes);
     put(256);
     if (n > 0) {
         int ent = in[0];
         for (size_t i = 1; i < n; ++i) {
             const uint32_t c = in[i];
             const uint32_t key = ((uint32_t)ent << 8) | c;
-            const uint64_t tag = ((uint64_t)gen << 20) | key;
             const uint32_t b = ((key * 2654435761u) >> 20) & (uint32_t)(kLzwHashSlots / 2 - 1);
-            const uint64_t s0 = tab[2 * b], s1 = tab[2 * b + 1];
-            if ((s0 >> 12) == tag) { ent = (int)(s0 & 0xFFFu); continue; }
-            if ((s1 >> 12) == tag) { ent = (int)(s1 & 0xFFFu); continue; }
+            const uint64_t pair = buckets[b];
+            const uint32_t s0 = (uint32_t)pair, s1 = (uint32_t)(pair >> 32);
+            if ((s0 >> 12) == key && s0 != ~0u) { ent = (int)(s0 & 0xFFFu); continue; }
+            if ((s1 >> 12) == key && s1 != ~0u) { ent = (int)(s1 & 0xFFFu); continue; }
             put(ent);
-            const uint64_t slot = (tag << 12) | (uint64_t)next;
-            // a way left over from an earlier generation first, else the one the byte picks
-            const uint32_t way = (uint32_t)(s0 >> 32) != gen ? 0u : (uint32_t)(s1 >> 32) != gen ? 1u : (c & 1u);
-            tab[2 * b + way] = slot;
+            // an empty way first, else the one the byte picks (the older entry is forgotten)
+            const uint32_t way = s0 == ~0u ? 0u : s1 == ~0u ? 1u : (c & 1u);
+            const uint64_t slot = (uint64_t)((key << 12) | (uint32_t)next);
+            buckets[b] = way ? ((pair & 0xFFFFFFFFull) | (slot << 32)) : ((pair & ~0xFFFFFFFFull) | slot);  // same word from every lane
             ent = (int)c;
             ++next;
-            if (next == 4094) {  // table full: Clear, and forget everything by moving to the next generation
+            if (next == 4094) {  // table full: Clear, and forget everything
                 put(256);
-                ++gen;
+                lzw_hash_wipe(buckets, lane0, lane1, nlanes);
                 nbits = 9;
                 next = 258;
                 maxcode = 511;

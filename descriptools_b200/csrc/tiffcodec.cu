@@ -10,8 +10,8 @@
 // halve the bytes crossing PCIe.
 //
 // The way back (example.py:216-217 writes one class map; the chain writes seven rasters) mirrors it: a warp gathers
-// its tile from the raster, applies the predictor, LZW-encodes it (lzw.cuh: forgetful 2-way hash dictionary, table
-// resets by generation number) into a worst-case slot; a second kernel packs the streams back to back so that one
+// its tile from the raster, applies the predictor, LZW-encodes it (lzw.cuh: forgetful 2-way hash dictionary of 32-bit
+// slots) into a worst-case slot; a second kernel packs the streams back to back so that one
 // device-to-host copy and one file write carry a whole group of tiles.
 //
 // Everything a lane does is in __host__ __device__ phase functions; dtb_selftest_tiff_decode_host() /
@@ -28,9 +28,15 @@
 namespace dtb {
 namespace {
 
-constexpr int TD_WARPS = 4;  // warps per CTA
+constexpr int TD_WARPS = 4;  // warps per CTA, string / hash tables in global memory
 constexpr int TD_LANES = 32;
 constexpr int TD_CTAS_PER_SM = 8;  // 64 registers x 128 threads: 8 CTAs fill the register file
+// tables in shared memory: 32 KB per warp, 7 warps = 224 KB of the 227 KB a CTA may have, one CTA per SM.  Fewer chunks
+// in flight (1 036 instead of 4 736) but a table access costs tens of cycles instead of an L2 / DRAM round trip.
+constexpr int TS_WARPS = 7;
+constexpr size_t TS_TABLE_BYTES = 32768;
+static_assert(sizeof(LzwPackedSlot) * kLzwTableSlots == TS_TABLE_BYTES, "decoder table must be 32 KB");
+static_assert(sizeof(uint32_t) * kLzwHashSlots == TS_TABLE_BYTES, "encoder table must be 32 KB");
 
 struct ChunkGeom {
     int64_t cy, cx;        // chunk row / column
@@ -168,17 +174,21 @@ __host__ __device__ inline void td_zero(const dtb_tiff_layout &L, const ChunkGeo
     }
 }
 
-__global__ void __launch_bounds__(TD_WARPS *TD_LANES)
+extern __shared__ __align__(16) uint8_t tc_smem[];  // TS_WARPS tables when the kernel is instantiated with SMEM
+
+template <int WARPS, bool SMEM>
+__global__ void __launch_bounds__(WARPS *TD_LANES)
 tiff_decode_kernel(dtb_tiff_layout L, const uint8_t *__restrict__ comp, const uint64_t *__restrict__ comp_off,
                    const uint64_t *__restrict__ comp_len, int64_t first_chunk, int64_t n_chunks, uint8_t *__restrict__ out,
                    uint8_t *__restrict__ ws, int64_t n_warps, unsigned long long *__restrict__ status)
 {
     const int lane = threadIdx.x % TD_LANES;
-    const int64_t warp = (int64_t)blockIdx.x * TD_WARPS + threadIdx.x / TD_LANES;
+    const int64_t warp = (int64_t)blockIdx.x * WARPS + threadIdx.x / TD_LANES;
     if (warp >= n_warps) return;
     const size_t per = td_scratch_bytes(L);
     uint8_t *buf = ws + (size_t)warp * per;
-    LzwPackedSlot *tab = reinterpret_cast<LzwPackedSlot *>(buf + (per - sizeof(LzwPackedSlot) * kLzwTableSlots));
+    LzwPackedSlot *tab = SMEM ? reinterpret_cast<LzwPackedSlot *>(tc_smem + (threadIdx.x / TD_LANES) * TS_TABLE_BYTES)
+                              : reinterpret_cast<LzwPackedSlot *>(buf + (per - sizeof(LzwPackedSlot) * kLzwTableSlots));
     for (int64_t c = warp; c < n_chunks; c += n_warps) {
         const ChunkGeom g = td_geom(L, first_chunk + c);
         const uint64_t off = comp_off[c], len = comp_len[c];
@@ -224,7 +234,7 @@ __host__ __device__ inline size_t te_bound(const dtb_tiff_layout &L)
 
 __host__ __device__ inline size_t te_scratch_bytes(const dtb_tiff_layout &L)
 {
-    return ((te_raw_bytes(L) + 15) & ~(size_t)15) + sizeof(uint64_t) * kLzwHashSlots;
+    return ((te_raw_bytes(L) + 15) & ~(size_t)15) + sizeof(uint32_t) * kLzwHashSlots;
 }
 
 // ---- phase 1 (all lanes per row): raster -> scratch chunk.  A partial tile is padded by repeating its last
@@ -276,34 +286,33 @@ __host__ __device__ inline void te_predict(const dtb_tiff_layout &L, const Chunk
 
 // ---- phase 3: scratch chunk -> encoded slot; returns the encoded size (the same in every lane) ----
 __host__ __device__ inline int64_t te_encode(const dtb_tiff_layout &L, const ChunkGeom &g, const uint8_t *buf, uint8_t *slot, size_t bound,
-                                             uint64_t *tab, uint32_t &gen, int lane0, int lane1)
+                                             uint64_t *tab, int lane0, int lane1)
 {
-    if (L.compression == 5) return lzw_encode(buf, (size_t)g.raw_bytes, slot, bound, tab, gen);
+    if (L.compression == 5) return lzw_encode(buf, (size_t)g.raw_bytes, slot, bound, tab, lane0, lane1, TD_LANES);
     for (int l = lane0; l < lane1; ++l)
         for (int64_t i = l; i < g.raw_bytes; i += TD_LANES) slot[i] = buf[i];
     return g.raw_bytes;
 }
 
-__global__ void __launch_bounds__(TD_WARPS *TD_LANES)
+template <int WARPS, bool SMEM>
+__global__ void __launch_bounds__(WARPS *TD_LANES)
 tiff_encode_kernel(dtb_tiff_layout L, const uint8_t *__restrict__ raster, int64_t first_chunk, int64_t n_chunks,
                    uint8_t *__restrict__ enc, long long *__restrict__ sizes, uint8_t *__restrict__ ws, int64_t n_warps)
 {
     const int lane = threadIdx.x % TD_LANES;
-    const int64_t warp = (int64_t)blockIdx.x * TD_WARPS + threadIdx.x / TD_LANES;
+    const int64_t warp = (int64_t)blockIdx.x * WARPS + threadIdx.x / TD_LANES;
     if (warp >= n_warps) return;
     const size_t per = te_scratch_bytes(L), bound = te_bound(L);
     uint8_t *buf = ws + (size_t)warp * per;
-    uint64_t *tab = reinterpret_cast<uint64_t *>(buf + (per - sizeof(uint64_t) * kLzwHashSlots));
-    for (int i = lane; i < kLzwHashSlots; i += TD_LANES) tab[i] = 0;  // generations restart with every launch
-    uint32_t gen = 0;
-    __syncwarp();
+    uint64_t *tab = SMEM ? reinterpret_cast<uint64_t *>(tc_smem + (threadIdx.x / TD_LANES) * TS_TABLE_BYTES)
+                         : reinterpret_cast<uint64_t *>(buf + (per - sizeof(uint32_t) * kLzwHashSlots));
     for (int64_t c = warp; c < n_chunks; c += n_warps) {
         const ChunkGeom g = td_geom(L, first_chunk + c);
         te_gather(L, g, raster, buf, lane);
         __syncwarp();
         te_predict(L, g, buf, lane);
         __syncwarp();
-        const int64_t n = te_encode(L, g, buf, enc + (size_t)c * bound, bound, tab, gen, lane, lane + 1);
+        const int64_t n = te_encode(L, g, buf, enc + (size_t)c * bound, bound, tab, lane, lane + 1);
         if (lane == 0) sizes[c] = n;
         __syncwarp();  // the scratch chunk is reused by this warp's next chunk
     }
@@ -334,6 +343,23 @@ int64_t td_warp_cap()
         if (v >= 1 && v <= TD_CTAS_PER_SM) ctas = v;
     }
     return (int64_t)kNumSMs * ctas * TD_WARPS;
+}
+
+// where the tables live: DTB_TIFF_TABLES=shared | global (default global)
+bool tc_tables_in_smem()
+{
+    const char *e = getenv("DTB_TIFF_TABLES");
+    return e && strcmp(e, "shared") == 0;
+}
+
+// the shared-memory instantiations need the opt-in to 224 KB of dynamic shared memory, once per process
+template <typename K>
+cudaError_t tc_allow_smem(K kernel, bool &done)
+{
+    if (done) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TS_WARPS * TS_TABLE_BYTES));
+    if (e == cudaSuccess) done = true;
+    return e;
 }
 
 int td_validate_common(const dtb_tiff_layout *L)
@@ -393,16 +419,26 @@ int dtb_tiff_decode_chunks(const dtb_tiff_layout *lay, const uint8_t *comp, cons
     const size_t per = td_scratch_bytes(*lay);
     if (ws_bytes < per + 256) return DTB_ERR_WORKSPACE;
     int64_t warps = (int64_t)((ws_bytes - 256) / per);
-    const int64_t cap = td_warp_cap();
+    const bool smem = tc_tables_in_smem();
+    const int64_t cap = smem ? (int64_t)kNumSMs * TS_WARPS : td_warp_cap();
     if (warps > cap) warps = cap;
     if (warps > n_chunks) warps = n_chunks;
     // scratch chunks start 256-byte aligned
     uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-    const unsigned blocks = (unsigned)((warps + TD_WARPS - 1) / TD_WARPS);
     cudaStream_t st = as_stream(stream);
-    DTB_KERNEL("tiff_decode_kernel", st,
-               tiff_decode_kernel<<<blocks, TD_WARPS * TD_LANES, 0, st>>>(*lay, comp, comp_off, comp_len, first_chunk, n_chunks,
-                                                                         (uint8_t *)out, base, warps, status));
+    if (smem) {
+        static bool allowed = false;
+        DTB_CUDA(tc_allow_smem(tiff_decode_kernel<TS_WARPS, true>, allowed));
+        const unsigned blocks = (unsigned)((warps + TS_WARPS - 1) / TS_WARPS);
+        DTB_KERNEL("tiff_decode_kernel<shared>", st,
+                   tiff_decode_kernel<TS_WARPS, true><<<blocks, TS_WARPS * TD_LANES, TS_WARPS * TS_TABLE_BYTES, st>>>(
+                       *lay, comp, comp_off, comp_len, first_chunk, n_chunks, (uint8_t *)out, base, warps, status));
+    } else {
+        const unsigned blocks = (unsigned)((warps + TD_WARPS - 1) / TD_WARPS);
+        DTB_KERNEL("tiff_decode_kernel", st,
+                   tiff_decode_kernel<TD_WARPS, false><<<blocks, TD_WARPS * TD_LANES, 0, st>>>(
+                       *lay, comp, comp_off, comp_len, first_chunk, n_chunks, (uint8_t *)out, base, warps, status));
+    }
     return DTB_OK;
 }
 
@@ -464,15 +500,25 @@ int dtb_tiff_encode_chunks(const dtb_tiff_layout *lay, const void *raster, int64
     const size_t per = te_scratch_bytes(*lay);
     if (ws_bytes < per + 256) return DTB_ERR_WORKSPACE;
     int64_t warps = (int64_t)((ws_bytes - 256) / per);
-    const int64_t cap = td_warp_cap();
+    const bool smem = tc_tables_in_smem();
+    const int64_t cap = smem ? (int64_t)kNumSMs * TS_WARPS : td_warp_cap();
     if (warps > cap) warps = cap;
     if (warps > n_chunks) warps = n_chunks;
     uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-    const unsigned blocks = (unsigned)((warps + TD_WARPS - 1) / TD_WARPS);
     cudaStream_t st = as_stream(stream);
-    DTB_KERNEL("tiff_encode_kernel", st,
-               tiff_encode_kernel<<<blocks, TD_WARPS * TD_LANES, 0, st>>>(*lay, (const uint8_t *)raster, first_chunk, n_chunks, enc,
-                                                                         sizes, base, warps));
+    if (smem) {
+        static bool allowed = false;
+        DTB_CUDA(tc_allow_smem(tiff_encode_kernel<TS_WARPS, true>, allowed));
+        const unsigned blocks = (unsigned)((warps + TS_WARPS - 1) / TS_WARPS);
+        DTB_KERNEL("tiff_encode_kernel<shared>", st,
+                   tiff_encode_kernel<TS_WARPS, true><<<blocks, TS_WARPS * TD_LANES, TS_WARPS * TS_TABLE_BYTES, st>>>(
+                       *lay, (const uint8_t *)raster, first_chunk, n_chunks, enc, sizes, base, warps));
+    } else {
+        const unsigned blocks = (unsigned)((warps + TD_WARPS - 1) / TD_WARPS);
+        DTB_KERNEL("tiff_encode_kernel", st,
+                   tiff_encode_kernel<TD_WARPS, false><<<blocks, TD_WARPS * TD_LANES, 0, st>>>(
+                       *lay, (const uint8_t *)raster, first_chunk, n_chunks, enc, sizes, base, warps));
+    }
     return DTB_OK;
 }
 
@@ -498,13 +544,12 @@ int dtb_selftest_tiff_encode_host(const dtb_tiff_layout *lay, const void *raster
     const size_t per = te_scratch_bytes(L), bound = te_bound(L);
     std::vector<uint8_t> scratch(per, 0);
     uint8_t *buf = scratch.data();
-    uint64_t *tab = reinterpret_cast<uint64_t *>(buf + (per - sizeof(uint64_t) * kLzwHashSlots));
-    uint32_t gen = 0;
+    uint64_t *tab = reinterpret_cast<uint64_t *>(buf + (per - sizeof(uint32_t) * kLzwHashSlots));
     for (int64_t c = 0; c < n_chunks; ++c) {
         const ChunkGeom g = td_geom(L, first_chunk + c);
         for (int lane = 0; lane < TD_LANES; ++lane) te_gather(L, g, (const uint8_t *)raster_host, buf, lane);
         for (int lane = 0; lane < TD_LANES; ++lane) te_predict(L, g, buf, lane);
-        sizes_host[c] = te_encode(L, g, buf, enc_host + (size_t)c * bound, bound, tab, gen, 0, TD_LANES);
+        sizes_host[c] = te_encode(L, g, buf, enc_host + (size_t)c * bound, bound, tab, 0, TD_LANES);
     }
     return DTB_OK;
 }
