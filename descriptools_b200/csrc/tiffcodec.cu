@@ -345,11 +345,17 @@ int64_t td_warp_cap()
     return (int64_t)kNumSMs * ctas * TD_WARPS;
 }
 
-// where the tables live: DTB_TIFF_TABLES=shared | global (default global)
-bool tc_tables_in_smem()
+// Where the tables live.  Measured on a B200 (profiles/r1z_raster_codec_tables_16384.json): a warp with its table in
+// shared memory runs ~2.4x faster, but only 1 036 of them are resident against 4 736 with the tables in global memory --
+// so shared memory wins while a launch has at most two shared-memory waves of chunks.  DTB_TIFF_TABLES=shared | global
+// overrides the choice.
+bool tc_tables_in_smem(int64_t n_chunks)
 {
-    const char *e = getenv("DTB_TIFF_TABLES");
-    return e && strcmp(e, "shared") == 0;
+    if (const char *e = getenv("DTB_TIFF_TABLES")) {
+        if (strcmp(e, "shared") == 0) return true;
+        if (strcmp(e, "global") == 0) return false;
+    }
+    return n_chunks <= 2 * (int64_t)kNumSMs * TS_WARPS;
 }
 
 // the shared-memory instantiations need the opt-in to 224 KB of dynamic shared memory, once per process
@@ -419,7 +425,7 @@ int dtb_tiff_decode_chunks(const dtb_tiff_layout *lay, const uint8_t *comp, cons
     const size_t per = td_scratch_bytes(*lay);
     if (ws_bytes < per + 256) return DTB_ERR_WORKSPACE;
     int64_t warps = (int64_t)((ws_bytes - 256) / per);
-    const bool smem = tc_tables_in_smem();
+    const bool smem = tc_tables_in_smem(n_chunks);
     const int64_t cap = smem ? (int64_t)kNumSMs * TS_WARPS : td_warp_cap();
     if (warps > cap) warps = cap;
     if (warps > n_chunks) warps = n_chunks;
@@ -500,7 +506,7 @@ int dtb_tiff_encode_chunks(const dtb_tiff_layout *lay, const void *raster, int64
     const size_t per = te_scratch_bytes(*lay);
     if (ws_bytes < per + 256) return DTB_ERR_WORKSPACE;
     int64_t warps = (int64_t)((ws_bytes - 256) / per);
-    const bool smem = tc_tables_in_smem();
+    const bool smem = tc_tables_in_smem(n_chunks);
     const int64_t cap = smem ? (int64_t)kNumSMs * TS_WARPS : td_warp_cap();
     if (warps > cap) warps = cap;
     if (warps > n_chunks) warps = n_chunks;

@@ -341,7 +341,8 @@ class DatasetWriter:
             if gdal_metadata:
                 self._set(_TAG_GDAL_METADATA, _T_ASCII, gdal_metadata)
         except Exception:
-            self.close()
+            self.closed = True
+            lib.dtbio_close_writer(self._h)  # no chunks yet: the library removes the file
             raise
 
     def _set(self, tag, ttype, value):

@@ -244,6 +244,9 @@ def test_errors_are_reported_not_guessed(tmp_path):
         with rio.open(tmp_path / "x.tif", "w", width=4, height=4, dtype="uint8") as dst:
             dst.write(np.zeros((5, 4), np.uint8))
     assert not os.path.exists(tmp_path / "x.tif")
+    with pytest.raises(rio.RasterError, match="GeoKeys"):
+        rio.open(tmp_path / "y.tif", "w", width=4, height=4, dtype="uint8", crs="EPSG:32722")
+    assert not os.path.exists(tmp_path / "y.tif")
 
 
 def _decode_like_the_device(path, first=0, count=None):
@@ -457,6 +460,10 @@ def test_reference_fixtures_decode_to_the_golden_inputs(tmp_path):
     np.testing.assert_array_equal(flood, ex["flood"])
     for name in ("12_dem", "12_fdr", "12_fac", "WB_12_100y"):
         np.testing.assert_array_equal(rio.open(f"{REF_EXAMPLE}/input/{name}.tif").read(1), _pil_read(f"{REF_EXAMPLE}/input/{name}.tif"))
+    for name in ("12_dem", "12_fdr", "12_fac", "WB_12_100y"):  # GDAL's LZW streams through the device decoder's lane code
+        out, status, _ = _decode_like_the_device(f"{REF_EXAMPLE}/input/{name}.tif")
+        assert status == 0
+        np.testing.assert_array_equal(out, _pil_read(f"{REF_EXAMPLE}/input/{name}.tif"))
     src = rio.open(f"{REF_EXAMPLE}/input/12_dem.tif")
     assert src.crs.to_epsg() == 32722 and src.block_shapes == [(128, 128)] and src.compression == "lzw"
     # example.py:201-217 on the reference's own class map: same pixels, same georeferencing, same layout
