@@ -152,7 +152,7 @@ def output_dtypes(dem_dtype: np.dtype, n_cells: int) -> dict:
 
 def pipeline_files(dem_path, out_dir, river_threshold: int, px: float | None = None, n_gfi: float = 0.4,
                    scale_factor: float = 0.1, size: float | None = None, outputs=STAGE_OUTPUTS, compress: str = "lzw",
-                   blocksize: int = 256, block_bytes: int = 256 << 20, threads: int = 0, decode: str = "host", encode: str = "host") -> dict:
+                   blocksize: int = 256, block_bytes: int = 256 << 20, threads: int = 0, decode: str = "auto", encode: str = "auto") -> dict:
     """The chain from a DEM GeoTIFF to one GeoTIFF per descriptor (`out_dir/<name>.tif`), what a user of the
     reference does around the descriptor calls with rasterio (example.py:33, :42-43, :201-217).
 
@@ -162,6 +162,8 @@ def pipeline_files(dem_path, out_dir, river_threshold: int, px: float | None = N
     Results are encoded block by block as they are copied back (raster.write_from_device; `encode="device"` encodes the
     tiles on the GPU and copies only the compressed bytes), tiled and compressed,
     with the DEM's georeferencing; nodata is -100 (0 for the D8 codes, like 12_fdr.tif).
+    `decode` / `encode`: "device", "host", or "auto" (default) = the device codec whenever it can take the file
+    (stored or LZW chunks), the host codec for the rest (Deflate, PackBits, chunks over 1 MiB).
     Returns {name: path}.
     """
     import torch

@@ -491,6 +491,22 @@ def chunk_table(reader: "DatasetReader"):
     return lay, across, off, cnt
 
 
+def device_decode_supported(reader: "DatasetReader") -> bool:
+    """can dtb_tiff_decode_chunks take this file?  (stored or LZW chunks of at most 1 MiB; the library decides)"""
+    from ._lib import lib as cuda_lib
+
+    lay = chunk_table(reader)[0]
+    return int(cuda_lib.dtb_tiff_decode_workspace_bytes(ctypes.byref(lay), 1)) > 0
+
+
+def device_encode_supported(writer: "DatasetWriter") -> bool:
+    """can dtb_tiff_encode_chunks produce this file's chunks?  (stored or LZW; the library decides)"""
+    from ._lib import lib as cuda_lib
+
+    lay = writer.chunk_layout()[0]
+    return int(cuda_lib.dtb_tiff_encode_bound(ctypes.byref(lay))) > 0
+
+
 def _read_to_device_chunks(reader, out, block_bytes: int, copy, group_chunks=None):
     """read_to_device(decode="device"): the compressed chunks go over PCIe as they lie in the file and are decoded
     by dtb_tiff_decode_chunks, one warp per chunk.  File spans are read into two pinned staging buffers; reading
@@ -566,16 +582,19 @@ def read_to_device(src, device=None, out=None, block_bytes: int = 256 << 20, thr
     decode="host": two pinned staging blocks; while block k is copied to the device on `stream` (default: a private
     copy stream) the codec's thread team decodes block k+1.
     decode="device": the compressed chunks are copied instead and decoded on the device (stored and LZW files;
-    anything else raises -- nothing falls back silently); `group_chunks` overrides the number of chunks per launch."""
+    anything else raises -- nothing falls back silently); `group_chunks` overrides the number of chunks per launch.
+    decode="auto": "device" when device_decode_supported(reader), else "host"."""
     import torch
 
     from . import device as _device
 
-    if decode not in ("host", "device"):
-        raise RasterError("decode must be 'host' or 'device'")
+    if decode not in ("host", "device", "auto"):
+        raise RasterError("decode must be 'host', 'device' or 'auto'")
     dev = torch.device(device) if device is not None else _device.require_cuda()
     reader = src if isinstance(src, DatasetReader) else DatasetReader(src)
     try:
+        if decode == "auto":  # the device codec when it can take the file: an explicit choice between two complete paths
+            decode = "device" if device_decode_supported(reader) and (out is None or out.is_contiguous()) else "host"
         if decode == "device":
             tdt = getattr(torch, reader.dtypes[0])
             if out is None:
@@ -687,11 +706,12 @@ def write_from_device(path, tensor, block_bytes: int = 256 << 20, threads: int =
 
     encode="host": row blocks; block k+1 is copied to its pinned staging buffer while the thread team encodes block k.
     encode="device": the chunks are encoded on the device and only the compressed bytes cross PCIe (stored and LZW
-    files; anything else raises -- nothing falls back silently)."""
+    files; anything else raises -- nothing falls back silently).
+    encode="auto": "device" when device_encode_supported(writer), else "host"."""
     import torch
 
-    if encode not in ("host", "device"):
-        raise RasterError("encode must be 'host' or 'device'")
+    if encode not in ("host", "device", "auto"):
+        raise RasterError("encode must be 'host', 'device' or 'auto'")
     if not tensor.is_cuda or tensor.dim() != 2:
         raise RasterError("write_from_device needs a 2-D CUDA tensor")
     rows, cols = tensor.shape
@@ -703,6 +723,8 @@ def write_from_device(path, tensor, block_bytes: int = 256 << 20, threads: int =
         raise RasterError("write_from_device: dtype of the file must be the tensor's (convert on the device first)")
     w = DatasetWriter(path, threads=threads, **meta)
     try:
+        if encode == "auto":
+            encode = "device" if device_encode_supported(w) and tensor.is_contiguous() else "host"
         if encode == "device":
             if not tensor.is_contiguous():
                 raise RasterError("write_from_device(encode='device') needs a contiguous tensor")

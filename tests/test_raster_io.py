@@ -415,6 +415,29 @@ def test_device_decoder_lane_code_big_endian_and_damage(tmp_path):
     assert _lib.lib.dtb_tiff_decode_chunks(ctypes.byref(lay), 1, 1, 1, 8, 2, 1, 1, 1 << 20, 1, None) == -1  # 9 chunks only
 
 
+def test_device_codec_selection_asks_the_library(tmp_path):
+    """pipeline_files(decode="auto", encode="auto") takes the device codec exactly when libdtb200 says it can"""
+    a = _rand((300, 300), "float32", seed=3)
+    cases = [(dict(compress="lzw", predictor=3, tiled=True, blockxsize=128, blockysize=128), True, True),
+             (dict(compress="none", blockysize=8), True, True),
+             (dict(compress="deflate", tiled=True, blockxsize=128, blockysize=128), False, False),
+             (dict(compress="lzw", blockysize=300), True, True),
+             (dict(compress="lzw", tiled=True, blockxsize=1024, blockysize=512), False, True)]  # 2 MiB chunks: decode needs <= 1 MiB
+    for kw, dec, enc in cases:
+        p = tmp_path / "s.tif"
+        with rio.open(p, "w", width=300, height=300, dtype="float32", **kw) as w:
+            assert rio.device_encode_supported(w) == enc, kw
+            w.write(a)
+        with rio.open(p) as r:
+            assert rio.device_decode_supported(r) == dec, kw
+    from PIL import Image
+
+    Image.fromarray(a).save(str(tmp_path / "pb.tif"), compression="packbits")
+    assert not rio.device_decode_supported(rio.open(tmp_path / "pb.tif"))
+    with pytest.raises(rio.RasterError, match="decode must be"):
+        rio.read_to_device(tmp_path / "pb.tif", decode="gpu")
+
+
 def test_damaged_headers_come_back_as_errors(tmp_path):
     """a file may claim anything: absurd chunk sizes and truncated data are reported, no exception crosses the C ABI"""
     def tiff(entries, data=b"\x80\x00\x40\x40"):
@@ -529,7 +552,7 @@ def test_pipeline_from_file_to_files(tmp_path):
                   nodata=-3.4028230607370965e38, crs=crs, transform=rio.Affine(12.5, 0, 1000.0, 0, -12.5, 9000.0)) as dst:
         dst.write(stored)
     want = pipeline.pipeline(np.where(hole, np.float32(-100), dem), 12.5, 300)
-    for where in ("host", "device"):
+    for where in ("host", "device", "auto"):
         paths = pipeline.pipeline_files(p, tmp_path / ("out_" + where), river_threshold=300, block_bytes=200_000, decode=where, encode=where)
         assert sorted(paths) == sorted(pipeline.STAGE_OUTPUTS)
         for name, path in paths.items():
