@@ -68,7 +68,8 @@ class HandArgs(Structure):
 
 class TiffLayout(Structure):
     _fields_ = [("rows", c_int64), ("cols", c_int64), ("bps", c_int32), ("predictor", c_int32), ("compression", c_int32),
-                ("tiled", c_int32), ("chunk_rows", c_int32), ("chunk_cols", c_int32), ("big_endian", c_int32)]
+                ("tiled", c_int32), ("chunk_rows", c_int32), ("chunk_cols", c_int32), ("big_endian", c_int32),
+                ("row_lo", c_int64), ("row_hi", c_int64)]
 
 
 class FlowaccArgs(Structure):

@@ -440,6 +440,24 @@ class BandRunner:
         for b, d in zip(self.bands, dem_rows):
             b.dem.copy_(d, non_blocking=True)
 
+    def load_file(self, path, decode: str = "auto", nodata=None):
+        """Every local band decodes its own rows of a float32 DEM GeoTIFF straight into its device buffer
+        (raster.read_to_device(rows=...): with decode="device" only the band's compressed tiles cross PCIe); the file's
+        nodata value (or `nodata`) becomes the path's sentinel -100, as example.py:42-43 does on the host."""
+        from . import raster
+
+        with raster.open(path) as src:
+            if src.shape != (self.rows, self.cols):
+                raise ValueError(f"{path}: raster is {src.shape}, the runner was built for {(self.rows, self.cols)}")
+            if src.dtypes[0] != "float32":
+                raise TypeError(f"{path}: row bands take float32 DEMs, the file holds {src.dtypes[0]}")
+            nd = src.nodata if nodata is None else nodata
+            for b in self.bands:
+                raster.read_to_device(src, out=b.dem, rows=(b.r0, b.r1), decode=decode)
+                if nd is not None:
+                    b.dem.masked_fill_(b.dem == nd, -100)
+                b.dem.masked_fill_(torch.isnan(b.dem), -100)
+
     def step(self, events=None, hook=None, check=True):
         """One pass of the chain; `events` (4 CUDA events) are recorded at the stage boundaries and `hook(i)` is
         called after stage i (1 slope+D8, 2 flow accumulation, 3 HAND/GFI) has been enqueued.

@@ -147,9 +147,12 @@ __host__ __device__ inline void td_phase3(const dtb_tiff_layout &L, const ChunkG
 {
     const int64_t width = g.row_bytes / L.bps;
     const int64_t bytes = g.ncols * L.bps;
+    const int64_t lo = L.row_lo, hi = L.row_hi > 0 ? L.row_hi : L.rows;  // the rows `out` holds
     for (int64_t r = 0; r < g.data_rows; ++r) {
+        const int64_t R = g.cy * L.chunk_rows + r;
+        if (R < lo || R >= hi) continue;
         const uint8_t *row = buf + r * g.row_bytes;
-        uint8_t *dst = out + ((g.cy * L.chunk_rows + r) * L.cols + g.x0) * L.bps;
+        uint8_t *dst = out + ((R - lo) * L.cols + g.x0) * L.bps;
         if (L.predictor == 3) {
             // sample i, byte b (little-endian) sits in plane bps-1-b at position i
             for (int64_t i = lane; i < g.ncols; i += TD_LANES)
@@ -168,8 +171,11 @@ __host__ __device__ inline void td_phase3(const dtb_tiff_layout &L, const ChunkG
 __host__ __device__ inline void td_zero(const dtb_tiff_layout &L, const ChunkGeom &g, uint8_t *out, int lane)
 {
     const int64_t bytes = g.ncols * L.bps;
+    const int64_t lo = L.row_lo, hi = L.row_hi > 0 ? L.row_hi : L.rows;
     for (int64_t r = 0; r < g.data_rows; ++r) {
-        uint8_t *dst = out + ((g.cy * L.chunk_rows + r) * L.cols + g.x0) * L.bps;
+        const int64_t R = g.cy * L.chunk_rows + r;
+        if (R < lo || R >= hi) continue;
+        uint8_t *dst = out + ((R - lo) * L.cols + g.x0) * L.bps;
         for (int64_t i = lane; i < bytes; i += TD_LANES) dst[i] = 0;
     }
 }
@@ -376,6 +382,8 @@ int td_validate_common(const dtb_tiff_layout *L)
     if (L->tiled && L->chunk_cols <= 0) return DTB_ERR_INVALID;
     if (L->compression != 1 && L->compression != 5) return DTB_ERR_UNSUPPORTED;
     if (L->compression == 1 && L->predictor != 1) return DTB_ERR_INVALID;  // the predictor belongs to the codec
+    if (L->row_lo != 0 || L->row_hi != 0)
+        if (L->row_lo < 0 || L->row_lo >= L->row_hi || L->row_hi > L->rows) return DTB_ERR_INVALID;
     return DTB_OK;
 }
 
@@ -384,6 +392,7 @@ int te_validate(const dtb_tiff_layout *L)
     const int v = td_validate_common(L);
     if (v != DTB_OK) return v;
     if (L->big_endian) return DTB_ERR_UNSUPPORTED;  // files are written little-endian
+    if (L->row_lo != 0 || L->row_hi != 0) return DTB_ERR_UNSUPPORTED;  // whole rasters only
     if (L->predictor == 3 && L->bps < 4) return DTB_ERR_INVALID;
     return DTB_OK;
 }

@@ -507,7 +507,12 @@ def device_encode_supported(writer: "DatasetWriter") -> bool:
     return int(cuda_lib.dtb_tiff_encode_bound(ctypes.byref(lay))) > 0
 
 
-def _read_to_device_chunks(reader, out, block_bytes: int, copy, group_chunks=None):
+def _band_chunks(row_lo: int, row_hi: int, chunk_rows: int, across: int) -> tuple:
+    """[first, last) of the chunks that hold raster rows [row_lo, row_hi)"""
+    return (row_lo // chunk_rows) * across, -(-row_hi // chunk_rows) * across
+
+
+def _read_to_device_chunks(reader, out, block_bytes: int, copy, group_chunks=None, rows=None):
     """read_to_device(decode="device"): the compressed chunks go over PCIe as they lie in the file and are decoded
     by dtb_tiff_decode_chunks, one warp per chunk.  File spans are read into two pinned staging buffers; reading
     span k+1 overlaps the copy and decode of span k on `copy`."""
@@ -520,10 +525,14 @@ def _read_to_device_chunks(reader, out, block_bytes: int, copy, group_chunks=Non
     if lay.compression not in (1, 5):
         raise RasterError(f"decode='device' handles stored and LZW chunks, not {reader.compression}; use decode='host'")
     dev = out.device
-    n = off.size
+    c_lo, c_hi = 0, off.size
+    if rows is not None:  # a row band: `out` holds rows [rows[0], rows[1]) and the kernel stores only those
+        lay.row_lo, lay.row_hi = int(rows[0]), int(rows[1])
+        c_lo, c_hi = _band_chunks(lay.row_lo, lay.row_hi, lay.chunk_rows, across)
+    n = c_hi - c_lo
     chunk_raw = lay.chunk_rows * lay.chunk_cols * lay.bps
     per_group = group_chunks or _chunks_per_group(n, across, chunk_raw, block_bytes)
-    groups = [(g0, min(n, g0 + per_group)) for g0 in range(0, n, per_group)]
+    groups = [(g0, min(c_hi, g0 + per_group)) for g0 in range(c_lo, c_hi, per_group)]
     spans = []
     for g0, g1 in groups:
         live = cnt[g0:g1] > 0
@@ -575,7 +584,7 @@ def _read_to_device_chunks(reader, out, block_bytes: int, copy, group_chunks=Non
 
 
 def read_to_device(src, device=None, out=None, block_bytes: int = 256 << 20, threads: int = 0, stream=None, decode: str = "host",
-                   group_chunks: int | None = None):
+                   group_chunks: int | None = None, rows: tuple | None = None):
     """Decode a raster into a CUDA tensor.  Returns the tensor (dtype of the file); the current stream waits for
     the last copy.  `src` is a path or a DatasetReader.
 
@@ -583,7 +592,9 @@ def read_to_device(src, device=None, out=None, block_bytes: int = 256 << 20, thr
     copy stream) the codec's thread team decodes block k+1.
     decode="device": the compressed chunks are copied instead and decoded on the device (stored and LZW files;
     anything else raises -- nothing falls back silently); `group_chunks` overrides the number of chunks per launch.
-    decode="auto": "device" when device_decode_supported(reader), else "host"."""
+    decode="auto": "device" when device_decode_supported(reader), else "host".
+    rows=(r0, r1): only that row band of the raster (the tensor has r1 - r0 rows) -- what one rank of a row-band run
+    loads (bands.BandRunner.load_file)."""
     import torch
 
     from . import device as _device
@@ -595,31 +606,34 @@ def read_to_device(src, device=None, out=None, block_bytes: int = 256 << 20, thr
     try:
         if decode == "auto":  # the device codec when it can take the file: an explicit choice between two complete paths
             decode = "device" if device_decode_supported(reader) and (out is None or out.is_contiguous()) else "host"
-        if decode == "device":
-            tdt = getattr(torch, reader.dtypes[0])
-            if out is None:
-                out = torch.empty(reader.shape, dtype=tdt, device=dev)
-            elif tuple(out.shape) != reader.shape or out.dtype != tdt or not out.is_cuda or not out.is_contiguous():
-                raise RasterError("read_to_device: `out` must be a contiguous CUDA tensor of the raster's shape and dtype")
-            return _read_to_device_chunks(reader, out, block_bytes, stream if stream is not None else torch.cuda.Stream(device=out.device),
-                                          group_chunks)
+        first, last = (0, reader.height) if rows is None else (int(rows[0]), int(rows[1]))
+        if not 0 <= first < last <= reader.height:
+            raise RasterError(f"read_to_device: rows {rows} outside the raster")
+        shape = (last - first, reader.width)
         tdt = getattr(torch, reader.dtypes[0])
-        rows, cols = reader.shape
+        if decode == "device":
+            if out is None:
+                out = torch.empty(shape, dtype=tdt, device=dev)
+            elif tuple(out.shape) != shape or out.dtype != tdt or not out.is_cuda or not out.is_contiguous():
+                raise RasterError("read_to_device: `out` must be a contiguous CUDA tensor of the (band of the) raster's shape and dtype")
+            return _read_to_device_chunks(reader, out, block_bytes, stream if stream is not None else torch.cuda.Stream(device=out.device),
+                                          group_chunks, None if rows is None else (first, last))
+        nrows, cols = shape
         if out is None:
-            out = torch.empty((rows, cols), dtype=tdt, device=dev)
-        elif tuple(out.shape) != (rows, cols) or out.dtype != tdt or not out.is_cuda:
-            raise RasterError("read_to_device: `out` must be a CUDA tensor of the raster's shape and dtype")
-        br = _block_rows(rows, reader.block_shapes[0][0], cols, out.element_size(), block_bytes)
-        stage = [torch.empty((br, cols), dtype=tdt).pin_memory() for _ in range(2 if rows > br else 1)]
+            out = torch.empty(shape, dtype=tdt, device=dev)
+        elif tuple(out.shape) != shape or out.dtype != tdt or not out.is_cuda:
+            raise RasterError("read_to_device: `out` must be a CUDA tensor of the (band of the) raster's shape and dtype")
+        br = _block_rows(nrows, reader.block_shapes[0][0], cols, out.element_size(), block_bytes)
+        stage = [torch.empty((br, cols), dtype=tdt).pin_memory() for _ in range(2 if nrows > br else 1)]
         free = [None] * len(stage)
         copy = stream if stream is not None else torch.cuda.Stream(device=out.device)
         copy.wait_stream(torch.cuda.current_stream(out.device))  # `out` may reuse memory the current stream still works on
-        for k, r0 in enumerate(range(0, rows, br)):
-            n = min(br, rows - r0)
+        for k, r0 in enumerate(range(0, nrows, br)):
+            n = min(br, nrows - r0)
             s = k % len(stage)
             if free[s] is not None:
                 free[s].synchronize()  # the copy that last read this staging block has finished
-            reader.read_rows(r0, n, stage[s], threads)
+            reader.read_rows(first + r0, n, stage[s], threads)
             with torch.cuda.stream(copy):
                 out[r0:r0 + n].copy_(stage[s][:n], non_blocking=True)
                 free[s] = torch.cuda.Event()

@@ -278,7 +278,8 @@ int dtb_minmax_scale(const void *mat, int mat_dtype, int64_t n, double mn, doubl
  *   comp         device buffer with the compressed bytes; chunk first_chunk + i is comp[comp_off[i] ..
  *                comp_off[i] + comp_len[i]); comp_off / comp_len are DEVICE arrays; comp_len[i] == 0 = absent
  *                chunk (reads as zeros).
- *   out          device pointer to the WHOLE raster (rows x cols samples of bps bytes, dense).
+ *   out          device pointer to the raster (rows x cols samples of bps bytes, dense), or to the row band
+ *                [lay->row_lo, lay->row_hi) of it.
  *   ws           dtb_tiff_decode_workspace_bytes(lay, n_chunks) bytes (one scratch chunk + string table per
  *                resident warp; fewer bytes = fewer warps, at least one).
  *   status       device word, zeroed by the caller: stays 0, or receives ((chunk + 1) << 3) | reason for the
@@ -294,6 +295,9 @@ typedef struct dtb_tiff_layout {
     int32_t chunk_rows;  /* TileLength or RowsPerStrip                        */
     int32_t chunk_cols;  /* TileWidth (ignored for strips)                    */
     int32_t big_endian;  /* samples stored most significant byte first        */
+    /* decode only: `out` holds raster rows [row_lo, row_hi) (a row band: out points at row row_lo) and only those
+     * rows are stored; both 0 = the whole raster.  Encoding takes whole rasters (both must be 0). */
+    int64_t row_lo, row_hi;
 } dtb_tiff_layout;
 size_t dtb_tiff_decode_workspace_bytes(const dtb_tiff_layout *lay, int64_t n_chunks);
 int dtb_tiff_decode_chunks(const dtb_tiff_layout *lay, const uint8_t *comp, const uint64_t *comp_off,

@@ -249,7 +249,7 @@ def test_errors_are_reported_not_guessed(tmp_path):
     assert not os.path.exists(tmp_path / "y.tif")
 
 
-def _decode_like_the_device(path, first=0, count=None):
+def _decode_like_the_device(path, first=0, count=None, rows=None):
     """the tile-decoding kernel's per-lane code (csrc/tiffcodec.cu), run lane by lane on the CPU by the library's self-test
     entry point: same geometry, LZW, byte order, predictor and store code the warps execute"""
     from descriptools_b200 import _lib
@@ -258,6 +258,11 @@ def _decode_like_the_device(path, first=0, count=None):
         lay, across, off, cnt = rio.chunk_table(r)
         shape, dtype = r.shape, r.dtypes[0]
     data = np.fromfile(path, dtype=np.uint8)
+    if rows is not None:  # a row band: the output holds only those rows
+        lay.row_lo, lay.row_hi = rows
+        shape = (rows[1] - rows[0], shape[1])
+        first, last = rio._band_chunks(rows[0], rows[1], lay.chunk_rows, across)
+        count = last - first
     out = np.full(shape, 7, dtype=dtype)
     status = ctypes.c_ulonglong(99)
     n = off.size - first if count is None else count
@@ -289,6 +294,11 @@ def test_device_decoder_lane_code_on_the_cpu(tmp_path, dtype, layout, compress, 
     assert status == 0
     np.testing.assert_array_equal(out[r0:r1], a[r0:r1])
     assert (out[:r0] == 7).all() and (out[r1:] == 7).all()
+    # a row band that starts and ends inside chunks: exactly its rows, nothing written outside the band's buffer
+    for band in ((70, 141), (0, 64), (150, 157), (3, 4)):
+        out, status, _ = _decode_like_the_device(path, rows=band)
+        assert status == 0 and out.shape == (band[1] - band[0], 203)
+        np.testing.assert_array_equal(out, a[band[0]:band[1]], err_msg=str(band))
 
 
 def _encode_like_the_device(path, a, **kw):
@@ -632,3 +642,35 @@ def test_tiles_encoded_on_the_device(tmp_path, dtype, layout, compress, predicto
     with pytest.raises(rio.RasterError, match="encode='host'"):
         rio.write_from_device(p, t, encode="device", compress="deflate")
     assert not os.path.exists(p)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("decode", ["host", "device"])
+def test_row_bands_from_a_file(tmp_path, decode):
+    """read_to_device(rows=...) and BandRunner.load_file: every band decodes its own rows; the band run on the file
+    equals the single-raster run on the array, bit for bit"""
+    import oracle
+    import torch
+
+    from descriptools_b200 import bands, pipeline
+
+    dem = oracle.conditioned_dem(640, 330, seed=17)
+    hole = np.zeros(dem.shape, bool)
+    hole[100:140, 40:90] = True  # stored with the file's own nodata value, normalised to -100 by load_file
+    p = tmp_path / "dem.tif"
+    with rio.open(p, "w", width=330, height=640, dtype="float32", compress="lzw", predictor=3, tiled=True, blockxsize=128, blockysize=128,
+                  nodata=-9999.0) as dst:
+        dst.write(np.where(hole, np.float32(-9999.0), dem))
+    for band in ((0, 640), (64, 320), (320, 640), (130, 131)):  # seams inside tiles
+        t = rio.read_to_device(p, rows=band, decode=decode, group_chunks=3 if decode == "device" else None, block_bytes=100_000)
+        np.testing.assert_array_equal(t.cpu().numpy(), np.where(hole, np.float32(-9999.0), dem)[band[0]:band[1]], err_msg=str(band))
+    clean = np.where(hole, np.float32(-100), dem)
+    ref = pipeline.run_device(torch.from_numpy(clean).cuda(), 12.5, 300)
+    runner = bands.BandRunner(640, 330, 12.5, 300, 0.4, 0.1, nbands=2)
+    runner.load_file(p, decode=decode)
+    runner.step()
+    torch.cuda.synchronize()
+    outs = runner.outputs()
+    for name in ("slope", "d8", "acc", "idx", "fdist", "hand", "gfi"):
+        got = torch.cat([o[name] for o in outs], 0).cpu().numpy()
+        np.testing.assert_array_equal(got, ref[name].cpu().numpy(), err_msg=name)
