@@ -1,0 +1,211 @@
+// inflate.cuh -- zlib / Deflate (RFC 1950, RFC 1951) decoding for the device tile decoder (tiffcodec.cu) and its
+// CPU replay.  GeoTIFFs written with COMPRESS=DEFLATE hold one zlib stream per tile or strip.
+//
+// Same execution model as the LZW decoder in lzw.cuh: a whole warp runs the decoder in lock step (identical state in
+// every lane, uniform control flow, broadcast loads, table stores of the same value from every lane), and the only
+// work that is spread over the lanes is the copy of a match -- `byte i = source[i mod distance]`, which also covers
+// the overlapping matches Deflate uses for runs.  Huffman codes are decoded canonically, one bit per step, from the
+// per-length counts and the symbols sorted by code (about 1 KB of tables per warp, in the warp's table area).
+// The Adler-32 trailer is not checked: a damaged chunk shows up as a bad code, a bad distance or a short chunk.
+// `lane0, lane1, nlanes` as in lzw.cuh.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "lzw.cuh"  // DTB_LZW_HD, DTB_LZW_WARP_SYNC
+
+namespace dtb {
+
+struct InflateScratch {
+    uint16_t len_count[16], len_symbol[288];   // literal / length code
+    uint16_t dist_count[16], dist_symbol[32];  // distance code
+    uint16_t offs[16];
+    uint8_t lengths[320];                      // code lengths while a dynamic block's header is read
+};
+
+struct InflateBits {
+    const uint8_t *in;
+    size_t n, ip;
+    uint64_t buf;
+    int cnt;
+    bool starved;  // asked for bits past the end of the input
+};
+
+// k <= 16 bits, least significant first; bytes are fetched only when needed, so fewer than 8 bits are ever left over
+DTB_LZW_HD uint32_t inflate_bits(InflateBits &b, int k)
+{
+    while (b.cnt < k) {
+        uint32_t byte = 0;
+        if (b.ip < b.n) byte = b.in[b.ip++];
+        else b.starved = true;
+        b.buf |= (uint64_t)byte << b.cnt;
+        b.cnt += 8;
+    }
+    const uint32_t v = (uint32_t)(b.buf & ((1u << k) - 1u));
+    b.buf >>= k;
+    b.cnt -= k;
+    return v;
+}
+
+// canonical Huffman decoding: codes of one length are consecutive, and the first code of each length follows from the
+// counts of the shorter ones.  Returns the symbol or -1 (no such code).
+DTB_LZW_HD int inflate_symbol(InflateBits &b, const uint16_t *count, const uint16_t *symbol)
+{
+    int code = 0, first = 0, index = 0;
+    for (int len = 1; len <= 15; ++len) {
+        code |= (int)inflate_bits(b, 1);
+        const int c = count[len];
+        if (code - c < first) return symbol[index + (code - first)];
+        index += c;
+        first += c;
+        first <<= 1;
+        code <<= 1;
+    }
+    return -1;
+}
+
+// Tables for the code whose symbol i has length[i] bits (0 = unused).  Returns 0 for a complete code, a negative
+// number for an over-subscribed one, a positive number for an incomplete one.
+DTB_LZW_HD int inflate_build(uint16_t *count, uint16_t *symbol, uint16_t *offs, const uint8_t *length, int n)
+{
+    for (int len = 0; len <= 15; ++len) count[len] = 0;
+    for (int i = 0; i < n; ++i) count[length[i]] = (uint16_t)(count[length[i]] + 1);
+    if (count[0] == n) return 0;  // no codes at all: complete, and decoding anything with it fails
+    int left = 1;
+    for (int len = 1; len <= 15; ++len) {
+        left <<= 1;
+        left -= count[len];
+        if (left < 0) return left;
+    }
+    offs[1] = 0;
+    for (int len = 1; len < 15; ++len) offs[len + 1] = (uint16_t)(offs[len] + count[len]);
+    for (int i = 0; i < n; ++i)
+        if (length[i] != 0) {
+            symbol[offs[length[i]]] = (uint16_t)i;
+            offs[length[i]] = (uint16_t)(offs[length[i]] + 1);
+        }
+    return left;
+}
+
+// order in which the code-length code's own lengths are stored (RFC 1951, 3.2.7), five bits per entry
+DTB_LZW_HD int inflate_order(int i)
+{
+    // 16 17 18 0 8 7 9 6 10 5 11 4 | 12 3 13 2 14 1 15
+    const uint64_t lo = 16ull | 17ull << 5 | 18ull << 10 | 0ull << 15 | 8ull << 20 | 7ull << 25 | 9ull << 30 | 6ull << 35 | 10ull << 40 |
+                        5ull << 45 | 11ull << 50 | 4ull << 55;
+    const uint64_t hi = 12ull | 3ull << 5 | 13ull << 10 | 2ull << 15 | 14ull << 20 | 1ull << 25 | 15ull << 30;
+    return i < 12 ? (int)((lo >> (5 * i)) & 31u) : (int)((hi >> (5 * (i - 12))) & 31u);
+}
+
+// Decodes at most `cap` bytes of the zlib stream `in` into `out`.  Returns the number of bytes produced or -1 for a
+// damaged stream.
+DTB_LZW_HD int64_t zlib_inflate(const uint8_t *in, size_t n, uint8_t *out, size_t cap, InflateScratch *t, int lane0 = 0, int lane1 = 1,
+                                int nlanes = 1)
+{
+    if (n < 2) return -1;
+    const uint32_t cmf = in[0], flg = in[1];
+    if ((cmf & 0x0Fu) != 8u || ((cmf << 8) | flg) % 31u != 0u || (flg & 0x20u)) return -1;  // not Deflate, bad check, preset dictionary
+    InflateBits b{in, n, 2, 0, 0, false};
+    size_t op = 0;
+    bool last = false;
+    while (!last && op < cap) {
+        last = inflate_bits(b, 1) != 0;
+        const uint32_t type = inflate_bits(b, 2);
+        if (b.starved) return -1;
+        if (type == 0) {  // stored: the rest of the byte is skipped, LEN, ~LEN, then LEN bytes
+            b.buf = 0;
+            b.cnt = 0;
+            if (b.ip + 4 > n) return -1;
+            const uint32_t len = in[b.ip] | ((uint32_t)in[b.ip + 1] << 8), nlen = in[b.ip + 2] | ((uint32_t)in[b.ip + 3] << 8);
+            if (len != (~nlen & 0xFFFFu)) return -1;
+            b.ip += 4;
+            if (b.ip + len > n) return -1;
+            const size_t k = len < cap - op ? len : cap - op;
+            for (int l = lane0; l < lane1; ++l)
+                for (size_t i = (size_t)l; i < k; i += (size_t)nlanes) out[op + i] = in[b.ip + i];
+            b.ip += len;
+            op += k;
+            continue;
+        }
+        if (type == 3) return -1;
+        if (type == 1) {  // fixed code
+            for (int i = 0; i < 144; ++i) t->lengths[i] = 8;
+            for (int i = 144; i < 256; ++i) t->lengths[i] = 9;
+            for (int i = 256; i < 280; ++i) t->lengths[i] = 7;
+            for (int i = 280; i < 288; ++i) t->lengths[i] = 8;
+            inflate_build(t->len_count, t->len_symbol, t->offs, t->lengths, 288);
+            for (int i = 0; i < 30; ++i) t->lengths[i] = 5;
+            inflate_build(t->dist_count, t->dist_symbol, t->offs, t->lengths, 30);
+        } else {  // dynamic code: the code lengths are themselves Huffman coded
+            const int nlen = (int)inflate_bits(b, 5) + 257, ndist = (int)inflate_bits(b, 5) + 1, ncode = (int)inflate_bits(b, 4) + 4;
+            if (nlen > 286 || ndist > 30) return -1;
+            for (int i = 0; i < 19; ++i) t->lengths[i] = 0;
+            for (int i = 0; i < ncode; ++i) t->lengths[inflate_order(i)] = (uint8_t)inflate_bits(b, 3);
+            if (inflate_build(t->len_count, t->len_symbol, t->offs, t->lengths, 19) != 0) return -1;  // must be complete
+            int index = 0;
+            while (index < nlen + ndist) {
+                const int sym = inflate_symbol(b, t->len_count, t->len_symbol);
+                if (sym < 0 || b.starved) return -1;
+                if (sym < 16) {
+                    t->lengths[index++] = (uint8_t)sym;
+                } else {
+                    int prev = 0, rep;
+                    if (sym == 16) {
+                        if (index == 0) return -1;
+                        prev = t->lengths[index - 1];
+                        rep = 3 + (int)inflate_bits(b, 2);
+                    } else if (sym == 17) {
+                        rep = 3 + (int)inflate_bits(b, 3);
+                    } else {
+                        rep = 11 + (int)inflate_bits(b, 7);
+                    }
+                    if (index + rep > nlen + ndist) return -1;
+                    while (rep--) t->lengths[index++] = (uint8_t)prev;
+                }
+            }
+            if (t->lengths[256] == 0) return -1;  // no end-of-block code
+            // the distance lengths follow the literal / length ones; build that table first, its lengths are read in place
+            int err = inflate_build(t->dist_count, t->dist_symbol, t->offs, t->lengths + nlen, ndist);
+            if (err != 0 && (err < 0 || ndist != t->dist_count[0] + t->dist_count[1])) return -1;  // incomplete only with a single code
+            err = inflate_build(t->len_count, t->len_symbol, t->offs, t->lengths, nlen);
+            if (err != 0 && (err < 0 || nlen != t->len_count[0] + t->len_count[1])) return -1;
+        }
+        // the block's symbols
+        for (;;) {
+            int sym = inflate_symbol(b, t->len_count, t->len_symbol);
+            if (sym < 0 || b.starved) return -1;
+            if (sym < 256) {
+                out[op++] = (uint8_t)sym;  // every lane stores the same byte
+                if (op == cap) return (int64_t)op;
+                continue;
+            }
+            if (sym == 256) break;
+            sym -= 257;
+            if (sym >= 29) return -1;
+            // length: 3..10 directly, then groups of four per extra bit, 258 for the last symbol
+            const int lext = sym < 8 || sym == 28 ? 0 : (sym - 4) >> 2;
+            const uint32_t len = (sym < 8 ? 3u + (uint32_t)sym : sym == 28 ? 258u : 3u + ((4u + ((uint32_t)sym & 3u)) << lext)) + inflate_bits(b, lext);
+            const int ds = inflate_symbol(b, t->dist_count, t->dist_symbol);
+            if (ds < 0 || ds >= 30) return -1;
+            const int dext = ds < 4 ? 0 : (ds >> 1) - 1;
+            const size_t dist = (ds < 4 ? 1u + (uint32_t)ds : 1u + ((2u + ((uint32_t)ds & 1u)) << dext)) + inflate_bits(b, dext);
+            if (b.starved || dist > op) return -1;
+            const size_t k = len < cap - op ? len : cap - op;
+            DTB_LZW_WARP_SYNC();  // the source bytes were stored by other lanes
+            const uint8_t *s = out + (op - dist);
+            uint8_t *d = out + op;
+            if (dist >= k) {
+                for (int l = lane0; l < lane1; ++l)
+                    for (size_t i = (size_t)l; i < k; i += (size_t)nlanes) d[i] = s[i];
+            } else {
+                for (int l = lane0; l < lane1; ++l)
+                    for (size_t i = (size_t)l; i < k; i += (size_t)nlanes) d[i] = s[i % dist];
+            }
+            op += k;
+            if (op == cap) return (int64_t)op;
+        }
+    }
+    return (int64_t)op;
+}
+
+}  // namespace dtb

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "inflate.cuh"
 #include "lzw.cuh"
 
 namespace dtb {
@@ -37,6 +38,8 @@ constexpr int TS_WARPS = 7;
 constexpr size_t TS_TABLE_BYTES = 32768;
 static_assert(sizeof(LzwPackedSlot) * kLzwTableSlots == TS_TABLE_BYTES, "decoder table must be 32 KB");
 static_assert(sizeof(uint32_t) * kLzwHashSlots == TS_TABLE_BYTES, "encoder table must be 32 KB");
+static_assert(sizeof(InflateScratch) <= TS_TABLE_BYTES, "the Huffman tables live in the warp's table area");
+constexpr int TC_LZW = 5, TC_DEFLATE = 8;  // TIFF compression codes (stored chunks run through the LZW instantiation)
 
 struct ChunkGeom {
     int64_t cy, cx;        // chunk row / column
@@ -80,12 +83,15 @@ __host__ __device__ inline size_t td_scratch_bytes(const dtb_tiff_layout &L)
 __host__ __device__ inline long long td_status(int64_t chunk, int reason) { return (long long)(((chunk + 1) << 3) | reason); }
 
 // ---- phase 1 (all lanes in lock step): compressed bytes -> scratch chunk.  Returns bytes produced or a negative
-// reason, the same value in every lane.  [lane0, lane1) of nlanes: see lzw.cuh. ----
-__host__ __device__ inline int64_t td_phase1(const dtb_tiff_layout &L, const ChunkGeom &g, const uint8_t *comp, uint64_t len,
-                                             uint8_t *buf, LzwPackedSlot *tab, int lane0, int lane1)
+// reason, the same value in every lane.  [lane0, lane1) of nlanes: see lzw.cuh.  CODEC is a template parameter so
+// that each kernel carries one decoder only. ----
+template <int CODEC>
+__host__ __device__ inline int64_t td_phase1(const ChunkGeom &g, const uint8_t *comp, uint64_t len, uint8_t *buf, void *tab, int lane0,
+                                             int lane1)
 {
-    if (L.compression == 5) return lzw_decode(comp, (size_t)len, buf, (size_t)g.raw_bytes, tab, lane0, lane1, TD_LANES);
-    return -1;
+    if (CODEC == TC_DEFLATE)
+        return zlib_inflate(comp, (size_t)len, buf, (size_t)g.raw_bytes, static_cast<InflateScratch *>(tab), lane0, lane1, TD_LANES);
+    return lzw_decode(comp, (size_t)len, buf, (size_t)g.raw_bytes, static_cast<LzwPackedSlot *>(tab), lane0, lane1, TD_LANES);
 }
 
 // stored chunks: all lanes copy the bytes into the scratch chunk (the predictor works in place)
@@ -182,7 +188,7 @@ __host__ __device__ inline void td_zero(const dtb_tiff_layout &L, const ChunkGeo
 
 extern __shared__ __align__(16) uint8_t tc_smem[];  // TS_WARPS tables when the kernel is instantiated with SMEM
 
-template <int WARPS, bool SMEM>
+template <int WARPS, bool SMEM, int CODEC>
 __global__ void __launch_bounds__(WARPS *TD_LANES)
 tiff_decode_kernel(dtb_tiff_layout L, const uint8_t *__restrict__ comp, const uint64_t *__restrict__ comp_off,
                    const uint64_t *__restrict__ comp_len, int64_t first_chunk, int64_t n_chunks, uint8_t *__restrict__ out,
@@ -207,7 +213,7 @@ tiff_decode_kernel(dtb_tiff_layout L, const uint8_t *__restrict__ comp, const ui
             got = (long long)(len < (uint64_t)g.raw_bytes ? len : (uint64_t)g.raw_bytes);
             td_copy_stored(comp + off, (uint64_t)got, buf, lane);
         } else {
-            got = td_phase1(L, g, comp + off, len, buf, tab, lane, lane + 1);
+            got = td_phase1<CODEC>(g, comp + off, len, buf, tab, lane, lane + 1);
         }
         if (got < g.row_bytes * g.data_rows) {
             if (lane == 0) atomicCAS(status, 0ull, (unsigned long long)td_status(first_chunk + c, got == -2 ? 2 : got < 0 ? 1 : 3));
@@ -380,7 +386,7 @@ int td_validate_common(const dtb_tiff_layout *L)
     if (L->bps != 1 && L->bps != 2 && L->bps != 4 && L->bps != 8) return DTB_ERR_INVALID;
     if (L->predictor < 1 || L->predictor > 3) return DTB_ERR_INVALID;
     if (L->tiled && L->chunk_cols <= 0) return DTB_ERR_INVALID;
-    if (L->compression != 1 && L->compression != 5) return DTB_ERR_UNSUPPORTED;
+    if (L->compression != 1 && L->compression != TC_LZW && L->compression != TC_DEFLATE) return DTB_ERR_UNSUPPORTED;
     if (L->compression == 1 && L->predictor != 1) return DTB_ERR_INVALID;  // the predictor belongs to the codec
     if (L->row_lo != 0 || L->row_hi != 0)
         if (L->row_lo < 0 || L->row_lo >= L->row_hi || L->row_hi > L->rows) return DTB_ERR_INVALID;
@@ -391,6 +397,7 @@ int te_validate(const dtb_tiff_layout *L)
 {
     const int v = td_validate_common(L);
     if (v != DTB_OK) return v;
+    if (L->compression == TC_DEFLATE) return DTB_ERR_UNSUPPORTED;  // chunks are written stored or LZW-compressed
     if (L->big_endian) return DTB_ERR_UNSUPPORTED;  // files are written little-endian
     if (L->row_lo != 0 || L->row_hi != 0) return DTB_ERR_UNSUPPORTED;  // whole rasters only
     if (L->predictor == 3 && L->bps < 4) return DTB_ERR_INVALID;
@@ -442,17 +449,30 @@ int dtb_tiff_decode_chunks(const dtb_tiff_layout *lay, const uint8_t *comp, cons
     uint8_t *base = reinterpret_cast<uint8_t *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     cudaStream_t st = as_stream(stream);
     if (smem) {
-        static bool allowed = false;
-        DTB_CUDA(tc_allow_smem(tiff_decode_kernel<TS_WARPS, true>, allowed));
         const unsigned blocks = (unsigned)((warps + TS_WARPS - 1) / TS_WARPS);
-        DTB_KERNEL("tiff_decode_kernel<shared>", st,
-                   tiff_decode_kernel<TS_WARPS, true><<<blocks, TS_WARPS * TD_LANES, TS_WARPS * TS_TABLE_BYTES, st>>>(
-                       *lay, comp, comp_off, comp_len, first_chunk, n_chunks, (uint8_t *)out, base, warps, status));
+        if (lay->compression == TC_DEFLATE) {
+            static bool allowed = false;
+            DTB_CUDA(tc_allow_smem(tiff_decode_kernel<TS_WARPS, true, TC_DEFLATE>, allowed));
+            DTB_KERNEL("tiff_inflate_kernel<shared>", st,
+                       tiff_decode_kernel<TS_WARPS, true, TC_DEFLATE><<<blocks, TS_WARPS * TD_LANES, TS_WARPS * TS_TABLE_BYTES, st>>>(
+                           *lay, comp, comp_off, comp_len, first_chunk, n_chunks, (uint8_t *)out, base, warps, status));
+        } else {
+            static bool allowed = false;
+            DTB_CUDA(tc_allow_smem(tiff_decode_kernel<TS_WARPS, true, TC_LZW>, allowed));
+            DTB_KERNEL("tiff_decode_kernel<shared>", st,
+                       tiff_decode_kernel<TS_WARPS, true, TC_LZW><<<blocks, TS_WARPS * TD_LANES, TS_WARPS * TS_TABLE_BYTES, st>>>(
+                           *lay, comp, comp_off, comp_len, first_chunk, n_chunks, (uint8_t *)out, base, warps, status));
+        }
     } else {
         const unsigned blocks = (unsigned)((warps + TD_WARPS - 1) / TD_WARPS);
-        DTB_KERNEL("tiff_decode_kernel", st,
-                   tiff_decode_kernel<TD_WARPS, false><<<blocks, TD_WARPS * TD_LANES, 0, st>>>(
-                       *lay, comp, comp_off, comp_len, first_chunk, n_chunks, (uint8_t *)out, base, warps, status));
+        if (lay->compression == TC_DEFLATE)
+            DTB_KERNEL("tiff_inflate_kernel", st,
+                       tiff_decode_kernel<TD_WARPS, false, TC_DEFLATE><<<blocks, TD_WARPS * TD_LANES, 0, st>>>(
+                           *lay, comp, comp_off, comp_len, first_chunk, n_chunks, (uint8_t *)out, base, warps, status));
+        else
+            DTB_KERNEL("tiff_decode_kernel", st,
+                       tiff_decode_kernel<TD_WARPS, false, TC_LZW><<<blocks, TD_WARPS * TD_LANES, 0, st>>>(
+                           *lay, comp, comp_off, comp_len, first_chunk, n_chunks, (uint8_t *)out, base, warps, status));
     }
     return DTB_OK;
 }
@@ -481,7 +501,8 @@ int dtb_selftest_tiff_decode_host(const dtb_tiff_layout *lay, const uint8_t *com
             got = (long long)(len < (uint64_t)g.raw_bytes ? len : (uint64_t)g.raw_bytes);
             for (int lane = 0; lane < TD_LANES; ++lane) td_copy_stored(comp_host + off, (uint64_t)got, buf, lane);
         } else {
-            got = td_phase1(L, g, comp_host + off, len, buf, tab, 0, TD_LANES);
+            got = L.compression == TC_DEFLATE ? td_phase1<TC_DEFLATE>(g, comp_host + off, len, buf, tab, 0, TD_LANES)
+                                              : td_phase1<TC_LZW>(g, comp_host + off, len, buf, tab, 0, TD_LANES);
         }
         if (got < g.row_bytes * g.data_rows) {
             if (*status_host == 0) *status_host = (unsigned long long)td_status(first_chunk + c, got == -2 ? 2 : got < 0 ? 1 : 3);

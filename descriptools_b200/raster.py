@@ -491,8 +491,13 @@ def chunk_table(reader: "DatasetReader"):
     return lay, across, off, cnt
 
 
+# what decode="auto" hands to the device: the codecs whose kernels have been measured on a B200 (profiles/r1z_*).  The
+# Deflate kernel is there (decode="device") but stays off the default path until it has been run and timed on the device.
+_AUTO_DEVICE_COMPRESSIONS = ("none", "lzw")
+
+
 def device_decode_supported(reader: "DatasetReader") -> bool:
-    """can dtb_tiff_decode_chunks take this file?  (stored or LZW chunks of at most 1 MiB; the library decides)"""
+    """can dtb_tiff_decode_chunks take this file?  (stored, LZW or Deflate chunks of at most 1 MiB; the library decides)"""
     from ._lib import lib as cuda_lib
 
     lay = chunk_table(reader)[0]
@@ -522,8 +527,9 @@ def _read_to_device_chunks(reader, out, block_bytes: int, copy, group_chunks=Non
     from ._lib import lib as cuda_lib
 
     lay, across, off, cnt = chunk_table(reader)
-    if lay.compression not in (1, 5):
-        raise RasterError(f"decode='device' handles stored and LZW chunks, not {reader.compression}; use decode='host'")
+    if not device_decode_supported(reader):
+        raise RasterError(f"decode='device' handles stored, LZW and Deflate chunks of at most 1 MiB, not this file ({reader.compression}, "
+                          f"{reader.block_shapes[0]} chunks); use decode='host'")
     dev = out.device
     c_lo, c_hi = 0, off.size
     if rows is not None:  # a row band: `out` holds rows [rows[0], rows[1]) and the kernel stores only those
@@ -590,9 +596,9 @@ def read_to_device(src, device=None, out=None, block_bytes: int = 256 << 20, thr
 
     decode="host": two pinned staging blocks; while block k is copied to the device on `stream` (default: a private
     copy stream) the codec's thread team decodes block k+1.
-    decode="device": the compressed chunks are copied instead and decoded on the device (stored and LZW files;
+    decode="device": the compressed chunks are copied instead and decoded on the device (stored, LZW and Deflate files;
     anything else raises -- nothing falls back silently); `group_chunks` overrides the number of chunks per launch.
-    decode="auto": "device" when device_decode_supported(reader), else "host".
+    decode="auto": "device" for stored and LZW files the device decoder can take, else "host".
     rows=(r0, r1): only that row band of the raster (the tensor has r1 - r0 rows) -- what one rank of a row-band run
     loads (bands.BandRunner.load_file)."""
     import torch
@@ -605,7 +611,8 @@ def read_to_device(src, device=None, out=None, block_bytes: int = 256 << 20, thr
     reader = src if isinstance(src, DatasetReader) else DatasetReader(src)
     try:
         if decode == "auto":  # the device codec when it can take the file: an explicit choice between two complete paths
-            decode = "device" if device_decode_supported(reader) and (out is None or out.is_contiguous()) else "host"
+            on_device = reader.compression in _AUTO_DEVICE_COMPRESSIONS and device_decode_supported(reader)
+            decode = "device" if on_device and (out is None or out.is_contiguous()) else "host"
         first, last = (0, reader.height) if rows is None else (int(rows[0]), int(rows[1]))
         if not 0 <= first < last <= reader.height:
             raise RasterError(f"read_to_device: rows {rows} outside the raster")

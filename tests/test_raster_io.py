@@ -368,6 +368,97 @@ def test_device_encoder_table_resets_and_compression_ratio(tmp_path):
     assert os.path.getsize(p) < 1.05 * os.path.getsize(q)
 
 
+@pytest.mark.parametrize("dtype", ["uint8", "int16", "uint32", "float32", "float64"])
+@pytest.mark.parametrize("layout", ["strips", "tiles"])
+@pytest.mark.parametrize("predictor", [1, 2, 3])
+def test_device_inflate_lane_code_on_the_cpu(tmp_path, dtype, layout, predictor):
+    """Deflate chunks (zlib streams: dynamic, fixed and stored blocks) through the device decoder's lane code"""
+    if predictor == 3 and np.dtype(dtype).kind != "f":
+        pytest.skip("floating-point predictor")
+    path = tmp_path / "z.tif"
+    kw = dict(tiled=True, blockxsize=48, blockysize=64) if layout == "tiles" else dict(blockysize=7)
+    for smooth in (True, False):  # compressible (dynamic codes, long matches) and noise (stored / near-stored blocks)
+        a = _rand((157, 203), dtype, seed=31, smooth=smooth)
+        with rio.open(path, "w", width=203, height=157, dtype=dtype, compress="deflate", predictor=predictor, **kw) as dst:
+            dst.write(a)
+        out, status, _ = _decode_like_the_device(path)
+        assert status == 0
+        np.testing.assert_array_equal(out, a)
+        out, status, _ = _decode_like_the_device(path, rows=(60, 131))
+        assert status == 0
+        np.testing.assert_array_equal(out, a[60:131])
+
+
+def test_device_inflate_block_types_and_damage(tmp_path):
+    import zlib
+
+    from descriptools_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    raw = {"runs": np.repeat(rng.integers(0, 4, 700, dtype=np.uint8), 27)[:16384],       # overlapping matches, distance 1
+           "text": np.frombuffer((b"flow accumulation and HAND " * 700)[:16384], np.uint8),
+           "noise": rng.integers(0, 256, 16384, dtype=np.uint8),
+           "zeros": np.zeros(16384, np.uint8)}
+    lay = _lib.TiffLayout(rows=128, cols=128, bps=1, predictor=1, compression=8, tiled=1, chunk_rows=128, chunk_cols=128, big_endian=0)
+
+    def lane_decode(stream):
+        comp = np.frombuffer(stream, np.uint8).copy()
+        off, cnt = np.zeros(1, np.uint64), np.array([comp.size], np.uint64)
+        out = np.full((128, 128), 7, np.uint8)
+        st = ctypes.c_ulonglong(0)
+        assert _lib.lib.dtb_selftest_tiff_decode_host(ctypes.byref(lay), comp.ctypes.data, off.ctypes.data, cnt.ctypes.data, 0, 1,
+                                                      out.ctypes.data, ctypes.byref(st)) == 0
+        return out.ravel(), st.value
+
+    for name, data in raw.items():
+        for level, strategy in ((9, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (0, zlib.Z_DEFAULT_STRATEGY),
+                                (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE)):
+            c = zlib.compressobj(level, zlib.DEFLATED, 15, 9, strategy)
+            stream = c.compress(data.tobytes()) + c.flush()
+            out, status = lane_decode(stream)
+            assert status == 0, (name, level, strategy)
+            np.testing.assert_array_equal(out, data, err_msg=f"{name} level {level} strategy {strategy}")
+    # several flushed blocks in one stream (stored, fixed and dynamic mixed)
+    c = zlib.compressobj(6)
+    stream = b"".join(c.compress(raw["text"][i:i + 3000].tobytes()) + c.flush(zlib.Z_FULL_FLUSH) for i in range(0, 16384, 3000)) + c.flush()
+    out, status = lane_decode(stream)
+    assert status == 0
+    np.testing.assert_array_equal(out, raw["text"])
+    # damage is reported as a corrupt chunk, never a crash: truncation, flipped bits, a bad header
+    good = zlib.compress(raw["text"].tobytes(), 6)
+    for bad in (good[:len(good) // 2], good[:2] + bytes([good[2] ^ 0x06]) + good[3:], b"\x78\x9d" + good[2:], b"\x00\x00" + good[2:], good[:1]):
+        out, status = lane_decode(bad)
+        assert status & 7 in (1, 3) and status >> 3 == 1
+    for k in range(40):  # random corruption anywhere in the stream
+        b = bytearray(good)
+        for _ in range(3):
+            b[rng.integers(2, len(b))] ^= 1 << int(rng.integers(0, 8))
+        out, status = lane_decode(bytes(b))
+        assert status == 0 or (status & 7 in (1, 3))
+
+
+@pytest.mark.parametrize("name", ["fuzz_lzw", "fuzz_inflate"])
+def test_decoders_under_sanitizers(tmp_path, name):
+    """the coders shared by host and device (csrc/lzw.cuh, csrc/inflate.cuh), compiled with AddressSanitizer + UBSan and fed
+    intact, truncated and bit-flipped streams from exact-size heap blocks: a damaged file may fail to decode, it must never
+    read or write outside its buffers (on the device that would be a fault, not an exception)"""
+    import shutil
+    import subprocess
+
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    src = os.path.join(REPO, "tests", "fuzz", name + ".cpp")
+    exe = str(tmp_path / name)
+    build = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", src, "-o", exe, "-lz"],
+                           capture_output=True, text=True, cwd=os.path.dirname(src))
+    if build.returncode != 0 and "sanitize" in build.stderr.lower() + build.stdout.lower():
+        pytest.skip("sanitizer runtime not installed")
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([exe, "500"], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-4000:]
+    assert "0 problems" in run.stdout
+
+
 def test_device_decoder_lane_code_big_endian_and_damage(tmp_path):
     from PIL import Image
 
@@ -473,7 +564,7 @@ def test_device_codec_selection_asks_the_library(tmp_path):
     a = _rand((300, 300), "float32", seed=3)
     cases = [(dict(compress="lzw", predictor=3, tiled=True, blockxsize=128, blockysize=128), True, True),
              (dict(compress="none", blockysize=8), True, True),
-             (dict(compress="deflate", tiled=True, blockxsize=128, blockysize=128), False, False),
+             (dict(compress="deflate", tiled=True, blockxsize=128, blockysize=128), True, False),  # decodes, is not written
              (dict(compress="lzw", blockysize=300), True, True),
              (dict(compress="lzw", tiled=True, blockxsize=1024, blockysize=512), False, True)]  # 2 MiB chunks: decode needs <= 1 MiB
     for kw, dec, enc in cases:
@@ -487,6 +578,7 @@ def test_device_codec_selection_asks_the_library(tmp_path):
 
     Image.fromarray(a).save(str(tmp_path / "pb.tif"), compression="packbits")
     assert not rio.device_decode_supported(rio.open(tmp_path / "pb.tif"))
+    assert "deflate" not in rio._AUTO_DEVICE_COMPRESSIONS  # decode="auto" keeps Deflate on the host codec for now
     with pytest.raises(rio.RasterError, match="decode must be"):
         rio.read_to_device(tmp_path / "pb.tif", decode="gpu")
 
@@ -640,11 +732,12 @@ def test_tiles_decoded_on_the_device(tmp_path, dtype, layout, compress, predicto
 
 @pytest.mark.gpu
 def test_device_decoder_reports_damage_and_refuses_what_it_cannot_do(tmp_path):
+    from PIL import Image
+
     a = _rand((300, 300), "uint8", seed=13, smooth=False)
     p = tmp_path / "d.tif"
-    with rio.open(p, "w", width=300, height=300, dtype="uint8", compress="deflate", tiled=True, blockxsize=64, blockysize=64) as dst:
-        dst.write(a)
-    with pytest.raises(rio.RasterError, match="deflate"):
+    Image.fromarray(a).save(str(p), compression="packbits")
+    with pytest.raises(rio.RasterError, match="packbits"):
         rio.read_to_device(p, decode="device")
     q = tmp_path / "l.tif"
     with rio.open(q, "w", width=300, height=300, dtype="uint8", compress="lzw", tiled=True, blockxsize=64, blockysize=64) as dst:
