@@ -507,7 +507,9 @@ def test_device_decoder_lane_code_big_endian_and_damage(tmp_path):
     assert st.value == 0
     np.testing.assert_array_equal(out, want)
     # argument checks need no device
-    lay.compression = 8
+    lay.compression = 8  # Deflate: decoded, never written
+    assert _lib.lib.dtb_tiff_decode_workspace_bytes(ctypes.byref(lay), 4) > 0 and _lib.lib.dtb_tiff_encode_bound(ctypes.byref(lay)) == 0
+    lay.compression = 32773  # PackBits: host codec only
     assert _lib.lib.dtb_tiff_decode_workspace_bytes(ctypes.byref(lay), 4) == 0
     assert _lib.lib.dtb_tiff_decode_chunks(ctypes.byref(lay), 1, 1, 1, 0, 1, 1, 1, 1 << 20, 1, None) == -4
     lay.compression = 5
