@@ -1,5 +1,5 @@
-// inflate.cuh -- zlib / Deflate (RFC 1950, RFC 1951) decoding for the device tile decoder (tiffcodec.cu) and its
-// CPU replay.  GeoTIFFs written with COMPRESS=DEFLATE hold one zlib stream per tile or strip.
+// inflate.cuh -- zlib / Deflate (RFC 1950, RFC 1951) and PackBits decoding for the device tile decoder (tiffcodec.cu)
+// and its CPU replay.  GeoTIFFs written with COMPRESS=DEFLATE hold one zlib stream per tile or strip.
 //
 // Same execution model as the LZW decoder in lzw.cuh: a whole warp runs the decoder in lock step (identical state in
 // every lane, uniform control flow, broadcast loads, table stores of the same value from every lane), and the only
@@ -203,6 +203,36 @@ DTB_LZW_HD int64_t zlib_inflate(const uint8_t *in, size_t n, uint8_t *out, size_
             }
             op += k;
             if (op == cap) return (int64_t)op;
+        }
+    }
+    return (int64_t)op;
+}
+
+// PackBits (TIFF 6.0 section 9; compression 32773): a header byte h, then h + 1 literal bytes (0 <= h <= 127) or one
+// byte repeated 1 - h times (-127 <= h <= -1); -128 is a no-op.  Both kinds of run are written by the lanes together.
+// Returns the number of bytes produced (input that ends inside a run just ends the output).
+DTB_LZW_HD int64_t packbits_decode_lanes(const uint8_t *in, size_t n, uint8_t *out, size_t cap, int lane0 = 0, int lane1 = 1,
+                                         int nlanes = 1)
+{
+    size_t ip = 0, op = 0;
+    while (ip < n && op < cap) {
+        const int h = (int8_t)in[ip++];
+        if (h >= 0) {
+            size_t k = (size_t)h + 1;
+            if (k > n - ip) k = n - ip;
+            const size_t w = k < cap - op ? k : cap - op;
+            for (int l = lane0; l < lane1; ++l)
+                for (size_t i = (size_t)l; i < w; i += (size_t)nlanes) out[op + i] = in[ip + i];
+            ip += k;
+            op += w;
+        } else if (h != -128) {
+            if (ip >= n) break;
+            const uint8_t v = in[ip++];
+            const size_t k = (size_t)(1 - h);
+            const size_t w = k < cap - op ? k : cap - op;
+            for (int l = lane0; l < lane1; ++l)
+                for (size_t i = (size_t)l; i < w; i += (size_t)nlanes) out[op + i] = v;
+            op += w;
         }
     }
     return (int64_t)op;

@@ -39,7 +39,7 @@ constexpr size_t TS_TABLE_BYTES = 32768;
 static_assert(sizeof(LzwPackedSlot) * kLzwTableSlots == TS_TABLE_BYTES, "decoder table must be 32 KB");
 static_assert(sizeof(uint32_t) * kLzwHashSlots == TS_TABLE_BYTES, "encoder table must be 32 KB");
 static_assert(sizeof(InflateScratch) <= TS_TABLE_BYTES, "the Huffman tables live in the warp's table area");
-constexpr int TC_LZW = 5, TC_DEFLATE = 8;  // TIFF compression codes (stored chunks run through the LZW instantiation)
+constexpr int TC_LZW = 5, TC_DEFLATE = 8, TC_PACKBITS = 32773;  // TIFF compression codes (stored chunks run through the LZW instantiation)
 
 struct ChunkGeom {
     int64_t cy, cx;        // chunk row / column
@@ -89,6 +89,7 @@ template <int CODEC>
 __host__ __device__ inline int64_t td_phase1(const ChunkGeom &g, const uint8_t *comp, uint64_t len, uint8_t *buf, void *tab, int lane0,
                                              int lane1)
 {
+    if (CODEC == TC_PACKBITS) return packbits_decode_lanes(comp, (size_t)len, buf, (size_t)g.raw_bytes, lane0, lane1, TD_LANES);
     if (CODEC == TC_DEFLATE)
         return zlib_inflate(comp, (size_t)len, buf, (size_t)g.raw_bytes, static_cast<InflateScratch *>(tab), lane0, lane1, TD_LANES);
     return lzw_decode(comp, (size_t)len, buf, (size_t)g.raw_bytes, static_cast<LzwPackedSlot *>(tab), lane0, lane1, TD_LANES);
@@ -386,8 +387,8 @@ int td_validate_common(const dtb_tiff_layout *L)
     if (L->bps != 1 && L->bps != 2 && L->bps != 4 && L->bps != 8) return DTB_ERR_INVALID;
     if (L->predictor < 1 || L->predictor > 3) return DTB_ERR_INVALID;
     if (L->tiled && L->chunk_cols <= 0) return DTB_ERR_INVALID;
-    if (L->compression != 1 && L->compression != TC_LZW && L->compression != TC_DEFLATE) return DTB_ERR_UNSUPPORTED;
-    if (L->compression == 1 && L->predictor != 1) return DTB_ERR_INVALID;  // the predictor belongs to the codec
+    if (L->compression != 1 && L->compression != TC_LZW && L->compression != TC_DEFLATE && L->compression != TC_PACKBITS) return DTB_ERR_UNSUPPORTED;
+    if ((L->compression == 1 || L->compression == TC_PACKBITS) && L->predictor != 1) return DTB_ERR_INVALID;  // the predictor belongs to LZW / Deflate
     if (L->row_lo != 0 || L->row_hi != 0)
         if (L->row_lo < 0 || L->row_lo >= L->row_hi || L->row_hi > L->rows) return DTB_ERR_INVALID;
     return DTB_OK;
@@ -397,7 +398,7 @@ int te_validate(const dtb_tiff_layout *L)
 {
     const int v = td_validate_common(L);
     if (v != DTB_OK) return v;
-    if (L->compression == TC_DEFLATE) return DTB_ERR_UNSUPPORTED;  // chunks are written stored or LZW-compressed
+    if (L->compression == TC_DEFLATE || L->compression == TC_PACKBITS) return DTB_ERR_UNSUPPORTED;  // chunks are written stored or LZW-compressed
     if (L->big_endian) return DTB_ERR_UNSUPPORTED;  // files are written little-endian
     if (L->row_lo != 0 || L->row_hi != 0) return DTB_ERR_UNSUPPORTED;  // whole rasters only
     if (L->predictor == 3 && L->bps < 4) return DTB_ERR_INVALID;
@@ -450,7 +451,13 @@ int dtb_tiff_decode_chunks(const dtb_tiff_layout *lay, const uint8_t *comp, cons
     cudaStream_t st = as_stream(stream);
     if (smem) {
         const unsigned blocks = (unsigned)((warps + TS_WARPS - 1) / TS_WARPS);
-        if (lay->compression == TC_DEFLATE) {
+        if (lay->compression == TC_PACKBITS) {
+            static bool allowed = false;
+            DTB_CUDA(tc_allow_smem(tiff_decode_kernel<TS_WARPS, true, TC_PACKBITS>, allowed));
+            DTB_KERNEL("tiff_packbits_kernel<shared>", st,
+                       tiff_decode_kernel<TS_WARPS, true, TC_PACKBITS><<<blocks, TS_WARPS * TD_LANES, TS_WARPS * TS_TABLE_BYTES, st>>>(
+                           *lay, comp, comp_off, comp_len, first_chunk, n_chunks, (uint8_t *)out, base, warps, status));
+        } else if (lay->compression == TC_DEFLATE) {
             static bool allowed = false;
             DTB_CUDA(tc_allow_smem(tiff_decode_kernel<TS_WARPS, true, TC_DEFLATE>, allowed));
             DTB_KERNEL("tiff_inflate_kernel<shared>", st,
@@ -465,7 +472,11 @@ int dtb_tiff_decode_chunks(const dtb_tiff_layout *lay, const uint8_t *comp, cons
         }
     } else {
         const unsigned blocks = (unsigned)((warps + TD_WARPS - 1) / TD_WARPS);
-        if (lay->compression == TC_DEFLATE)
+        if (lay->compression == TC_PACKBITS)
+            DTB_KERNEL("tiff_packbits_kernel", st,
+                       tiff_decode_kernel<TD_WARPS, false, TC_PACKBITS><<<blocks, TD_WARPS * TD_LANES, 0, st>>>(
+                           *lay, comp, comp_off, comp_len, first_chunk, n_chunks, (uint8_t *)out, base, warps, status));
+        else if (lay->compression == TC_DEFLATE)
             DTB_KERNEL("tiff_inflate_kernel", st,
                        tiff_decode_kernel<TD_WARPS, false, TC_DEFLATE><<<blocks, TD_WARPS * TD_LANES, 0, st>>>(
                            *lay, comp, comp_off, comp_len, first_chunk, n_chunks, (uint8_t *)out, base, warps, status));
@@ -501,8 +512,9 @@ int dtb_selftest_tiff_decode_host(const dtb_tiff_layout *lay, const uint8_t *com
             got = (long long)(len < (uint64_t)g.raw_bytes ? len : (uint64_t)g.raw_bytes);
             for (int lane = 0; lane < TD_LANES; ++lane) td_copy_stored(comp_host + off, (uint64_t)got, buf, lane);
         } else {
-            got = L.compression == TC_DEFLATE ? td_phase1<TC_DEFLATE>(g, comp_host + off, len, buf, tab, 0, TD_LANES)
-                                              : td_phase1<TC_LZW>(g, comp_host + off, len, buf, tab, 0, TD_LANES);
+            got = L.compression == TC_DEFLATE    ? td_phase1<TC_DEFLATE>(g, comp_host + off, len, buf, tab, 0, TD_LANES)
+                  : L.compression == TC_PACKBITS ? td_phase1<TC_PACKBITS>(g, comp_host + off, len, buf, tab, 0, TD_LANES)
+                                                 : td_phase1<TC_LZW>(g, comp_host + off, len, buf, tab, 0, TD_LANES);
         }
         if (got < g.row_bytes * g.data_rows) {
             if (*status_host == 0) *status_host = (unsigned long long)td_status(first_chunk + c, got == -2 ? 2 : got < 0 ? 1 : 3);

@@ -492,12 +492,12 @@ def chunk_table(reader: "DatasetReader"):
 
 
 # what decode="auto" hands to the device: the codecs whose kernels have been measured on a B200 (profiles/r1z_*).  The
-# Deflate kernel is there (decode="device") but stays off the default path until it has been run and timed on the device.
+# Deflate and PackBits kernels are there (decode="device") but stay off the default path until they have run on a device.
 _AUTO_DEVICE_COMPRESSIONS = ("none", "lzw")
 
 
 def device_decode_supported(reader: "DatasetReader") -> bool:
-    """can dtb_tiff_decode_chunks take this file?  (stored, LZW or Deflate chunks of at most 1 MiB; the library decides)"""
+    """can dtb_tiff_decode_chunks take this file?  (stored, LZW, Deflate or PackBits chunks of at most 1 MiB; the library decides)"""
     from ._lib import lib as cuda_lib
 
     lay = chunk_table(reader)[0]
@@ -528,7 +528,7 @@ def _read_to_device_chunks(reader, out, block_bytes: int, copy, group_chunks=Non
 
     lay, across, off, cnt = chunk_table(reader)
     if not device_decode_supported(reader):
-        raise RasterError(f"decode='device' handles stored, LZW and Deflate chunks of at most 1 MiB, not this file ({reader.compression}, "
+        raise RasterError(f"decode='device' handles stored, LZW, Deflate and PackBits chunks of at most 1 MiB, not this file ({reader.compression}, "
                           f"{reader.block_shapes[0]} chunks); use decode='host'")
     dev = out.device
     c_lo, c_hi = 0, off.size

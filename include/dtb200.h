@@ -269,9 +269,10 @@ int dtb_minmax_scale(const void *mat, int mat_dtype, int64_t n, double mn, doubl
 
 /* ---- raster files: GeoTIFF chunks decoded on the device ---------
  * Replaces the pixel decode inside rasterio's `rio.open(p).read(1)` (Example/example.py:33-39) for tiled or
- * striped single-band files that are stored, LZW- or Deflate-compressed (GDAL wrote 12_dem / 12_fdr / 12_fac with LZW):
+ * striped single-band files that are stored, LZW-, Deflate- or PackBits-compressed (GDAL wrote 12_dem / 12_fdr / 12_fac
+ * with LZW):
  * the compressed chunks are copied to the device as they lie in the file and one warp decodes each chunk
- * (LZW or Deflate, byte order, predictor 2 / 3) into the raster.  File parsing stays on the host (include/dtb200_io.h).
+ * (LZW, Deflate or PackBits, byte order, predictor 2 / 3) into the raster.  File parsing stays on the host (include/dtb200_io.h).
  *   lay          geometry of the file (a chunk decodes to at most 1 MiB: DTB_ERR_UNSUPPORTED otherwise); chunk i covers chunk-row i / across, chunk-column i % across
  *                (across = ceil(cols / chunk_cols) for tiles, 1 for strips); tiles are stored whole, the last
  *                strip holds only the rows that exist.
@@ -290,7 +291,7 @@ typedef struct dtb_tiff_layout {
     int64_t rows, cols;
     int32_t bps;         /* bytes per sample: 1, 2, 4, 8                     */
     int32_t predictor;   /* 1 none, 2 horizontal differencing, 3 floating point */
-    int32_t compression; /* 1 stored, 5 LZW, 8 Deflate (decode only)          */
+    int32_t compression; /* 1 stored, 5 LZW; decode only: 8 Deflate, 32773 PackBits */
     int32_t tiled;       /* 1 tiles, 0 strips                                 */
     int32_t chunk_rows;  /* TileLength or RowsPerStrip                        */
     int32_t chunk_cols;  /* TileWidth (ignored for strips)                    */

@@ -389,6 +389,23 @@ def test_device_inflate_lane_code_on_the_cpu(tmp_path, dtype, layout, predictor)
         np.testing.assert_array_equal(out, a[60:131])
 
 
+@pytest.mark.parametrize("dtype", ["uint8", "uint16", "int32", "float32"])
+def test_device_packbits_lane_code_on_the_cpu(tmp_path, dtype):
+    """PackBits strips as libtiff writes them, through the device decoder's lane code"""
+    from PIL import Image
+
+    p = str(tmp_path / "pb.tif")
+    for a in (_rand((301, 333), dtype, seed=5), np.repeat(_rand((301, 9), dtype, seed=6, smooth=False), 37, axis=1)):  # literals; long runs
+        Image.fromarray(a).save(p, compression="packbits")
+        assert rio.open(p).compression == "packbits"
+        out, status, _ = _decode_like_the_device(p)
+        assert status == 0
+        np.testing.assert_array_equal(out, a)
+        out, status, _ = _decode_like_the_device(p, rows=(100, 211))
+        assert status == 0
+        np.testing.assert_array_equal(out, a[100:211])
+
+
 def test_device_inflate_block_types_and_damage(tmp_path):
     import zlib
 
@@ -509,7 +526,9 @@ def test_device_decoder_lane_code_big_endian_and_damage(tmp_path):
     # argument checks need no device
     lay.compression = 8  # Deflate: decoded, never written
     assert _lib.lib.dtb_tiff_decode_workspace_bytes(ctypes.byref(lay), 4) > 0 and _lib.lib.dtb_tiff_encode_bound(ctypes.byref(lay)) == 0
-    lay.compression = 32773  # PackBits: host codec only
+    lay.compression = 32773  # PackBits: decoded, never written
+    assert _lib.lib.dtb_tiff_decode_workspace_bytes(ctypes.byref(lay), 4) > 0 and _lib.lib.dtb_tiff_encode_bound(ctypes.byref(lay)) == 0
+    lay.compression = 7  # JPEG: neither
     assert _lib.lib.dtb_tiff_decode_workspace_bytes(ctypes.byref(lay), 4) == 0
     assert _lib.lib.dtb_tiff_decode_chunks(ctypes.byref(lay), 1, 1, 1, 0, 1, 1, 1, 1 << 20, 1, None) == -4
     lay.compression = 5
@@ -579,8 +598,9 @@ def test_device_codec_selection_asks_the_library(tmp_path):
     from PIL import Image
 
     Image.fromarray(a).save(str(tmp_path / "pb.tif"), compression="packbits")
-    assert not rio.device_decode_supported(rio.open(tmp_path / "pb.tif"))
-    assert "deflate" not in rio._AUTO_DEVICE_COMPRESSIONS  # decode="auto" keeps Deflate on the host codec for now
+    assert rio.device_decode_supported(rio.open(tmp_path / "pb.tif"))
+    # decode="auto" keeps Deflate and PackBits on the host codec until their kernels have run on a device
+    assert rio._AUTO_DEVICE_COMPRESSIONS == ("none", "lzw")
     with pytest.raises(rio.RasterError, match="decode must be"):
         rio.read_to_device(tmp_path / "pb.tif", decode="gpu")
 
@@ -734,12 +754,11 @@ def test_tiles_decoded_on_the_device(tmp_path, dtype, layout, compress, predicto
 
 @pytest.mark.gpu
 def test_device_decoder_reports_damage_and_refuses_what_it_cannot_do(tmp_path):
-    from PIL import Image
-
     a = _rand((300, 300), "uint8", seed=13, smooth=False)
     p = tmp_path / "d.tif"
-    Image.fromarray(a).save(str(p), compression="packbits")
-    with pytest.raises(rio.RasterError, match="packbits"):
+    with rio.open(p, "w", width=2048, height=600, dtype="uint8", compress="lzw", tiled=True, blockxsize=2048, blockysize=1024) as dst:
+        dst.write(np.zeros((600, 2048), np.uint8))  # 2 MiB tiles: more than the device decoder's string table addresses
+    with pytest.raises(rio.RasterError, match="1 MiB"):
         rio.read_to_device(p, decode="device")
     q = tmp_path / "l.tif"
     with rio.open(q, "w", width=300, height=300, dtype="uint8", compress="lzw", tiled=True, blockxsize=64, blockysize=64) as dst:
