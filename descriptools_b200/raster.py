@@ -35,7 +35,6 @@ _COMPRESSION = {"none": 1, "lzw": 5, "deflate": 8, "packbits": 32773}
 _COMPRESSION_NAME = {v: k for k, v in _COMPRESSION.items()}
 # TIFF field types used for the georeferencing tags
 _T_ASCII, _T_SHORT, _T_DOUBLE = 2, 3, 12
-_GEO_TAGS = (33550, 33922, 34264, 34735, 34736, 34737)  # scale, tiepoint, transformation, GeoKey directory / doubles / ascii
 _TAG_GDAL_METADATA, _TAG_GDAL_NODATA = 42112, 42113
 
 
