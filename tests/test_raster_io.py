@@ -580,6 +580,25 @@ def test_random_shapes_layouts_and_codecs(tmp_path):
         np.testing.assert_array_equal(out, a, err_msg=what)
 
 
+def test_launch_planning_is_exact():
+    """the pure planning helpers behind the device paths: which chunks hold a row band, how many chunks go into a launch"""
+    assert rio._band_chunks(0, 640, 128, 3) == (0, 15)
+    assert rio._band_chunks(64, 320, 128, 3) == (0, 9)      # seams inside tiles: the tiles on both sides are included
+    assert rio._band_chunks(320, 640, 128, 3) == (6, 15)
+    assert rio._band_chunks(130, 131, 128, 3) == (3, 6)
+    assert rio._band_chunks(5, 6, 7, 1) == (0, 1)
+    for n, across, raw, block in [(1024, 32, 262144, 256 << 20), (24649, 157, 262144, 256 << 20), (97969, 313, 65536, 256 << 20),
+                                  (4, 2, 262144, 200_000), (63, 1, 99456, 1 << 20), (1, 1, 10, 1), (10**6, 1000, 1 << 20, 1 << 30)]:
+        g = rio._chunks_per_group(n, across, raw, block)
+        assert 1 <= g <= n and (g % across == 0 or g == n), (n, across, g)
+        assert g * raw <= (4 << 30) + across * raw                      # bounded staging
+        if n >= 2 * rio._WARPS_IN_FLIGHT:
+            assert g >= rio._WARPS_IN_FLIGHT                            # a launch fills the device ...
+            assert -(-n // g) >= 2                                      # ... and there are launches to overlap with the copies
+    assert rio._block_rows(1000, 128, 777, 4, 1 << 20) == 256 and rio._block_rows(1, 128, 330, 4, 100_000) == 1
+    assert rio._block_rows(40000, 5, 40000, 4, 256 << 20) % 5 == 0
+
+
 def test_device_codec_selection_asks_the_library(tmp_path):
     """pipeline_files(decode="auto", encode="auto") takes the device codec exactly when libdtb200 says it can"""
     a = _rand((300, 300), "float32", seed=3)
