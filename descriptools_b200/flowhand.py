@@ -69,3 +69,18 @@ def flow_accumulation(flow_direction, nodata=-100):
     fdr = fdr_to_u8(flow_direction)
     dt = torch.int32 if fdr.size < 2**31 else torch.int64
     return to_host(device.flow_accumulation(to_dev(fdr), dtype=dt, nodata_fill=nodata)).astype(np.int64)
+
+
+def fill_depressions(dem):
+    """Hydrological conditioning: every cell is raised to the lowest level from which water can
+    leave the raster (or reach a nodata cell) along a strictly descending path -- priority-flood + epsilon, the epsilon
+    being one float32 step.  The reference's fixtures were conditioned by an external GIS before example.py:33-39 reads
+    them; an unconditioned DEM leaves interior pits, where D8 has no code and the accumulation stops.  float32 in (other
+    dtypes are converted if exact), float32 out; -100 / NaN cells stay as they are."""
+    d = dem_to_native(dem)
+    if d.dtype != np.float32:
+        d = d.astype(np.float32)  # int16 elevations: exact
+    t = to_dev(d).clone()
+    device.fill_depressions(t)
+    return to_host(t)
+

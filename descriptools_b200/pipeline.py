@@ -152,7 +152,8 @@ def output_dtypes(dem_dtype: np.dtype, n_cells: int) -> dict:
 
 def pipeline_files(dem_path, out_dir, river_threshold: int, px: float | None = None, n_gfi: float = 0.4,
                    scale_factor: float = 0.1, size: float | None = None, outputs=STAGE_OUTPUTS, compress: str = "lzw",
-                   blocksize: int = 256, block_bytes: int = 256 << 20, threads: int = 0, decode: str = "auto", encode: str = "auto") -> dict:
+                   blocksize: int = 256, block_bytes: int = 256 << 20, threads: int = 0, decode: str = "auto", encode: str = "auto",
+                   condition: bool = False) -> dict:
     """The chain from a DEM GeoTIFF to one GeoTIFF per descriptor (`out_dir/<name>.tif`), what a user of the
     reference does around the descriptor calls with rasterio (example.py:33, :42-43, :201-217).
 
@@ -162,6 +163,8 @@ def pipeline_files(dem_path, out_dir, river_threshold: int, px: float | None = N
     Results are encoded block by block as they are copied back (raster.write_from_device; `encode="device"` encodes the
     tiles on the GPU and copies only the compressed bytes), tiled and compressed,
     with the DEM's georeferencing; nodata is -100 (0 for the D8 codes, like 12_fdr.tif).
+    `condition=True` fills the DEM's depressions on the device first (device.fill_depressions) --
+    for DEMs that no GIS has conditioned yet (float32 only).
     `decode` / `encode`: "device", "host", or "auto" (default) = the device codec whenever it can take the file
     (stored or LZW chunks), the host codec for the rest (Deflate, PackBits, chunks over 1 MiB).
     Returns {name: path}.
@@ -184,6 +187,10 @@ def pipeline_files(dem_path, out_dir, river_threshold: int, px: float | None = N
         dem.masked_fill_(dem == nodata, -100)
     if dem.dtype == torch.float32:
         dem.masked_fill_(torch.isnan(dem), -100)
+    if condition:
+        if dem.dtype != torch.float32:
+            raise TypeError("condition=True needs a float32 DEM (the filling raises cells by single float32 steps)")
+        device.fill_depressions(dem)
     res = run_device(dem, float(px), int(river_threshold), n_gfi, scale_factor, size)
     os.makedirs(out_dir, exist_ok=True)
     paths = {}

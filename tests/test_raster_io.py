@@ -850,3 +850,27 @@ def test_row_bands_from_a_file(tmp_path, decode):
     for name in ("slope", "d8", "acc", "idx", "fdist", "hand", "gfi"):
         got = torch.cat([o[name] for o in outs], 0).cpu().numpy()
         np.testing.assert_array_equal(got, ref[name].cpu().numpy(), err_msg=name)
+
+
+@pytest.mark.gpu
+def test_unconditioned_dem_file_is_conditioned_on_the_device(tmp_path):
+    """flowhand.fill_depressions == the oracle's priority flood; pipeline_files(condition=True) on a raw DEM
+    file == the array pipeline on the conditioned DEM"""
+    import oracle
+    import descriptools_b200.flowhand as flowhand
+    from descriptools_b200 import pipeline
+
+    raw = oracle.synth_dem(300, 420, 0, 77)
+    raw[120:150, 200:260] = -100
+    want = oracle.priority_flood_eps(raw)
+    assert (want != raw).sum() > 50  # there were pits
+    np.testing.assert_array_equal(flowhand.fill_depressions(raw), want)
+    np.testing.assert_array_equal(flowhand.fill_depressions(want), want)  # a fixed point
+    p = tmp_path / "raw.tif"
+    with rio.open(p, "w", width=420, height=300, dtype="float32", compress="lzw", predictor=3, tiled=True, blockxsize=128, blockysize=128,
+                  nodata=-100) as dst:
+        dst.write(raw)
+    paths = pipeline.pipeline_files(p, tmp_path / "out", river_threshold=300, px=12.5, condition=True)
+    ref = pipeline.pipeline(want, 12.5, 300)
+    for name, path in paths.items():
+        np.testing.assert_array_equal(rio.open(path).read(1), ref[name], err_msg=name)
