@@ -582,7 +582,7 @@ def _read_to_device_chunks(reader, out, block_bytes: int, copy, group_chunks=Non
     copy.synchronize()
     code = int(status.item())
     if code:
-        reason = {1: "corrupt LZW stream", 2: "pre-6.0 LZW", 3: "chunk decodes short"}.get(code & 7, "decode error")
+        reason = {1: "corrupt compressed stream", 2: "pre-6.0 LZW", 3: "chunk decodes short"}.get(code & 7, "decode error")
         raise RasterError(f"{reader.name}: chunk {(code >> 3) - 1}: {reason}")
     torch.cuda.current_stream(dev).wait_stream(copy)
     return out
