@@ -4,8 +4,9 @@
 // Same execution model as the LZW decoder in lzw.cuh: a whole warp runs the decoder in lock step (identical state in
 // every lane, uniform control flow, broadcast loads, table stores of the same value from every lane), and the only
 // work that is spread over the lanes is the copy of a match -- `byte i = source[i mod distance]`, which also covers
-// the overlapping matches Deflate uses for runs.  Huffman codes are decoded canonically, one bit per step, from the
-// per-length counts and the symbols sorted by code (about 1 KB of tables per warp, in the warp's table area).
+// the overlapping matches Deflate uses for runs.  Huffman codes of up to nine bits are decoded with one table look-up,
+// longer ones canonically, one bit per step, from the per-length counts and the symbols sorted by code (about 3 KB of
+// tables per warp, in the warp's table area).
 // The Adler-32 trailer is not checked: a damaged chunk shows up as a bad code, a bad distance or a short chunk.
 // `lane0, lane1, nlanes` as in lzw.cuh.
 #pragma once
@@ -16,9 +17,13 @@
 
 namespace dtb {
 
+constexpr int kInflateFastBits = 9;  // codes up to this length are decoded with one table look-up
+
 struct InflateScratch {
-    uint16_t len_count[16], len_symbol[288];   // literal / length code
+    uint16_t len_count[16], len_symbol[288];   // literal / length code: codes per length, symbols sorted by code
     uint16_t dist_count[16], dist_symbol[32];  // distance code
+    uint16_t len_fast[1 << kInflateFastBits];  // next 9 stream bits -> (symbol << 4) | code length, 0 = a longer code
+    uint16_t dist_fast[1 << kInflateFastBits];
     uint16_t offs[16];
     uint8_t lengths[320];                      // code lengths while a dynamic block's header is read
 };
@@ -27,23 +32,37 @@ struct InflateBits {
     const uint8_t *in;
     size_t n, ip;
     uint64_t buf;
-    int cnt;
-    bool starved;  // asked for bits past the end of the input
+    int cnt;       // bits in buf
+    int fake;      // of which zero padding past the end of the input (always the topmost ones)
+    bool starved;  // padding bits were consumed: the stream ended early
 };
 
-// k <= 16 bits, least significant first; bytes are fetched only when needed, so fewer than 8 bits are ever left over
-DTB_LZW_HD uint32_t inflate_bits(InflateBits &b, int k)
+// at least k <= 16 bits in the buffer (least significant first); past the end of the input the buffer is padded with
+// zeros, which only counts as an error once such bits are consumed -- so looking ahead near the end is harmless
+DTB_LZW_HD void inflate_fill(InflateBits &b, int k)
 {
     while (b.cnt < k) {
-        uint32_t byte = 0;
-        if (b.ip < b.n) byte = b.in[b.ip++];
-        else b.starved = true;
-        b.buf |= (uint64_t)byte << b.cnt;
+        if (b.ip < b.n) b.buf |= (uint64_t)b.in[b.ip++] << b.cnt;
+        else b.fake += 8;
         b.cnt += 8;
     }
-    const uint32_t v = (uint32_t)(b.buf & ((1u << k) - 1u));
+}
+
+DTB_LZW_HD void inflate_drop(InflateBits &b, int k)
+{
     b.buf >>= k;
     b.cnt -= k;
+    if (b.cnt < b.fake) {
+        b.starved = true;
+        b.fake = b.cnt;
+    }
+}
+
+DTB_LZW_HD uint32_t inflate_bits(InflateBits &b, int k)
+{
+    inflate_fill(b, k);
+    const uint32_t v = (uint32_t)(b.buf & ((1u << k) - 1u));
+    inflate_drop(b, k);
     return v;
 }
 
@@ -87,6 +106,41 @@ DTB_LZW_HD int inflate_build(uint16_t *count, uint16_t *symbol, uint16_t *offs, 
     return left;
 }
 
+// One-look-up table for the codes of at most kInflateFastBits bits, from the counts and sorted symbols inflate_build
+// left: the j-th symbol of length L has the code first(L) + j (RFC 1951, 3.2.2), Huffman codes enter the stream most
+// significant bit first, so the index is the bit-reversed code, repeated for every value of the bits that follow it.
+DTB_LZW_HD void inflate_build_fast(uint16_t *fast, const uint16_t *count, const uint16_t *symbol)
+{
+    for (int i = 0; i < (1 << kInflateFastBits); ++i) fast[i] = 0;
+    int code = 0, index = 0;
+    for (int len = 1; len <= kInflateFastBits; ++len) {
+        code <<= 1;  // first code of this length
+        for (int j = 0; j < (int)count[len]; ++j) {
+            int c = code + j, r = 0;
+            for (int k = 0; k < len; ++k) {
+                r = (r << 1) | (c & 1);
+                c >>= 1;
+            }
+            const uint16_t e = (uint16_t)((symbol[index + j] << 4) | len);
+            for (int i = r; i < (1 << kInflateFastBits); i += 1 << len) fast[i] = e;
+        }
+        code += count[len];
+        index += count[len];
+    }
+}
+
+// a symbol of the literal / length or distance code: table look-up, canonical decoding for the rare long codes
+DTB_LZW_HD int inflate_symbol_fast(InflateBits &b, const uint16_t *fast, const uint16_t *count, const uint16_t *symbol)
+{
+    inflate_fill(b, kInflateFastBits);
+    const uint32_t e = fast[b.buf & ((1u << kInflateFastBits) - 1u)];
+    if (e != 0) {
+        inflate_drop(b, (int)(e & 15u));
+        return (int)(e >> 4);
+    }
+    return inflate_symbol(b, count, symbol);
+}
+
 // order in which the code-length code's own lengths are stored (RFC 1951, 3.2.7), five bits per entry
 DTB_LZW_HD int inflate_order(int i)
 {
@@ -105,7 +159,7 @@ DTB_LZW_HD int64_t zlib_inflate(const uint8_t *in, size_t n, uint8_t *out, size_
     if (n < 2) return -1;
     const uint32_t cmf = in[0], flg = in[1];
     if ((cmf & 0x0Fu) != 8u || ((cmf << 8) | flg) % 31u != 0u || (flg & 0x20u)) return -1;  // not Deflate, bad check, preset dictionary
-    InflateBits b{in, n, 2, 0, 0, false};
+    InflateBits b{in, n, 2, 0, 0, 0, false};
     size_t op = 0;
     bool last = false;
     while (!last && op < cap) {
@@ -113,8 +167,10 @@ DTB_LZW_HD int64_t zlib_inflate(const uint8_t *in, size_t n, uint8_t *out, size_
         const uint32_t type = inflate_bits(b, 2);
         if (b.starved) return -1;
         if (type == 0) {  // stored: the rest of the byte is skipped, LEN, ~LEN, then LEN bytes
+            b.ip -= (size_t)((b.cnt - b.fake) >> 3);  // whole bytes looked at ahead of time go back to the input
             b.buf = 0;
             b.cnt = 0;
+            b.fake = 0;
             if (b.ip + 4 > n) return -1;
             const uint32_t len = in[b.ip] | ((uint32_t)in[b.ip + 1] << 8), nlen = in[b.ip + 2] | ((uint32_t)in[b.ip + 3] << 8);
             if (len != (~nlen & 0xFFFFu)) return -1;
@@ -170,9 +226,11 @@ DTB_LZW_HD int64_t zlib_inflate(const uint8_t *in, size_t n, uint8_t *out, size_
             err = inflate_build(t->len_count, t->len_symbol, t->offs, t->lengths, nlen);
             if (err != 0 && (err < 0 || nlen != t->len_count[0] + t->len_count[1])) return -1;
         }
+        inflate_build_fast(t->len_fast, t->len_count, t->len_symbol);
+        inflate_build_fast(t->dist_fast, t->dist_count, t->dist_symbol);
         // the block's symbols
         for (;;) {
-            int sym = inflate_symbol(b, t->len_count, t->len_symbol);
+            int sym = inflate_symbol_fast(b, t->len_fast, t->len_count, t->len_symbol);
             if (sym < 0 || b.starved) return -1;
             if (sym < 256) {
                 out[op++] = (uint8_t)sym;  // every lane stores the same byte
@@ -185,7 +243,7 @@ DTB_LZW_HD int64_t zlib_inflate(const uint8_t *in, size_t n, uint8_t *out, size_
             // length: 3..10 directly, then groups of four per extra bit, 258 for the last symbol
             const int lext = sym < 8 || sym == 28 ? 0 : (sym - 4) >> 2;
             const uint32_t len = (sym < 8 ? 3u + (uint32_t)sym : sym == 28 ? 258u : 3u + ((4u + ((uint32_t)sym & 3u)) << lext)) + inflate_bits(b, lext);
-            const int ds = inflate_symbol(b, t->dist_count, t->dist_symbol);
+            const int ds = inflate_symbol_fast(b, t->dist_fast, t->dist_count, t->dist_symbol);
             if (ds < 0 || ds >= 30) return -1;
             const int dext = ds < 4 ? 0 : (ds >> 1) - 1;
             const size_t dist = (ds < 4 ? 1u + (uint32_t)ds : 1u + ((2u + ((uint32_t)ds & 1u)) << dext)) + inflate_bits(b, dext);
