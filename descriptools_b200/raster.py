@@ -539,10 +539,13 @@ def _read_to_device_chunks(reader, out, block_bytes: int, copy, group_chunks=Non
     per_group = group_chunks or _chunks_per_group(n, across, chunk_raw, block_bytes)
     groups = [(g0, min(c_hi, g0 + per_group)) for g0 in range(c_lo, c_hi, per_group)]
     spans = []
+    file_size = os.path.getsize(reader.name)
     for g0, g1 in groups:
         live = cnt[g0:g1] > 0
         lo = int(off[g0:g1][live].min()) if live.any() else 0
         hi = int((off[g0:g1] + cnt[g0:g1])[live].max()) if live.any() else 0
+        if hi > file_size:  # a damaged chunk table must not size the staging buffers
+            raise RasterError(f"{reader.name}: chunk table points outside the file")
         spans.append((lo, hi))
     biggest = max(1, max(hi - lo for lo, hi in spans))
     stage = [torch.empty(biggest, dtype=torch.uint8).pin_memory() for _ in range(min(2, len(groups)))]
