@@ -516,6 +516,15 @@ def _band_chunks(row_lo: int, row_hi: int, chunk_rows: int, across: int) -> tupl
     return (row_lo // chunk_rows) * across, -(-row_hi // chunk_rows) * across
 
 
+def _check_chunk_table(name: str, off: np.ndarray, cnt: np.ndarray, file_size: int) -> None:
+    """every chunk must lie inside the file: the device decoder reads exactly the bytes the table names, and a damaged
+    table must neither size the staging buffers nor send a warp past the end of the compressed data"""
+    size = np.uint64(file_size)
+    bad = (cnt > size) | (off > size - np.minimum(cnt, size))
+    if bool(bad[cnt > 0].any()):
+        raise RasterError(f"{name}: chunk table points outside the file")
+
+
 def _read_to_device_chunks(reader, out, block_bytes: int, copy, group_chunks=None, rows=None):
     """read_to_device(decode="device"): the compressed chunks go over PCIe as they lie in the file and are decoded
     by dtb_tiff_decode_chunks, one warp per chunk.  File spans are read into two pinned staging buffers; reading
@@ -539,13 +548,11 @@ def _read_to_device_chunks(reader, out, block_bytes: int, copy, group_chunks=Non
     per_group = group_chunks or _chunks_per_group(n, across, chunk_raw, block_bytes)
     groups = [(g0, min(c_hi, g0 + per_group)) for g0 in range(c_lo, c_hi, per_group)]
     spans = []
-    file_size = os.path.getsize(reader.name)
+    _check_chunk_table(reader.name, off[c_lo:c_hi], cnt[c_lo:c_hi], os.path.getsize(reader.name))
     for g0, g1 in groups:
         live = cnt[g0:g1] > 0
         lo = int(off[g0:g1][live].min()) if live.any() else 0
         hi = int((off[g0:g1] + cnt[g0:g1])[live].max()) if live.any() else 0
-        if hi > file_size:  # a damaged chunk table must not size the staging buffers
-            raise RasterError(f"{reader.name}: chunk table points outside the file")
         spans.append((lo, hi))
     biggest = max(1, max(hi - lo for lo, hi in spans))
     stage = [torch.empty(biggest, dtype=torch.uint8).pin_memory() for _ in range(min(2, len(groups)))]

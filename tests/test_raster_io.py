@@ -595,6 +595,11 @@ def test_launch_planning_is_exact():
         if n >= 2 * rio._WARPS_IN_FLIGHT:
             assert g >= rio._WARPS_IN_FLIGHT                            # a launch fills the device ...
             assert -(-n // g) >= 2                                      # ... and there are launches to overlap with the copies
+    ok_off, ok_cnt = np.array([8, 100, 0], np.uint64), np.array([92, 50, 0], np.uint64)
+    rio._check_chunk_table("f", ok_off, ok_cnt, 150)  # exactly to the end of the file; an absent chunk is fine
+    for off, cnt in (([8, 100], [92, 51]), ([8, 2**63], [92, 2**63]), ([151], [1]), ([0], [2**64 - 1])):
+        with pytest.raises(rio.RasterError, match="outside the file"):
+            rio._check_chunk_table("f", np.array(off, np.uint64), np.array(cnt, np.uint64), 150)
     assert rio._block_rows(1000, 128, 777, 4, 1 << 20) == 256 and rio._block_rows(1, 128, 330, 4, 100_000) == 1
     assert rio._block_rows(40000, 5, 40000, 4, 256 << 20) % 5 == 0
 
