@@ -384,9 +384,9 @@ int read_ifd(dtbio_reader *r) {
     }
     const int esz = r->big ? 20 : 12, csz = r->big ? 8 : 2, inl = r->big ? 8 : 4;
     uint8_t cnt[8];
-    if (ifd + csz > r->file_size || !pread_all(r->fd, cnt, csz, ifd)) return fail(DTBIO_ERR_FORMAT, "IFD offset outside the file");
+    if (ifd > r->file_size - csz || !pread_all(r->fd, cnt, csz, ifd)) return fail(DTBIO_ERR_FORMAT, "IFD offset outside the file");
     uint64_t n = r->big ? rd64(cnt) : rd16(cnt);
-    if (n == 0 || n > 65535 || ifd + csz + n * esz > r->file_size) return fail(DTBIO_ERR_FORMAT, "implausible IFD entry count");
+    if (n == 0 || n > 65535 || n * esz > r->file_size - ifd - csz) return fail(DTBIO_ERR_FORMAT, "implausible IFD entry count");
     std::vector<uint8_t> ent(n * esz);
     if (!pread_all(r->fd, ent.data(), ent.size(), ifd + csz)) return fail(DTBIO_ERR_IO, "cannot read the IFD");
     for (uint64_t i = 0; i < n; ++i) {
@@ -400,14 +400,15 @@ int read_ifd(dtbio_reader *r) {
         Tag t;
         t.type = type;
         t.count = count;
-        t.data.resize(bytes);
         const uint8_t *val = e + (r->big ? 12 : 8);
         if (bytes <= (uint64_t)inl) {
-            memcpy(t.data.data(), val, bytes);
+            t.data.assign(val, val + bytes);
         } else {
             uint64_t off = r->big ? rd64(val) : rd32(val);
-            if (off + bytes > r->file_size || !pread_all(r->fd, t.data.data(), bytes, off))
+            if (bytes > r->file_size || off > r->file_size - bytes)  // before anything is allocated for it
                 return fail(DTBIO_ERR_FORMAT, "tag " + std::to_string(tag) + " points outside the file");
+            t.data.resize(bytes);
+            if (!pread_all(r->fd, t.data.data(), bytes, off)) return fail(DTBIO_ERR_IO, "cannot read tag " + std::to_string(tag));
         }
         if (r->swap) swap_bytes(t.data.data(), bytes / swap_unit(type), swap_unit(type));
         r->tags[tag] = std::move(t);
@@ -506,7 +507,7 @@ int decode_chunk(dtbio_reader *r, int64_t chunk, int64_t row0, int64_t row1, uin
         for (int64_t y = y0; y < y1; ++y) memset(dst + (y - row0) * stride + x0 * L.bps, 0, copy_bytes);
         return DTBIO_OK;
     }
-    if (off + len > r->file_size) return fail(DTBIO_ERR_FORMAT, "chunk " + std::to_string(chunk) + " lies outside the file");
+    if (len > r->file_size || off > r->file_size - len) return fail(DTBIO_ERR_FORMAT, "chunk " + std::to_string(chunk) + " lies outside the file");
     const int comp = r->info.compression;
     if (comp == DTBIO_COMP_NONE && r->info.predictor == 1 && !r->swap) {
         // read just the rows that are wanted, straight into place when the chunk spans whole rows
