@@ -454,11 +454,12 @@ def test_device_inflate_block_types_and_damage(tmp_path):
         assert status == 0 or (status & 7 in (1, 3))
 
 
-@pytest.mark.parametrize("name", ["fuzz_lzw", "fuzz_inflate"])
+@pytest.mark.parametrize("name", ["fuzz_lzw", "fuzz_inflate", "fuzz_reader"])
 def test_decoders_under_sanitizers(tmp_path, name):
     """the coders shared by host and device (csrc/lzw.cuh, csrc/inflate.cuh), compiled with AddressSanitizer + UBSan and fed
     intact, truncated and bit-flipped streams from exact-size heap blocks: a damaged file may fail to decode, it must never
-    read or write outside its buffers (on the device that would be a fault, not an exception)"""
+    read or write outside its buffers (on the device that would be a fault, not an exception).  fuzz_reader does the same
+    to the host library as a whole: valid files of every layout with bytes flipped in the header, the IFD and the chunks"""
     import shutil
     import subprocess
 
@@ -466,12 +467,12 @@ def test_decoders_under_sanitizers(tmp_path, name):
         pytest.skip("no g++")
     src = os.path.join(REPO, "tests", "fuzz", name + ".cpp")
     exe = str(tmp_path / name)
-    build = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", src, "-o", exe, "-lz"],
+    build = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-pthread", src, "-o", exe, "-lz"],
                            capture_output=True, text=True, cwd=os.path.dirname(src))
     if build.returncode != 0 and "sanitize" in build.stderr.lower() + build.stdout.lower():
         pytest.skip("sanitizer runtime not installed")
     assert build.returncode == 0, build.stderr
-    run = subprocess.run([exe, "500"], capture_output=True, text=True, timeout=300)
+    run = subprocess.run([exe, "500", str(tmp_path)], capture_output=True, text=True, timeout=300)  # fuzz_reader: whole damaged files
     assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-4000:]
     assert "0 problems" in run.stdout
 
