@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdtb200.so")
+LIB_PATH = os.environ.get("DTB_LIB_PATH") or os.path.join(_HERE, "libdtb200.so")  # override: debugging builds only
 
 DTB_F32, DTB_I16 = 0, 1
 DTB_I32, DTB_I64 = 0, 1

@@ -27,6 +27,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace dtb {
@@ -42,7 +44,7 @@ constexpr int RPT = TH / 8;       // rows per thread
 constexpr int STAGES = 3;
 constexpr int STAGE_BYTES = ((BOXW * BOXH * 4 + 127) / 128) * 128;
 constexpr int TMA_BYTES = BOXW * BOXH * 4;
-constexpr size_t SMEM_TMA = (size_t)STAGES * STAGE_BYTES + 256;
+constexpr size_t SMEM_TMA = (size_t)STAGES * STAGE_BYTES + 256;  // + full / empty barriers + tile ids
 
 struct SlopeConsts {
     double px;   // cardinal step            (slope.py:250)
@@ -50,6 +52,7 @@ struct SlopeConsts {
     double kc;   // 100 / px
     double kd;   // 100 / pd
     float r32;   // (float)(px / pd)
+    float kc_hi, kc_lop, kc_lom, kd_hi, kd_lop, kd_lom;  // v2 strip: k = k_hi + k_lo to 2^-48; k_lo+- = k_lo +- 2^-44 k
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -382,7 +385,276 @@ __device__ __forceinline__ void stencil_strip_fast(const float *tile, int gx, in
     }
 }
 
-// ---- TMA persistent kernel (f32, cols % 4 == 0, 16-byte aligned bases) ----------------------
+
+// ---- lean strip (v2): packed f32x2 arithmetic, no f64, no conversions --------------------------------
+// Issue-rate facts measured on B200 (scripts/pipe_probe.cu, profiles/r2b_pipe_probe.txt; clocks per warp
+// instruction per SM sub-partition): FADD/FFMA 1, FADD2/FFMA2 2 (two results per issue slot), FMNMX3 / FSET /
+// FSETP / FSEL / LOP3 / SHF / PRMT / IMAD 2, FLO 8, F2F (f32<->f64) 8.5.  The v1 strip spent 2 F2F + 1 FLO (25
+// clocks of the XU pipe) and ~34 half-rate ALU instructions per cell.  v2, per PAIR of horizontally adjacent cells:
+//   * the 8 elevation differences of both cells by 8 FADD2 (operands are register pairs: a row is held both as
+//     cell-aligned pairs P and as the pairs M shifted by one column);
+//   * class maxima by FMNMX3 (never NaN: an undefined neighbour -- off-raster NaN, NaN in the data -- is
+//     skipped exactly like slope.py:247 skips -100);
+//   * first maximum in scan order (strict '<', slope.py:250,255): l_k = [d_k != max] by FSET, then the index
+//     of the first winner j = l0 (1 + l1 (1 + l2)) by two FFMA2 per class;
+//   * slope of BOTH classes without f64: s+- = RN(a k_hi + RN(a k_lo+-)) (one FMUL2 + one FFMA2 each), where
+//     k_hi + k_lo = 100/d to 2^-48 and k_lo+- = k_lo +- 2^-44 (100/d).  The fused multiply-add rounds the exact
+//     sum once, so s- <= f32(f64(a)/d*100) <= s+ (the reference's three roundings move the real value by < 2^-50
+//     relative, the bracket is 2^-44 wide); s+ == s- pins the result, otherwise the row takes the exact path
+//     (about one cell in 10^6).  S = max(S_card, S_diag) (all roundings are monotone); cardinal wins iff
+//     S_card > S_diag; S_card == S_diag > 0 cannot be decided in f32 and takes the exact path;
+//   * no positive gradient (S == 0): q = 1 adds 8 to the cell's nibble, the byte permute below then yields code
+//     0 (selector nibbles 8..15 replicate the sign bit of a table byte; the cardinal bytes have none), the
+//     slope is +0; the outlet rule (first undefined neighbour) needs the exact path only if the window holds a
+//     NaN, which is tested only for rows that have a pit;
+//   * 0 < S < 2^-30 (where the products above could lose bits to underflow) makes q fractional; q (q - 1) != 0
+//     is accumulated on the FMA pipe and tested once per row of four cells.
+typedef unsigned long long p2;  // two packed f32 (an aligned register pair)
+__device__ __forceinline__ p2 pk(float lo, float hi) { p2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(p2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ p2 add2(p2 a, p2 b) { p2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ p2 sub2(p2 a, p2 b) { p2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ p2 mul2(p2 a, p2 b) { p2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ p2 fma2(p2 a, p2 b, p2 c) { p2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float max3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float set_neu(float a, float b) { float r; asm("set.neu.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float fma_sat(float a, float b, float c) { float r; asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+struct Row2 {
+    p2 P0, P1;      // (w1,w2) (w3,w4): the thread's four cells
+    p2 M0, M1, M2;  // (w0,w1) (w2,w3) (w4,w5): the same row shifted by one column
+    bool bad;       // a value <= -100 among the six: nodata (slope.py:231,247); NaN is not "bad", it is skipped
+};
+
+// The shifted pairs are copies of the LDS.128 result next to the two halo values; the copies are volatile asm so
+// that the compiler keeps the pairs of the three window rows in registers instead of rebuilding them per row.
+__device__ __forceinline__ void load_row2(uint32_t a /* shared address of the thread's first cell */, Row2 &r)
+{
+    float x, y, z, w;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(a));
+    const float w0 = lds_f32(a - 4), w5 = lds_f32(a + 16);
+    float x2, y2, z2, w2;
+    asm volatile("mov.b32 %0, %1;" : "=f"(x2) : "f"(x));
+    asm volatile("mov.b32 %0, %1;" : "=f"(y2) : "f"(y));
+    asm volatile("mov.b32 %0, %1;" : "=f"(z2) : "f"(z));
+    asm volatile("mov.b32 %0, %1;" : "=f"(w2) : "f"(w));
+    r.P0 = pk(x, y);
+    r.P1 = pk(z, w);
+    r.M0 = pk(w0, x2);
+    r.M1 = pk(y2, z2);
+    r.M2 = pk(w2, w5);
+    r.bad = fminf(min3(min3(w0, x, y), z, w), w5) <= ND_F;
+}
+
+struct FastK {
+    p2 kc_hi, kc_lop, kc_lom, kd_hi, kd_lop, kd_lom;  // 100/px and 100/(px sqrt2): f32 hi, and lo +- 2^-44 k
+    p2 one, four, eight, w256;
+};
+
+// one pair of horizontally adjacent cells.  C: centres; the other eight: the neighbours in each direction.
+// N accumulates the two cells' selector nibbles (lane 0: even cell, lane 1: odd cell), scaled by W (1 or 256).
+template <int W>
+__device__ __forceinline__ void cell_pair2(p2 C, p2 qN, p2 qS, p2 qW, p2 qE, p2 qNW, p2 qNE, p2 qSW, p2 qSE, const FastK &k, float &Sa,
+                                           float &Sb, p2 &N, p2 &acc, bool &redo)
+{
+    float nA, nB, sA, sB, wA, wB, eA, eB, nwA, nwB, neA, neB, swA, swB, seA, seB;
+    upk(sub2(C, qN), nA, nB);
+    upk(sub2(C, qS), sA, sB);
+    upk(sub2(C, qW), wA, wB);
+    upk(sub2(C, qE), eA, eB);
+    upk(sub2(C, qNW), nwA, nwB);
+    upk(sub2(C, qNE), neA, neB);
+    upk(sub2(C, qSW), swA, swB);
+    upk(sub2(C, qSE), seA, seB);
+    // class maxima, floor 0 (slope.py:244: m starts at 0); NaN differences are ignored by FMNMX
+    const float acA = max3(max3(nA, wA, eA), sA, 0.0f), acB = max3(max3(nB, wB, eB), sB, 0.0f);
+    const float adA = max3(max3(nwA, neA, swA), seA, 0.0f), adB = max3(max3(nwB, neB, swB), seB, 0.0f);
+    // losers among the first three of each class in scan order (N,W,E,[S]) / (NW,NE,SW,[SE]); NaN loses
+    const p2 lN = pk(set_neu(nA, acA), set_neu(nB, acB)), lW = pk(set_neu(wA, acA), set_neu(wB, acB)),
+             lE = pk(set_neu(eA, acA), set_neu(eB, acB));
+    const p2 lNW = pk(set_neu(nwA, adA), set_neu(nwB, adB)), lNE = pk(set_neu(neA, adA), set_neu(neB, adB)),
+             lSW = pk(set_neu(swA, adA), set_neu(swB, adB));
+    const p2 jc = fma2(lN, fma2(lW, lE, lW), lN);                      // 0..3 = N W E S
+    const p2 jd4 = add2(fma2(lNW, fma2(lNE, lSW, lNE), lNW), k.four);  // 4..7 = NW NE SW SE
+    // slope bracket of both classes
+    const p2 ac = pk(acA, acB), ad = pk(adA, adB);
+    float cpA, cpB, cmA, cmB, dpA, dpB, dmA, dmB;
+    upk(fma2(ac, k.kc_hi, mul2(ac, k.kc_lop)), cpA, cpB);
+    upk(fma2(ac, k.kc_hi, mul2(ac, k.kc_lom)), cmA, cmB);
+    upk(fma2(ad, k.kd_hi, mul2(ad, k.kd_lop)), dpA, dpB);
+    upk(fma2(ad, k.kd_hi, mul2(ad, k.kd_lom)), dmA, dmB);
+    redo |= (cpA != cmA) | (cpB != cmB) | (dpA != dmA) | (dpB != dmB);  // rounding in doubt (or NaN / inf)
+    Sa = fmaxf(cpA, dpA);
+    Sb = fmaxf(cpB, dpB);
+    // q = [no positive gradient]; fractional for 0 < S < 2^-30: accumulate q (q - 1) <= 0 (exactly 0 for q in {0, 1})
+    const p2 q = pk(fma_sat(Sa, -1073741824.0f, 1.0f), fma_sat(Sb, -1073741824.0f, 1.0f));
+    acc = fma2(q, sub2(q, k.one), acc);
+    // class: u = [S_card >= S_diag]; S_card == S_diag > 0 is undecidable here (z == 0 and q == 0)
+    float zA, zB, qA, qB;
+    upk(sub2(pk(cpA, cpB), pk(dpA, dpB)), zA, zB);
+    upk(q, qA, qB);
+    redo |= (zA == -qA) | (zB == -qB);
+    const p2 u = pk(fma_sat(zA, 1.2676506e30f, 1.0f), fma_sat(zB, 1.2676506e30f, 1.0f));
+    const p2 m = fma2(q, k.eight, fma2(u, sub2(jc, jd4), jd4));  // selector nibble: 0..7, or 8..11 for a pit
+    if (W == 1) N = add2(N, m);
+    else N = fma2(m, k.w256, N);
+}
+
+// the exact path for one row of four cells, stored straight to the outputs
+__device__ __noinline__ void slow_row_store(const float *tile, int trow, int tcol0, double px, double pd, float *slope, uint8_t *d8)
+{
+    float4 s4;
+    uint32_t codes;
+    slow_row(tile, trow, tcol0, px, pd, s4, codes);
+    if (slope) *reinterpret_cast<float4 *>(slope) = s4;
+    if (d8) *reinterpret_cast<uint32_t *>(d8) = codes;
+}
+
+// 4 columns x RPT rows of one staged tile.  sbase / dbase: the outputs; off: element offset of the strip's first
+// cell; nrows: how many of the strip's rows are inside the output (0..RPT)
+template <bool WS, bool WD>
+__device__ __forceinline__ void stencil_strip_v2(const float *tile, int gx, int ry0, const SlopeConsts &kk, const FastK &k,
+                                                 float *__restrict__ sbase, uint8_t *__restrict__ dbase, int64_t off, int64_t cols,
+                                                 int nrows)
+{
+    const int tcol0 = 4 * gx + HALO_L;
+    const uint32_t a = smem_u32(tile + ry0 * BOXW + tcol0);
+    Row2 U, M, D;
+    load_row2(a, U);
+    load_row2(a + BOXW * 4, M);
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        load_row2(a + (2 + i) * BOXW * 4, D);
+        if (i < nrows) {
+            float *sp = sbase + off;
+            uint8_t *dp = dbase + off;
+            if (U.bad | M.bad | D.bad) {  // nodata somewhere in the 3x6 window
+                slow_row_store(tile, ry0 + 1 + i, tcol0, kk.px, kk.pd, WS ? sp : nullptr, WD ? dp : nullptr);
+            } else {
+                p2 N = pk(0.0f, 0.0f), acc = pk(0.0f, 0.0f);
+                bool redo = false;
+                float4 s4;
+                cell_pair2<1>(M.P0, U.P0, D.P0, M.M0, M.M1, U.M0, U.M1, D.M0, D.M1, k, s4.x, s4.y, N, acc, redo);
+                cell_pair2<256>(M.P1, U.P1, D.P1, M.M1, M.M2, U.M1, U.M2, D.M1, D.M2, k, s4.z, s4.w, N, acc, redo);
+                float n0, n1, a0, a1;
+                upk(N, n0, n1);
+                upk(acc, a0, a1);
+                // 2^23 + sum of nibble_c 16^c: the low mantissa bits are the byte-permute selector
+                const uint32_t sel = __float_as_uint(fmaf(n1, 16.0f, n0 + 8388608.0f));
+                // selector nibble 0..7 picks a table byte; 8..11 (a pit) replicates the sign bit of a cardinal byte = 0.
+                // (PTX prmt; CUDA's __byte_perm masks the nibbles to three bits.)
+                uint32_t codes;
+                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(codes) : "r"(0x04011040u), "r"(0x02088020u), "r"(sel));  // S E W N | SE SW NE NW
+                if (WS) *reinterpret_cast<float4 *>(sp) = s4;
+                if (WD) *reinterpret_cast<uint32_t *>(dp) = codes;
+                redo |= !(a0 + a1 == 0.0f);
+#ifdef DTB_DEBUG_FORCE_REDO
+                redo = true;
+#endif
+                if (!redo && (sel & 0x8888u)) {
+                    // a pit: its code is the first undefined neighbour; here only a NaN can be one
+                    float x0, x1;
+                    upk(add2(add2(add2(U.M0, U.M1), add2(U.M2, M.M0)), add2(add2(M.M1, M.M2), add2(add2(D.M0, D.M1), D.M2))), x0, x1);
+                    redo = !(x0 + x1 == x0 + x1);
+                }
+                if (redo) slow_row_store(tile, ry0 + 1 + i, tcol0, kk.px, kk.pd, WS ? sp : nullptr, WD ? dp : nullptr);
+            }
+        }
+        off += cols;
+        U = M;
+        M = D;
+    }
+}
+
+// ---- TMA persistent kernels (f32, cols % 4 == 0, 16-byte aligned bases) -----------------------------
+// Tile scheduler state: one (next tile, CTAs done) pair per launch slot; the last CTA to run dry resets its slot.
+__device__ unsigned int g_tile_sched[64][2];
+
+// v2: warps consume tiles independently.  full[s]: the TMA load of stage s has landed (and tile_xy[s] is valid);
+// empty[s]: all eight warps are done reading stage s.  Lane 0 of warp 0 is the producer: after its own strip of
+// tile number `it` it refills the stage of tile it-1 (whose readers have, as a rule, long finished), so no warp
+// ever waits for another one at a CTA-wide barrier.  Tiles are handed out by an atomic counter (row-major order:
+// the CTAs of the grid sweep the raster together, which keeps the DRAM pages and the L2 halo reuse local).
+template <bool WS, bool WD, int MINB>
+__global__ void __launch_bounds__(NTHREADS, MINB)
+slope_d8_tma2_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_begin, int64_t row_end, int64_t cols, int tiles_x,
+                     int ntiles, SlopeConsts k, float *__restrict__ slope, uint8_t *__restrict__ d8, int sched_slot)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 127u) != 0u) __trap();  // TMA destination alignment
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES);
+    uint64_t *empty = full + STAGES;
+    int *tile_xy = reinterpret_cast<int *>(empty + STAGES);  // (tx, ty) per stage; tx < 0: no more tiles
+    const int tid = threadIdx.x;
+    unsigned int *sched = g_tile_sched[sched_slot];
+
+    // producer only (tid 0): fetch the next tile, publish it in `stage`, start its load
+    auto produce = [&](int stage) -> bool {
+        const int tile = (int)atomicAdd(&sched[0], 1u);
+        if (tile >= ntiles) {
+            tile_xy[2 * stage] = -1;
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
+            if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {  // every CTA has drawn its last ticket
+                sched[0] = 0;
+                sched[1] = 0;
+            }
+            return false;
+        }
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        tile_xy[2 * stage] = tx;
+        tile_xy[2 * stage + 1] = ty;
+        mbar_expect_tx(&full[stage], TMA_BYTES);
+        tma_load_2d(smem + (size_t)stage * STAGE_BYTES, &dem_map, tx * TW - HALO_L, (int)(row_begin + (int64_t)ty * TH - 1), &full[stage]);
+        return true;
+    };
+
+    bool more = true;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NTHREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < STAGES && more; ++s) more = produce(s);
+    }
+    __syncthreads();
+
+    const int gx = tid & 31, gy = tid >> 5;
+    FastK fk;
+    fk.kc_hi = pk(k.kc_hi, k.kc_hi); fk.kc_lop = pk(k.kc_lop, k.kc_lop); fk.kc_lom = pk(k.kc_lom, k.kc_lom);
+    fk.kd_hi = pk(k.kd_hi, k.kd_hi); fk.kd_lop = pk(k.kd_lop, k.kd_lop); fk.kd_lom = pk(k.kd_lom, k.kd_lom);
+    fk.one = pk(1.0f, 1.0f); fk.four = pk(4.0f, 4.0f); fk.eight = pk(8.0f, 8.0f); fk.w256 = pk(256.0f, 256.0f);
+    const int64_t out_rows = row_end - row_begin;
+
+    for (int it = 0;; ++it) {
+        const int stage = it % STAGES;
+        mbar_wait(&full[stage], (uint32_t)(it / STAGES) & 1u);
+        const int tx = tile_xy[2 * stage], ty = tile_xy[2 * stage + 1];
+        if (tx < 0) break;
+        const float *tbuf = reinterpret_cast<const float *>(smem + (size_t)stage * STAGE_BYTES);
+        const int64_t orow = (int64_t)ty * TH + gy * RPT, ocol = (int64_t)tx * TW + 4 * gx;
+        const int64_t left = out_rows - orow;
+        const int nrows = ocol < cols ? (left < RPT ? (left < 0 ? 0 : (int)left) : RPT) : 0;
+        stencil_strip_v2<WS, WD>(tbuf, gx, gy * RPT, k, fk, slope, d8, orow * cols + ocol, cols, nrows);
+        __syncwarp();
+        if (gx == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[stage])) : "memory");
+        if (tid == 0 && more && it >= 1) {
+            const int ps = (it - 1) % STAGES;
+            mbar_wait(&empty[ps], (uint32_t)((it - 1) / STAGES) & 1u);
+            more = produce(ps);  // tile number it-1+STAGES
+        }
+    }
+}
+
+// v1 (round 1): CTA-wide barrier per tile, static tile stride; kept for A/B runs (DTB_STENCIL_V1)
 __global__ void __launch_bounds__(NTHREADS, 3)
 slope_d8_tma_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_begin, int64_t row_end, int64_t cols,
                     int tiles_x, int ntiles, SlopeConsts k, float *__restrict__ slope, uint8_t *__restrict__ d8)
@@ -418,8 +690,7 @@ slope_d8_tma_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_beg
         mbar_wait(&full[stage], parity);
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         const float *tbuf = reinterpret_cast<const float *>(smem + (size_t)stage * STAGE_BYTES);
-        stencil_strip_fast(tbuf, gx, gy * RPT, k, (int64_t)ty * TH, row_end - row_begin, (int64_t)tx * TW + 4 * gx, cols,
-                           slope, d8);
+        stencil_strip_fast(tbuf, gx, gy * RPT, k, (int64_t)ty * TH, row_end - row_begin, (int64_t)tx * TW + 4 * gx, cols, slope, d8);
         __syncthreads();  // every thread is done reading this stage
         if (tid == 0) {
             const int next = tile + STAGES * gridDim.x;
@@ -490,6 +761,12 @@ extern "C" int dtb_slope_d8(const void *dem, int dem_dtype, int64_t buf_rows, in
     k.kc = 100.0 / k.px;
     k.kd = 100.0 / k.pd;
     k.r32 = (float)(k.px / k.pd);
+    k.kc_hi = (float)k.kc;
+    k.kc_lop = (float)(k.kc - (double)k.kc_hi + ldexp(k.kc, -44));
+    k.kc_lom = (float)(k.kc - (double)k.kc_hi - ldexp(k.kc, -44));
+    k.kd_hi = (float)k.kd;
+    k.kd_lop = (float)(k.kd - (double)k.kd_hi + ldexp(k.kd, -44));
+    k.kd_lom = (float)(k.kd - (double)k.kd_hi - ldexp(k.kd, -44));
 
     const int64_t nrows = row_end - row_begin;
     const int tiles_x = (int)((cols + TW - 1) / TW);
@@ -513,13 +790,38 @@ extern "C" int dtb_slope_d8(const void *dem, int dem_dtype, int64_t buf_rows, in
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
         if (r != CUDA_SUCCESS) return cuda_fail_msg("cuTensorMapEncodeTiled failed");
+        static const bool use_v1 = getenv("DTB_STENCIL_V1") != nullptr;  // A/B aid: the round-1 kernel
+        if (use_v1) {
+            static bool attr1 = false;
+            if (!attr1) {
+                DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
+                attr1 = true;
+            }
+            const int grid = ntiles < 3 * kNumSMs ? ntiles : 3 * kNumSMs;
+            DTB_KERNEL("slope_d8_tma_kernel", st, (slope_d8_tma_kernel<<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8)));
+            return DTB_OK;
+        }
         static bool attr_set = false;
         if (!attr_set) {
-            DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
+            DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma2_kernel<true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
+            DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma2_kernel<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
+            DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma2_kernel<true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
+            DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma2_kernel<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
             attr_set = true;
         }
-        const int grid = ntiles < 3 * kNumSMs ? ntiles : 3 * kNumSMs;
-        DTB_KERNEL("slope_d8_tma_kernel", st, slope_d8_tma_kernel<<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8));
+        static const bool occ2 = getenv("DTB_STENCIL_OCC2") != nullptr;  // A/B aid: 2 CTAs per SM, 128 registers
+        static std::atomic<unsigned> slot_ctr{0};
+        const int slot = (int)(slot_ctr.fetch_add(1) % 64u);
+        const int per_sm = occ2 ? 2 : 3;
+        const int grid = ntiles < per_sm * kNumSMs ? ntiles : per_sm * kNumSMs;
+        if (slope && d8 && occ2)
+            DTB_KERNEL("slope_d8_tma_kernel", st, (slope_d8_tma2_kernel<true, true, 2><<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8, slot)));
+        else if (slope && d8)
+            DTB_KERNEL("slope_d8_tma_kernel", st, (slope_d8_tma2_kernel<true, true, 3><<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8, slot)));
+        else if (slope)
+            DTB_KERNEL("slope_d8_tma_kernel", st, (slope_d8_tma2_kernel<true, false, 3><<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8, slot)));
+        else
+            DTB_KERNEL("slope_d8_tma_kernel", st, (slope_d8_tma2_kernel<false, true, 3><<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8, slot)));
     } else if (dem_dtype == DTB_F32) {
         DTB_KERNEL("slope_d8_generic_kernel<f32>", st, slope_d8_generic_kernel<float><<<ntiles, NTHREADS, 0, st>>>((const float *)dem, buf_rows, row_begin, row_end, cols,
                                                                     tiles_x, k, slope, d8));
