@@ -428,29 +428,16 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
 }
 
 struct Row2 {
-    p2 P0, P1;      // (w1,w2) (w3,w4): the thread's four cells
-    p2 M0, M1, M2;  // (w0,w1) (w2,w3) (w4,w5): the same row shifted by one column
-    bool bad;       // a value <= -100 among the six: nodata (slope.py:231,247); NaN is not "bad", it is skipped
+    float w[6];  // w[1..4]: the thread's four cells (one LDS.128: aligned register pairs), w[0], w[5]: the halo columns
+    bool bad;    // a value <= -100 among the six: nodata (slope.py:231,247); NaN is not "bad", it is skipped
 };
 
-// The shifted pairs are copies of the LDS.128 result next to the two halo values; the copies are volatile asm so
-// that the compiler keeps the pairs of the three window rows in registers instead of rebuilding them per row.
 __device__ __forceinline__ void load_row2(uint32_t a /* shared address of the thread's first cell */, Row2 &r)
 {
-    float x, y, z, w;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(a));
-    const float w0 = lds_f32(a - 4), w5 = lds_f32(a + 16);
-    float x2, y2, z2, w2;
-    asm volatile("mov.b32 %0, %1;" : "=f"(x2) : "f"(x));
-    asm volatile("mov.b32 %0, %1;" : "=f"(y2) : "f"(y));
-    asm volatile("mov.b32 %0, %1;" : "=f"(z2) : "f"(z));
-    asm volatile("mov.b32 %0, %1;" : "=f"(w2) : "f"(w));
-    r.P0 = pk(x, y);
-    r.P1 = pk(z, w);
-    r.M0 = pk(w0, x2);
-    r.M1 = pk(y2, z2);
-    r.M2 = pk(w2, w5);
-    r.bad = fminf(min3(min3(w0, x, y), z, w), w5) <= ND_F;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.w[1]), "=f"(r.w[2]), "=f"(r.w[3]), "=f"(r.w[4]) : "r"(a));
+    r.w[0] = lds_f32(a - 4);
+    r.w[5] = lds_f32(a + 16);
+    r.bad = fminf(min3(min3(r.w[0], r.w[1], r.w[2]), r.w[3], r.w[4]), r.w[5]) <= ND_F;
 }
 
 struct FastK {
@@ -458,21 +445,25 @@ struct FastK {
     p2 one, four, eight, w256;
 };
 
-// one pair of horizontally adjacent cells.  C: centres; the other eight: the neighbours in each direction.
+// one pair of horizontally adjacent cells: columns j, j+1 (1 or 3) of the window rows U (above), M, D (below);
+// H[t] = M.w[t] - M.w[t+1]: the horizontal differences of the centre row, each used by both of its cells.
+// Only the vertical differences are packed (their operands are the aligned pairs of the LDS.128 results); the
+// shifted directions would need copies into new register pairs, which cost more issue slots than scalar FADDs.
+// (Sharing the vertical / diagonal differences between consecutive rows as well was measured: the 12 carried
+// registers spill at 80 registers per thread and cost more than the 11 FADDs per row they save.)
 // N accumulates the two cells' selector nibbles (lane 0: even cell, lane 1: odd cell), scaled by W (1 or 256).
 template <int W>
-__device__ __forceinline__ void cell_pair2(p2 C, p2 qN, p2 qS, p2 qW, p2 qE, p2 qNW, p2 qNE, p2 qSW, p2 qSE, const FastK &k, float &Sa,
-                                           float &Sb, p2 &N, p2 &acc, bool &redo)
+__device__ __forceinline__ void cell_pair2(const Row2 &U, const Row2 &M, const Row2 &D, const float (&H)[5], const int j, const FastK &k,
+                                           float &Sa, float &Sb, p2 &N, p2 &acc, bool &redo)
 {
-    float nA, nB, sA, sB, wA, wB, eA, eB, nwA, nwB, neA, neB, swA, swB, seA, seB;
-    upk(sub2(C, qN), nA, nB);
-    upk(sub2(C, qS), sA, sB);
-    upk(sub2(C, qW), wA, wB);
-    upk(sub2(C, qE), eA, eB);
-    upk(sub2(C, qNW), nwA, nwB);
-    upk(sub2(C, qNE), neA, neB);
-    upk(sub2(C, qSW), swA, swB);
-    upk(sub2(C, qSE), seA, seB);
+    float nA, nB, sA, sB;
+    const p2 C = pk(M.w[j], M.w[j + 1]);
+    upk(sub2(C, pk(U.w[j], U.w[j + 1])), nA, nB);
+    upk(sub2(C, pk(D.w[j], D.w[j + 1])), sA, sB);
+    const float cA = M.w[j], cB = M.w[j + 1];
+    const float wA = -H[j - 1], wB = -H[j], eA = H[j], eB = H[j + 1];
+    const float nwA = cA - U.w[j - 1], nwB = cB - U.w[j], neA = cA - U.w[j + 1], neB = cB - U.w[j + 2];
+    const float swA = cA - D.w[j - 1], swB = cB - D.w[j], seA = cA - D.w[j + 1], seB = cB - D.w[j + 2];
     // class maxima, floor 0 (slope.py:244: m starts at 0); NaN differences are ignored by FMNMX
     const float acA = max3(max3(nA, wA, eA), sA, 0.0f), acB = max3(max3(nB, wB, eB), sB, 0.0f);
     const float adA = max3(max3(nwA, neA, swA), seA, 0.0f), adB = max3(max3(nwB, neB, swB), seB, 0.0f);
@@ -517,6 +508,80 @@ __device__ __noinline__ void slow_row_store(const float *tile, int trow, int tco
     if (d8) *reinterpret_cast<uint32_t *>(d8) = codes;
 }
 
+// One row of four cells, given the three window rows.  Returns true when the exact path has to redo the row.
+__device__ __forceinline__ bool fast_row2(const Row2 &U, const Row2 &M, const Row2 &D, const FastK &k, float4 &s4, uint32_t &codes,
+                                          uint32_t &sel)
+{
+    float H[5];
+#pragma unroll
+    for (int t = 0; t <= 4; ++t) H[t] = M.w[t] - M.w[t + 1];
+    p2 N = pk(0.0f, 0.0f), acc = pk(0.0f, 0.0f);
+    bool redo = false;
+    cell_pair2<1>(U, M, D, H, 1, k, s4.x, s4.y, N, acc, redo);
+    cell_pair2<256>(U, M, D, H, 3, k, s4.z, s4.w, N, acc, redo);
+    float n0, n1, a0, a1;
+    upk(N, n0, n1);
+    upk(acc, a0, a1);
+    // 2^23 + sum of nibble_c 16^c: the low mantissa bits are the byte-permute selector
+    sel = __float_as_uint(fmaf(n1, 16.0f, n0 + 8388608.0f));
+    // selector nibble 0..7 picks a table byte; 8..11 (a pit) replicates the sign bit of a cardinal byte = 0.
+    // (PTX prmt; CUDA's __byte_perm masks the nibbles to three bits.)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(codes) : "r"(0x04011040u), "r"(0x02088020u), "r"(sel));  // S E W N | SE SW NE NW
+    return redo | !(a0 + a1 == 0.0f);
+}
+
+// a pit's code is its first undefined neighbour: does the window hold a NaN (off-raster, NaN in
+// the data, nodata rewritten by robust_row_store)?
+__device__ __forceinline__ bool window_has_nan(const Row2 &U, const Row2 &M, const Row2 &D)
+{
+    float x = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) x += (U.w[t] + M.w[t]) + D.w[t];
+    return !(x == x);
+}
+
+// A row whose window holds nodata (<= -100).  Values equal to -100 are rewritten as NaN, which the fast arithmetic
+// skips exactly like the reference skips a -100 neighbour (slope.py:247: FMNMX ignores NaN, FSET.NEU makes it a
+// loser); values below -100 stay what they are for their neighbours (the reference does not skip them either);
+// nodata centres (<= -100, slope.py:231) get slope -100, code 0.  Only what is still undecided (a pit next to an
+// undefined neighbour, a rounding in doubt) goes on to the exact path.
+__device__ __noinline__ void robust_row_store(const float *tile, int trow, int tcol0, double px, double pd, float kc_hi, float kc_lop,
+                                              float kc_lom, float kd_hi, float kd_lop, float kd_lom, float *slope, uint8_t *d8)
+{
+    FastK k;
+    k.kc_hi = pk(kc_hi, kc_hi); k.kc_lop = pk(kc_lop, kc_lop); k.kc_lom = pk(kc_lom, kc_lom);
+    k.kd_hi = pk(kd_hi, kd_hi); k.kd_lop = pk(kd_lop, kd_lop); k.kd_lom = pk(kd_lom, kd_lom);
+    k.one = pk(1.0f, 1.0f); k.four = pk(4.0f, 4.0f); k.eight = pk(8.0f, 8.0f); k.w256 = pk(256.0f, 256.0f);
+    const float qnan = __int_as_float(0x7fc00000);
+    Row2 R[3];
+    unsigned nd = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+            const float v = tile[(trow - 1 + j) * BOXW + tcol0 - 1 + t];
+            if (j == 1 && t >= 1 && t <= 4 && v <= ND_F) nd |= 1u << (t - 1);
+            R[j].w[t] = v == ND_F ? qnan : v;
+        }
+    float4 s4 = make_float4(ND_F, ND_F, ND_F, ND_F);
+    uint32_t codes = 0, sel = 0;
+    bool redo = false;
+    if (nd != 15u) {
+        redo = fast_row2(R[0], R[1], R[2], k, s4, codes, sel);
+        if (nd & 1u) { s4.x = ND_F; codes &= 0xFFFFFF00u; sel &= ~0x000Fu; }
+        if (nd & 2u) { s4.y = ND_F; codes &= 0xFFFF00FFu; sel &= ~0x00F0u; }
+        if (nd & 4u) { s4.z = ND_F; codes &= 0xFF00FFFFu; sel &= ~0x0F00u; }
+        if (nd & 8u) { s4.w = ND_F; codes &= 0x00FFFFFFu; sel &= ~0xF000u; }
+        if (!redo && (sel & 0x8888u)) redo = window_has_nan(R[0], R[1], R[2]);
+    }
+    if (redo) {
+        slow_row_store(tile, trow, tcol0, px, pd, slope, d8);
+    } else {
+        if (slope) *reinterpret_cast<float4 *>(slope) = s4;
+        if (d8) *reinterpret_cast<uint32_t *>(d8) = codes;
+    }
+}
+
 // 4 columns x RPT rows of one staged tile.  sbase / dbase: the outputs; off: element offset of the strip's first
 // cell; nrows: how many of the strip's rows are inside the output (0..RPT)
 template <bool WS, bool WD>
@@ -529,47 +594,40 @@ __device__ __forceinline__ void stencil_strip_v2(const float *tile, int gx, int 
     Row2 U, M, D;
     load_row2(a, U);
     load_row2(a + BOXW * 4, M);
+    const int64_t off0 = off;
+    unsigned later = 0;  // bit i: row i goes to the exact path, bit 8+i: to the nodata path (after the loop: no calls in it)
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
         load_row2(a + (2 + i) * BOXW * 4, D);
         if (i < nrows) {
-            float *sp = sbase + off;
-            uint8_t *dp = dbase + off;
             if (U.bad | M.bad | D.bad) {  // nodata somewhere in the 3x6 window
-                slow_row_store(tile, ry0 + 1 + i, tcol0, kk.px, kk.pd, WS ? sp : nullptr, WD ? dp : nullptr);
+                later |= 0x100u << i;
             } else {
-                p2 N = pk(0.0f, 0.0f), acc = pk(0.0f, 0.0f);
-                bool redo = false;
                 float4 s4;
-                cell_pair2<1>(M.P0, U.P0, D.P0, M.M0, M.M1, U.M0, U.M1, D.M0, D.M1, k, s4.x, s4.y, N, acc, redo);
-                cell_pair2<256>(M.P1, U.P1, D.P1, M.M1, M.M2, U.M1, U.M2, D.M1, D.M2, k, s4.z, s4.w, N, acc, redo);
-                float n0, n1, a0, a1;
-                upk(N, n0, n1);
-                upk(acc, a0, a1);
-                // 2^23 + sum of nibble_c 16^c: the low mantissa bits are the byte-permute selector
-                const uint32_t sel = __float_as_uint(fmaf(n1, 16.0f, n0 + 8388608.0f));
-                // selector nibble 0..7 picks a table byte; 8..11 (a pit) replicates the sign bit of a cardinal byte = 0.
-                // (PTX prmt; CUDA's __byte_perm masks the nibbles to three bits.)
-                uint32_t codes;
-                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(codes) : "r"(0x04011040u), "r"(0x02088020u), "r"(sel));  // S E W N | SE SW NE NW
-                if (WS) *reinterpret_cast<float4 *>(sp) = s4;
-                if (WD) *reinterpret_cast<uint32_t *>(dp) = codes;
-                redo |= !(a0 + a1 == 0.0f);
+                uint32_t codes, sel;
+                bool redo = fast_row2(U, M, D, k, s4, codes, sel);
+                if (WS) *reinterpret_cast<float4 *>(sbase + off) = s4;
+                if (WD) *reinterpret_cast<uint32_t *>(dbase + off) = codes;
 #ifdef DTB_DEBUG_FORCE_REDO
                 redo = true;
 #endif
-                if (!redo && (sel & 0x8888u)) {
-                    // a pit: its code is the first undefined neighbour; here only a NaN can be one
-                    float x0, x1;
-                    upk(add2(add2(add2(U.M0, U.M1), add2(U.M2, M.M0)), add2(add2(M.M1, M.M2), add2(add2(D.M0, D.M1), D.M2))), x0, x1);
-                    redo = !(x0 + x1 == x0 + x1);
-                }
-                if (redo) slow_row_store(tile, ry0 + 1 + i, tcol0, kk.px, kk.pd, WS ? sp : nullptr, WD ? dp : nullptr);
+                if (!redo && (sel & 0x8888u)) redo = window_has_nan(U, M, D);
+                if (redo) later |= 1u << i;
             }
         }
         off += cols;
         U = M;
         M = D;
+    }
+    if (later) {
+#pragma unroll 1
+        for (int i = 0; i < RPT; ++i) {
+            float *sp = WS ? sbase + off0 + i * cols : nullptr;
+            uint8_t *dp = WD ? dbase + off0 + i * cols : nullptr;
+            if (later >> i & 1u) slow_row_store(tile, ry0 + 1 + i, tcol0, kk.px, kk.pd, sp, dp);
+            if (later >> (8 + i) & 1u)
+                robust_row_store(tile, ry0 + 1 + i, tcol0, kk.px, kk.pd, kk.kc_hi, kk.kc_lop, kk.kc_lom, kk.kd_hi, kk.kd_lop, kk.kd_lom, sp, dp);
+        }
     }
 }
 
@@ -578,9 +636,9 @@ __device__ __forceinline__ void stencil_strip_v2(const float *tile, int gx, int 
 __device__ unsigned int g_tile_sched[64][2];
 
 // v2: warps consume tiles independently.  full[s]: the TMA load of stage s has landed (and tile_xy[s] is valid);
-// empty[s]: all eight warps are done reading stage s.  Lane 0 of warp 0 is the producer: after its own strip of
-// tile number `it` it refills the stage of tile it-1 (whose readers have, as a rule, long finished), so no warp
-// ever waits for another one at a CTA-wide barrier.  Tiles are handed out by an atomic counter (row-major order:
+// empty[s]: all eight warps are done reading stage s.  Lane 0 of warp 0 is the producer: before its own strip of
+// tile number `it` it refills the stage of tile it-1 (two tiles of look-ahead), so only that one warp ever waits
+// for the others, and nobody at a CTA-wide barrier.  Tiles are handed out by an atomic counter (row-major order:
 // the CTAs of the grid sweep the raster together, which keeps the DRAM pages and the L2 halo reuse local).
 template <bool WS, bool WD, int MINB>
 __global__ void __launch_bounds__(NTHREADS, MINB)
@@ -610,6 +668,12 @@ slope_d8_tma2_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_be
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         tile_xy[2 * stage] = tx;
         tile_xy[2 * stage + 1] = ty;
+#ifdef DTB_DEBUG_COMPUTEONLY
+        if (tile >= 3 * (int)gridDim.x) {  // timing aid: later tiles reuse what the stage holds (no DRAM reads)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
+            return true;
+        }
+#endif
         mbar_expect_tx(&full[stage], TMA_BYTES);
         tma_load_2d(smem + (size_t)stage * STAGE_BYTES, &dem_map, tx * TW - HALO_L, (int)(row_begin + (int64_t)ty * TH - 1), &full[stage]);
         return true;
@@ -639,6 +703,11 @@ slope_d8_tma2_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_be
         mbar_wait(&full[stage], (uint32_t)(it / STAGES) & 1u);
         const int tx = tile_xy[2 * stage], ty = tile_xy[2 * stage + 1];
         if (tx < 0) break;
+        if (tid == 0 && more && it >= 1) {  // refill the stage of the previous tile before computing this one: two tiles ahead
+            const int ps = (it - 1) % STAGES;
+            mbar_wait(&empty[ps], (uint32_t)((it - 1) / STAGES) & 1u);
+            more = produce(ps);  // tile number it-1+STAGES
+        }
         const float *tbuf = reinterpret_cast<const float *>(smem + (size_t)stage * STAGE_BYTES);
         const int64_t orow = (int64_t)ty * TH + gy * RPT, ocol = (int64_t)tx * TW + 4 * gx;
         const int64_t left = out_rows - orow;
@@ -646,11 +715,6 @@ slope_d8_tma2_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_be
         stencil_strip_v2<WS, WD>(tbuf, gx, gy * RPT, k, fk, slope, d8, orow * cols + ocol, cols, nrows);
         __syncwarp();
         if (gx == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[stage])) : "memory");
-        if (tid == 0 && more && it >= 1) {
-            const int ps = (it - 1) % STAGES;
-            mbar_wait(&empty[ps], (uint32_t)((it - 1) / STAGES) & 1u);
-            more = produce(ps);  // tile number it-1+STAGES
-        }
     }
 }
 
@@ -804,18 +868,18 @@ extern "C" int dtb_slope_d8(const void *dem, int dem_dtype, int64_t buf_rows, in
         static bool attr_set = false;
         if (!attr_set) {
             DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma2_kernel<true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
-            DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma2_kernel<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
+            DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma2_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
             DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma2_kernel<true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
             DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma2_kernel<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
             attr_set = true;
         }
-        static const bool occ2 = getenv("DTB_STENCIL_OCC2") != nullptr;  // A/B aid: 2 CTAs per SM, 128 registers
+        static const bool occ2 = getenv("DTB_STENCIL_OCC2") != nullptr;  // A/B aid: 4 CTAs per SM, 64 registers
         static std::atomic<unsigned> slot_ctr{0};
         const int slot = (int)(slot_ctr.fetch_add(1) % 64u);
-        const int per_sm = occ2 ? 2 : 3;
+        const int per_sm = occ2 ? 4 : 3;
         const int grid = ntiles < per_sm * kNumSMs ? ntiles : per_sm * kNumSMs;
         if (slope && d8 && occ2)
-            DTB_KERNEL("slope_d8_tma_kernel", st, (slope_d8_tma2_kernel<true, true, 2><<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8, slot)));
+            DTB_KERNEL("slope_d8_tma_kernel", st, (slope_d8_tma2_kernel<true, true, 4><<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8, slot)));
         else if (slope && d8)
             DTB_KERNEL("slope_d8_tma_kernel", st, (slope_d8_tma2_kernel<true, true, 3><<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8, slot)));
         else if (slope)
