@@ -5,25 +5,29 @@
 // the neighbour that last raised the running maximum in scan order NW,N,NE,W,E,SW,S,SE;
 // outlets point at their first undefined neighbour).  Bit-exact against oracle/dt_oracle.c.
 //
-// B200 design: persistent CTAs (3 per SM) walk 128x32-cell tiles in row-major order; each
-// tile plus its halo (a 136x34 f32 box starting 4 columns left of the tile: the TMA unit
-// faults unless the box's innermost start coordinate is 16-byte aligned -- measured on B200,
-// scripts/tma_probe.cu) is staged in shared memory by TMA
-// (cp.async.bulk.tensor.2d, out-of-bounds elements filled with NaN, which stands in for
-// the reference's -100 padding ring) through a 3-stage mbarrier ring, so the next two
-// tiles are in flight while one is computed.  A thread owns 4 columns x 4 rows and slides
-// a 3-row register window down its strip: LDS.128+LDS.64 per row, every elevation
-// difference computed once and used by both endpoints (19 FSUB per 4 cells), results
+// B200 design: persistent CTAs (3 per SM) draw 128x32-cell tiles from an atomic counter in
+// row-major order; each tile plus its halo (a 136x34 f32 box starting 4 columns left of the
+// tile: the TMA unit faults unless the box's innermost start coordinate is 16-byte aligned --
+// measured on B200, scripts/tma_probe.cu) is staged in shared memory by TMA
+// (cp.async.bulk.tensor.2d, out-of-bounds elements filled with NaN, which stands in for the
+// reference's -100 padding ring) through a 3-stage ring of full / empty mbarriers: the eight
+// warps of a CTA consume a tile independently, only the producer lane waits for "all warps
+// are done with this stage" before it refills it, two tiles ahead.  With the arithmetic
+// stubbed out this skeleton moves 9 B/cell at the measured HBM copy peak (0.137 ms for
+// 10 000 x 10 000); the kernel is bound by instruction issue, so the strip below is written
+// for instruction count and pipe balance (see "lean strip").  A thread owns 4 columns x 4
+// rows and slides a 3-row register window down its strip: LDS.128 + 2 LDS.32 per row, results
 // leave as one STG.128 (slope) and one STG.32 (four D8 codes) per row.
 //
-// Exactness without f64 divides in the hot loop (the reference divides in f64 inside the
-// 8-neighbour loop, slope.py:249-257):
+// Exactness without f64 in the hot loop (the reference divides in f64 inside the 8-neighbour
+// loop, slope.py:249-257):
 //   * within a class (cardinal / diagonal) the divisor is a common positive constant, so
 //     comparing the f32 differences is equivalent to comparing the f64 gradients;
-//   * cardinal-vs-diagonal is decided in f32 with a 1e-6 guard band and falls back to the
-//     two f64 divisions only inside the band;
-//   * slope = f32(f64(diff)/d*100) is computed as f64(diff)*(100/d) and falls back to the
-//     exact expression when the product sits within 16 ulp of an f32 rounding boundary.
+//   * slope = f32(f64(diff)/d*100) is bracketed by two fused multiply-adds with a two-term
+//     f32 constant for 100/d; when both ends round to the same f32 that is the answer, else
+//     the row goes to the literal f64 loop (slow_row);
+//   * cardinal-vs-diagonal is decided on those exact f32 slopes (all roundings are monotone);
+//     equal non-zero slopes go to slow_row.
 #include <math.h>
 #include <stdlib.h>
 
@@ -249,14 +253,11 @@ __device__ __forceinline__ void stencil_strip(const float *tile, int gx, int ry0
     }
 }
 
-// ---- fast strip for the TMA kernel ------------------------------------------------------------
-// Same arithmetic as stencil_strip, organised for the B200 issue ports: the compare/select chains
-// (ALU port, half rate) are replaced by 3-input max reductions, a sign-bit mask of (difference - class
-// maximum) built with funnel shifts, and one priority encode.  Everything that is rare is delegated, one
-// row of four cells at a time, to slow_row(): the literal per-neighbour loop of slope.py:244-258 over the
-// staged raw values.  Rare = the 3x6 window holds an undefined value (off-raster NaN or anything <= -100:
-// nodata centres slope.py:231, skipped neighbours slope.py:247), no positive gradient (outlet rule),
-// cardinal/diagonal near-tie, a product next to an f32 rounding boundary, sub-/super-normal range.
+// ---- the exact path ----------------------------------------------------------------------------
+// Everything that is rare in the lean strip below -- a cell with no positive gradient next to an undefined value
+// (outlet rule), a slope product within 2^-44 of an f32 rounding boundary, equal cardinal and diagonal slopes,
+// sub-range values -- is delegated, one row of four cells at a time, to slow_row(): the literal per-neighbour
+// loop of slope.py:244-258 over the staged raw values.
 __device__ __noinline__ void slow_row(const float *tile, int trow, int tcol0, double px, double pd, float4 &slope4, uint32_t &codes)
 {
     // trow/tcol0: position of the first of the four cells inside the staged box
@@ -286,105 +287,6 @@ __device__ __noinline__ void slow_row(const float *tile, int trow, int tcol0, do
     }
     slope4 = make_float4(out[0], out[1], out[2], out[3]);
 }
-
-// one staged row: 6 values around the thread's 4 cells; `bad` = some value is NaN or <= -100
-__device__ __forceinline__ void load_row_fast(const float *p, float (&w)[6], bool &bad)
-{
-    const float4 a = *reinterpret_cast<const float4 *>(p);
-    w[0] = p[-1]; w[1] = a.x; w[2] = a.y; w[3] = a.z; w[4] = a.w; w[5] = p[4];
-    bad = false;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) bad |= !(w[j] > ND_F);
-}
-
-__device__ __forceinline__ void stencil_strip_fast(const float *tile, int gx, int ry0, const SlopeConsts &k, int64_t out_row0,
-                                                   int64_t out_rows, int64_t c_first, int64_t cols, float *__restrict__ slope,
-                                                   uint8_t *__restrict__ d8)
-{
-    const float *base = tile + 4 * gx + HALO_L;
-    float up[6], mid[6], dn[6];
-    bool bad_up, bad_mid, bad_dn;
-    load_row_fast(base + (ry0)*BOXW, up, bad_up);
-    load_row_fast(base + (ry0 + 1) * BOXW, mid, bad_mid);
-    float vSp[6], sEp[6], sWp[6];
-#pragma unroll
-    for (int j = 1; j <= 4; ++j) vSp[j] = up[j] - mid[j];
-#pragma unroll
-    for (int j = 0; j <= 3; ++j) sEp[j] = up[j] - mid[j + 1];
-#pragma unroll
-    for (int j = 2; j <= 5; ++j) sWp[j] = up[j] - mid[j - 1];
-
-#pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-        load_row_fast(base + (ry0 + 2 + i) * BOXW, dn, bad_dn);
-        float hE[5], vS[6], sE[5], sW[6];
-#pragma unroll
-        for (int j = 0; j <= 4; ++j) hE[j] = mid[j] - mid[j + 1];
-#pragma unroll
-        for (int j = 1; j <= 4; ++j) vS[j] = mid[j] - dn[j];
-#pragma unroll
-        for (int j = 0; j <= 4; ++j) sE[j] = mid[j] - dn[j + 1];
-#pragma unroll
-        for (int j = 1; j <= 5; ++j) sW[j] = mid[j] - dn[j - 1];
-
-        float s_out[4];
-        uint32_t bsel = 0;
-        bool slow = bad_up | bad_mid | bad_dn;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int j = c + 1;
-            const float dN = -vSp[j], dW = -hE[j - 1], dE = hE[j], dS = vS[j];
-            const float dNW = -sEp[j - 1], dNE = -sWp[j + 1], dSW = sW[j], dSE = sE[j];
-            const float ac = fmaxf(fmaxf(fmaxf(fmaxf(dN, dW), dE), dS), 0.0f);
-            const float ad = fmaxf(fmaxf(fmaxf(fmaxf(dNW, dNE), dSW), dSE), 0.0f);
-            const float t = ad * k.r32;
-            const bool use_c = ac >= t;
-            const float a = use_c ? ac : ad;
-            // neighbours below their class maximum: sign bit of (d - max); scan order NW,N,NE,W,E,SW,S,SE from bit 7 down
-            unsigned lose = 0;
-            lose = __funnelshift_l(__float_as_uint(dNW - ad), lose, 1);
-            lose = __funnelshift_l(__float_as_uint(dN - ac), lose, 1);
-            lose = __funnelshift_l(__float_as_uint(dNE - ad), lose, 1);
-            lose = __funnelshift_l(__float_as_uint(dW - ac), lose, 1);
-            lose = __funnelshift_l(__float_as_uint(dE - ac), lose, 1);
-            lose = __funnelshift_l(__float_as_uint(dSW - ad), lose, 1);
-            lose = __funnelshift_l(__float_as_uint(dS - ac), lose, 1);
-            lose = __funnelshift_l(__float_as_uint(dSE - ad), lose, 1);
-            const unsigned win = ~lose & (use_c ? 0x5Au : 0xA5u);
-            // highest set bit = first maximum in scan order (strict '<', slope.py:250,255); one nibble per cell, turned
-            // into the four code bytes by a single byte permute below (no winner: the row takes the slow path)
-            unsigned hb;
-            asm("bfind.u32 %0, %1;" : "=r"(hb) : "r"(win));
-            bsel += hb << (4 * c);
-            const double y = (double)a * (use_c ? k.kc : k.kd);
-            s_out[c] = (float)y;
-            // range (no positive gradient, subnormal / huge), cardinal-diagonal near-tie, product within 16 ulp(f64)
-            // of an f32 rounding boundary
-            slow |= (__float_as_uint(a) - 0x0D800000u >= 0x7E000000u - 0x0D800000u) | (fabsf(ac - t) <= 1e-6f * t) |
-                    ((((uint32_t)__double2loint(y) + 0x10u - 0x10000000u) & 0x1FFFFFE0u) == 0u);
-        }
-        float4 s4 = make_float4(s_out[0], s_out[1], s_out[2], s_out[3]);
-        uint32_t codes = __byte_perm(0x01080402u, 0x20408010u, bsel);  // SE,S,SW,E | W,NE,N,NW
-        if (slow) slow_row(tile, ry0 + 1 + i, 4 * gx + HALO_L, k.px, k.pd, s4, codes);
-        const int64_t orow = out_row0 + ry0 + i;
-        if (orow >= 0 && orow < out_rows && c_first < cols) {
-            const int64_t o = orow * cols + c_first;
-            if (slope) *reinterpret_cast<float4 *>(slope + o) = s4;
-            if (d8) *reinterpret_cast<uint32_t *>(d8 + o) = codes;
-        }
-#pragma unroll
-        for (int j = 0; j < 6; ++j) { up[j] = mid[j]; mid[j] = dn[j]; }
-#pragma unroll
-        for (int j = 1; j <= 4; ++j) vSp[j] = vS[j];
-#pragma unroll
-        for (int j = 0; j <= 3; ++j) sEp[j] = sE[j];
-#pragma unroll
-        for (int j = 2; j <= 5; ++j) sWp[j] = sW[j];
-        bad_up = bad_mid;
-        bad_mid = bad_dn;
-    }
-}
-
 
 // ---- lean strip (v2): packed f32x2 arithmetic, no f64, no conversions --------------------------------
 // Issue-rate facts measured on B200 (scripts/pipe_probe.cu, profiles/r2b_pipe_probe.txt; clocks per warp
@@ -420,6 +322,8 @@ __device__ __forceinline__ float max3(float a, float b, float c) { float r; asm(
 __device__ __forceinline__ float min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float set_neu(float a, float b) { float r; asm("set.neu.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float fma_sat(float a, float b, float c) { float r; asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float mul_sat(float a, float b) { float r; asm("mul.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ bool equ(float a, float b) { return !(a < b || a > b); }  // equal or unordered
 __device__ __forceinline__ float lds_f32(uint32_t addr)
 {
     float v;
@@ -429,20 +333,20 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
 
 struct Row2 {
     float w[6];  // w[1..4]: the thread's four cells (one LDS.128: aligned register pairs), w[0], w[5]: the halo columns
-    bool bad;    // a value <= -100 among the six: nodata (slope.py:231,247); NaN is not "bad", it is skipped
 };
 
-__device__ __forceinline__ void load_row2(uint32_t a /* shared address of the thread's first cell */, Row2 &r)
+// lo: running minimum of everything the strip has loaded (NaN ignored): <= -100 means nodata somewhere in it
+__device__ __forceinline__ void load_row2(uint32_t a /* shared address of the thread's first cell */, Row2 &r, float &lo)
 {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.w[1]), "=f"(r.w[2]), "=f"(r.w[3]), "=f"(r.w[4]) : "r"(a));
     r.w[0] = lds_f32(a - 4);
     r.w[5] = lds_f32(a + 16);
-    r.bad = fminf(min3(min3(r.w[0], r.w[1], r.w[2]), r.w[3], r.w[4]), r.w[5]) <= ND_F;
+    lo = min3(min3(min3(lo, r.w[0], r.w[1]), r.w[2], r.w[3]), r.w[4], r.w[5]);
 }
 
 struct FastK {
     p2 kc_hi, kc_lop, kc_lom, kd_hi, kd_lop, kd_lom;  // 100/px and 100/(px sqrt2): f32 hi, and lo +- 2^-44 k
-    p2 one, four, eight, w256;
+    p2 one, four, neg8, w256;
 };
 
 // one pair of horizontally adjacent cells: columns j, j+1 (1 or 3) of the window rows U (above), M, D (below);
@@ -452,7 +356,7 @@ struct FastK {
 // (Sharing the vertical / diagonal differences between consecutive rows as well was measured: the 12 carried
 // registers spill at 80 registers per thread and cost more than the 11 FADDs per row they save.)
 // N accumulates the two cells' selector nibbles (lane 0: even cell, lane 1: odd cell), scaled by W (1 or 256).
-template <int W>
+template <int W, bool CX>
 __device__ __forceinline__ void cell_pair2(const Row2 &U, const Row2 &M, const Row2 &D, const float (&H)[5], const int j, const FastK &k,
                                            float &Sa, float &Sb, p2 &N, p2 &acc, bool &redo)
 {
@@ -477,23 +381,36 @@ __device__ __forceinline__ void cell_pair2(const Row2 &U, const Row2 &M, const R
     // slope bracket of both classes
     const p2 ac = pk(acA, acB), ad = pk(adA, adB);
     float cpA, cpB, cmA, cmB, dpA, dpB, dmA, dmB;
-    upk(fma2(ac, k.kc_hi, mul2(ac, k.kc_lop)), cpA, cpB);
-    upk(fma2(ac, k.kc_hi, mul2(ac, k.kc_lom)), cmA, cmB);
+    if (CX) {
+        // 100/px is a power of two (px = 12.5, 25, 50, ...): a * (100/px) is exact in f32, and f32(f64(a)/px*100) is that
+        // number (the reference's two f64 roundings move it by < 2^-51 relative, far inside half an f32 ulp)
+        upk(mul2(ac, k.kc_hi), cpA, cpB);
+        cmA = cpA;
+        cmB = cpB;
+    } else {
+        upk(fma2(ac, k.kc_hi, mul2(ac, k.kc_lop)), cpA, cpB);
+        upk(fma2(ac, k.kc_hi, mul2(ac, k.kc_lom)), cmA, cmB);
+    }
     upk(fma2(ad, k.kd_hi, mul2(ad, k.kd_lop)), dpA, dpB);
     upk(fma2(ad, k.kd_hi, mul2(ad, k.kd_lom)), dmA, dmB);
-    redo |= (cpA != cmA) | (cpB != cmB) | (dpA != dmA) | (dpB != dmB);  // rounding in doubt (or NaN / inf)
+    if (CX) redo |= (dpA != dmA) | (dpB != dmB);  // the cardinal product is one correctly rounded multiplication, like the reference's
+    else redo |= (cpA != cmA) | (cpB != cmB) | (dpA != dmA) | (dpB != dmB);               // rounding in doubt (or NaN / inf)
     Sa = fmaxf(cpA, dpA);
     Sb = fmaxf(cpB, dpB);
-    // q = [no positive gradient]; fractional for 0 < S < 2^-30: accumulate q (q - 1) <= 0 (exactly 0 for q in {0, 1})
-    const p2 q = pk(fma_sat(Sa, -1073741824.0f, 1.0f), fma_sat(Sb, -1073741824.0f, 1.0f));
-    acc = fma2(q, sub2(q, k.one), acc);
-    // class: u = [S_card >= S_diag]; S_card == S_diag > 0 is undecidable here (z == 0 and q == 0)
-    float zA, zB, qA, qB;
+    // p = [positive gradient] = sat(S 2^100): exactly 0 iff S == 0, exactly 1 iff S >= 2^-100, fractional in between (the
+    // sub-range where the products above lose bits to underflow: exact path) -- accumulate p (p - 1) <= 0, exactly 0 for
+    // p in {0, 1} (nothing is absorbed, unlike (acc + p^2) - p)
+    const p2 pp = pk(mul_sat(Sa, 1.2676506e30f), mul_sat(Sb, 1.2676506e30f));
+    const p2 pm1 = sub2(pp, k.one);
+    acc = fma2(pp, pm1, acc);
+    // class: u = [S_card >= S_diag]; undecidable here: S_card == S_diag > 0 (z == 0 and p == 1), and both infinite (z NaN)
+    float zA, zB, mA, mB;
     upk(sub2(pk(cpA, cpB), pk(dpA, dpB)), zA, zB);
-    upk(q, qA, qB);
-    redo |= (zA == -qA) | (zB == -qB);
-    const p2 u = pk(fma_sat(zA, 1.2676506e30f, 1.0f), fma_sat(zB, 1.2676506e30f, 1.0f));
-    const p2 m = fma2(q, k.eight, fma2(u, sub2(jc, jd4), jd4));  // selector nibble: 0..7, or 8..11 for a pit
+    upk(pm1, mA, mB);
+    redo |= equ(zA, mA) | equ(zB, mB);
+    const p2 u = pk(fma_sat(zA, 8.507059e37f, 1.0f), fma_sat(zB, 8.507059e37f, 1.0f));
+    // selector nibble - 8: -8..-1 for a direction, 0..3 for a pit (the strip adds the 8 back: 8..11 select "code 0")
+    const p2 m = fma2(pp, k.neg8, fma2(u, sub2(jc, jd4), jd4));
     if (W == 1) N = add2(N, m);
     else N = fma2(m, k.w256, N);
 }
@@ -509,6 +426,7 @@ __device__ __noinline__ void slow_row_store(const float *tile, int trow, int tco
 }
 
 // One row of four cells, given the three window rows.  Returns true when the exact path has to redo the row.
+template <bool CX>
 __device__ __forceinline__ bool fast_row2(const Row2 &U, const Row2 &M, const Row2 &D, const FastK &k, float4 &s4, uint32_t &codes,
                                           uint32_t &sel)
 {
@@ -517,13 +435,13 @@ __device__ __forceinline__ bool fast_row2(const Row2 &U, const Row2 &M, const Ro
     for (int t = 0; t <= 4; ++t) H[t] = M.w[t] - M.w[t + 1];
     p2 N = pk(0.0f, 0.0f), acc = pk(0.0f, 0.0f);
     bool redo = false;
-    cell_pair2<1>(U, M, D, H, 1, k, s4.x, s4.y, N, acc, redo);
-    cell_pair2<256>(U, M, D, H, 3, k, s4.z, s4.w, N, acc, redo);
+    cell_pair2<1, CX>(U, M, D, H, 1, k, s4.x, s4.y, N, acc, redo);
+    cell_pair2<256, CX>(U, M, D, H, 3, k, s4.z, s4.w, N, acc, redo);
     float n0, n1, a0, a1;
     upk(N, n0, n1);
     upk(acc, a0, a1);
-    // 2^23 + sum of nibble_c 16^c: the low mantissa bits are the byte-permute selector
-    sel = __float_as_uint(fmaf(n1, 16.0f, n0 + 8388608.0f));
+    // 2^23 + sum of nibble_c 16^c (the 8 every cell_pair2 left out: 0x8888): the low mantissa bits are the byte-permute selector
+    sel = __float_as_uint(fmaf(n1, 16.0f, n0 + (8388608.0f + 34952.0f)));
     // selector nibble 0..7 picks a table byte; 8..11 (a pit) replicates the sign bit of a cardinal byte = 0.
     // (PTX prmt; CUDA's __byte_perm masks the nibbles to three bits.)
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(codes) : "r"(0x04011040u), "r"(0x02088020u), "r"(sel));  // S E W N | SE SW NE NW
@@ -551,7 +469,7 @@ __device__ __noinline__ void robust_row_store(const float *tile, int trow, int t
     FastK k;
     k.kc_hi = pk(kc_hi, kc_hi); k.kc_lop = pk(kc_lop, kc_lop); k.kc_lom = pk(kc_lom, kc_lom);
     k.kd_hi = pk(kd_hi, kd_hi); k.kd_lop = pk(kd_lop, kd_lop); k.kd_lom = pk(kd_lom, kd_lom);
-    k.one = pk(1.0f, 1.0f); k.four = pk(4.0f, 4.0f); k.eight = pk(8.0f, 8.0f); k.w256 = pk(256.0f, 256.0f);
+    k.one = pk(1.0f, 1.0f); k.four = pk(4.0f, 4.0f); k.neg8 = pk(-8.0f, -8.0f); k.w256 = pk(256.0f, 256.0f);
     const float qnan = __int_as_float(0x7fc00000);
     Row2 R[3];
     unsigned nd = 0;
@@ -567,7 +485,7 @@ __device__ __noinline__ void robust_row_store(const float *tile, int trow, int t
     uint32_t codes = 0, sel = 0;
     bool redo = false;
     if (nd != 15u) {
-        redo = fast_row2(R[0], R[1], R[2], k, s4, codes, sel);
+        redo = fast_row2<false>(R[0], R[1], R[2], k, s4, codes, sel);
         if (nd & 1u) { s4.x = ND_F; codes &= 0xFFFFFF00u; sel &= ~0x000Fu; }
         if (nd & 2u) { s4.y = ND_F; codes &= 0xFFFF00FFu; sel &= ~0x00F0u; }
         if (nd & 4u) { s4.z = ND_F; codes &= 0xFF00FFFFu; sel &= ~0x0F00u; }
@@ -584,7 +502,7 @@ __device__ __noinline__ void robust_row_store(const float *tile, int trow, int t
 
 // 4 columns x RPT rows of one staged tile.  sbase / dbase: the outputs; off: element offset of the strip's first
 // cell; nrows: how many of the strip's rows are inside the output (0..RPT)
-template <bool WS, bool WD>
+template <bool WS, bool WD, bool CX>
 __device__ __forceinline__ void stencil_strip_v2(const float *tile, int gx, int ry0, const SlopeConsts &kk, const FastK &k,
                                                  float *__restrict__ sbase, uint8_t *__restrict__ dbase, int64_t off, int64_t cols,
                                                  int nrows)
@@ -592,41 +510,44 @@ __device__ __forceinline__ void stencil_strip_v2(const float *tile, int gx, int 
     const int tcol0 = 4 * gx + HALO_L;
     const uint32_t a = smem_u32(tile + ry0 * BOXW + tcol0);
     Row2 U, M, D;
-    load_row2(a, U);
-    load_row2(a + BOXW * 4, M);
+    float lo = 3.0e38f;
+    load_row2(a, U, lo);
+    load_row2(a + BOXW * 4, M, lo);
     const int64_t off0 = off;
-    unsigned later = 0;  // bit i: row i goes to the exact path, bit 8+i: to the nodata path (after the loop: no calls in it)
+    unsigned later = 0;  // bit i: row i of the strip goes to the exact path (after the loop: keeps the calls out of it)
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
-        load_row2(a + (2 + i) * BOXW * 4, D);
+        load_row2(a + (2 + i) * BOXW * 4, D, lo);
+        float4 s4;
+        uint32_t codes, sel;
+        bool redo = fast_row2<CX>(U, M, D, k, s4, codes, sel);
         if (i < nrows) {
-            if (U.bad | M.bad | D.bad) {  // nodata somewhere in the 3x6 window
-                later |= 0x100u << i;
-            } else {
-                float4 s4;
-                uint32_t codes, sel;
-                bool redo = fast_row2(U, M, D, k, s4, codes, sel);
-                if (WS) *reinterpret_cast<float4 *>(sbase + off) = s4;
-                if (WD) *reinterpret_cast<uint32_t *>(dbase + off) = codes;
-#ifdef DTB_DEBUG_FORCE_REDO
-                redo = true;
-#endif
-                if (!redo && (sel & 0x8888u)) redo = window_has_nan(U, M, D);
-                if (redo) later |= 1u << i;
-            }
+            if (WS) *reinterpret_cast<float4 *>(sbase + off) = s4;
+            if (WD) *reinterpret_cast<uint32_t *>(dbase + off) = codes;
         }
+#ifdef DTB_DEBUG_FORCE_REDO
+        redo = true;
+#endif
+        if (!redo && (sel & 0x8888u)) redo = window_has_nan(U, M, D);
+        if (redo) later |= 1u << i;
         off += cols;
         U = M;
         M = D;
     }
+    // Nodata (<= -100, slope.py:231,247) anywhere in the 6 x 6 values this strip has seen: what the loop stored for it is
+    // discarded and every row is redone by the nodata path (one test per strip instead of one per row; nodata comes in
+    // blobs, and the lean arithmetic cannot fault on it).
+    const bool nodata = lo <= ND_F;
+    if (nodata) later = 0xFu;
+    later &= (1u << nrows) - 1u;
     if (later) {
 #pragma unroll 1
         for (int i = 0; i < RPT; ++i) {
+            if (!(later >> i & 1u)) continue;
             float *sp = WS ? sbase + off0 + i * cols : nullptr;
             uint8_t *dp = WD ? dbase + off0 + i * cols : nullptr;
-            if (later >> i & 1u) slow_row_store(tile, ry0 + 1 + i, tcol0, kk.px, kk.pd, sp, dp);
-            if (later >> (8 + i) & 1u)
-                robust_row_store(tile, ry0 + 1 + i, tcol0, kk.px, kk.pd, kk.kc_hi, kk.kc_lop, kk.kc_lom, kk.kd_hi, kk.kd_lop, kk.kd_lom, sp, dp);
+            if (nodata) robust_row_store(tile, ry0 + 1 + i, tcol0, kk.px, kk.pd, kk.kc_hi, kk.kc_lop, kk.kc_lom, kk.kd_hi, kk.kd_lop, kk.kd_lom, sp, dp);
+            else slow_row_store(tile, ry0 + 1 + i, tcol0, kk.px, kk.pd, sp, dp);
         }
     }
 }
@@ -640,7 +561,7 @@ __device__ unsigned int g_tile_sched[64][2];
 // tile number `it` it refills the stage of tile it-1 (two tiles of look-ahead), so only that one warp ever waits
 // for the others, and nobody at a CTA-wide barrier.  Tiles are handed out by an atomic counter (row-major order:
 // the CTAs of the grid sweep the raster together, which keeps the DRAM pages and the L2 halo reuse local).
-template <bool WS, bool WD, int MINB>
+template <bool WS, bool WD, bool CX, int MINB>
 __global__ void __launch_bounds__(NTHREADS, MINB)
 slope_d8_tma2_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_begin, int64_t row_end, int64_t cols, int tiles_x,
                      int ntiles, SlopeConsts k, float *__restrict__ slope, uint8_t *__restrict__ d8, int sched_slot)
@@ -668,12 +589,6 @@ slope_d8_tma2_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_be
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         tile_xy[2 * stage] = tx;
         tile_xy[2 * stage + 1] = ty;
-#ifdef DTB_DEBUG_COMPUTEONLY
-        if (tile >= 3 * (int)gridDim.x) {  // timing aid: later tiles reuse what the stage holds (no DRAM reads)
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
-            return true;
-        }
-#endif
         mbar_expect_tx(&full[stage], TMA_BYTES);
         tma_load_2d(smem + (size_t)stage * STAGE_BYTES, &dem_map, tx * TW - HALO_L, (int)(row_begin + (int64_t)ty * TH - 1), &full[stage]);
         return true;
@@ -695,7 +610,7 @@ slope_d8_tma2_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_be
     FastK fk;
     fk.kc_hi = pk(k.kc_hi, k.kc_hi); fk.kc_lop = pk(k.kc_lop, k.kc_lop); fk.kc_lom = pk(k.kc_lom, k.kc_lom);
     fk.kd_hi = pk(k.kd_hi, k.kd_hi); fk.kd_lop = pk(k.kd_lop, k.kd_lop); fk.kd_lom = pk(k.kd_lom, k.kd_lom);
-    fk.one = pk(1.0f, 1.0f); fk.four = pk(4.0f, 4.0f); fk.eight = pk(8.0f, 8.0f); fk.w256 = pk(256.0f, 256.0f);
+    fk.one = pk(1.0f, 1.0f); fk.four = pk(4.0f, 4.0f); fk.neg8 = pk(-8.0f, -8.0f); fk.w256 = pk(256.0f, 256.0f);
     const int64_t out_rows = row_end - row_begin;
 
     for (int it = 0;; ++it) {
@@ -712,54 +627,9 @@ slope_d8_tma2_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_be
         const int64_t orow = (int64_t)ty * TH + gy * RPT, ocol = (int64_t)tx * TW + 4 * gx;
         const int64_t left = out_rows - orow;
         const int nrows = ocol < cols ? (left < RPT ? (left < 0 ? 0 : (int)left) : RPT) : 0;
-        stencil_strip_v2<WS, WD>(tbuf, gx, gy * RPT, k, fk, slope, d8, orow * cols + ocol, cols, nrows);
+        stencil_strip_v2<WS, WD, CX>(tbuf, gx, gy * RPT, k, fk, slope, d8, orow * cols + ocol, cols, nrows);
         __syncwarp();
         if (gx == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[stage])) : "memory");
-    }
-}
-
-// v1 (round 1): CTA-wide barrier per tile, static tile stride; kept for A/B runs (DTB_STENCIL_V1)
-__global__ void __launch_bounds__(NTHREADS, 3)
-slope_d8_tma_kernel(const __grid_constant__ CUtensorMap dem_map, int64_t row_begin, int64_t row_end, int64_t cols,
-                    int tiles_x, int ntiles, SlopeConsts k, float *__restrict__ slope, uint8_t *__restrict__ d8)
-{
-    extern __shared__ __align__(1024) unsigned char smem[];
-    if ((smem_u32(smem) & 127u) != 0u) __trap();  // TMA destination alignment
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES);
-    const int tid = threadIdx.x;
-
-    auto issue = [&](int tile, int stage) {
-        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        mbar_expect_tx(&full[stage], TMA_BYTES);
-        tma_load_2d(smem + (size_t)stage * STAGE_BYTES, &dem_map, tx * TW - HALO_L, (int)(row_begin + (int64_t)ty * TH - 1),
-                    &full[stage]);
-    };
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int s = 0; s < STAGES; ++s) {
-            const int tile = blockIdx.x + s * gridDim.x;
-            if (tile < ntiles) issue(tile, s);
-        }
-    }
-    __syncthreads();
-
-    const int gx = tid & 31, gy = tid >> 5;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int stage = it % STAGES;
-        const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(&full[stage], parity);
-        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const float *tbuf = reinterpret_cast<const float *>(smem + (size_t)stage * STAGE_BYTES);
-        stencil_strip_fast(tbuf, gx, gy * RPT, k, (int64_t)ty * TH, row_end - row_begin, (int64_t)tx * TW + 4 * gx, cols, slope, d8);
-        __syncthreads();  // every thread is done reading this stage
-        if (tid == 0) {
-            const int next = tile + STAGES * gridDim.x;
-            if (next < ntiles) issue(next, stage);
-        }
     }
 }
 
@@ -854,38 +724,34 @@ extern "C" int dtb_slope_d8(const void *dem, int dem_dtype, int64_t buf_rows, in
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
         if (r != CUDA_SUCCESS) return cuda_fail_msg("cuTensorMapEncodeTiled failed");
-        static const bool use_v1 = getenv("DTB_STENCIL_V1") != nullptr;  // A/B aid: the round-1 kernel
-        if (use_v1) {
-            static bool attr1 = false;
-            if (!attr1) {
-                DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
-                attr1 = true;
-            }
-            const int grid = ntiles < 3 * kNumSMs ? ntiles : 3 * kNumSMs;
-            DTB_KERNEL("slope_d8_tma_kernel", st, (slope_d8_tma_kernel<<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8)));
-            return DTB_OK;
-        }
-        static bool attr_set = false;
-        if (!attr_set) {
-            DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma2_kernel<true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
-            DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma2_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
-            DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma2_kernel<true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
-            DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma2_kernel<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TMA));
-            attr_set = true;
-        }
-        static const bool occ2 = getenv("DTB_STENCIL_OCC2") != nullptr;  // A/B aid: 4 CTAs per SM, 64 registers
+        static const bool no_cx = getenv("DTB_STENCIL_NOCX") != nullptr;  // A/B aid: general cardinal factor even when exact
+        // 100/px a power of two: the cardinal slope product is exact (see cell_pair2)
+        int e2 = 0;
+        const bool cx = !no_cx && frexp(k.kc, &e2) == 0.5 && k.kc >= 1.0 / 1048576.0 && k.kc <= 1048576.0;
         static std::atomic<unsigned> slot_ctr{0};
         const int slot = (int)(slot_ctr.fetch_add(1) % 64u);
-        const int per_sm = occ2 ? 4 : 3;
+        const int per_sm = 3;  // 79 registers; 4 CTAs at 64 registers measured the same (profiles/r2p_stencil.txt)
         const int grid = ntiles < per_sm * kNumSMs ? ntiles : per_sm * kNumSMs;
-        if (slope && d8 && occ2)
-            DTB_KERNEL("slope_d8_tma_kernel", st, (slope_d8_tma2_kernel<true, true, 4><<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8, slot)));
-        else if (slope && d8)
-            DTB_KERNEL("slope_d8_tma_kernel", st, (slope_d8_tma2_kernel<true, true, 3><<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8, slot)));
-        else if (slope)
-            DTB_KERNEL("slope_d8_tma_kernel", st, (slope_d8_tma2_kernel<true, false, 3><<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8, slot)));
-        else
-            DTB_KERNEL("slope_d8_tma_kernel", st, (slope_d8_tma2_kernel<false, true, 3><<<grid, NTHREADS, SMEM_TMA, st>>>(map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8, slot)));
+#define DTB_LAUNCH_TMA2(WS, WD, CX, MINB)                                                                                              \
+    do {                                                                                                                               \
+        static bool attr = false;                                                                                                      \
+        if (!attr) {                                                                                                                   \
+            DTB_CUDA(cudaFuncSetAttribute(slope_d8_tma2_kernel<WS, WD, CX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                          (int)SMEM_TMA));                                                                            \
+            attr = true;                                                                                                               \
+        }                                                                                                                              \
+        DTB_KERNEL("slope_d8_tma_kernel", st, (slope_d8_tma2_kernel<WS, WD, CX, MINB><<<grid, NTHREADS, SMEM_TMA, st>>>(              \
+                                                  map, row_begin, row_end, cols, tiles_x, ntiles, k, slope, d8, slot)));              \
+    } while (0)
+        if (slope && d8) {
+            if (cx) DTB_LAUNCH_TMA2(true, true, true, 3);
+            else DTB_LAUNCH_TMA2(true, true, false, 3);
+        } else if (slope) {
+            DTB_LAUNCH_TMA2(true, false, false, 3);
+        } else {
+            DTB_LAUNCH_TMA2(false, true, false, 3);
+        }
+#undef DTB_LAUNCH_TMA2
     } else if (dem_dtype == DTB_F32) {
         DTB_KERNEL("slope_d8_generic_kernel<f32>", st, slope_d8_generic_kernel<float><<<ntiles, NTHREADS, 0, st>>>((const float *)dem, buf_rows, row_begin, row_end, cols,
                                                                     tiles_x, k, slope, d8));

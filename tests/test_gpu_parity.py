@@ -44,6 +44,19 @@ def synth(rows, cols, seed, holes=True):
 
 
 # ---- slope + D8 -------------------------------------------------------------------------------
+def check_slope_d8(mods, dem, px):
+    """all three launch forms (slope only, D8 only, both outputs -- the fused kernel of the chain) against the oracle"""
+    from descriptools_b200 import device
+
+    with np.errstate(all="ignore"):
+        s_ref, d_ref = oracle.slope_d8(dem, px)
+    np.testing.assert_array_equal(mods["slope"].sloper(dem, px).astype(np.float32), s_ref)
+    np.testing.assert_array_equal(mods["flowhand"].flow_direction_d8(dem, px), d_ref)
+    s, d = device.slope_d8(torch.from_numpy(np.ascontiguousarray(dem)).cuda(), px)
+    np.testing.assert_array_equal(s.cpu().numpy(), s_ref)
+    np.testing.assert_array_equal(d.cpu().numpy(), d_ref)
+
+
 @pytest.mark.parametrize("shape", [(1, 1), (1, 7), (5, 1), (3, 3), (64, 128), (65, 129), (130, 260), (257, 516), (100, 1534 // 2)])
 def test_slope_d8_f32_bit_exact(mods, shape):
     rng = np.random.default_rng(shape[0] * 1000 + shape[1])
@@ -83,6 +96,52 @@ def test_slope_d8_near_tie_card_vs_diag(mods, px):
     s_ref, d_ref = oracle.slope_d8(dem, px)
     np.testing.assert_array_equal(mods["slope"].sloper(dem, px), s_ref.astype(np.float64))
     np.testing.assert_array_equal(mods["flowhand"].flow_direction_d8(dem, px), d_ref)
+
+
+@pytest.mark.parametrize("px", [12.5, 25.0, 0.5, 30.0, 1.0, 7.77])
+def test_slope_d8_tma_path_exact(mods, px):
+    """the TMA kernel's lean strip (width % 4 == 0): power-of-two and general 100/px, several tiles, pits everywhere."""
+    rng = np.random.default_rng(int(px * 100))
+    dem = (np.cumsum(rng.standard_normal((300, 512)), axis=1) * 3 + rng.standard_normal((300, 512)) + 400).astype(np.float32)
+    check_slope_d8(mods, dem, px)
+
+
+@pytest.mark.parametrize("scale", [1e-30, 1e-38, 1e-42, 1e25, 1e36])
+def test_slope_d8_extreme_ranges(mods, scale):
+    """sub-range and huge elevations (products that underflow / overflow in f32): the lean strip must hand them to the
+    exact path, results stay bit-exact (incl. inf slopes where the reference overflows f32)."""
+    rng = np.random.default_rng(11)
+    with np.errstate(over="ignore", under="ignore"):
+        dem = (rng.standard_normal((96, 256)) * scale).astype(np.float32)
+    dem[10:14, 20:28] = 0.0
+    dem[40, 100] = np.inf
+    dem[60, 30] = -np.inf
+    check_slope_d8(mods, dem, 12.5)
+    check_slope_d8(mods, dem, 30.0)
+
+
+def test_slope_d8_rounding_ties(mods):
+    """differences whose slope product is exactly half-way between two f32 (px = 1: a * 100 with a on a coarse grid) --
+    the bracket of the lean strip straddles the boundary and the exact path must decide (round-half-even)."""
+    rng = np.random.default_rng(5)
+    dem = np.full((128, 256), 500.0, np.float32)
+    dem[1::2, 1::2] = np.float32(500.0) - (rng.integers(1, 1 << 20, (64, 128)) * np.float32(2.0 ** -15)).astype(np.float32)
+    for px in (1.0, 2.0, 12.5, 0.25):
+        check_slope_d8(mods, dem, px)
+
+
+def test_slope_d8_nodata_holes_and_outlets(mods):
+    """nodata blobs (-100 and values below -100), NaNs and pits next to them: the nodata row path and the outlet rule."""
+    rng = np.random.default_rng(21)
+    dem = (np.cumsum(rng.standard_normal((260, 384)), axis=0) * 2 + 300).astype(np.float32)
+    yy, xx = np.mgrid[0:260, 0:384]
+    for (cy, cx, r) in [(60, 70, 30), (150, 200, 55), (200, 350, 40), (10, 380, 15)]:
+        dem[(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = -100
+    dem[100:104, 10:30] = -250.0
+    dem[rng.integers(0, 260, 40), rng.integers(0, 384, 40)] = np.nan
+    dem[120:140, 300:320] = 123.0  # a flat: pits with defined neighbours only
+    check_slope_d8(mods, dem, 12.5)
+    check_slope_d8(mods, dem, 10.0)
 
 
 def test_slope_example_int16_golden(mods, ex):
