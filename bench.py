@@ -14,8 +14,13 @@ DEM is sharded into N contiguous row bands (configs[3]; "scaling": "strong").
   roofline : dominant stage, algorithmic bytes / CUDA-event time vs measured HBM peak
   cpu_baseline : the oracle port (oracle/dt_oracle.c, OpenMP) on a bounded sample, rank 0, N=1
 
---impl reference times the reference's CPU path on the host cores: the reference is Python/Numba
-and is not on the GPU box, so this arm runs the oracle port (kind "port").
+  verified : device-side identities of the timed result (csrc/verify.cu), summed over ranks
+
+--impl reference times the reference's own CPU path on the host cores: the unmodified reference installed under
+baseline/_ref (pip --target, git-ignored, travels with the snapshot) through its compiled Numba CPU-jit twins
+(baseline/ref_bench.py, kind "reference", 1 core: they are serial loops); D8 and flow accumulation, which the
+reference does not implement, are timed with the oracle port and reported separately.  If numba or baseline/_ref is
+missing the arm falls back to the oracle port over the whole chain (kind "port") and says why.
 """
 import argparse
 import json
@@ -29,8 +34,11 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 PX, RIVER_THR, N_GFI, B_GFI = 12.5, 128000, 0.4, 0.1
-BYTES_PER_CELL = {"slope_d8": 9, "flowacc": 5, "hand_gfi": 41}  # SURVEY.md 8(d), int32 indices
-CHAIN_BYTES = 55
+# SURVEY.md 8(d), int32 indices.  HAND + GFI are ONE fused pass here: its compulsory traffic is the 25 B of the HAND row
+# (d8 1 + acc 4 + dem 4 in, gather dem[idx] 4, idx + fdist + hand 12 out) plus the 4 B GFI raster and the acc[idx] gather
+# 4 B = 33 B, not the 41 B of SURVEY's two separate kernels (which re-read hand and idx).
+BYTES_PER_CELL = {"slope_d8": 9, "flowacc": 5, "hand_gfi": 33}
+CHAIN_BYTES = 55  # the chain figure keeps SURVEY's per-stage sum (9 + 5 + 25 + 16): it is the published roofline target
 # algorithmic bytes per cell of the individual kernels: what one launch must move
 KERNEL_BYTES = {
     "slope_d8_tma_kernel": 9,      # dem 4 R, slope 4 W, d8 1 W
@@ -39,7 +47,12 @@ KERNEL_BYTES = {
     "hand_tile_kernel": 33,        # d8 1, acc 4, dem 4 R; gathers dem[idx] 4 + acc[idx] 4; idx, fdist, hand, gfi 16 W
     "hand_tile_kernel<table>": 30, # successor table 2 R instead of d8 + acc (fused chain)
 }
-SAMPLE_ROWS = SAMPLE_COLS = 3072  # bounded CPU sample
+# what the dominant kernel cannot avoid moving through DRAM: table 2 + dem 4 in, four rasters 16 out (the dem[idx] / acc[idx]
+# gathers are resolved once per tile exit and served by L2)
+KERNEL_COMPULSORY_BYTES = {"hand_tile_kernel<table>": 22, "slope_d8_tma_kernel": 9, "fa_tile_kernel": 7}
+SAMPLE_ROWS = SAMPLE_COLS = 3072  # bounded CPU sample of the OpenMP port
+REF_SAMPLE = 1536                    # bounded sample of the single-threaded reference (about 1 s per step)
+GPU_REF_SAMPLE = 4096                # the reference's own Numba-CUDA kernels on the same GPU
 
 
 def measured_hbm_peak():
@@ -112,62 +125,170 @@ class ClockSampler:
                 "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def cpu_reference(steps, warmup):
+def _subprocess_json(cmd, timeout):
+    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1), NUMBA_NUM_THREADS=str(os.cpu_count() or 1))
+    env.pop("NUMBA_ENABLE_CUDASIM", None)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError((r.stderr or r.stdout).strip().splitlines()[-1][:300] if (r.stderr or r.stdout).strip() else f"rc {r.returncode}")
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    if "error" in out:
+        raise RuntimeError(out["error"])
+    return out
+
+
+def cpu_port(steps, warmup):
     """the oracle port over the chain, timed in a process of its own (oracle/cpu_bench.py: no torch in the process,
     OpenMP team = all host cores even under torchrun, which exports OMP_NUM_THREADS=1)"""
-    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
     cmd = [sys.executable, os.path.join(REPO, "oracle", "cpu_bench.py"), str(SAMPLE_ROWS), str(SAMPLE_COLS), str(steps), str(warmup),
            str(PX), str(RIVER_THR), str(N_GFI), str(B_GFI)]
-    out = subprocess.run(cmd, capture_output=True, text=True, env=env, check=True).stdout.strip().splitlines()[-1]
-    return json.loads(out)
+    r = _subprocess_json(cmd, 1800)
+    sample = f"{SAMPLE_ROWS}x{SAMPLE_COLS} f32 dtb-synth-v1 DEM per step, river = acc > {RIVER_THR}; oracle/dt_oracle.c with OpenMP"
+    return {"value": r["cells"] * len(r["seconds"]) / sum(r["seconds"]) / 1e6, "unit": "Mcells/s", "cores": r["cores"], "kind": "port",
+            "sample": sample, "seconds": r["seconds"]}
+
+
+def cpu_reference(steps, warmup, mode="cpu", n=REF_SAMPLE):
+    """the unmodified reference (baseline/_ref) in a process of its own: baseline/ref_bench.py"""
+    cmd = [sys.executable, os.path.join(REPO, "baseline", "ref_bench.py"), mode, str(n), str(n), str(steps), str(warmup), str(PX),
+           str(RIVER_THR), str(N_GFI), str(B_GFI)]
+    r = _subprocess_json(cmd, 3000)
+    what = ("slope_sequential_jit + fdist_indexes_sequential_jit + hand_calculator + geomorphic_flood_index_sequential_jit (1 core)"
+            if mode == "cpu" else "sloper + flow_hand_index + gfi_calculator: its Numba-CUDA kernels, host arrays in / out per call")
+    sample = (f"{n}x{n} f32 dtb-synth-v1 DEM per step, river = acc > {RIVER_THR}; reference {what}; D8 + flow accumulation (absent "
+              f"from the reference) by oracle/dt_oracle.c on {r['port_cores']} cores, included")
+    out = {"value": r["cells"] * len(r["seconds"]) / sum(r["seconds"]) / 1e6, "unit": "Mcells/s", "cores": r["cores"],
+           "kind": "reference", "sample": sample, "seconds": r["seconds"], "stage_seconds": r["stage_seconds"],
+           "reference_only_value": r["cells"] * len(r["seconds"]) / sum(r["reference_seconds"]) / 1e6, "numba": r.get("numba")}
+    if "device" in r:
+        out["device"] = r["device"]
+    return out
+
+
+def cpu_baseline(steps, warmup):
+    """reference if it runs on this box, else the port -- and why"""
+    try:
+        return cpu_reference(steps, warmup)
+    except Exception as ex:
+        out = cpu_port(steps, warmup)
+        out["fallback_reason"] = "reference CPU path unavailable: " + repr(ex)[:200]
+        return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference(args.steps, args.warmup)
-    dt = sum(r["seconds"])
-    val = r["cells"] * args.steps / dt / 1e6
-    sample = f"{SAMPLE_ROWS}x{SAMPLE_COLS} f32 dtb-synth-v1 DEM per step, river = acc > {RIVER_THR}; oracle/dt_oracle.c with OpenMP"
-    print(json.dumps({
+    r = cpu_baseline(args.steps, args.warmup)
+    secs = r.pop("seconds")
+    dt = sum(secs)
+    val = r["value"]
+    line = {
         "impl": "reference", "metric": "DEM Mcells/s slope->D8->flowacc->HAND->GFI", "value": val, "unit": "Mcells/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(len(secs), 1),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args), "sample": r["sample"]},
+        "cpu_baseline": r,
         "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
+    print(json.dumps(line))
 
 
-def stencil_config1(peak):
-    """BASELINE.json configs[1]: synthetic 10k x 10k f32 DEM, fused slope + D8 only, 1 GPU (inputs + outputs 0.9 GB > L2)."""
+def _time_launches(run, reps=10, warm=3):
     import torch
 
-    from descriptools_b200 import device
-
-    n = 10000
-    dem = device.conditioned_dem(n, n)
-    slope = torch.empty((n, n), dtype=torch.float32, device="cuda")
-    d8 = torch.empty((n, n), dtype=torch.uint8, device="cuda")
-
-    def run():
-        device.check(device.lib.dtb_slope_d8(dem.data_ptr(), 0, n, n, 0, n, PX, slope.data_ptr(), d8.data_ptr(),
-                                             torch.cuda.current_stream().cuda_stream), "dtb_slope_d8")
-
-    for _ in range(3):
+    for _ in range(warm):
         run()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
     e0.record()
     for _ in range(reps):
         run()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    gbs = 9 * n * n / (ms * 1e-3) / 1e9
-    return {"workload": "synthetic 10000x10000 f32 DEM, fused slope + D8 stencil", "ms": ms, "mcells_s": n * n / ms / 1e3,
-            "bytes_per_cell": 9, "achieved_gbs": gbs, "frac": gbs / peak}
+    return e0.elapsed_time(e1) / reps
+
+
+def stencil_config1(peak):
+    """BASELINE.json configs[1]: synthetic 10k x 10k f32 DEM, fused slope + D8 only, 1 GPU (inputs + outputs 0.9 GB > L2).
+    Headline: the conditioned DEM at the chain's px = 12.5.  Beside it, so that the figure is not a best case: a px whose
+    100/px is not a power of two (general cardinal product), the unconditioned DEM (pits), and nodata holes (16 %)."""
+    import torch
+
+    from descriptools_b200 import device
+
+    n = 10000
+    raw = device.synth_dem(n, n)
+    dem = raw.clone()
+    device.fill_depressions(dem)
+    holes = dem.clone()
+    g = torch.Generator(device="cpu").manual_seed(7)
+    k = 10
+    cy, cx = (torch.rand(k * k, generator=g) * n).long().tolist(), (torch.rand(k * k, generator=g) * n).long().tolist()
+    rr = (40 + torch.rand(k * k, generator=g) * 360).long().tolist()
+    for y, x, r in zip(cy, cx, rr):
+        y0, y1, x0, x1 = max(0, y - r), min(n, y + r + 1), max(0, x - r), min(n, x + r + 1)
+        yy = torch.arange(y0, y1, device="cuda").view(-1, 1) - y
+        xx = torch.arange(x0, x1, device="cuda").view(1, -1) - x
+        holes[y0:y1, x0:x1][(yy * yy + xx * xx) <= r * r] = -100.0
+    slope = torch.empty((n, n), dtype=torch.float32, device="cuda")
+    d8 = torch.empty((n, n), dtype=torch.uint8, device="cuda")
+
+    def timed(t, px):
+        def run():
+            device.check(device.lib.dtb_slope_d8(t.data_ptr(), 0, n, n, 0, n, px, slope.data_ptr(), d8.data_ptr(),
+                                                 torch.cuda.current_stream().cuda_stream), "dtb_slope_d8")
+        ms = _time_launches(run)
+        gbs = 9 * n * n / (ms * 1e-3) / 1e9
+        return {"ms": ms, "achieved_gbs": gbs, "frac": gbs / peak}
+
+    head = timed(dem, PX)
+    out = {"workload": "synthetic 10000x10000 f32 DEM (depression-filled), fused slope + D8 stencil, px = 12.5", "ms": head["ms"],
+           "mcells_s": n * n / head["ms"] / 1e3, "bytes_per_cell": 9, "achieved_gbs": head["achieved_gbs"], "frac": head["frac"],
+           "variants": {"px_30 (100/px not a power of two)": timed(dem, 30.0), "unconditioned (pits)": timed(raw, PX),
+                        "nodata_holes (%.1f %% nodata)" % (100 * float((holes <= -100).float().mean())): timed(holes, PX)}}
+    return out
+
+
+def extra_kernels(peak):
+    """the kernels outside the headline chain (SURVEY.md 8d bytes): downslope, TI + MTI, ln(hl/H), calibration counts --
+    10k x 10k, CUDA-event time of the call, algorithmic bytes / time against the HBM peak"""
+    import torch
+
+    from descriptools_b200 import device, pipeline
+
+    n = 10000
+    dem = device.conditioned_dem(n, n)
+    res = pipeline.run_device(dem, PX, 2000)
+    slope_rad = device.slope_to_radians(res["slope"])
+    cells = n * n
+    out = {}
+
+    def rec(name, ms, bpc, note):
+        gbs = bpc * cells / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "bytes_per_cell": bpc, "achieved_gbs": gbs, "frac": gbs / peak, "note": note}
+
+    rec("downslope_kernel", _time_launches(lambda: device.downslope(dem, res["d8"], PX, 5.0), reps=5, warm=2), 9,
+        "dem 4 + d8 1 in, f32 out; plus the walks (mean ~10 moves of 5 B, served by L2)")
+    rec("ti_mti_kernel", _time_launches(lambda: device.ti_mti(res["acc"], slope_rad, PX, 0.1), reps=5, warm=2), 16,
+        "acc 4 + slope 4 in, TI + MTI out; f64 tan / log / pow")
+    rec("lnhlh_kernel", _time_launches(lambda: device.ln_hl_H(res["hand"], res["acc"], N_GFI, B_GFI, PX), reps=5, warm=2), 12,
+        "hand 4 + acc 4 in, f32 out; f64 log / pow")
+    rec("slope_rad_kernel", _time_launches(lambda: device.slope_to_radians(res["slope"]), reps=5, warm=2), 8, "f32 in, f32 out; atanf")
+    try:
+        from descriptools_b200 import evaluation as ev
+
+        desc = res["hand"]
+        bench_map = (res["acc"] > 2000).to(torch.int8)
+        ths = torch.linspace(0.0, 30.0, 32, dtype=torch.float64).tolist()
+        ctr = ev._Counter(desc, False, -100.0, bench_map, "under")
+        rec("eval_counts_kernel", _time_launches(lambda: ctr.counts(ths), reps=5, warm=2), 5,
+            "descriptor 4 + benchmark 1 in; 32 thresholds per pass (evaluation.py:32-85 makes one pass per threshold)")
+    except Exception as ex:  # the calibration module's device entry is optional here
+        out["eval_counts_kernel"] = {"error": repr(ex)[:160]}
+    del res, dem, slope_rad
+    device.workspace.release()
+    torch.cuda.empty_cache()
+    return out
 
 
 def workload_name(args):
@@ -270,6 +391,15 @@ def run_ours(args):
         runner.check_deferred()  # every boundary solve of the timed steps resolved (else the run is invalid: raises)
     kernel_ms = _lib.profile_collect()
     _lib.profile_enable(False)
+    # ---- the timed result itself is checked: device-side identities (csrc/verify.cu), summed over the bands ----
+    if world == 1:
+        cnt = device.chain_check(outs["d8"], outs["acc"], RIVER_THR, idx=outs["idx"], dem=dem, hand=outs["hand"])
+    else:
+        o = runner.bands[0].outputs()
+        cnt = device.chain_check(o["d8"], o["acc"], RIVER_THR, idx=o["idx"], dem=runner.bands[0].dem, hand=o["hand"],
+                                 row0=runner.bands[0].r0, total_rows=rows)
+        dist.all_reduce(cnt)
+    verdict = device.chain_verdict(cnt.tolist())
     ms = t_start.elapsed_time(t_end)
     for e in events:
         for i, k in enumerate(stage_ms):
@@ -384,10 +514,16 @@ def run_ours(args):
                 "frac": (dk.get("achieved_gbs") or 0.0) / peak, "traffic": traffic, "peak_kind": peak_kind + " (burst copy)",
                 "bytes_per_launch": (dk.get("bytes_per_cell") or 0) * cells_launch, "avg_launch_ms": dk.get("avg_launch_ms"),
                 "chain_frac": CHAIN_BYTES * n_cells / (ms_step * 1e-3) / 1e9 / peak_total, "stages": stages, "kernels": kernels}
+    cb = KERNEL_COMPULSORY_BYTES.get(dom)
+    if cb is not None and dk.get("avg_launch_ms"):
+        # the same kernel against the bytes it cannot avoid moving through DRAM (gathers that L2 serves left out)
+        roofline["compulsory"] = {"bytes_per_cell": cb, "achieved_gbs": cb * cells_launch / (dk["avg_launch_ms"] * 1e-3) / 1e9}
+        roofline["compulsory"]["frac"] = roofline["compulsory"]["achieved_gbs"] / peak
     if per_rank_kernel_ms is not None:
         roofline["per_rank_kernel_ms"] = per_rank_kernel_ms
     if world == 1 and not args.no_cpu:
         roofline["stencil_10k"] = stencil_config1(peak)
+        roofline["extra"] = extra_kernels(peak)
 
     line = {
         "metric": "DEM Mcells/s slope->D8->flowacc->HAND->GFI", "value": value, "unit": "Mcells/s", "n_gpus": world,
@@ -396,12 +532,26 @@ def run_ours(args):
         "config": {"workload": workload_name(args), "rows": rows, "cols": cols, "px": PX, "river_threshold": RIVER_THR,
                    "parallelism": "1 GPU" if world == 1 else f"{world} row bands", "l2": "inputs larger than L2 (no flush needed)"},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "verified": verdict["verified"], "verification": verdict,
     }
     if world == 1 and not args.no_cpu:
-        r = cpu_reference(1, 1)
-        line["cpu_baseline"] = {"value": r["cells"] / r["seconds"][0] / 1e6, "unit": "Mcells/s", "cores": r["cores"], "kind": "port",
-                                "sample": f"{SAMPLE_ROWS}x{SAMPLE_COLS} f32 dtb-synth-v1 DEM, same chain, oracle/dt_oracle.c with OpenMP "
-                                          "(separate process)"}
+        r = cpu_baseline(1, 1)
+        r.pop("seconds", None)
+        line["cpu_baseline"] = r
+        if r["kind"] == "reference":  # the OpenMP port beside it (what round 1 reported): a much stronger CPU arm
+            try:
+                pr = cpu_port(1, 1)
+                pr.pop("seconds", None)
+                line["cpu_baseline_port"] = pr
+            except Exception as ex:
+                line["cpu_baseline_port"] = {"error": repr(ex)[:200]}
+        try:  # the reference's own Numba-CUDA kernels on this very GPU, through its public entry points
+            g = cpu_reference(2, 1, mode="gpu", n=GPU_REF_SAMPLE)
+            g.pop("seconds", None)
+            g["kind"] = "reference numba-cuda"
+            line["gpu_baseline"] = g
+        except Exception as ex:
+            line["gpu_baseline"] = {"error": repr(ex)[:200]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -116,11 +116,13 @@ SIGNATURES = {
     "dtb_hand_boundary_solve": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dtb_hand_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "dtb_hand": (c_int, [POINTER(HandArgs), c_void_p, c_size_t, c_void_p]),
-    "dtb_hand_from_index": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "dtb_chain_check": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                c_void_p, c_void_p]),
+    "dtb_hand_from_index": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "dtb_downslope": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_double, c_double, c_int64, c_void_p, c_void_p]),
     "dtb_downslope_rows": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_double, c_double, c_int64,
                                    c_void_p, c_void_p]),
-    "dtb_river_accumulation": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "dtb_river_accumulation": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "dtb_gfi": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_double, c_double, c_double, c_void_p, c_void_p]),
     "dtb_lnhlh": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_double, c_double, c_double, c_void_p, c_void_p]),
     "dtb_ti_mti": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p]),

@@ -697,13 +697,18 @@ hand_band_summary_kernel(TileView v, int side, const unsigned long long *__restr
 
 template <typename T, typename IDX>
 __global__ void __launch_bounds__(H_THREADS)
-hand_from_index_kernel(const T *__restrict__ dem, const IDX *__restrict__ idx, int64_t n, T *__restrict__ hand)
+hand_from_index_kernel(const T *__restrict__ dem, const IDX *__restrict__ idx, int64_t n, T *__restrict__ hand, int32_t *__restrict__ oob)
 {
     const int64_t p = (int64_t)blockIdx.x * H_THREADS + threadIdx.x;
     if (p >= n) return;
-    const int64_t i = (int64_t)idx[p];
-    // numpy fancy indexing wraps negative indices; -100 is masked out anyway (flowhand.py:436)
-    hand[p] = hand_value<T>(dem[p], i != ND_I, dem, i != ND_I ? i : 0);
+    int64_t i = (int64_t)idx[p];
+    bool ok = i != ND_I;      // -100 is masked out (flowhand.py:436)
+    if (ok && i < 0) i += n;  // numpy fancy indexing wraps negative indices
+    if (ok && (i < 0 || i >= n)) {  // an IndexError in the reference: never dereferenced here
+        if (oob) *oob = 1;
+        ok = false;
+    }
+    hand[p] = hand_value<T>(dem[p], ok, dem, ok ? i : 0);
 }
 
 // ---- band boundary graph (multi-GPU): what lies behind the halo rows of every band -------------------
@@ -930,7 +935,7 @@ extern "C" int dtb_hand(const dtb_hand_args *a, void *ws, size_t ws_bytes, void 
 }
 
 extern "C" int dtb_hand_from_index(const void *dem, int dem_dtype, const void *idx, int idx_dtype, int64_t n, void *hand,
-                                   void *stream)
+                                   int32_t *oob, void *stream)
 {
     using namespace dtb;
     if (!dem || !idx || !hand || n < 0) return DTB_ERR_INVALID;
@@ -938,13 +943,13 @@ extern "C" int dtb_hand_from_index(const void *dem, int dem_dtype, const void *i
     cudaStream_t st = as_stream(stream);
     const unsigned blocks = (unsigned)((n + H_THREADS - 1) / H_THREADS);
     if (dem_dtype == DTB_F32 && idx_dtype == DTB_I64)
-        hand_from_index_kernel<float, int64_t><<<blocks, H_THREADS, 0, st>>>((const float *)dem, (const int64_t *)idx, n, (float *)hand);
+        hand_from_index_kernel<float, int64_t><<<blocks, H_THREADS, 0, st>>>((const float *)dem, (const int64_t *)idx, n, (float *)hand, oob);
     else if (dem_dtype == DTB_F32 && idx_dtype == DTB_I32)
-        hand_from_index_kernel<float, int32_t><<<blocks, H_THREADS, 0, st>>>((const float *)dem, (const int32_t *)idx, n, (float *)hand);
+        hand_from_index_kernel<float, int32_t><<<blocks, H_THREADS, 0, st>>>((const float *)dem, (const int32_t *)idx, n, (float *)hand, oob);
     else if (dem_dtype == DTB_I16 && idx_dtype == DTB_I64)
-        hand_from_index_kernel<int16_t, int64_t><<<blocks, H_THREADS, 0, st>>>((const int16_t *)dem, (const int64_t *)idx, n, (int16_t *)hand);
+        hand_from_index_kernel<int16_t, int64_t><<<blocks, H_THREADS, 0, st>>>((const int16_t *)dem, (const int64_t *)idx, n, (int16_t *)hand, oob);
     else if (dem_dtype == DTB_I16 && idx_dtype == DTB_I32)
-        hand_from_index_kernel<int16_t, int32_t><<<blocks, H_THREADS, 0, st>>>((const int16_t *)dem, (const int32_t *)idx, n, (int16_t *)hand);
+        hand_from_index_kernel<int16_t, int32_t><<<blocks, H_THREADS, 0, st>>>((const int16_t *)dem, (const int32_t *)idx, n, (int16_t *)hand, oob);
     else
         return DTB_ERR_INVALID;
     DTB_LAUNCH_CHECK("hand_from_index_kernel");

@@ -27,11 +27,17 @@ inline unsigned pw_blocks(int64_t n)
 
 template <typename ACC, typename IDX>
 __global__ void __launch_bounds__(PW_THREADS)
-river_acc_kernel(const ACC *__restrict__ acc, const IDX *__restrict__ idx, int64_t n, ACC *__restrict__ out)
+river_acc_kernel(const ACC *__restrict__ acc, const IDX *__restrict__ idx, int64_t n, ACC *__restrict__ out, int32_t *__restrict__ oob)
 {
     for (int64_t i = (int64_t)blockIdx.x * PW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * PW_THREADS) {
-        const int64_t j = (int64_t)idx[i];
-        out[i] = acc[j != ND_I ? j : 0];
+        int64_t j = (int64_t)idx[i];
+        if (j == ND_I) j = 0;       // gfi.py:141-143: idx == -100 reads fac.flat[0]
+        else if (j < 0) j += n;     // NumPy / Numba wrap negative flat indices
+        if (j < 0 || j >= n) {      // an IndexError in the reference: never dereferenced here
+            if (oob) *oob = 1;
+            j = 0;
+        }
+        out[i] = acc[j];
     }
 }
 
@@ -86,20 +92,20 @@ slope_rad_kernel(const float *__restrict__ pct, int64_t n, float *__restrict__ r
 using namespace dtb;
 
 extern "C" int dtb_river_accumulation(const void *acc, int acc_dtype, const void *idx, int idx_dtype, int64_t n, void *out,
-                                      void *stream)
+                                      int32_t *oob, void *stream)
 {
     if (!acc || !idx || !out || n < 0) return DTB_ERR_INVALID;
     if (n == 0) return DTB_OK;
     cudaStream_t st = as_stream(stream);
     const unsigned b = pw_blocks(n);
     if (acc_dtype == DTB_I64 && idx_dtype == DTB_I64)
-        river_acc_kernel<int64_t, int64_t><<<b, PW_THREADS, 0, st>>>((const int64_t *)acc, (const int64_t *)idx, n, (int64_t *)out);
+        river_acc_kernel<int64_t, int64_t><<<b, PW_THREADS, 0, st>>>((const int64_t *)acc, (const int64_t *)idx, n, (int64_t *)out, oob);
     else if (acc_dtype == DTB_I64 && idx_dtype == DTB_I32)
-        river_acc_kernel<int64_t, int32_t><<<b, PW_THREADS, 0, st>>>((const int64_t *)acc, (const int32_t *)idx, n, (int64_t *)out);
+        river_acc_kernel<int64_t, int32_t><<<b, PW_THREADS, 0, st>>>((const int64_t *)acc, (const int32_t *)idx, n, (int64_t *)out, oob);
     else if (acc_dtype == DTB_I32 && idx_dtype == DTB_I64)
-        river_acc_kernel<int32_t, int64_t><<<b, PW_THREADS, 0, st>>>((const int32_t *)acc, (const int64_t *)idx, n, (int32_t *)out);
+        river_acc_kernel<int32_t, int64_t><<<b, PW_THREADS, 0, st>>>((const int32_t *)acc, (const int64_t *)idx, n, (int32_t *)out, oob);
     else if (acc_dtype == DTB_I32 && idx_dtype == DTB_I32)
-        river_acc_kernel<int32_t, int32_t><<<b, PW_THREADS, 0, st>>>((const int32_t *)acc, (const int32_t *)idx, n, (int32_t *)out);
+        river_acc_kernel<int32_t, int32_t><<<b, PW_THREADS, 0, st>>>((const int32_t *)acc, (const int32_t *)idx, n, (int32_t *)out, oob);
     else
         return DTB_ERR_INVALID;
     DTB_LAUNCH_CHECK("river_acc_kernel");

@@ -163,6 +163,7 @@ def hand(fdr: torch.Tensor, dem: torch.Tensor | None, px: float, river: torch.Te
         a.dem_dtype = _dem_dtype(dem)
     a.dem = _ptr(dem)
     a.rows, a.cols, a.px, a.max_moves = rows, cols, float(px), int(max_moves)
+    _same_shape(flow_direction=fdr, river=river, flow_accumulation=acc, dem=dem)
     given, out = out, {}
     if want_fdist:
         out["fdist"] = _out(given, "fdist", (rows, cols), torch.float32, dev)
@@ -188,16 +189,34 @@ def hand(fdr: torch.Tensor, dem: torch.Tensor | None, px: float, river: torch.Te
     return out
 
 
+def _same_shape(**named):
+    """every raster of one call covers the same grid (the kernels index them with one linear index)"""
+    it = iter(named.items())
+    n0, t0 = next(it)
+    for n, t in it:
+        if t is not None and (tuple(t.shape) != tuple(t0.shape) or t.device != t0.device):
+            raise ValueError(f"{n} {tuple(t.shape)} on {t.device} does not match {n0} {tuple(t0.shape)} on {t0.device}")
+
+
+def _raise_if_oob(flag: torch.Tensor, what: str):
+    if int(flag.item()):  # one 4-byte read back: these two calls return host-visible results anyway
+        raise IndexError(f"{what}: index out of bounds for the raster (the reference's NumPy / Numba gather raises here too)")
+
+
 def hand_from_index(dem: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     dem, idx = _chk2d(dem, "dem"), _chk2d(idx, "idx")
+    _same_shape(dem=dem, idx=idx)
     out = torch.empty_like(dem)
-    check(lib.dtb_hand_from_index(_ptr(dem), _dem_dtype(dem), _ptr(idx), _int_dtype(idx), dem.numel(), _ptr(out), _stream()),
-          "dtb_hand_from_index")
+    oob = torch.zeros(1, dtype=torch.int32, device=dem.device)
+    check(lib.dtb_hand_from_index(_ptr(dem), _dem_dtype(dem), _ptr(idx), _int_dtype(idx), dem.numel(), _ptr(out), _ptr(oob),
+                                  _stream()), "dtb_hand_from_index")
+    _raise_if_oob(oob, "hand_calculator")
     return out
 
 
 def downslope(dem: torch.Tensor, fdr: torch.Tensor, px: float, delta: float, max_moves: int = 0) -> torch.Tensor:
     dem, fdr = _chk2d(dem, "dem"), _chk2d(fdr, "fdr")
+    _same_shape(dem=dem, fdr=fdr)
     rows, cols = dem.shape
     out = torch.empty((rows, cols), dtype=torch.float32, device=dem.device)
     check(lib.dtb_downslope(_ptr(dem), _dem_dtype(dem), _ptr(fdr), rows, cols, float(px), float(delta), int(max_moves),
@@ -207,14 +226,18 @@ def downslope(dem: torch.Tensor, fdr: torch.Tensor, px: float, delta: float, max
 
 def river_accumulation(acc: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     acc, idx = _chk2d(acc, "acc"), _chk2d(idx, "idx")
+    _same_shape(acc=acc, idx=idx)
     out = torch.empty_like(acc)
-    check(lib.dtb_river_accumulation(_ptr(acc), _int_dtype(acc), _ptr(idx), _int_dtype(idx), acc.numel(), _ptr(out), _stream()),
-          "dtb_river_accumulation")
+    oob = torch.zeros(1, dtype=torch.int32, device=acc.device)
+    check(lib.dtb_river_accumulation(_ptr(acc), _int_dtype(acc), _ptr(idx), _int_dtype(idx), acc.numel(), _ptr(out), _ptr(oob),
+                                     _stream()), "dtb_river_accumulation")
+    _raise_if_oob(oob, "river_accumulation")
     return out
 
 
 def gfi(hand_t: torch.Tensor, racc: torch.Tensor, n: float, b: float, size: float) -> torch.Tensor:
     hand_t, racc = _chk2d(hand_t, "hand"), _chk2d(racc, "racc")
+    _same_shape(hand=hand_t, river_accumulation=racc)
     out = torch.empty(hand_t.shape, dtype=torch.float32, device=hand_t.device)
     check(lib.dtb_gfi(_ptr(hand_t), _dem_dtype(hand_t), _ptr(racc), _int_dtype(racc), hand_t.numel(), float(n), float(b),
                       float(size), _ptr(out), _stream()), "dtb_gfi")
@@ -223,6 +246,7 @@ def gfi(hand_t: torch.Tensor, racc: torch.Tensor, n: float, b: float, size: floa
 
 def ln_hl_H(hand_t: torch.Tensor, acc: torch.Tensor, n: float, b: float, size: float) -> torch.Tensor:
     hand_t, acc = _chk2d(hand_t, "hand"), _chk2d(acc, "acc")
+    _same_shape(hand=hand_t, flow_accumulation=acc)
     out = torch.empty(hand_t.shape, dtype=torch.float32, device=hand_t.device)
     check(lib.dtb_lnhlh(_ptr(hand_t), _dem_dtype(hand_t), _ptr(acc), _int_dtype(acc), hand_t.numel(), float(n), float(b),
                         float(size), _ptr(out), _stream()), "dtb_lnhlh")
@@ -233,6 +257,7 @@ def ti_mti(acc: torch.Tensor, slope_rad: torch.Tensor, px: float, n: float, want
     acc, slope_rad = _chk2d(acc, "acc"), _chk2d(slope_rad, "slope")
     if slope_rad.dtype != torch.float32:
         raise TypeError("slope must be float32 (radians)")
+    _same_shape(flow_accumulation=acc, slope=slope_rad)
     ti = torch.empty(acc.shape, dtype=torch.float32, device=acc.device) if want_ti else None
     mti = torch.empty(acc.shape, dtype=torch.float32, device=acc.device) if want_mti else None
     check(lib.dtb_ti_mti(_ptr(acc), _int_dtype(acc), _ptr(slope_rad), acc.numel(), float(px), float(n), _ptr(ti), _ptr(mti),
@@ -245,6 +270,30 @@ def slope_to_radians(slope_pct: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(slope_pct)
     check(lib.dtb_slope_to_radians(_ptr(slope_pct), slope_pct.numel(), _ptr(out), _stream()), "dtb_slope_to_radians")
     return out
+
+
+def chain_check(d8: torch.Tensor, acc: torch.Tensor, river_threshold: int, idx: torch.Tensor | None = None,
+                dem: torch.Tensor | None = None, hand: torch.Tensor | None = None, row0: int = 0,
+                total_rows: int | None = None) -> torch.Tensor:
+    """Identities of a finished chain over one raster / row band -> 8 uint64 counters on the device (csrc/verify.cu)."""
+    d8, acc = _chk2d(d8, "d8"), _chk2d(acc, "acc")
+    _same_shape(d8=d8, acc=acc, idx=idx, dem=dem, hand=hand)
+    rows, cols = d8.shape
+    out = torch.zeros(8, dtype=torch.int64, device=d8.device)
+    if (dem is not None and dem.dtype != torch.float32) or (hand is not None and hand.dtype != torch.float32):
+        dem = hand = None  # the HAND identity is checked for float32 rasters only
+    check(lib.dtb_chain_check(_ptr(d8), _ptr(acc), _int_dtype(acc), _ptr(idx), _int_dtype(idx) if idx is not None else 0, _ptr(dem),
+                              _ptr(hand), rows, cols, int(row0), int(rows if total_rows is None else total_rows),
+                              int(river_threshold), _ptr(out), _stream()), "dtb_chain_check")
+    return out
+
+
+def chain_verdict(counters) -> dict:
+    """counters: the (summed over bands) result of chain_check -> {"verified": bool, ...}"""
+    c = [int(v) for v in counters]
+    return {"verified": c[0] == c[1] and c[2] == c[3] == c[4] == c[5] == 0, "valid_cells": c[1], "root_mass": c[0],
+            "count_not_sum_of_tributaries": c[2], "idx_not_river": c[3], "river_not_self": c[4], "hand_mismatch": c[5], "no_river": c[6],
+            "idx_in_other_band": c[7]}
 
 
 # ---- benchmark support -----------------------------------------------------------------

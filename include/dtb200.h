@@ -213,9 +213,20 @@ typedef struct dtb_hand_band {
 size_t dtb_hand_workspace_bytes(int64_t rows, int64_t cols);
 int dtb_hand(const dtb_hand_args *args, void *ws, size_t ws_bytes, void *stream);
 
-/* hand_calculator alone (flowhand.py:414-442) on a caller-supplied index raster */
+/* hand_calculator alone (flowhand.py:414-442) on a caller-supplied index raster.  Indices other than -100 address
+ * dem.flat like NumPy does (negative ones count from the end); an index outside [-n, n) -- an IndexError in the
+ * reference -- is never dereferenced: the cell gets -100 and *oob (a device int32, may be NULL) is set to 1. */
 int dtb_hand_from_index(const void *dem, int dem_dtype, const void *idx, int idx_dtype,
-                        int64_t n, void *hand, void *stream);
+                        int64_t n, void *hand, int32_t *oob, void *stream);
+
+/* ---- self-check of a finished chain (no reference counterpart) ---------------------------
+ * Size-independent identities of D8 / accumulation / river index / HAND over rows [row0, row0 + rows) of a raster with
+ * total_rows rows, counted into out[0..7] (device, zeroed by the call; csrc/verify.cu lists them): summed over all
+ * bands, out[0] == out[1] and out[2..5] == 0 for a correct chain.  idx / dem / hand may be NULL (accumulation only).
+ * Used by bench.py after its timed region at sizes no CPU oracle reaches; tests/ pin it against the oracle. */
+int dtb_chain_check(const uint8_t *d8, const void *acc, int acc_dtype, const void *idx, int idx_dtype,
+                    const float *dem, const float *hand, int64_t rows, int64_t cols, int64_t row0,
+                    int64_t total_rows, int64_t river_threshold, unsigned long long *out, void *stream);
 
 /* ---- downslope index -------------------------------------------------------------------
  * Replaces downslope_cpu + downslope_gpu (downslope.py:379-431, 434-532) AND the CPU
@@ -232,14 +243,15 @@ int dtb_downslope_rows(const void *dem, int dem_dtype, const uint8_t *fdr, int64
                        float *out, void *stream);
 
 /* ---- pointwise indices -----------------------------------------------------------------
- * dtb_river_accumulation: gfi.py:118-147.  out has acc's dtype.
+ * dtb_river_accumulation: gfi.py:118-147.  out has acc's dtype.  Index handling as in
+ *          dtb_hand_from_index (out-of-range cells read element 0, *oob is set).
  * dtb_gfi: geomorphic_flood_index_cpu/_gpu (gfi.py:210-264, 267-294); racc is the
  *          pre-gathered river accumulation.
  * dtb_lnhlh: ln_hl_H_cpu/_gpu (gfi.py:349-400, 403-440).
  * dtb_ti_mti: topographic_index_cpu + both kernels (topoindexes.py:170-230, 233-295)
  *          in one pass; ti / mti may each be NULL. */
 int dtb_river_accumulation(const void *acc, int acc_dtype, const void *idx, int idx_dtype,
-                           int64_t n, void *out, void *stream);
+                           int64_t n, void *out, int32_t *oob, void *stream);
 int dtb_gfi(const void *hand, int hand_dtype, const void *racc, int acc_dtype, int64_t n,
             double expo, double scale, double size, float *out, void *stream);
 int dtb_lnhlh(const void *hand, int hand_dtype, const void *acc, int acc_dtype, int64_t n,

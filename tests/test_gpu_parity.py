@@ -335,6 +335,52 @@ def test_ti_mti_example(mods, ex):
 
 
 # ---- the fused chain ----------------------------------------------------------------------------
+def test_slope_to_radians_matches_example_glue():
+    """dtb_slope_to_radians == the host glue of example.py:63-64: arctan(S / 100) in f32, nodata patched back to -100."""
+    from descriptools_b200 import device
+
+    rng = np.random.default_rng(4)
+    dem = (rng.standard_normal((96, 160)) * 30 + 200).astype(np.float32)
+    dem[rng.random(dem.shape) < 0.1] = -100
+    slope = oracle.slope_d8(dem, PX)[0]
+    want = np.arctan(slope / np.float32(100)).astype(np.float32)  # example.py:63
+    want = np.where(dem == -100, np.float32(-100), want).astype(np.float32)  # example.py:64
+    got = device.slope_to_radians(torch.from_numpy(slope).cuda()).cpu().numpy()
+    assert got.dtype == np.float32
+    np.testing.assert_array_equal(got == -100, want == -100)
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)  # CUDA atanf vs NumPy arctan: 1-2 ulp
+
+
+def test_gathers_follow_numpy_index_rules(mods):
+    """hand_calculator / river_accumulation on caller-supplied indices: -100 is the mask, other negative indices wrap like
+    NumPy's, an index outside the raster raises IndexError (as the reference's fancy indexing does), and rasters of
+    different shapes are refused before anything is launched."""
+    rng = np.random.default_rng(12)
+    rows, cols = 40, 56
+    n = rows * cols
+    dem = (rng.standard_normal((rows, cols)) * 10 + 100).astype(np.float32)
+    fac = rng.integers(0, 5000, (rows, cols)).astype(np.int64)
+    idx = rng.integers(0, n, (rows, cols)).astype(np.int64)
+    idx[rng.random(idx.shape) < 0.2] = -100
+    idx[3, 4], idx[7, 9] = -1, -n  # NumPy: last element, first element
+    ref_hand = np.where((dem != -100) & (idx != -100), dem - dem.reshape(-1)[idx], -100).astype(np.float32)  # flowhand.py:436
+    ref_hand = np.where((ref_hand < 0) & (ref_hand != -100), 0, ref_hand).astype(np.float32)               # flowhand.py:438
+    np.testing.assert_array_equal(mods["flowhand"].hand_calculator(dem, idx), ref_hand)
+    ref_racc = np.where(idx != -100, fac.reshape(-1)[idx], fac.reshape(-1)[0])  # gfi.py:141-143
+    np.testing.assert_array_equal(mods["gfi"].river_accumulation(fac, idx), ref_racc)
+    for bad in (n, n + 12345, -n - 1):
+        idx2 = idx.copy()
+        idx2[5, 5] = bad
+        with pytest.raises(IndexError):
+            mods["flowhand"].hand_calculator(dem, idx2)
+        with pytest.raises(IndexError):
+            mods["gfi"].river_accumulation(fac, idx2)
+    with pytest.raises(ValueError):
+        mods["gfi"].river_accumulation(fac, idx[:-1])
+    with pytest.raises(ValueError):
+        mods["flowhand"].hand_calculator(dem[:, :-1], idx)
+
+
 @pytest.mark.parametrize("shape,thr", [((512, 640), 300), ((1000, 1200), 2000)])
 def test_pipeline_vs_oracle(shape, thr):
     from descriptools_b200 import pipeline
@@ -415,6 +461,42 @@ def test_pipeline_properties_large():
     s_ref, d_ref = oracle.slope_d8(dem[:300].cpu().numpy(), PX, 0, 299)
     np.testing.assert_array_equal(res["slope"][:299].cpu().numpy(), s_ref)
     np.testing.assert_array_equal(d8[:299].cpu().numpy(), d_ref)
+
+
+def test_chain_check_identities_and_detection():
+    """dtb_chain_check (what bench.py prints as "verified"): green on a correct chain -- whole raster and summed over
+    row bands -- and red when one accumulation count, one river index or one HAND value is off."""
+    from descriptools_b200 import device, pipeline
+
+    rows, cols, thr = 1024, 768, 500
+    dem = device.conditioned_dem(rows, cols, seed=5)
+    res = pipeline.run_device(dem, PX, thr)
+    full = device.chain_check(res["d8"], res["acc"], thr, idx=res["idx"], dem=dem, hand=res["hand"]).tolist()
+    v = device.chain_verdict(full)
+    assert v["verified"] and v["valid_cells"] == rows * cols and v["idx_in_other_band"] == 0
+    # the same rasters cut into three bands: the counters add up to the whole-raster ones (except the cross-band ones)
+    tot = torch.zeros(8, dtype=torch.int64, device="cuda")
+    for a, b in [(0, 320), (320, 704), (704, rows)]:
+        tot += device.chain_check(res["d8"][a:b].contiguous(), res["acc"][a:b].contiguous(), thr, idx=res["idx"][a:b].contiguous(),
+                                  dem=dem[a:b].contiguous(), hand=res["hand"][a:b].contiguous(), row0=a, total_rows=rows)
+    vb = device.chain_verdict(tot.tolist())
+    assert vb["verified"] and vb["valid_cells"] == rows * cols and vb["root_mass"] == rows * cols
+    # against the oracle's own accumulation: the identity really is "every cell counted once at its root"
+    acc_ref, left = oracle.flow_accumulation(res["d8"].cpu().numpy())
+    assert left == 0
+    np.testing.assert_array_equal(res["acc"].cpu().numpy(), acc_ref)
+    # detection
+    bad = res["acc"].clone()
+    bad[rows // 2, cols // 2] += 1
+    assert not device.chain_verdict(device.chain_check(res["d8"], bad, thr, idx=res["idx"], dem=dem, hand=res["hand"]).tolist())["verified"]
+    ok = torch.nonzero((res["idx"] >= 0) & (res["acc"] <= thr))
+    r, c = int(ok[len(ok) // 2][0]), int(ok[len(ok) // 2][1])
+    bad_idx = res["idx"].clone()
+    bad_idx[r, c] = r * cols + c  # itself: not a river cell
+    assert device.chain_verdict(device.chain_check(res["d8"], res["acc"], thr, idx=bad_idx, dem=dem, hand=res["hand"]).tolist())["idx_not_river"] == 1
+    bad_hand = res["hand"].clone()
+    bad_hand[r, c] += 1.0
+    assert device.chain_verdict(device.chain_check(res["d8"], res["acc"], thr, idx=res["idx"], dem=dem, hand=bad_hand).tolist())["hand_mismatch"] == 1
 
 
 # ---- row bands (multi-GPU decomposition, k logical bands on one GPU) ------------------------------
