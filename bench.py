@@ -309,6 +309,9 @@ def run_ours(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
+    from descriptools_b200 import bands as _bands
+
+    numa_cpus = _bands.bind_to_gpu_numa(local)  # before any pinned allocation: host rasters next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rows, cols = args.rows, args.cols
@@ -530,7 +533,8 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "rows": rows, "cols": cols, "px": PX, "river_threshold": RIVER_THR,
-                   "parallelism": "1 GPU" if world == 1 else f"{world} row bands", "l2": "inputs larger than L2 (no flush needed)"},
+                   "parallelism": "1 GPU" if world == 1 else f"{world} row bands", "l2": "inputs larger than L2 (no flush needed)",
+                   "host_cores_bound": len(numa_cpus) if numa_cpus else None},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "verified": verdict["verified"], "verification": verdict,
     }

@@ -4,13 +4,13 @@ The reference scales a raster by a *serial* loop over tiles on one GPU (slope.py
 with each tile; flowhand.py:282-402 pre-resolves separator lines and hands them to the tiles as look-up rows).
 Here the same decomposition runs in parallel, one process per GPU (torch.distributed / NCCL):
 
-  * slope + D8      : 1 DEM row exchanged with each neighbour (send/recv), then 1 row of D8 codes;
+  * slope + D8      : 2 DEM rows exchanged with each neighbour (send/recv); the band computes the codes of its halo row itself;
   * flow accumulation: every band runs its tile pass and node sweep with zero inflow and emits a boundary
-                      summary (dtb_flowacc_band, DTB_FA_SUMMARY); the summaries are gathered on rank 0, which
-                      solves the boundary graph (`solve_flowacc_boundary`) and scatters the inflow carried by
-                      each halo row; a second node sweep + the final tile pass finish the band;
+                      summary (dtb_flowacc_band, DTB_FA_SUMMARY); the summaries are all-gathered and every rank
+                      solves the (small) boundary graph (`solve_flowacc_boundary`) for the inflow carried by its
+                      halo rows; a second node sweep + the final tile pass finish the band;
   * HAND / GFI      : same pattern (dtb_hand band modes + `solve_hand_boundary`); paths may cross seams many
-                      times, so rank 0 does real pointer jumping over the boundary nodes.
+                      times, so the solve is real pointer jumping over the boundary nodes.
 
 Band seams sit on multiples of 64 rows (the tile edge of the device kernels).  Results are bit-identical to the
 single-GPU run.  The boundary solvers are pure torch (device-agnostic) so the whole driver can be exercised on
@@ -194,9 +194,12 @@ class Band:
         rows = self.rows
         f32, u8, i64 = torch.float32, torch.uint8, torch.int64
         mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)
-        self.dem_buf = torch.full((rows + 2, cols), float("nan"), dtype=f32, device=device)   # halo rows 0 and rows+1
-        self.d8_buf = torch.zeros((rows + 2, cols), dtype=u8, device=device)
-        self.slope = mk((rows, cols), f32)
+        # two halo rows of elevations on each side: the band computes the D8 codes of its one halo row of codes itself
+        # (the same inputs give the neighbour's own codes bit for bit), so a step needs ONE exchange, not two
+        self.dem_buf = torch.full((rows + 4, cols), float("nan"), dtype=f32, device=device)   # halo rows 0,1 and rows+2,rows+3
+        self.d8_buf = torch.zeros((rows + 2, cols), dtype=u8, device=device)                  # halo rows 0 and rows+1
+        self.slope_buf = mk((rows + 2, cols), f32)
+        self.slope = self.slope_buf[1:rows + 1]
         self.acc = mk((rows, cols), self.int_dt)
         self.fdist, self.hand, self.gfi = mk((rows, cols), f32), mk((rows, cols), f32), mk((rows, cols), f32)
         self.idx = mk((rows, cols), self.int_dt)
@@ -211,7 +214,7 @@ class Band:
     # views
     @property
     def dem(self):
-        return self.dem_buf[1:self.rows + 1]
+        return self.dem_buf[2:self.rows + 2]
 
     @property
     def d8(self):
@@ -227,8 +230,9 @@ class Band:
 
     # stages
     def slope_d8(self):
-        self._check(self.lib.dtb_slope_d8(self.dem_buf.data_ptr(), 0, self.rows + 2, self.cols, 1, self.rows + 1, self.px,
-                                          self.slope.data_ptr(), self.d8.data_ptr(), self._stream()), "dtb_slope_d8")
+        # rows 1 .. rows+2 of the elevation buffer = the band plus one halo row on each side (whose slope is discarded)
+        self._check(self.lib.dtb_slope_d8(self.dem_buf.data_ptr(), 0, self.rows + 4, self.cols, 1, self.rows + 3, self.px,
+                                          self.slope_buf.data_ptr(), self.d8_buf.data_ptr(), self._stream()), "dtb_slope_d8")
 
     def _fa_args(self, mode):
         from ._lib import DTB_I32, DTB_I64, FlowaccArgs
@@ -389,32 +393,53 @@ class DistExchange:
     def halo(self, items):
         (first_row, last_row, above, below), = items
         d, ops = self.dist, []
+        peer = (lambda r: d.get_global_rank(self.group, r)) if self.group is not None else (lambda r: r)  # P2POp wants global ranks
         if self.rank > 0:
-            ops += [d.P2POp(d.isend, first_row, self.rank - 1, self.group), d.P2POp(d.irecv, above, self.rank - 1, self.group)]
+            ops += [d.P2POp(d.isend, first_row, peer(self.rank - 1), self.group), d.P2POp(d.irecv, above, peer(self.rank - 1), self.group)]
         if self.rank + 1 < self.world:
-            ops += [d.P2POp(d.isend, last_row, self.rank + 1, self.group), d.P2POp(d.irecv, below, self.rank + 1, self.group)]
+            ops += [d.P2POp(d.isend, last_row, peer(self.rank + 1), self.group), d.P2POp(d.irecv, below, peer(self.rank + 1), self.group)]
         if ops:
             for w in d.batch_isend_irecv(ops):
                 w.wait()
 
     def solve(self, per_band, solver, rounds=ROUNDS):
-        """gather the summaries on rank 0, solve the boundary graph there, scatter the answers"""
+        """all-gather the summaries; every rank solves the (small) boundary graph itself and keeps its own answer: one
+        collective per solve and no rank waits for rank 0 to prepare and scatter"""
         (mine,), d = per_band, self.dist
         mine = mine.contiguous()
-        gathered = [torch.empty_like(mine) for _ in range(self.world)] if self.rank == 0 else None
-        d.gather(mine, gathered, dst=0, group=self.group)
-        parts = None
-        out = torch.empty(self._out_shape(mine, solver), dtype=mine.dtype, device=mine.device)
-        if self.rank == 0:
-            res, flag = self.graphed(solver, torch.stack(gathered, 0), rounds)
-            self.flags.append(flag.clone())
-            parts = [res[i].contiguous() for i in range(self.world)]
-        d.scatter(out, parts, src=0, group=self.group)
-        return [out]
+        everyone = torch.empty((self.world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+        if mine.is_cuda:
+            d.all_gather_into_tensor(everyone.view(-1), mine.view(-1), group=self.group)
+        else:  # gloo (the CPU tests)
+            d.all_gather(list(everyone.unbind(0)), mine, group=self.group)
+        res, flag = self.graphed(solver, everyone, rounds)
+        self.flags.append(flag.clone())
+        return [res[self.rank].clone()]
 
-    @staticmethod
-    def _out_shape(mine, solver):
-        return (2, mine.shape[1]) if solver is solve_flowacc_boundary else tuple(mine.shape)
+
+def bind_to_gpu_numa(device_index: int) -> list[int] | None:
+    """Pin this process to the CPU cores next to its GPU (NVML's affinity mask) BEFORE it allocates pinned host buffers:
+    cudaHostAlloc places the pages on the calling thread's NUMA node, and a host raster that sits on the other socket
+    crosses the inter-socket link on every H2D / D2H copy.  Returns the cores, or None if NVML / the mask is unavailable."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[device_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
 
 
 # ---- the driver --------------------------------------------------------------------------------------
@@ -476,7 +501,7 @@ class BandRunner:
             if not self._unresolved():
                 return
             rounds += 6  # a chain of more than 2**rounds seam crossings: repeat the step with more doubling rounds
-            if rounds > 66:
+            if rounds > 32:  # the library's limit (dtb_hand_boundary_solve); 2**32 crossings cannot happen without a cycle
                 raise RuntimeError("band boundary graph did not resolve (cycle across band seams)")
 
     def check_deferred(self):
@@ -490,10 +515,7 @@ class BandRunner:
         """one host sync per step: did every boundary solve resolve?  (all ranks must agree on repeating)"""
         flags = self.x.flags
         bad = torch.stack([f.to(torch.int32) for f in flags]).sum() if flags else None
-        if isinstance(self.x, DistExchange):
-            t = bad.reshape(1).clone() if bad is not None else torch.zeros(1, dtype=torch.int32, device=self.bands[0].dev)
-            self.x.dist.broadcast(t, src=0, group=self.x.group)
-            return bool(t.item())
+        # (with one band per rank every rank has solved the same boundary graphs: the flags agree without a collective)
         return bool(bad.item()) if bad is not None else False
 
     def step_host(self, dem_host: list, pinned_out: list):
@@ -530,10 +552,9 @@ class BandRunner:
 
         B = self.bands
         rec(0)
-        self.x.halo([(b.dem_buf[1], b.dem_buf[b.rows], b.dem_buf[0], b.dem_buf[b.rows + 1]) for b in B])
+        self.x.halo([(b.dem_buf[2:4], b.dem_buf[b.rows:b.rows + 2], b.dem_buf[0:2], b.dem_buf[b.rows + 2:b.rows + 4]) for b in B])
         for b in B:
             b.slope_d8()
-        self.x.halo([(b.d8_buf[1], b.d8_buf[b.rows], b.d8_buf[0], b.d8_buf[b.rows + 1]) for b in B])
         rec(1)
         if self.nbands == 1:
             B[0].flowacc_finish(None)

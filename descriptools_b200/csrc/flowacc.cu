@@ -490,6 +490,45 @@ fa_node_sweep_kernel(int64_t nnodes, const uint32_t *__restrict__ link, unsigned
     }
 }
 
+// Band FINISH: the SUMMARY call has already swept the node forest with zero inflow from the halo rows.  What the
+// boundary solve adds is a constant per seam entry: every node downstream of the entry gains exactly that much, so the
+// forest is not swept again -- each entry node of the first / last tile row adds its halo inflow to itself and to the
+// nodes along its chain (plain atomic adds: they commute, no pending counts involved).
+__global__ void __launch_bounds__(256)
+fa_node_inflow_kernel(int64_t tile0, int64_t nslots, int64_t rows, int64_t cols, int tiles_x, const uint32_t *__restrict__ meta,
+                      const uint32_t *__restrict__ link, const int64_t *__restrict__ inflow_above,
+                      const int64_t *__restrict__ inflow_below, unsigned long long *nstate)
+{
+    const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k >= nslots) return;
+    const int64_t node = tile0 * SLOTS + k;
+    const unsigned inmask = (meta[node] >> 16) & 0xFFu;
+    if (!inmask) return;
+    const int64_t tile = node / SLOTS;
+    int lr, lc;
+    slot_cell((int)(node % SLOTS), lr, lc);
+    const int64_t gr = (tile / tiles_x) * T + lr, gc = (tile % tiles_x) * T + lc;
+    uint64_t delta = 0;
+    for (int b = 0; b < 8; ++b) {
+        if (!((inmask >> b) & 1u)) continue;
+        int dr, dc;
+        nbr_offset(b, dr, dc);
+        const int64_t ur = gr + dr, uc = gc + dc;
+        if (ur < 0) delta += inflow_above ? (uint64_t)inflow_above[uc] : 0ull;
+        else if (ur >= rows) delta += inflow_below ? (uint64_t)inflow_below[uc] : 0ull;
+    }
+    if (!delta) return;
+    delta &= N_CNT;
+    uint32_t q = (uint32_t)node;
+    atomicAdd(&nstate[q], (unsigned long long)delta);
+    for (;;) {
+        const uint32_t l = __ldg(&link[q]);
+        if (l & LINK_OUT) break;  // LINK_NONE or out of the band
+        atomicAdd(&nstate[l], (unsigned long long)delta);
+        q = l;
+    }
+}
+
 // ---- cyclic grids: single-level sweep over the whole raster (gated on counters[0] != 0) -----------
 constexpr uint64_t F_CNT = (1ull << 44) - 1ull, F_PEND_ONE = 1ull << 44, F_SRC = 1ull << 63;
 constexpr int FLAT_BLOCKS = kNumSMs * 8;
@@ -722,9 +761,25 @@ int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
         DTB_CUDA(cudaMemsetAsync(counters, 0, 256, st));
         DTB_KERNEL("fa_tile_kernel", st, fa_tile_kernel<ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, exitw, link, meta, acc, (ACC)a->nodata_fill, counters, table));
     }
-    DTB_KERNEL("fa_node_init_kernel", st, fa_node_init_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, a->rows, a->cols, v.tiles_x, exitw, meta, a->inflow_above,
-                                                 a->inflow_below, nstate));
-    DTB_KERNEL("fa_node_sweep_kernel", st, fa_node_sweep_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, link, nstate));
+    if (a->mode != DTB_FA_FINISH) {
+        DTB_KERNEL("fa_node_init_kernel", st, fa_node_init_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, a->rows, a->cols, v.tiles_x, exitw, meta, a->inflow_above,
+                                                     a->inflow_below, nstate));
+        DTB_KERNEL("fa_node_sweep_kernel", st, fa_node_sweep_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, link, nstate));
+    } else {
+        // the node states of the SUMMARY call (zero halo inflow) + what each seam entry receives, pushed down its chain
+        const int64_t tiles_y = (a->rows + T - 1) / T;
+        const int64_t nslots = (int64_t)v.tiles_x * SLOTS;
+        const unsigned nbs = (unsigned)((nslots + 255) / 256);
+        if (a->inflow_above)
+            DTB_KERNEL("fa_node_inflow_kernel", st, fa_node_inflow_kernel<<<nbs, 256, 0, st>>>(0, nslots, a->rows, a->cols, v.tiles_x, meta, link,
+                                                               a->inflow_above, tiles_y == 1 ? a->inflow_below : nullptr, nstate));
+        if (a->inflow_below && tiles_y > 1)
+            DTB_KERNEL("fa_node_inflow_kernel", st, fa_node_inflow_kernel<<<nbs, 256, 0, st>>>((tiles_y - 1) * v.tiles_x, nslots, a->rows, a->cols, v.tiles_x,
+                                                               meta, link, nullptr, a->inflow_below, nstate));
+        else if (a->inflow_below && !a->inflow_above)
+            DTB_KERNEL("fa_node_inflow_kernel", st, fa_node_inflow_kernel<<<nbs, 256, 0, st>>>(0, nslots, a->rows, a->cols, v.tiles_x, meta, link, nullptr,
+                                                               a->inflow_below, nstate));
+    }
 
     if (a->mode == DTB_FA_SUMMARY) {
         const unsigned nbc = (unsigned)((a->cols + 255) / 256);

@@ -103,8 +103,9 @@ int dtb_flowacc(const uint8_t *d8, int64_t rows, int64_t cols, void *acc, int ac
  *                     own first/last-row cell it leaves through (side 0 = above, 1 = below), or -1
  *                     if it ends in the band.
  *       acc receives the tile-local counts (an intermediate the FINISH call completes in place).
- *   mode DTB_FA_FINISH  : node sweep with the resolved inflow + final tile pass writing acc;
- *       reuses the tile summaries the SUMMARY call left in the same, untouched workspace.
+ *   mode DTB_FA_FINISH  : adds the resolved inflow to the node counts the SUMMARY call left in the same,
+ *       untouched workspace (each seam entry pushes its inflow down its chain: the forest is not
+ *       swept a second time), then the final tile pass writes acc.
  * The band driver (descriptools_b200/bands.py) solves the boundary graph between the two calls.
  * Cross-band D8 cycles are not detected (dtb_slope_d8 never produces cycles). */
 enum { DTB_FA_FULL = 0, DTB_FA_SUMMARY = 1, DTB_FA_FINISH = 2 };
