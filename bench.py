@@ -348,26 +348,27 @@ def run_ours(args):
     else:
         from descriptools_b200 import bands
 
+        # rank 0 generates and depression-fills the WHOLE DEM on its own GPU before anything else is allocated (untimed):
+        # at 100 000 x 100 000 that is 40 GB + 50 GB of workspace on one 180 GB B200, 5.5 s (profiles/r2_fill_100k.txt) --
+        # the same conditioning as the 1-GPU workload, whatever the number of bands.  --unconditioned keeps the old
+        # per-rank synthesis without filling (pits end flow paths early; not the headline workload).
+        full = None
+        if rank == 0 and not args.unconditioned:
+            full = device.conditioned_dem(rows, cols)
+            device.workspace.release()
+            torch.cuda.empty_cache()
         runner = bands.BandRunner(rows, cols, PX, RIVER_THR, N_GFI, B_GFI)
         band = runner.bands[0]
         if args.unconditioned:
-            # continental sizes (BASELINE configs[4]): no single GPU can hold the DEM for depression filling; every rank
-            # synthesises its own band of the same recipe (row offset), unfilled -- pits end flow paths early
             band.dem.copy_(device.synth_dem(band.rows, cols, band.r0))
-        # rank 0 generates and depression-fills the whole DEM (untimed), bands travel over NCCL
         elif rank == 0:
-            full = device.conditioned_dem(rows, cols)
             for i in range(1, world):
-                dist.send(full[runner.edges[i]:runner.edges[i + 1]].contiguous(), dst=i)
+                dist.send(full[runner.edges[i]:runner.edges[i + 1]], dst=i)  # row slices are contiguous
             band.dem.copy_(full[runner.edges[0]:runner.edges[1]])
             del full
-            device.workspace.release()
             torch.cuda.empty_cache()
         else:
-            tmp = torch.empty((band.rows, cols), dtype=torch.float32, device="cuda")
-            dist.recv(tmp, src=0)
-            band.dem.copy_(tmp)
-            del tmp
+            dist.recv(band.dem, src=0)
         torch.cuda.synchronize()
 
         def step(timed):

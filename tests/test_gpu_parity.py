@@ -499,6 +499,31 @@ def test_chain_check_identities_and_detection():
     assert device.chain_verdict(device.chain_check(res["d8"], res["acc"], thr, idx=res["idx"], dem=dem, hand=bad_hand).tolist())["hand_mismatch"] == 1
 
 
+def test_chain_above_2_31_cells_int64_verified():
+    """46 400 x 46 400 = 2.15e9 cells (> 2**31): counts and river indices are int64; the device-side identities of
+    dtb_chain_check stand in for the oracle at this size (they pin every accumulation count, the river index targets and
+    HAND).  Needs ~110 GB of device memory: skipped on smaller GPUs."""
+    from descriptools_b200 import device, pipeline
+
+    if torch.cuda.get_device_properties(0).total_memory < 150e9:
+        pytest.skip("needs a 180 GB GPU")
+    n = 46400
+    assert n * n > 2**31
+    dem = device.conditioned_dem(n, n, seed=3)
+    device.workspace.release()
+    torch.cuda.empty_cache()
+    res = pipeline.run_device(dem, PX, 128000)
+    assert res["acc"].dtype == torch.int64 and res["idx"].dtype == torch.int64
+    v = device.chain_verdict(device.chain_check(res["d8"], res["acc"], 128000, idx=res["idx"], dem=dem, hand=res["hand"]).tolist())
+    assert v["verified"], v
+    assert v["valid_cells"] == n * n and v["root_mass"] == n * n
+    assert int(res["idx"].max()) >= 2**31  # indices beyond int32 really occur
+    del res, dem
+    device.workspace.release()
+    pipeline.release_buffers()
+    torch.cuda.empty_cache()
+
+
 # ---- row bands (multi-GPU decomposition, k logical bands on one GPU) ------------------------------
 def weaving_dem(rows, cols, seam, amp=20.0, period=90.0):
     """a valley that weaves across row `seam` many times: every HAND / accumulation path re-enters bands"""
