@@ -571,13 +571,59 @@ class BandRunner:
                 b.hand_finish(r)
         rec(3)
 
-    def downslope(self, delta: float, max_moves: int = 0) -> list[torch.Tensor]:
+    def downslope(self, delta: float, max_moves: int = 0, halo_rows: int = 1024) -> list[torch.Tensor]:
         """Downslope index of every local band (downslope.py:317-376), after step() (it needs the D8 codes).
 
-        A downslope walk is cut by the drop it has reached, not by a band seam, and cannot be pointer-jumped, so the
-        reference's scheme -- tiles plus a global second pass over whatever left its tile (downslope.py:366-374) --
-        becomes: replicate DEM + D8 on every rank (one broadcast per band over NVLink, 5 bytes per cell) and let each
-        rank walk its own rows over the whole raster.  Exact, no iteration."""
+        A downslope walk is cut by the drop it has reached, not by a band seam, and cannot be pointer-jumped; but it is
+        local (hundreds of moves).  The reference's scheme -- tiles, then a global second pass over whatever left its
+        tile, flagged -50 (downslope.py:366-374, 526-529) -- becomes: every band walks inside a window of its own rows
+        plus `halo_rows` rows of DEM + D8 from each neighbour (one exchange); walks that would leave the window are
+        flagged -50 and counted, and as long as any rank counts one the halo is widened (x4) and the flagged bands walk
+        again.  No rank holds more than its band plus halo, unless a walk spans a whole neighbouring band: only then
+        does the driver fall back to replicating DEM + D8 (5 bytes per cell) on every rank."""
+        from ._lib import check, lib
+
+        dev = self.bands[0].dev
+        dist_x = isinstance(self.x, DistExchange)
+        h = max(int(halo_rows), 1)
+        while True:
+            items, wins = [], []
+            for b in self.bands:
+                ha = 0 if b.first else min(h, self.edges[b.index] - self.edges[b.index - 1])
+                hb = 0 if b.last else min(h, self.edges[b.index + 2] - self.edges[b.index + 1])
+                wd = torch.empty((ha + b.rows + hb, self.cols), dtype=torch.float32, device=dev)
+                w8 = torch.empty((ha + b.rows + hb, self.cols), dtype=torch.uint8, device=dev)
+                wd[ha:ha + b.rows].copy_(b.dem)
+                w8[ha:ha + b.rows].copy_(b.d8)
+                mine = min(h, b.rows)
+                items.append(((b.dem[:mine], b.d8[:mine]), (b.dem[b.rows - mine:], b.d8[b.rows - mine:]),
+                              (wd[:ha], w8[:ha]), (wd[ha + b.rows:], w8[ha + b.rows:])))
+                wins.append((wd, w8, ha, hb))
+            for k in range(2):  # elevations, then codes
+                self.x.halo([(it[0][k].contiguous(), it[1][k].contiguous(), it[2][k], it[3][k]) for it in items])
+            outs, esc = [], torch.zeros(1, dtype=torch.int64, device=dev)
+            complete = True
+            for b, (wd, w8, ha, hb) in zip(self.bands, wins):
+                out = torch.empty((b.rows, self.cols), dtype=torch.float32, device=dev)
+                check(lib.dtb_downslope_window(wd.data_ptr(), 0, w8.data_ptr(), ha + b.rows + hb, self.cols, ha, ha + b.rows, b.px,
+                                               float(delta), int(max_moves), out.data_ptr(), 0 if b.first else 1, 0 if b.last else 1,
+                                               esc.data_ptr(), b._stream()), "dtb_downslope_window")
+                outs.append(out)
+                complete &= (b.first or ha == self.edges[b.index] - self.edges[b.index - 1]) and \
+                            (b.last or hb == self.edges[b.index + 2] - self.edges[b.index + 1])
+            state = torch.stack([esc[0], torch.tensor(0 if complete else 1, dtype=torch.int64, device=dev)])
+            if dist_x:
+                self.x.dist.all_reduce(state, group=self.x.group)
+            escaped, widenable = (int(v) for v in state.tolist())
+            if escaped == 0:
+                return outs
+            if not widenable:  # every window already holds its whole neighbours: a walk spans more than a band
+                return self._downslope_replicated(delta, max_moves)
+            h *= 4
+
+    def _downslope_replicated(self, delta: float, max_moves: int = 0) -> list[torch.Tensor]:
+        """fallback of downslope(): DEM + D8 of the whole raster on every rank (one broadcast per band), each rank walks
+        its own rows over it.  Exact for any walk length."""
         from ._lib import check, lib
 
         dev = self.bands[0].dev

@@ -28,10 +28,14 @@ template <> struct Diff<int16_t> {
     static __device__ __forceinline__ double sub(int16_t a, int16_t b) { return (double)((int)a - (int)b); }  // i64 in Numba
 };
 
+// open_above / open_below: the buffer is a window of a larger raster (a row band plus halo rows) and its first / last row
+// is NOT the raster's edge: a walk that would leave through it cannot be finished here -- the cell gets the reference's
+// own "redo me" marker -50 (downslope.py:526-529) and *escaped counts it, for the band driver to widen the window.
 template <typename T>
 __global__ void __launch_bounds__(DS_THREADS)
 downslope_kernel(const T *__restrict__ dem, const uint8_t *__restrict__ fdr, int64_t rows, int64_t cols, int64_t row_begin,
-                 int64_t row_end, double px, double pd, double delta, int64_t max_moves, float *__restrict__ out)
+                 int64_t row_end, double px, double pd, double delta, int64_t max_moves, float *__restrict__ out, int open_above,
+                 int open_below, unsigned long long *__restrict__ escaped)
 {
     // cells of rows [row_begin, row_end) are computed (walks may wander over the whole raster); out starts at row_begin
     const int64_t n = (row_end - row_begin) * cols;
@@ -51,6 +55,11 @@ downslope_kernel(const T *__restrict__ dem, const uint8_t *__restrict__ fdr, int
         int dr, dc;
         if (d8_offset(f, dr, dc)) {
             const int64_t yy = y + dr, xx = x + dc;
+            if ((yy < 0 && open_above) || (yy >= rows && open_below)) {  // leaves the window, not the raster
+                out[o] = -50.0f;
+                atomicAdd(escaped, 1ull);
+                return;
+            }
             if (yy < 0 || yy >= rows || xx < 0 || xx >= cols) break;  // downslope.py:212-231
             const int64_t q = yy * cols + xx;
             const T zq = dem[q];
@@ -67,12 +76,14 @@ downslope_kernel(const T *__restrict__ dem, const uint8_t *__restrict__ fdr, int
 }  // namespace
 }  // namespace dtb
 
-extern "C" int dtb_downslope_rows(const void *dem, int dem_dtype, const uint8_t *fdr, int64_t rows, int64_t cols, int64_t row_begin,
-                                  int64_t row_end, double px, double delta, int64_t max_moves, float *out, void *stream)
+extern "C" int dtb_downslope_window(const void *dem, int dem_dtype, const uint8_t *fdr, int64_t rows, int64_t cols, int64_t row_begin,
+                                    int64_t row_end, double px, double delta, int64_t max_moves, float *out, int open_above,
+                                    int open_below, unsigned long long *escaped, void *stream)
 {
     using namespace dtb;
     if (!dem || !fdr || !out || rows <= 0 || cols <= 0 || !(px > 0.0) || row_begin < 0 || row_end > rows || row_begin > row_end)
         return DTB_ERR_INVALID;
+    if ((open_above || open_below) && !escaped) return DTB_ERR_INVALID;
     if (row_begin == row_end) return DTB_OK;
     if (max_moves <= 0) max_moves = 5000;
     const int64_t n = (row_end - row_begin) * cols;
@@ -80,16 +91,22 @@ extern "C" int dtb_downslope_rows(const void *dem, int dem_dtype, const uint8_t 
     cudaStream_t st = as_stream(stream);
     const double pd = px * sqrt(2.0);
     if (dem_dtype == DTB_F32)
-        DTB_KERNEL("downslope_kernel<f32>", st, downslope_kernel<float><<<blocks, DS_THREADS, 0, st>>>((const float *)dem, fdr, rows, cols, row_begin, row_end, px, pd, delta, max_moves, out));
+        DTB_KERNEL("downslope_kernel<f32>", st, downslope_kernel<float><<<blocks, DS_THREADS, 0, st>>>((const float *)dem, fdr, rows, cols, row_begin, row_end, px, pd, delta, max_moves, out, open_above, open_below, escaped));
     else if (dem_dtype == DTB_I16)
-        DTB_KERNEL("downslope_kernel<i16>", st, downslope_kernel<int16_t><<<blocks, DS_THREADS, 0, st>>>((const int16_t *)dem, fdr, rows, cols, row_begin, row_end, px, pd, delta, max_moves, out));
+        DTB_KERNEL("downslope_kernel<i16>", st, downslope_kernel<int16_t><<<blocks, DS_THREADS, 0, st>>>((const int16_t *)dem, fdr, rows, cols, row_begin, row_end, px, pd, delta, max_moves, out, open_above, open_below, escaped));
     else
         return DTB_ERR_INVALID;
     return DTB_OK;
 }
 
+extern "C" int dtb_downslope_rows(const void *dem, int dem_dtype, const uint8_t *fdr, int64_t rows, int64_t cols, int64_t row_begin,
+                                  int64_t row_end, double px, double delta, int64_t max_moves, float *out, void *stream)
+{
+    return dtb_downslope_window(dem, dem_dtype, fdr, rows, cols, row_begin, row_end, px, delta, max_moves, out, 0, 0, nullptr, stream);
+}
+
 extern "C" int dtb_downslope(const void *dem, int dem_dtype, const uint8_t *fdr, int64_t rows, int64_t cols, double px,
                              double delta, int64_t max_moves, float *out, void *stream)
 {
-    return dtb_downslope_rows(dem, dem_dtype, fdr, rows, cols, 0, rows, px, delta, max_moves, out, stream);
+    return dtb_downslope_window(dem, dem_dtype, fdr, rows, cols, 0, rows, px, delta, max_moves, out, 0, 0, nullptr, stream);
 }

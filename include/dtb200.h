@@ -236,12 +236,19 @@ int dtb_chain_check(const uint8_t *d8, const void *acc, int acc_dtype, const voi
 int dtb_downslope(const void *dem, int dem_dtype, const uint8_t *fdr, int64_t rows,
                   int64_t cols, double px, double delta, int64_t max_moves, float *out,
                   void *stream);
-/* rows [row_begin, row_end) only (out holds those rows); the walks still see the whole raster.  Row-band form: the
- * band driver replicates dem + fdr on every rank (NVLink broadcast) and each rank computes its own rows -- the
- * counterpart of the reference's "GPU pass per tile + global CPU pass over the -50 flags" (downslope.py:366-374). */
+/* rows [row_begin, row_end) only (out holds those rows); the walks still see the whole buffer. */
 int dtb_downslope_rows(const void *dem, int dem_dtype, const uint8_t *fdr, int64_t rows, int64_t cols,
                        int64_t row_begin, int64_t row_end, double px, double delta, int64_t max_moves,
                        float *out, void *stream);
+/* Row-band form: the buffer is a window of a larger raster -- a band plus halo rows on the sides that are open
+ * (open_above / open_below != 0: the first / last buffer row is not the raster's edge).  A walk that would leave the
+ * window through an open side cannot be finished in it: the cell gets -50, the reference's own "redo" marker
+ * (downslope.py:526-529), and *escaped (device, zeroed by the caller) counts it.  The band driver widens the halo until
+ * nothing escapes: the counterpart of the reference's "GPU pass per tile + global CPU pass over the -50 flags"
+ * (downslope.py:366-374), without any rank ever holding more than its band plus halo. */
+int dtb_downslope_window(const void *dem, int dem_dtype, const uint8_t *fdr, int64_t rows, int64_t cols,
+                         int64_t row_begin, int64_t row_end, double px, double delta, int64_t max_moves,
+                         float *out, int open_above, int open_below, unsigned long long *escaped, void *stream);
 
 /* ---- pointwise indices -----------------------------------------------------------------
  * dtb_river_accumulation: gfi.py:118-147.  out has acc's dtype.  Index handling as in

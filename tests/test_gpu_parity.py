@@ -777,6 +777,33 @@ def test_bands_downslope_equals_single_gpu():
     runner.step()
     got = torch.cat(runner.downslope(5.0), 0).cpu().numpy()
     np.testing.assert_array_equal(got, ref)
+    # a tiny halo: walks escape the window, the driver widens it (x4) until none does, then has to fall back to the
+    # replicated form when the windows already hold their whole neighbours -- same result every way
+    for h in (1, 7, 64):
+        np.testing.assert_array_equal(torch.cat(runner.downslope(5.0, halo_rows=h), 0).cpu().numpy(), ref)
+    np.testing.assert_array_equal(torch.cat(runner._downslope_replicated(5.0), 0).cpu().numpy(), ref)
+    assert not (got == -50).any()
+
+
+def test_downslope_window_marks_escaping_walks():
+    """dtb_downslope_window: cells whose walk leaves through an open side get the reference's -50 marker and are counted;
+    everything else equals the whole-raster result."""
+    from descriptools_b200 import device
+    from descriptools_b200._lib import check, lib
+
+    dem = synth(256, 200, 8, holes=False)
+    t = torch.from_numpy(dem).cuda()
+    _, d8 = device.slope_d8(t, PX)
+    ref = device.downslope(t, d8, PX, 5.0)
+    a, b = 96, 160  # window = rows [a-16, b+16), band = [a, b)
+    wd, w8 = t[a - 16:b + 16].contiguous(), d8[a - 16:b + 16].contiguous()
+    out = torch.empty((b - a, 200), dtype=torch.float32, device="cuda")
+    esc = torch.zeros(1, dtype=torch.int64, device="cuda")
+    check(lib.dtb_downslope_window(wd.data_ptr(), 0, w8.data_ptr(), b - a + 32, 200, 16, 16 + b - a, PX, 5.0, 0, out.data_ptr(), 1, 1,
+                                   esc.data_ptr(), torch.cuda.current_stream().cuda_stream), "dtb_downslope_window")
+    flagged = out == -50
+    assert int(esc.item()) == int(flagged.sum()) > 0
+    np.testing.assert_array_equal(out[~flagged].cpu().numpy(), ref[a:b][~flagged].cpu().numpy())
 
 
 def _hand_fused_vs_oracle(d8, dem, thr):
