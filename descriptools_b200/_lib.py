@@ -118,6 +118,7 @@ SIGNATURES = {
     "dtb_hand": (c_int, [POINTER(HandArgs), c_void_p, c_size_t, c_void_p]),
     "dtb_chain_check": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                 c_void_p, c_void_p]),
+    "dtb_nodata_to_sentinel_f32": (c_int, [c_void_p, c_int64, ctypes.c_float, c_int, c_void_p]),
     "dtb_hand_from_index": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "dtb_downslope": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_double, c_double, c_int64, c_void_p, c_void_p]),
     "dtb_downslope_window": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_double, c_double, c_int64,

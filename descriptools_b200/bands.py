@@ -478,10 +478,10 @@ class BandRunner:
                 raise TypeError(f"{path}: row bands take float32 DEMs, the file holds {src.dtypes[0]}")
             nd = src.nodata if nodata is None else nodata
             for b in self.bands:
+                from . import device as _device
+
                 raster.read_to_device(src, out=b.dem, rows=(b.r0, b.r1), decode=decode)
-                if nd is not None:
-                    b.dem.masked_fill_(b.dem == nd, -100)
-                b.dem.masked_fill_(torch.isnan(b.dem), -100)
+                _device.nodata_to_sentinel(b.dem, nd)
 
     def step(self, events=None, hook=None, check=True):
         """One pass of the chain; `events` (4 CUDA events) are recorded at the stage boundaries and `hook(i)` is

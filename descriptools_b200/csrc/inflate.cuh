@@ -163,6 +163,8 @@ DTB_LZW_HD int64_t zlib_inflate(const uint8_t *in, size_t n, uint8_t *out, size_
     size_t op = 0;
     bool last = false;
     while (!last && op < cap) {
+        // every lane rebuilds the same Huffman tables for a new block: no lane may still be decoding with the old ones
+        DTB_LZW_WARP_SYNC();
         last = inflate_bits(b, 1) != 0;
         const uint32_t type = inflate_bits(b, 2);
         if (b.starved) return -1;

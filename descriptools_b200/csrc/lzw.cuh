@@ -93,6 +93,8 @@ DTB_LZW_HD int64_t lzw_decode(const uint8_t *in, size_t n, uint8_t *out, size_t 
         have -= nbits;
         if (code == 257) break;
         if (code == 256) {
+            // every lane rewrites the same table slots after a Clear: no lane may still be reading the old generation
+            DTB_LZW_WARP_SYNC();
             nbits = 9;
             next = 258;
             fresh = true;

@@ -86,10 +86,29 @@ slope_rad_kernel(const float *__restrict__ pct, int64_t n, float *__restrict__ r
     }
 }
 
+// example.py:42-43 on the device, in one pass: the file's nodata value (and NaN) becomes the path's sentinel -100
+__global__ void __launch_bounds__(PW_THREADS)
+nodata_sentinel_kernel(float *__restrict__ dem, int64_t n, float nodata, int has_nodata)
+{
+    for (int64_t i = (int64_t)blockIdx.x * PW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * PW_THREADS) {
+        const float z = dem[i];
+        if (z != z || (has_nodata && z == nodata)) dem[i] = ND_F;
+    }
+}
+
 }  // namespace
 }  // namespace dtb
 
 using namespace dtb;
+
+extern "C" int dtb_nodata_to_sentinel_f32(float *dem, int64_t n, float nodata, int has_nodata, void *stream)
+{
+    if (!dem || n < 0) return DTB_ERR_INVALID;
+    if (n == 0) return DTB_OK;
+    cudaStream_t st = as_stream(stream);
+    DTB_KERNEL("nodata_sentinel_kernel", st, (nodata_sentinel_kernel<<<pw_blocks(n), PW_THREADS, 0, st>>>(dem, n, nodata, has_nodata)));
+    return DTB_OK;
+}
 
 extern "C" int dtb_river_accumulation(const void *acc, int acc_dtype, const void *idx, int idx_dtype, int64_t n, void *out,
                                       int32_t *oob, void *stream)

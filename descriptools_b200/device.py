@@ -265,6 +265,15 @@ def ti_mti(acc: torch.Tensor, slope_rad: torch.Tensor, px: float, n: float, want
     return ti, mti
 
 
+def nodata_to_sentinel(dem: torch.Tensor, nodata: float | None) -> torch.Tensor:
+    """in place: cells equal to `nodata` (if given) and NaN cells -> -100 (example.py:42-43); one pass"""
+    if dem.dtype != torch.float32 or not dem.is_cuda or not dem.is_contiguous():
+        raise ValueError("dem must be a contiguous float32 CUDA tensor")
+    check(lib.dtb_nodata_to_sentinel_f32(_ptr(dem), dem.numel(), float(nodata) if nodata is not None else 0.0,
+                                         1 if nodata is not None else 0, _stream()), "dtb_nodata_to_sentinel_f32")
+    return dem
+
+
 def slope_to_radians(slope_pct: torch.Tensor) -> torch.Tensor:
     slope_pct = _chk2d(slope_pct, "slope")
     out = torch.empty_like(slope_pct)

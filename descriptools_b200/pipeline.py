@@ -183,10 +183,10 @@ def pipeline_files(dem_path, out_dir, river_threshold: int, px: float | None = N
     if dem.dtype not in (torch.float32, torch.int16):
         # the kernels take the two DEM types the reference is used with (f32 rasters, int16 after example.py:33)
         dem = dem.to(torch.float32)
-    if nodata is not None:
-        dem.masked_fill_(dem == nodata, -100)
     if dem.dtype == torch.float32:
-        dem.masked_fill_(torch.isnan(dem), -100)
+        device.nodata_to_sentinel(dem, nodata)  # example.py:42-43, one pass (dtb_nodata_to_sentinel_f32)
+    elif nodata is not None:
+        dem.masked_fill_(dem == nodata, -100)   # int16 DEMs: plumbing only
     if condition:
         if dem.dtype != torch.float32:
             raise TypeError("condition=True needs a float32 DEM (the filling raises cells by single float32 steps)")

@@ -250,6 +250,11 @@ int dtb_downslope_window(const void *dem, int dem_dtype, const uint8_t *fdr, int
                          int64_t row_begin, int64_t row_end, double px, double delta, int64_t max_moves,
                          float *out, int open_above, int open_below, unsigned long long *escaped, void *stream);
 
+/* The host glue of example.py:42-43 on the device, one in-place pass over a float32 DEM: cells equal to the file's
+ * nodata value (has_nodata != 0) and NaN cells become the path's sentinel -100.  (It cannot live in the stencil's load
+ * alone: HAND reads the same DEM, hand_calculator flowhand.py:431-436.) */
+int dtb_nodata_to_sentinel_f32(float *dem, int64_t n, float nodata, int has_nodata, void *stream);
+
 /* ---- pointwise indices -----------------------------------------------------------------
  * dtb_river_accumulation: gfi.py:118-147.  out has acc's dtype.  Index handling as in
  *          dtb_hand_from_index (out-of-range cells read element 0, *oob is set).

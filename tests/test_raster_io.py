@@ -757,7 +757,11 @@ def test_pipeline_from_file_to_files(tmp_path):
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype,layout,compress,predictor", [("float32", "tiles", "lzw", 1), ("float32", "tiles", "lzw", 3), ("int16", "strips", "lzw", 2),
                                                              ("uint8", "tiles", "lzw", 1), ("int32", "tiles", "none", 1), ("float64", "strips", "none", 1),
-                                                             ("int64", "tiles", "lzw", 2)])
+                                                             ("int64", "tiles", "lzw", 2),
+                                                             # Deflate (zlib streams written by this library's host codec = zlib itself)
+                                                             ("float32", "tiles", "deflate", 1), ("float32", "tiles", "deflate", 3),
+                                                             ("int16", "strips", "deflate", 2), ("uint8", "tiles", "deflate", 1),
+                                                             ("float64", "strips", "deflate", 3), ("int32", "tiles", "deflate", 2)])
 def test_tiles_decoded_on_the_device(tmp_path, dtype, layout, compress, predictor):
     import torch
 
@@ -775,6 +779,40 @@ def test_tiles_decoded_on_the_device(tmp_path, dtype, layout, compress, predicto
     np.testing.assert_array_equal(t.cpu().numpy(), a)
     t = rio.read_to_device(p, decode="device")  # one span
     np.testing.assert_array_equal(t.cpu().numpy(), a)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["uint8", "uint16", "int32", "float32"])
+def test_packbits_and_noise_decoded_on_the_device(tmp_path, dtype):
+    """the device PackBits kernel on strips as libtiff (Pillow) writes them -- literal runs and long repeats -- and the
+    device Deflate kernel on incompressible data (stored / near-stored blocks, literal-only streams) and on long matches"""
+    import torch
+    from PIL import Image
+
+    p = str(tmp_path / "pb.tif")
+    for a in (_rand((301, 333), dtype, seed=5), np.repeat(_rand((301, 9), dtype, seed=6, smooth=False), 37, axis=1)):
+        Image.fromarray(a).save(p, compression="packbits")
+        assert rio.open(p).compression == "packbits"
+        t = rio.read_to_device(p, decode="device")
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(t.cpu().numpy(), a)
+        t = rio.read_to_device(p, decode="device", rows=(100, 211))
+        np.testing.assert_array_equal(t.cpu().numpy(), a[100:211])
+    q = tmp_path / "z.tif"
+    for smooth, block in ((False, 256), (True, 256), (True, 64)):
+        a = _rand((700, 900), dtype, seed=41, smooth=smooth)
+        if smooth:
+            a[100:300] = a[100]  # long matches across rows
+        with rio.open(q, "w", width=900, height=700, dtype=dtype, compress="deflate", tiled=True, blockxsize=block, blockysize=block) as dst:
+            dst.write(a)
+        t = rio.read_to_device(q, decode="device", group_chunks=5)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(t.cpu().numpy(), a)
+    # a long literal-only LZW stream (noise): the lock-step decoder's table fills and resets many times
+    a = _rand((1024, 1024), "uint8", seed=9, smooth=False)
+    with rio.open(q, "w", width=1024, height=1024, dtype="uint8", compress="lzw", tiled=True, blockxsize=512, blockysize=512) as dst:
+        dst.write(a)
+    np.testing.assert_array_equal(rio.read_to_device(q, decode="device").cpu().numpy(), a)
 
 
 @pytest.mark.gpu
