@@ -24,7 +24,7 @@ def require_cuda() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def _stream() -> int:
+def _stream() -> int:  # the current stream of the current device: compute calls run under torch.cuda.device(tensor.device)
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -59,18 +59,25 @@ class _Workspace:
 
     def __init__(self):
         self.buf = {}
+        self.fused = {}  # device index -> what the fused flow-accumulation call left in the "hand" workspace
 
-    def get(self, nbytes: int, stage: str = "shared") -> torch.Tensor:
-        key = (torch.cuda.current_device(), stage)
+    def get(self, nbytes: int, stage: str = "shared", device=None) -> torch.Tensor:
+        """scratch on `device` (default: the current one).  Calls on one device are ordered by the stream they are
+        enqueued on; two streams must not share a stage's scratch -- use one stream per device, as the drop-in does."""
+        index = torch.cuda.current_device() if device is None else torch.device(device).index
+        key = (index, stage)
         b = self.buf.get(key)
         if b is None or b.numel() < nbytes:
             self.buf[key] = None
-            b = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{key[0]}")
+            b = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{index}")
             self.buf[key] = b
+            if stage == "hand":
+                self.fused.pop(index, None)  # a new buffer holds no entry-node states
         return b
 
     def release(self):
         self.buf.clear()
+        self.fused.clear()
 
 
 workspace = _Workspace()
@@ -116,7 +123,7 @@ def flow_accumulation(d8: torch.Tensor, dtype: torch.dtype = torch.int32, nodata
     rows, cols = d8.shape
     acc = _out(out, "acc", (rows, cols), dtype, d8.device)
     nbytes = lib.dtb_flowacc_workspace_bytes(rows, cols)
-    ws = workspace.get(nbytes, "flowacc")
+    ws = workspace.get(nbytes, "flowacc", d8.device)
     left = ctypes.c_int64(0)
     a = FlowaccArgs()
     a.d8, a.rows, a.cols = _ptr(d8), rows, cols
@@ -125,9 +132,12 @@ def flow_accumulation(d8: torch.Tensor, dtype: torch.dtype = torch.int32, nodata
         a.unfinalised_host = ctypes.pointer(left)
     if fuse_hand_threshold is not None:
         hb = lib.dtb_hand_workspace_bytes(rows, cols)
-        hws = workspace.get(hb, "hand")
+        hws = workspace.get(hb, "hand", d8.device)
         a.hand_ws, a.hand_ws_bytes, a.hand_river_threshold = _ptr(hws), hb, int(fuse_hand_threshold)
-    check(lib.dtb_flowacc_band(ctypes.byref(a), _ptr(ws), nbytes, _stream()), "dtb_flowacc_band")
+    with torch.cuda.device(d8.device):
+        check(lib.dtb_flowacc_band(ctypes.byref(a), _ptr(ws), nbytes, _stream()), "dtb_flowacc_band")
+    if fuse_hand_threshold is not None:  # hand(entry_done=True) honours only exactly this state
+        workspace.fused[d8.device.index] = (d8.data_ptr(), acc.data_ptr(), (rows, cols), int(fuse_hand_threshold), _ptr(hws))
     return (acc, int(left.value)) if check_cycles else acc
 
 
@@ -184,8 +194,17 @@ def hand(fdr: torch.Tensor, dem: torch.Tensor | None, px: float, river: torch.Te
     a.fdist, a.idx, a.hand, a.gfi = _ptr(out.get("fdist")), _ptr(out.get("idx")), _ptr(out.get("hand")), _ptr(out.get("gfi"))
     a.entry_done = 1 if entry_done else 0
     nbytes = lib.dtb_hand_workspace_bytes(rows, cols)
-    ws = workspace.get(nbytes, "hand")
-    check(lib.dtb_hand(ctypes.byref(a), _ptr(ws), nbytes, _stream()), "dtb_hand")
+    ws = workspace.get(nbytes, "hand", dev)
+    if entry_done:
+        # the entry-node states must be the ones the fused flow accumulation of THIS raster and threshold left in THIS buffer
+        want = (fdr.data_ptr(), acc.data_ptr() if acc is not None else 0, (rows, cols), int(river_threshold), _ptr(ws))
+        if workspace.fused.get(dev.index) != want:
+            raise RuntimeError("hand(entry_done=True) must directly follow flow_accumulation(fuse_hand_threshold=...) on the same "
+                               "flow-direction raster, accumulation raster and threshold")
+    with torch.cuda.device(dev):
+        check(lib.dtb_hand(ctypes.byref(a), _ptr(ws), nbytes, _stream()), "dtb_hand")
+    if not entry_done:
+        workspace.fused.pop(dev.index, None)  # the workspace now holds this call's node states
     return out
 
 

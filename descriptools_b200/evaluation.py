@@ -50,8 +50,13 @@ class _Counter:
         self.ws = torch.empty(4 * 33 * 8, dtype=torch.uint8, device=desc_t.device)
 
     def counts(self, thresholds):
-        order = np.argsort(thresholds, kind="stable")
-        th = np.asarray(thresholds, np.float64)[order]
+        th = np.asarray(thresholds, np.float64)
+        if not self.is_f64:
+            # NumPy compares a float32 descriptor with a Python-float threshold in float32 (the scalar is cast down,
+            # evaluation.py:32-85 under NEP 50): round the thresholds the same way before the f64 comparison on the device
+            th = th.astype(np.float32).astype(np.float64)
+        order = np.argsort(th, kind="stable")
+        th = th[order]
         uniq, inv = np.unique(th, return_inverse=True)  # the kernel wants strictly ascending thresholds
         out = np.zeros((len(uniq), 4), np.int64)
         for a in range(0, len(uniq), 32):
@@ -122,6 +127,8 @@ def binary_map(descriptor_matrix, threshold, under):
     """evaluation.py:90-123: 1 where the descriptor is on the flooded side of the threshold, 0 elsewhere / nodata."""
     d, nodata, is_f64 = _dev_desc(descriptor_matrix)
     out = torch.empty(d.shape, dtype=torch.int8, device=d.device)
+    if not is_f64:
+        threshold = float(np.float32(threshold))  # float32 descriptor: NumPy compares in float32 (see _Counter.counts)
     check(lib.dtb_eval_class_map(d.data_ptr(), 1 if is_f64 else 0, None, d.numel(), nodata, float(threshold),
                                  1 if under == "under" else 0, out.data_ptr(), None, torch.cuda.current_stream().cuda_stream),
           "dtb_eval_class_map")

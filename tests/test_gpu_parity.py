@@ -763,6 +763,28 @@ def test_evaluation_counts_random_over_and_under():
         np.testing.assert_array_equal(cls, ref_cls)
 
 
+def test_evaluation_float32_thresholds_compare_like_numpy():
+    """cells exactly at float32(threshold): NumPy compares a float32 descriptor with a Python float in float32"""
+    import descriptools_b200.evaluation as ev
+
+    th = 0.1  # not representable: float32(0.1) > 0.1
+    desc = np.full((8, 16), np.float32(th), np.float32)
+    desc[0, 0] = -100.0  # the reference takes the value at [0, 0] for nodata (evaluation.py:110)
+    desc[1, :4] = np.float32(0.5)
+
+    def reference(d, under):  # evaluation.py:110-121, verbatim semantics
+        d = np.where(d == d[0, 0], np.nan, d)
+        hit = d <= th if under == "under" else d >= th
+        return np.where(np.isnan(d), 0, np.where(hit, 1, 0))
+
+    want = reference(desc, "under")  # float32 comparison: the cells at float32(0.1) > 0.1 still count as <= 0.1
+    assert want.sum() == desc.size - 5
+    np.testing.assert_array_equal(ev.binary_map(desc, th, "under"), want)
+    np.testing.assert_array_equal(ev.binary_map(desc, th, "over"), reference(desc, "over"))
+    d64 = desc.astype(np.float64)
+    np.testing.assert_array_equal(ev.binary_map(d64, th, "under"), reference(d64, "under"))  # float64: 0.1000000015 > 0.1
+
+
 def test_bands_downslope_equals_single_gpu():
     from descriptools_b200 import bands, device
 
