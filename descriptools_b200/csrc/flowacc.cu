@@ -479,14 +479,15 @@ fa_node_sweep_kernel(int64_t nnodes, const uint32_t *__restrict__ link, unsigned
     const uint64_t s = nstate[node];
     if (!(s & N_SRC)) return;
     uint64_t w = s & N_CNT;
-    uint32_t q = (uint32_t)node;
-    for (;;) {
-        const uint32_t l = __ldg(&link[q]);
-        if (l & LINK_OUT) break;  // LINK_NONE or out of the band
+    // The walk is a chain of dependent round trips to L2 (the main stem: ~2 000 nodes at 40k x 40k).  The link of the
+    // NEXT node is requested together with the atomic on it, not after its answer: one round trip per node, not two.
+    uint32_t l = __ldg(&link[node]);
+    while (!(l & LINK_OUT)) {  // LINK_NONE or out of the band
+        const uint32_t lnext = __ldg(&link[l]);
         const uint64_t old = atomicAdd(&nstate[l], (unsigned long long)(w - N_PEND_ONE));
         if (((old >> N_PEND_SHIFT) & N_PEND) != 1ull) break;
         w += old & N_CNT;
-        q = l;
+        l = lnext;
     }
 }
 
@@ -519,13 +520,11 @@ fa_node_inflow_kernel(int64_t tile0, int64_t nslots, int64_t rows, int64_t cols,
     }
     if (!delta) return;
     delta &= N_CNT;
-    uint32_t q = (uint32_t)node;
-    atomicAdd(&nstate[q], (unsigned long long)delta);
-    for (;;) {
-        const uint32_t l = __ldg(&link[q]);
-        if (l & LINK_OUT) break;  // LINK_NONE or out of the band
-        atomicAdd(&nstate[l], (unsigned long long)delta);
-        q = l;
+    atomicAdd(&nstate[node], (unsigned long long)delta);
+    uint32_t l = __ldg(&link[node]);
+    while (!(l & LINK_OUT)) {  // LINK_NONE or out of the band
+        atomicAdd(&nstate[l], (unsigned long long)delta);  // no return value needed: the loads alone form the chain
+        l = __ldg(&link[l]);
     }
 }
 
@@ -691,14 +690,13 @@ forest_sweep_kernel(int64_t n, const long long *__restrict__ next, unsigned long
     if (i >= n) return;
     if ((pend0[i] >> 44) != 0ull) return;  // not a source (pending as counted before the sweep started)
     uint64_t w = pend0[i] & F_CNT;
-    int64_t q = i;
-    for (;;) {
-        const long long t = next[q];
-        if (t < 0 || t >= n) break;
+    long long t = next[i];
+    while (t >= 0 && t < n) {
+        const long long tnext = next[t];  // requested together with the atomic (see fa_node_sweep_kernel)
         const uint64_t old = atomicAdd(&state[t], (unsigned long long)(w - F_PEND_ONE));
         if (((old >> 44) & 0x7FFFFull) != 1ull) break;
         w += old & F_CNT;
-        q = t;
+        t = tnext;
     }
 }
 __global__ void __launch_bounds__(256)
