@@ -249,7 +249,11 @@ fa_finish_tile(const int tile, const TileView &v, const uint32_t *__restrict__ m
 {
     typedef typename std::conditional<sizeof(ACC) == 8, unsigned long long, uint32_t>::type EXT;
     __shared__ uint16_t nxt[TCELLS];
-    __shared__ EXT ext[TCELLS];
+    // inflow added to each cell.  64-bit counts keep the two halves in separate words: a 64-bit shared-memory atomicAdd is
+    // a compare-and-swap loop (3.5x the time of the 32-bit form at 100 000 x 100 000), two native 32-bit adds with a
+    // carry are not
+    constexpr bool WIDE = sizeof(ACC) == 8;
+    __shared__ uint32_t ext[TCELLS], ext_hi[WIDE ? TCELLS : 1];
     const int tid = threadIdx.x;
     const int ty = tile / v.tiles_x, tx = tile - ty * v.tiles_x;
     const int64_t r0 = (int64_t)ty * T, c0 = (int64_t)tx * T;
@@ -275,6 +279,7 @@ fa_finish_tile(const int tile, const TileView &v, const uint32_t *__restrict__ m
             if (REDO) e &= ~NX_RIVER;  // river bits of the first run
             nxt[i * FT_THREADS + tid] = (uint16_t)e;
             ext[i * FT_THREADS + tid] = 0;
+            if (WIDE) ext_hi[i * FT_THREADS + tid] = 0;
             validmask |= (e != NX_NODATA ? 1u : 0u) << i;
         }
     }
@@ -296,7 +301,13 @@ fa_finish_tile(const int tile, const TileView &v, const uint32_t *__restrict__ m
         uint32_t q = my_slot, n16 = 0, ndiag = 0;
         int steps = 0;
         for (; steps < TCELLS; ++steps) {
-            atomicAdd(&ext[q], w);
+            if (!WIDE) {
+                atomicAdd(&ext[q], (uint32_t)w);
+            } else {
+                const uint32_t lo = (uint32_t)w, old = atomicAdd(&ext[q], lo);
+                const uint32_t hi = (uint32_t)((uint64_t)w >> 32) + ((uint32_t)(old + lo) < old ? 1u : 0u);
+                if (hi) atomicAdd(&ext_hi[q], hi);
+            }
             n16 = nxt[q];
             if ((n16 & W_NXT) >= W_EXIT) break;
             ndiag += n16 >> 14;  // no river bits yet: bit 14 = diagonal move
@@ -317,7 +328,11 @@ fa_finish_tile(const int tile, const TileView &v, const uint32_t *__restrict__ m
         EXT e[CPT];
         bool any = false;
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) { e[i] = ext[i * FT_THREADS + tid]; any |= e[i] != 0; }
+        for (int i = 0; i < CPT; ++i) {
+            e[i] = (EXT)ext[i * FT_THREADS + tid];
+            if (WIDE) e[i] |= (EXT)((uint64_t)ext_hi[i * FT_THREADS + tid] << 32);
+            any |= e[i] != 0;
+        }
         // cells off every entry path keep their tile-local count (< 4096): they can only be river cells for tiny thresholds
         const bool need = any || (HAND && (REDO || thr < (int64_t)TCELLS));
         if (need) {

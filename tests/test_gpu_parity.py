@@ -685,6 +685,38 @@ def test_forest_accumulate_cuda_matches_torch():
     assert bool(flag)
 
 
+def test_band_inflow_beyond_2_32_carries():
+    """int64 counts: inflow carried by the halo rows may exceed 2**32 (100 000 x 100 000).  The finish pass adds it in two
+    32-bit halves with a carry; acc must be linear in the inflow: acc(k) = acc(0) + k * (number of halo paths through the
+    cell), exactly, for k on both sides of 2**32 and for sums that wrap the low word."""
+    import ctypes
+
+    from descriptools_b200._lib import DTB_I64, FlowaccArgs, check, lib
+
+    dem = synth(192, 256, 14, holes=False)
+    t = torch.from_numpy(dem).cuda()
+    _, d8 = __import__("descriptools_b200").device.slope_d8(t, PX)
+    rows, cols = d8.shape
+    halo = torch.full((cols,), 4, dtype=torch.uint8, device="cuda")  # every halo cell above flows south into row 0
+    ws = torch.empty(lib.dtb_flowacc_workspace_bytes(rows, cols), dtype=torch.uint8, device="cuda")
+
+    def run(k):
+        acc = torch.empty((rows, cols), dtype=torch.int64, device="cuda")
+        inflow = torch.full((cols,), k, dtype=torch.int64, device="cuda")
+        a = FlowaccArgs()
+        a.d8, a.rows, a.cols, a.halo_above = d8.data_ptr(), rows, cols, halo.data_ptr()
+        a.inflow_above, a.acc, a.acc_dtype, a.nodata_fill, a.mode = inflow.data_ptr(), acc.data_ptr(), DTB_I64, -100, 0
+        check(lib.dtb_flowacc_band(ctypes.byref(a), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "flowacc")
+        torch.cuda.synchronize()
+        return acc
+
+    a0, a3 = run(0), run(3)
+    m = (a3 - a0) // 3
+    assert bool(((a3 - a0) % 3 == 0).all()) and int(m.max()) > 1  # several halo paths merge somewhere
+    for k in (2**32 - 1, 2**32 + 11, 2**31 + 5, 3 * 2**32 + 7):
+        np.testing.assert_array_equal(run(k).cpu().numpy(), (a0 + k * m).cpu().numpy())
+
+
 def test_bands_int64_equal_single_gpu():
     """the continental configuration's dtypes (int64 accumulation and indices) through the band path"""
     from descriptools_b200 import pipeline
