@@ -110,6 +110,8 @@ SIGNATURES = {
     "dtb_flowacc": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int64, c_void_p, c_size_t,
                             POINTER(c_int64), c_void_p]),
     "dtb_flowacc_band": (c_int, [POINTER(FlowaccArgs), c_void_p, c_size_t, c_void_p]),
+    "dtb_flowacc_boundary_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "dtb_flowacc_boundary_solve": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dtb_forest_workspace_bytes": (c_size_t, [c_int64]),
     "dtb_forest_accumulate": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dtb_hand_boundary_workspace_bytes": (c_size_t, [c_int64, c_int64]),

@@ -83,6 +83,7 @@ def forest_accumulate(nxt: torch.Tensor, base: torch.Tensor, rounds: int = ROUND
 
 _plan_cache = {}
 _hand_ws = {}
+_fa_ws = {}
 
 
 def _plan(n: int, cols: int, dev):
@@ -105,6 +106,19 @@ def solve_flowacc_boundary(summ: torch.Tensor, rounds: int = ROUNDS):
     """summ int64 [N, 6, cols]: exit_above, exit_below, term_above, term_below, d8 first row, d8 last row.
     Returns (inflow int64 [N, 2, cols]: (acc+1) carried by the halo row above / below each band, flag)."""
     n, _, cols = summ.shape
+    if summ.is_cuda:  # the library's solve (dtb_flowacc_boundary_solve); the torch form below serves CPU tensors
+        from ._lib import check, lib
+
+        summ = summ.contiguous()
+        key = (summ.device.index, n, cols)
+        if key not in _fa_ws:
+            _fa_ws[key] = (torch.empty(lib.dtb_flowacc_boundary_workspace_bytes(n, cols), dtype=torch.uint8, device=summ.device),
+                           torch.empty((n, 2, cols), dtype=torch.int64, device=summ.device),
+                           torch.zeros(1, dtype=torch.int32, device=summ.device))
+        ws, inflow, flag = _fa_ws[key]
+        check(lib.dtb_flowacc_boundary_solve(summ.data_ptr(), n, cols, inflow.data_ptr(), flag.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             torch.cuda.current_stream(summ.device).cuda_stream), "dtb_flowacc_boundary_solve")
+        return inflow, flag[0] != 0
     p = _plan(n, cols, summ.device)
     base = summ[:, 0:2, :]
     term = summ[:, 2:4, :]
@@ -229,10 +243,18 @@ class Band:
         check(code, what)
 
     # stages
-    def slope_d8(self):
-        # rows 1 .. rows+2 of the elevation buffer = the band plus one halo row on each side (whose slope is discarded)
-        self._check(self.lib.dtb_slope_d8(self.dem_buf.data_ptr(), 0, self.rows + 4, self.cols, 1, self.rows + 3, self.px,
-                                          self.slope_buf.data_ptr(), self.d8_buf.data_ptr(), self._stream()), "dtb_slope_d8")
+    def slope_d8(self, part: str = "all"):
+        """rows 1 .. rows+2 of the elevation buffer = the band plus one halo row on each side (whose slope is discarded).
+        part="interior": only the rows whose 3-row window lies inside the band (they need no halo: the driver runs them
+        while the halo exchange is in flight); part="edges": the two rows at each end, once the halo has arrived."""
+        r = self.rows
+        spans = {"all": [(1, r + 3)], "interior": [(3, r + 1)], "edges": [(1, 3), (r + 1, r + 3)]}[part]
+        for a, b in spans:
+            if b <= a:
+                continue
+            self._check(self.lib.dtb_slope_d8(self.dem_buf.data_ptr(), 0, r + 4, self.cols, a, b, self.px,
+                                              self.slope_buf[a - 1:].data_ptr(), self.d8_buf[a - 1:].data_ptr(), self._stream()),
+                        "dtb_slope_d8")
 
     def _fa_args(self, mode):
         from ._lib import DTB_I32, DTB_I64, FlowaccArgs
@@ -552,9 +574,24 @@ class BandRunner:
 
         B = self.bands
         rec(0)
-        self.x.halo([(b.dem_buf[2:4], b.dem_buf[b.rows:b.rows + 2], b.dem_buf[0:2], b.dem_buf[b.rows + 2:b.rows + 4]) for b in B])
-        for b in B:
-            b.slope_d8()
+        items = [(b.dem_buf[2:4], b.dem_buf[b.rows:b.rows + 2], b.dem_buf[0:2], b.dem_buf[b.rows + 2:b.rows + 4]) for b in B]
+        if isinstance(self.x, DistExchange) and B[0].dem_buf.is_cuda and min(b.rows for b in B) > 4:
+            # the exchange runs on its own stream while the stencil does every row that needs no halo
+            main = torch.cuda.current_stream(B[0].dev)
+            if not hasattr(self, "_comm"):
+                self._comm = torch.cuda.Stream(device=B[0].dev)
+            self._comm.wait_stream(main)  # the halo rows may still be read by the previous step's kernels
+            with torch.cuda.stream(self._comm):
+                self.x.halo(items)
+            for b in B:
+                b.slope_d8("interior")
+            main.wait_stream(self._comm)
+            for b in B:
+                b.slope_d8("edges")
+        else:
+            self.x.halo(items)
+            for b in B:
+                b.slope_d8()
         rec(1)
         if self.nbands == 1:
             B[0].flowacc_finish(None)

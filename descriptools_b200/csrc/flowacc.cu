@@ -724,6 +724,39 @@ forest_out_kernel(int64_t n, const unsigned long long *__restrict__ state, long 
     if ((s >> 44) & 0x7FFFFull) atomicOr(unresolved, 1);  // never finalised: the forest has a cycle
 }
 
+// ---- boundary graph between row bands (multi-GPU): the whole solve in the library ------------------------------
+// summ int64 [N][6][cols]: exit_above, exit_below, term_above, term_below, d8 first row, d8 last row of every band
+// (dtb_flowacc_band, DTB_FA_SUMMARY).  Node (b, side, c) = cell c of the first (side 0) / last (side 1) row of band b.
+__global__ void __launch_bounds__(256)
+fb_prep_kernel(const long long *__restrict__ summ, int64_t nbands, int64_t cols, long long *__restrict__ next, long long *__restrict__ base)
+{
+    const int64_t node = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (node >= 2 * nbands * cols) return;
+    const int64_t b = node / (2 * cols), rem = node - b * 2 * cols, side = rem / cols, c = rem - side * cols;
+    const long long w = summ[(b * 6 + side) * cols + c];
+    const long long code = summ[(b * 6 + 4 + side) * cols + c];
+    // column shift of the move across the seam: NW/SW -1, N/S 0, NE/SE +1 (flowhand.py:801-824)
+    const int64_t c2 = c + ((code == 128 || code == 2) ? 1 : 0) - ((code == 32 || code == 8) ? 1 : 0);
+    const int64_t b2 = side == 0 ? b - 1 : b + 1;
+    long long nx = -1;
+    if (w > 0 && b2 >= 0 && b2 < nbands && c2 >= 0 && c2 < cols) {
+        const long long t = summ[(b2 * 6 + 2 + (1 - side)) * cols + c2];  // where the landing cell's in-band path leaves
+        if (t >= 0) nx = (b2 * 2 + ((t >> 30) & 1)) * cols + (t & 0x3FFFFFFF);
+    }
+    next[node] = nx;
+    base[node] = w;
+}
+// inflow [N][2][cols]: (acc + 1) carried by the halo row above / below each band
+__global__ void __launch_bounds__(256)
+fb_inflow_kernel(const long long *__restrict__ f, int64_t nbands, int64_t cols, long long *__restrict__ inflow)
+{
+    const int64_t node = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (node >= 2 * nbands * cols) return;
+    const int64_t b = node / (2 * cols), rem = node - b * 2 * cols, side = rem / cols, c = rem - side * cols;
+    const int64_t b2 = side == 0 ? b - 1 : b + 1;  // above band b = last row of band b-1; below = first row of band b+1
+    inflow[node] = (b2 >= 0 && b2 < nbands) ? f[(b2 * 2 + (1 - side)) * cols + c] : 0;
+}
+
 struct NodeLayout {
     int64_t tiles, nnodes;
     size_t off_counters, off_exitw, off_link, off_meta, off_nstate, off_flat, total;
@@ -893,5 +926,31 @@ extern "C" int dtb_forest_accumulate(const int64_t *next, const int64_t *base, i
     DTB_CUDA(cudaMemcpyAsync(pend0, state, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));  // snapshot: who is a source
     DTB_KERNEL("forest_sweep_kernel", st, forest_sweep_kernel<<<nb, 256, 0, st>>>(n, (const long long *)next, state, pend0));
     DTB_KERNEL("forest_out_kernel", st, forest_out_kernel<<<nb, 256, 0, st>>>(n, state, (long long *)out, unresolved));
+    return DTB_OK;
+}
+
+extern "C" size_t dtb_flowacc_boundary_workspace_bytes(int64_t nbands, int64_t cols)
+{
+    if (nbands <= 0 || cols <= 0) return 0;
+    const int64_t n = 2 * nbands * cols;
+    return (size_t)n * 24 + dtb_forest_workspace_bytes(n);
+}
+
+extern "C" int dtb_flowacc_boundary_solve(const int64_t *summ, int64_t nbands, int64_t cols, int64_t *inflow, int *unresolved,
+                                          void *ws, size_t ws_bytes, void *stream)
+{
+    using namespace dtb;
+    if (!summ || !inflow || !unresolved || !ws || nbands <= 0 || cols <= 0) return DTB_ERR_INVALID;
+    if (cols >= (int64_t)1 << 30) return DTB_ERR_UNSUPPORTED;
+    if (ws_bytes < dtb_flowacc_boundary_workspace_bytes(nbands, cols)) return DTB_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    const int64_t n = 2 * nbands * cols;
+    long long *next = reinterpret_cast<long long *>(ws), *base = next + n, *f = base + n;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    DTB_KERNEL("fb_prep_kernel", st, (fb_prep_kernel<<<nb, 256, 0, st>>>((const long long *)summ, nbands, cols, next, base)));
+    const int rc = dtb_forest_accumulate((const int64_t *)next, (const int64_t *)base, n, (int64_t *)f, unresolved, f + n,
+                                         dtb_forest_workspace_bytes(n), stream);
+    if (rc != DTB_OK) return rc;
+    DTB_KERNEL("fb_inflow_kernel", st, (fb_inflow_kernel<<<nb, 256, 0, st>>>(f, nbands, cols, (long long *)inflow)));
     return DTB_OK;
 }

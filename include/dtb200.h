@@ -132,6 +132,14 @@ typedef struct dtb_flowacc_args {
 } dtb_flowacc_args;
 int dtb_flowacc_band(const dtb_flowacc_args *args, void *ws, size_t ws_bytes, void *stream);
 
+/* The boundary graph between row bands, solved in one call (every rank runs it on the all-gathered summaries):
+ * summ int64 [nbands][6][cols] = exit_above, exit_below, term_above, term_below, first and last row of D8 codes of every
+ * band (the DTB_FA_SUMMARY outputs); inflow int64 [nbands][2][cols] = what the halo row above / below each band carries
+ * (acc + 1), the inflow_above / inflow_below of the DTB_FA_FINISH calls.  *unresolved (device int): a cycle across seams. */
+size_t dtb_flowacc_boundary_workspace_bytes(int64_t nbands, int64_t cols);
+int dtb_flowacc_boundary_solve(const int64_t *summ, int64_t nbands, int64_t cols, int64_t *inflow, int *unresolved,
+                               void *ws, size_t ws_bytes, void *stream);
+
 /* Generic forest accumulation used by the band driver for the boundary graph between row bands:
  * out[i] = base[i] + sum of out[j] over all j with next[j] == i (next[j] < 0: no successor).
  * *unresolved (device int) becomes non-zero if the graph has a cycle.  ws: dtb_forest_workspace_bytes(n). */
