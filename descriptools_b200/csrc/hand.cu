@@ -13,8 +13,9 @@
 //       (entry nodes) walk their in-tile path: it ends on a river cell, fails, or leaves the tile
 //       into another entry node.  One 64-bit state per node.
 //   H2  hand_node_jump_kernel: pointer jumping over the entry nodes in global memory.  In-place and
-//       asynchronous: any state read is a valid description of that node's path, every launch at
-//       least doubles the hops covered, so ceil(log2(max_moves+1)) launches decide every node;
+//       asynchronous: any state read is a valid description of that node's path, every launch of
+//       2 compositions per node covers at least 3x the hops, so ceil(log3(max_moves+1)) launches
+//       (10 for the reference's 20 000 moves) decide every node;
 //       what is still ACTIVE then needs more than max_moves moves or sits on / drains into a
 //       cycle -> FAIL, the reference's outcomes (flowhand.py:826 code-0 landing, :830 cycle
 //       detector, :835 move cap, border exits :623-764).  A launch whose predecessor left
@@ -29,6 +30,7 @@
 // log(b*pow(A_r*size^2, n)/(H+0.01)) (gfi.py:292-294) rearranged to drop the pow; both are
 // correctly rounded far below the f32 the result is stored in.
 #include <math.h>
+#include <stdlib.h>
 
 #include "tiles.cuh"
 
@@ -784,10 +786,22 @@ hb_out_kernel(const long long *__restrict__ summ, int64_t n, int64_t cols, const
     for (int k = 0; k < 4; ++k) res[(b * 8 + out * 4 + k) * cols + c] = v[k];
 }
 
-inline int rounds_for(int64_t max_moves)
+// A launch in which every thread composes `jumps` times multiplies the hops every ACTIVE state covers by at least
+// jumps + 1 (each composed state covers at least what the shortest state covered when the launch began), so
+// ceil(log_{jumps+1}(max_moves + 1)) launches decide every node that max_moves moves can decide.
+inline int node_jumps()
+{
+    static const int j = [] {
+        const char *e = getenv("DTB_NODE_JUMPS");  // measurement aid
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= 16 ? v : 2;  // measured at 40k x 40k (profiles/r2z_node_jumps.txt): 2 is the fastest
+    }();
+    return j;
+}
+inline int rounds_for(int64_t max_moves, int jumps)
 {
     int r = 0;
-    while (((int64_t)1 << r) < max_moves + 1) ++r;
+    for (double cover = 1.0; cover < (double)max_moves + 1.0; cover *= jumps + 1) ++r;
     return r;
 }
 
@@ -905,9 +919,9 @@ extern "C" int dtb_hand(const dtb_hand_args *a, void *ws, size_t ws_bytes, void 
                 else hand_entry_kernel<int32_t><<<(unsigned)tiles, H_THREADS, 0, st>>>(v, rs, nstate, active);
             });
         }
-        const int rounds = rounds_for(max_moves);
+        const int jumps = node_jumps(), rounds = rounds_for(max_moves, jumps);
         for (int r = 1; r <= rounds; ++r) {
-            DTB_KERNEL("hand_node_jump_kernel", st, hand_node_jump_kernel<<<JUMP_BLOCKS, H_THREADS, 0, st>>>(nnodes, nstate, active, r, 2));
+            DTB_KERNEL("hand_node_jump_kernel", st, hand_node_jump_kernel<<<JUMP_BLOCKS, H_THREADS, 0, st>>>(nnodes, nstate, active, r, jumps));
         }
     }
     if (mode == DTB_HAND_SUMMARY) {
