@@ -27,28 +27,102 @@ __device__ __forceinline__ bool usable(T d, double nodata) { return !((double)d 
 __device__ __forceinline__ int remap(int f) { return f == 1 ? 2 : (f == ND_I ? 0 : f); }
 
 // hist[c][j], c = remapped benchmark value 0..3, j = 0..k: number of thresholds of the list that do NOT flag the cell
-// before the first one that does (under: first i with d <= th[i]; over: thresholds th[0..j-1] satisfy d >= th, j = count)
-template <typename T>
+// before the first one that does (under: first i with d <= th[i], i.e. j = #{th < d}; over: thresholds th[0..j-1] satisfy
+// d >= th, i.e. j = #{th <= d}).
+// Four cells per thread and pass (one 16 / 32-byte load of the descriptor, one 4-byte load of the benchmark); j by a
+// branch-free binary search over the threshold list in shared memory (padded to 32 entries with +inf); the lanes of a warp
+// that hit the same bin as the first of them are summed and added by it (eval_count).  CT = float when the descriptor is f32 and every threshold (and the nodata value)
+// is a float exactly: the comparison is the same, without a conversion to f64 per cell.
+template <typename T> struct alignas(sizeof(T) * 4) EvPack4 { T v[4]; };
+
+// bin of one cell, or -1 for a benchmark value outside {0, 1, 2, 3, -100}.  Branch-free: the class slot is the low three
+// bits of the benchmark byte (-100 = 0x9c -> 4; slots become avaliacao's classes when the block adds its counts to the global histogram);
+// a search step is one shared load at [offset + constant], one compare and one predicated add of the byte offset.
+// `nodata` arrives as NaN when it cannot equal a CT descriptor.
+template <typename T, typename CT, bool UNDER>
+__device__ __forceinline__ int eval_bin(T d0, int f, CT nodata, const CT *__restrict__ th, int k)
+{
+    const CT d = (CT)d0;
+    unsigned off = 0;
+    const char *base = reinterpret_cast<const char *>(th);
+#pragma unroll
+    for (int step = EV_MAXK / 2; step >= 1; step >>= 1) {
+        const CT t = *reinterpret_cast<const CT *>(base + off + (step - 1) * sizeof(CT));
+        if (UNDER ? t < d : t <= d) off += step * (unsigned)sizeof(CT);
+    }
+    const CT t = *reinterpret_cast<const CT *>(base + off);
+    if (UNDER ? t < d : t <= d) off += (unsigned)sizeof(CT);
+    int j = min((int)(off / sizeof(CT)), k);  // (d = +inf counts the +inf padding as well)
+    if (d != d || d == nodata) j = UNDER ? k : 0;  // never flagged
+    const bool valid = (unsigned)f <= 3u || f == ND_I;
+    return valid ? (f & 7) * (EV_MAXK + 1) + j : -1;
+}
+
+// One histogram update for the four cells of every lane: the cells that fall into the bin of the first lane's first valid
+// cell -- in a raster nearly all of them -- are counted with one redux and added by one lane; the others add on their own
+// (same-address shared atomics serialise, so per-cell atomics cost 32 passes per warp and cell).
+__device__ __forceinline__ void eval_count4(unsigned *sh, const int (&key)[4])
+{
+    const unsigned act = __activemask();
+    int first = key[0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) first = first >= 0 ? first : key[i];
+    const unsigned want = __ballot_sync(act, first >= 0);
+    if (!want) return;
+    const int lead = __ffs((int)want) - 1;
+    const int cand = __shfl_sync(act, first, lead);
+    unsigned hits = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hits += key[i] == cand ? 1u : 0u;
+    const unsigned sum = __reduce_add_sync(act, hits);
+    if ((int)(threadIdx.x & 31) == lead) atomicAdd(&sh[cand], sum);
+    if (hits != 4u) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (key[i] >= 0 && key[i] != cand) atomicAdd(&sh[key[i]], 1u);
+    }
+}
+
+constexpr int EV_SLOTS = 5;  // benchmark bytes 0, 1, 2, 3 and -100 (& 7 = 4)
+
+template <typename T, typename CT, bool VEC, bool UNDER>
 __global__ void __launch_bounds__(EV_THREADS)
-eval_hist_kernel(const T *__restrict__ desc, const int8_t *__restrict__ flood, int64_t n, double nodata, Thresholds t, int under,
+eval_hist_kernel(const T *__restrict__ desc, const int8_t *__restrict__ flood, int64_t n, double nodata, Thresholds t,
                  unsigned long long *__restrict__ hist)
 {
-    __shared__ unsigned sh[4 * (EV_MAXK + 1)];
-    for (int i = threadIdx.x; i < 4 * (EV_MAXK + 1); i += EV_THREADS) sh[i] = 0;
-    __syncthreads();
-    for (int64_t p = (int64_t)blockIdx.x * EV_THREADS + threadIdx.x; p < n; p += (int64_t)gridDim.x * EV_THREADS) {
-        const int c = remap((int)flood[p]);
-        if (c < 0 || c > 3) continue;
-        const T d = desc[p];
-        int j;
-        if (!usable(d, nodata)) j = under ? t.k : 0;  // never flagged
-        else if (under) { j = 0; while (j < t.k && !((double)d <= t.th[j])) ++j; }   // flagged by thresholds j..k-1
-        else { j = 0; while (j < t.k && (double)d >= t.th[j]) ++j; }                  // flagged by thresholds 0..j-1
-        atomicAdd(&sh[c * (EV_MAXK + 1) + j], 1u);
+    __shared__ unsigned sh[EV_SLOTS * (EV_MAXK + 1)];
+    __shared__ CT th[EV_MAXK + 1];
+    for (int i = threadIdx.x; i < EV_SLOTS * (EV_MAXK + 1); i += EV_THREADS) sh[i] = 0;
+    if (threadIdx.x <= EV_MAXK) {
+        const int i = threadIdx.x;
+        th[i] = i < t.k ? (CT)t.th[i] : (CT)__longlong_as_double(0x7ff0000000000000LL);  // +inf: never below a value
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 4 * (EV_MAXK + 1); i += EV_THREADS)
-        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+    // (a nodata value that is not a CT never equals a CT descriptor: compare with NaN then)
+    const CT nd = (double)(CT)nodata == nodata ? (CT)nodata : (CT)__longlong_as_double(0x7ff8000000000000LL);
+    const int64_t t0 = (int64_t)blockIdx.x * EV_THREADS + threadIdx.x, nt = (int64_t)gridDim.x * EV_THREADS;
+    const int64_t nv = VEC ? n / 4 : 0;
+    for (int64_t q = t0; q < nv; q += nt) {
+        const EvPack4<T> d = *reinterpret_cast<const EvPack4<T> *>(desc + 4 * q);
+        const char4 f = *reinterpret_cast<const char4 *>(flood + 4 * q);
+        const int fv[4] = {f.x, f.y, f.z, f.w};
+        int key[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) key[i] = eval_bin<T, CT, UNDER>(d.v[i], fv[i], nd, th, t.k);
+        eval_count4(sh, key);
+    }
+    for (int64_t p = 4 * nv + t0; p < n; p += nt) {
+        const int key = eval_bin<T, CT, UNDER>(desc[p], (int)flood[p], nd, th, t.k);
+        if (key >= 0) atomicAdd(&sh[key], 1u);
+    }
+    __syncthreads();
+    // slots -> avaliacao's classes (evaluation.py:149-150): 1 -> 2, -100 -> 0
+    for (int i = threadIdx.x; i < EV_SLOTS * (EV_MAXK + 1); i += EV_THREADS) {
+        if (!sh[i]) continue;
+        const int slot = i / (EV_MAXK + 1), j = i - slot * (EV_MAXK + 1);
+        const int c = slot == 1 ? 2 : (slot == 4 ? 0 : slot);
+        atomicAdd(&hist[c * (EV_MAXK + 1) + j], (unsigned long long)sh[i]);
+    }
 }
 
 template <typename T>
@@ -94,8 +168,23 @@ extern "C" int dtb_eval_counts(const void *desc, int desc_is_f64, const int8_t *
     for (int i = 0; i < EV_MAXK; ++i) t.th[i] = i < k ? thresholds_host[i] : 0.0;
     unsigned long long *hist = reinterpret_cast<unsigned long long *>(ws);
     DTB_CUDA(cudaMemsetAsync(hist, 0, 4 * (EV_MAXK + 1) * sizeof(unsigned long long), st));
-    if (desc_is_f64) DTB_KERNEL("eval_hist_kernel<f64>", st, eval_hist_kernel<double><<<EV_BLOCKS, EV_THREADS, 0, st>>>((const double *)desc, flood, n, nodata, t, under, hist));
-    else DTB_KERNEL("eval_hist_kernel<f32>", st, eval_hist_kernel<float><<<EV_BLOCKS, EV_THREADS, 0, st>>>((const float *)desc, flood, n, nodata, t, under, hist));
+    const bool vec = (reinterpret_cast<uintptr_t>(desc) % (desc_is_f64 ? 32 : 16)) == 0 && (reinterpret_cast<uintptr_t>(flood) % 4) == 0;
+    bool as_float = !desc_is_f64 && (double)(float)nodata == nodata;
+    for (int i = 0; i < k && as_float; ++i) as_float = (double)(float)thresholds_host[i] == thresholds_host[i];
+#define DTB_EVH2(NAME, T, CT, VEC, UNDER) \
+    DTB_KERNEL(NAME, st, (eval_hist_kernel<T, CT, VEC, UNDER><<<EV_BLOCKS, EV_THREADS, 0, st>>>((const T *)desc, flood, n, nodata, t, hist)))
+#define DTB_EVH(NAME, T, CT)                                   \
+    do {                                                       \
+        if (vec && under) DTB_EVH2(NAME, T, CT, true, true);   \
+        else if (vec) DTB_EVH2(NAME, T, CT, true, false);      \
+        else if (under) DTB_EVH2(NAME, T, CT, false, true);    \
+        else DTB_EVH2(NAME, T, CT, false, false);              \
+    } while (0)
+    if (desc_is_f64) DTB_EVH("eval_hist_kernel<f64>", double, double);
+    else if (as_float) DTB_EVH("eval_hist_kernel<f32>", float, float);
+    else DTB_EVH("eval_hist_kernel<f32,f64>", float, double);
+#undef DTB_EVH
+#undef DTB_EVH2
     unsigned long long h[4 * (EV_MAXK + 1)];
     DTB_CUDA(cudaMemcpyAsync(h, hist, sizeof(h), cudaMemcpyDeviceToHost, st));
     DTB_CUDA(cudaStreamSynchronize(st));

@@ -795,6 +795,66 @@ def test_evaluation_counts_random_over_and_under():
         np.testing.assert_array_equal(cls, ref_cls)
 
 
+def test_evaluation_counts_kernel_against_brute_force():
+    """dtb_eval_counts (one pass, up to 32 thresholds): float32 / float64 descriptors, under / over, NaN, +-inf, nodata,
+    benchmark values outside 0..3, a length that is not a multiple of 4, an unaligned view, thresholds that are floats
+    exactly (f32 comparison in the kernel) and thresholds that are not (f64 comparison)"""
+    import descriptools_b200.evaluation as ev
+
+    rng = np.random.default_rng(31)
+    n = 257 * 301 + 3
+    base = rng.random(n + 5) * 2.0 - 0.5
+    base[rng.random(n + 5) < 0.05] = np.nan
+    base[rng.random(n + 5) < 0.02] = np.inf
+    base[rng.random(n + 5) < 0.02] = -np.inf
+    base[rng.random(n + 5) < 0.1] = -100.0  # nodata
+    flood_all = rng.choice(np.array([0, 1, -100, 3, 7], np.int8), size=n + 5, p=[0.5, 0.3, 0.1, 0.05, 0.05])
+    grids = {"exact": np.linspace(-0.5, 1.5, 17), "inexact": np.linspace(-0.45, 1.45, 32) + 1e-9, "one": np.array([0.3])}
+    for dt in (np.float32, np.float64):
+        for off in (0, 1):  # off = 1: the device pointers are not 16-byte aligned
+            desc_t = torch.from_numpy(base.astype(dt)).cuda()[off:off + n]
+            flood_t = torch.from_numpy(flood_all).cuda()[off:off + n]
+            d = desc_t.cpu().numpy()
+            f = flood_t.cpu().numpy()
+            cmp_ = np.where(f == 1, 2, np.where(f == -100, 0, f)).astype(np.int64)
+            usable = ~np.isnan(d) & (d != dt(-100.0))
+            for under in ("under", "over"):
+                ctr = ev._Counter(desc_t, dt is np.float64, -100.0, flood_t, under)
+                for name, th in grids.items():
+                    got = ctr.counts(th.tolist())
+                    for i, t in enumerate(th):
+                        tt = dt(t)  # NumPy compares a float32 array with a Python float in float32
+                        with np.errstate(invalid="ignore"):
+                            hit = usable & ((d <= tt) if under == "under" else (d >= tt))
+                        cls = hit.astype(np.int64) + cmp_
+                        # classes above 3 (benchmark 3 + flagged) are not counted; benchmark values outside 0..3 are skipped
+                        ok = (cmp_ >= 0) & (cmp_ <= 3)
+                        want = [int(((cls == c) & ok).sum()) for c in range(4)]
+                        assert got[i].tolist() == want, (dt.__name__, off, under, name, i)
+    # the C ABI itself takes any f64 thresholds: a float32 descriptor is then compared in f64, (double)d <= th
+    import ctypes
+
+    from descriptools_b200._lib import check, lib
+
+    desc_t = torch.from_numpy(base[:n].astype(np.float32)).cuda()
+    flood_t = torch.from_numpy(flood_all[:n]).cuda()
+    d = desc_t.cpu().numpy().astype(np.float64)
+    cmp_ = np.where(flood_all[:n] == 1, 2, np.where(flood_all[:n] == -100, 0, flood_all[:n])).astype(np.int64)
+    ok = (cmp_ >= 0) & (cmp_ <= 3)
+    th = np.ascontiguousarray(grids["inexact"])
+    ws = torch.empty(4 * 33 * 8, dtype=torch.uint8, device="cuda")
+    for under in (1, 0):
+        res = np.zeros((len(th), 4), np.int64)
+        check(lib.dtb_eval_counts(desc_t.data_ptr(), 0, flood_t.data_ptr(), n, -100.0, th.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                  len(th), under, res.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ws.data_ptr(), ws.numel(),
+                                  torch.cuda.current_stream().cuda_stream), "dtb_eval_counts")
+        for i, t in enumerate(th):
+            with np.errstate(invalid="ignore"):
+                hit = ~np.isnan(d) & (d != -100.0) & ((d <= t) if under else (d >= t))
+            cls = hit.astype(np.int64) + cmp_
+            assert res[i].tolist() == [int(((cls == c) & ok).sum()) for c in range(4)], (under, i)
+
+
 def test_evaluation_float32_thresholds_compare_like_numpy():
     """cells exactly at float32(threshold): NumPy compares a float32 descriptor with a Python float in float32"""
     import descriptools_b200.evaluation as ev
