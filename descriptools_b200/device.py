@@ -55,17 +55,17 @@ def _int_dtype(t: torch.Tensor) -> int:
 
 
 class _Workspace:
-    """Cached scratch buffers per (device, stage), grown on demand (caller-owned from the ABI's view)."""
+    """Cached scratch buffers per (device, stage, stream), grown on demand (caller-owned from the ABI's view)."""
 
     def __init__(self):
         self.buf = {}
         self.fused = {}  # device index -> what the fused flow-accumulation call left in the "hand" workspace
 
     def get(self, nbytes: int, stage: str = "shared", device=None) -> torch.Tensor:
-        """scratch on `device` (default: the current one).  Calls on one device are ordered by the stream they are
-        enqueued on; two streams must not share a stage's scratch -- use one stream per device, as the drop-in does."""
+        """scratch on `device` (default: the current one) for the stream the call is enqueued on: calls on one stream are
+        ordered, two streams each get a buffer of their own."""
         index = torch.cuda.current_device() if device is None else torch.device(device).index
-        key = (index, stage)
+        key = (index, stage, torch.cuda.current_stream(index).cuda_stream)
         b = self.buf.get(key)
         if b is None or b.numel() < nbytes:
             self.buf[key] = None
