@@ -490,8 +490,10 @@ def chunk_table(reader: "DatasetReader"):
     return lay, across, off, cnt
 
 
-# what decode="auto" hands to the device: the codecs whose kernels have been measured on a B200 (profiles/r1z_*).  The
-# Deflate and PackBits kernels are there (decode="device") but stay off the default path until they have run on a device.
+# what decode="auto" hands to the device: the codecs whose kernels win there on a B200.  LZW does (profiles/r1z_*,
+# r2zf_raster_codecs_*: 4.7-4.8 GB/s against 3.3-3.7 from 16 host threads at 16384 x 16384).  The Deflate kernel is correct on
+# the device (tests/test_raster_io.py) but a draw -- 4.0-4.3 GB/s against 3.6-4.6 -- so Deflate and PackBits files take the
+# host team unless the caller asks for decode="device".
 _AUTO_DEVICE_COMPRESSIONS = ("none", "lzw")
 
 
