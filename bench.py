@@ -268,7 +268,7 @@ def extra_kernels(peak):
         out[name] = {"ms": ms, "bytes_per_cell": bpc, "achieved_gbs": gbs, "frac": gbs / peak, "note": note}
 
     rec("downslope_kernel", _time_launches(lambda: device.downslope(dem, res["d8"], PX, 5.0), reps=5, warm=2), 9,
-        "dem 4 + d8 1 in, f32 out; plus the walks: ~180 moves per cell on this DEM (5 B each, served by L2), see @workload")
+        "dem 4 + d8 1 in, f32 out; plus the walks: ~180 moves per cell on this DEM (5 B each, served by L2), issue-bound (~40 instructions per move), see @workload")
     rec("ti_mti_kernel", _time_launches(lambda: device.ti_mti(res["acc"], slope_rad, PX, 0.1), reps=5, warm=2), 16,
         "acc 4 + slope 4 in, TI + MTI out; f64 tan + two short logs")
     rec("lnhlh_kernel", _time_launches(lambda: device.ln_hl_H(res["hand"], res["acc"], N_GFI, B_GFI, PX), reps=5, warm=2), 12,

@@ -313,6 +313,34 @@ def test_downslope_synth_bit_exact(mods):
         np.testing.assert_array_equal(mods["downslope"].downsloper(dem, d8, PX, delta), oracle.downslope(dem, d8, PX, delta))
 
 
+def test_downslope_drop_limits_and_odd_codes(mods):
+    """the kernel tests "drop < delta" in the DEM's own type against a limit derived from delta on the host: deltas that
+    are not float32 values, tiny, zero, negative and NaN; int16 elevations with fractional deltas; grids with cells that
+    carry no or several direction bits (the walk stops there) -- all bit-exact against the oracle's f64 comparison"""
+    dem = synth(160, 211, 29)
+    _, d8 = oracle.slope_d8(dem, PX)
+    rng = np.random.default_rng(5)
+    odd = d8.copy()
+    hit = rng.random(odd.shape) < 0.02
+    odd[hit] = rng.choice(np.array([0, 3, 129, 255, 96], np.uint8), size=int(hit.sum()))
+    for delta in (5.1, 0.1 + 1e-9, 1e-50, 0.0, -3.0, float("nan"), 1e30):
+        for codes in (d8, odd):
+            np.testing.assert_array_equal(mods["downslope"].downsloper(dem, codes, PX, delta), oracle.downslope(dem, codes, PX, delta),
+                                          err_msg=f"delta={delta}")
+    # elevation differences that land exactly on float32 neighbours of delta
+    step = np.float32(5.1)
+    ramp = (np.float32(1000.0) - np.arange(64, dtype=np.float32)[None, :] * step) + np.zeros((8, 1), np.float32)
+    east = np.full(ramp.shape, 1, np.uint8)
+    for delta in (float(step), float(np.nextafter(step, np.float32(0))), float(np.nextafter(step, np.float32(10))), 5.1):
+        np.testing.assert_array_equal(mods["downslope"].downsloper(ramp, east, PX, delta), oracle.downslope(ramp, east, PX, delta),
+                                      err_msg=f"ramp delta={delta}")
+    dem16 = np.round(dem).astype(np.int16)
+    _, d16 = oracle.slope_d8(dem16, PX)
+    for delta in (4.5, 5, 5.0000001, -1.5, 1e9):
+        np.testing.assert_array_equal(mods["downslope"].downsloper(dem16, d16, PX, delta), oracle.downslope(dem16, d16, PX, delta),
+                                      err_msg=f"int16 delta={delta}")
+
+
 def test_gfi_lnhlh_example_golden(mods, ex):
     gold = load("example_cpujit.npz")
     _, idx, hand = oracle.flow_hand_index(ex["dem"], ex["fdr"], ex["river"], PX)
