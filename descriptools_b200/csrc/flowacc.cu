@@ -482,31 +482,33 @@ fa_tile_rehand_kernel(TileView v, int64_t tiles, const uint32_t *__restrict__ me
 }
 
 // ---- N: entry-node forest ---------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-fa_node_init_kernel(int64_t nnodes, int64_t rows, int64_t cols, int tiles_x, const uint32_t *__restrict__ exitw,
-                    const uint32_t *__restrict__ meta, const int64_t *__restrict__ inflow_above,
-                    const int64_t *__restrict__ inflow_below, unsigned long long *__restrict__ nstate)
+// One CTA per tile (its 256 slots); 32-bit arithmetic throughout -- the first form (flat 64-bit node numbers, a 64-bit
+// division per node) kept the issue slots 64 % busy for what is a gather of two words per feeding neighbour.
+__global__ void __launch_bounds__(SLOTS)
+fa_node_init_kernel(int rows, int cols, int tiles_x, const uint32_t *__restrict__ exitw, const uint32_t *__restrict__ meta,
+                    const int64_t *__restrict__ inflow_above, const int64_t *__restrict__ inflow_below,
+                    unsigned long long *__restrict__ nstate)
 {
-    const int64_t node = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (node >= nnodes) return;
+    const int tile = blockIdx.x, s = threadIdx.x;
+    const size_t node = (size_t)tile * SLOTS + s;
     const uint32_t m = meta[node];
     const unsigned inmask = (m >> 16) & 0xFFu;
     if (!inmask) { nstate[node] = 0ull; return; }
-    const int64_t tile = node / SLOTS;
-    const int s = (int)(node % SLOTS);
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     int lr, lc;
     slot_cell(s, lr, lc);
-    const int64_t gr = (tile / tiles_x) * T + lr, gc = (tile % tiles_x) * T + lc;
+    const int gr = ty * T + lr, gc = tx * T + lc;
     uint64_t base = 0, pend = 0;
+#pragma unroll
     for (int k = 0; k < 8; ++k) {
         if (!((inmask >> k) & 1u)) continue;
         int dr, dc;
         nbr_offset(k, dr, dc);
-        const int64_t ur = gr + dr, uc = gc + dc;
+        const int ur = gr + dr, uc = gc + dc;
         if (ur < 0) base += inflow_above ? (uint64_t)inflow_above[uc] : 0ull;
         else if (ur >= rows) base += inflow_below ? (uint64_t)inflow_below[uc] : 0ull;
         else {
-            const int64_t un = ((ur / T) * tiles_x + uc / T) * SLOTS + slot_of((int)(ur % T), (int)(uc % T));
+            const uint32_t un = (uint32_t)(((ur >> 6) * tiles_x + (uc >> 6)) * SLOTS + slot_of(ur & (T - 1), uc & (T - 1)));
             base += exitw[un];
             pend += (meta[un] >> 8) & 0xFFu;
         }
@@ -836,8 +838,9 @@ int run(const dtb_flowacc_args *a, void *ws, cudaStream_t st)
         DTB_KERNEL("fa_tile_kernel", st, fa_tile_kernel<ACC><<<(unsigned)L.tiles, FT_THREADS, 0, st>>>(v, exitw, link, meta, acc, (ACC)a->nodata_fill, counters, table));
     }
     if (a->mode != DTB_FA_FINISH) {
-        DTB_KERNEL("fa_node_init_kernel", st, fa_node_init_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, a->rows, a->cols, v.tiles_x, exitw, meta, a->inflow_above,
-                                                     a->inflow_below, nstate));
+        static_assert(T == 64 && SLOTS == 256, "fa_node_init_kernel: one CTA per tile, shifts by 6");
+        DTB_KERNEL("fa_node_init_kernel", st, fa_node_init_kernel<<<(unsigned)L.tiles, SLOTS, 0, st>>>((int)a->rows, (int)a->cols, v.tiles_x, exitw, meta,
+                                                     a->inflow_above, a->inflow_below, nstate));
         DTB_KERNEL("fa_node_sweep_kernel", st, fa_node_sweep_kernel<<<nb_nodes, 256, 0, st>>>(L.nnodes, link, nstate));
     } else {
         // the node states of the SUMMARY call (zero halo inflow) + what each seam entry receives, pushed down its chain
