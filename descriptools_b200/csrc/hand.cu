@@ -142,15 +142,21 @@ hand_node_jump_kernel(int64_t nnodes, unsigned long long *nstate, unsigned *__re
 {
     if (active[rnd - 1] == 0) return;
     unsigned still = 0;
-    for (int64_t q = (int64_t)blockIdx.x * H_THREADS + threadIdx.x; q < nnodes; q += (int64_t)gridDim.x * H_THREADS) {
-        uint64_t s = __ldcg(&nstate[q]);
-        if (kind_of(s) != KIND_ACTIVE || s == 0ull) continue;  // 0 = inactive slot
-        for (int j = 0; j < jumps; ++j) {
-            s = compose(s, __ldcg(&nstate[ptr_of(s)]));
-            if (kind_of(s) != KIND_ACTIVE) break;
+    // two states per thread and pass (16-byte loads): most of a launch is the scan over all slots (nnodes is a multiple of 256)
+    for (int64_t q = ((int64_t)blockIdx.x * H_THREADS + threadIdx.x) * 2; q < nnodes; q += (int64_t)gridDim.x * H_THREADS * 2) {
+        const ulonglong2 two = __ldcg(reinterpret_cast<const ulonglong2 *>(&nstate[q]));
+        const uint64_t in[2] = {two.x, two.y};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            uint64_t s = in[k];
+            if (kind_of(s) != KIND_ACTIVE || s == 0ull) continue;  // 0 = inactive slot
+            for (int j = 0; j < jumps; ++j) {
+                s = compose(s, __ldcg(&nstate[ptr_of(s)]));
+                if (kind_of(s) != KIND_ACTIVE) break;
+            }
+            __stcg(&nstate[q + k], s);
+            still += kind_of(s) == KIND_ACTIVE;
         }
-        __stcg(&nstate[q], s);
-        still += kind_of(s) == KIND_ACTIVE;
     }
     still = __reduce_add_sync(0xffffffffu, still);
     if ((threadIdx.x & 31) == 0 && still) atomicAdd(&active[rnd], still);
